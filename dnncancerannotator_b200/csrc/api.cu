@@ -1,0 +1,157 @@
+// C-ABI entry points that dispatch between kernel families, plus error plumbing.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dnnca {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+  return DNNCA_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;  // B200; not cached so a later call can still pick the real value up
+  }
+  return cached;
+}
+
+// kernel families (conv_generic.cu / conv_small.cu)
+int launch_conv_fprop_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, int, float);
+int launch_conv_dgrad_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, int, const dnnca_tensor_t*, int, float);
+int launch_conv_wgrad_generic(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*, int);
+int launch_tconv_fprop_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*);
+int launch_tconv_dgrad_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
+int launch_tconv_wgrad_generic(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
+// return 1 when the shape was handled, 0 when not covered, <0 on error
+int try_conv_fprop_small_f32(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
+int try_conv_fprop_small_bf16(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
+int try_conv_dgrad_small_f32(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
+int try_conv_dgrad_small_bf16(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
+int try_conv_wgrad_small_f32(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
+int try_conv_wgrad_small_bf16(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
+
+}  // namespace dnnca
+
+using namespace dnnca;
+
+static int g_force_generic = 0;
+
+extern "C" int dnnca_version(void) { return DNNCA_VERSION; }
+extern "C" const char* dnnca_last_error(void) { return g_err; }
+extern "C" int dnnca_sm_count(int* out) {
+  if (!out) return DNNCA_ERR_BAD_ARG;
+  *out = sm_count();
+  return DNNCA_OK;
+}
+// test hook: route every conv through the shape-generic kernels
+extern "C" int dnnca_debug_force_generic(int on) {
+  int old = g_force_generic;
+  g_force_generic = on;
+  return old;
+}
+
+static bool act_ok(int act) { return act == DNNCA_ACT_NONE || act == DNNCA_ACT_RELU || act == DNNCA_ACT_LEAKY; }
+
+extern "C" int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const float* w, const float* bias,
+                                  const dnnca_tensor_t* y, int ksize, int act, float alpha, double* stats) {
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && w, "conv2d_fprop: bad tensor arguments");
+  DNNCA_CHECK_ARG(same_nhw(x, y) && x->dtype == y->dtype, "conv2d_fprop: x and y must share n,h,w and dtype ('same' padding, stride 1)");
+  DNNCA_CHECK_ARG(act_ok(act), "conv2d_fprop: unknown activation %d", act);
+  if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_fprop: kernel size %d (only 1 and 3 are used by the reference models)", ksize);
+  cudaStream_t s = (cudaStream_t)stream;
+  int r = 0;
+  if (!g_force_generic) {
+    if (ksize == 3)
+      r = x->dtype == DNNCA_F32 ? try_conv_fprop_small_f32(s, x, w, bias, y, act, alpha, stats)
+                                : try_conv_fprop_small_bf16(s, x, w, bias, y, act, alpha, stats);
+    if (r < 0) return r;
+    if (r == 1) return DNNCA_OK;
+  }
+  r = launch_conv_fprop_generic(s, x, w, bias, y, ksize, act, alpha);
+  if (r != DNNCA_OK) return r;
+  if (stats) return dnnca_channel_stats(stream, y, stats);
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_conv2d_dgrad(void* stream, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
+                                  int ksize, const dnnca_tensor_t* mask, int act, float alpha) {
+  DNNCA_CHECK_ARG(view_ok(dz) && view_ok(dx) && w, "conv2d_dgrad: bad tensor arguments");
+  DNNCA_CHECK_ARG(same_nhw(dz, dx) && dz->dtype == dx->dtype, "conv2d_dgrad: dz and dx must share n,h,w and dtype");
+  DNNCA_CHECK_ARG(!mask || (view_ok(mask) && same_shape(mask, dx) && mask->dtype == dx->dtype), "conv2d_dgrad: bad mask");
+  DNNCA_CHECK_ARG(act_ok(act), "conv2d_dgrad: unknown activation %d", act);
+  if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_dgrad: kernel size %d", ksize);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!g_force_generic) {
+    int r = 0;
+    if (ksize == 3)
+      r = dx->dtype == DNNCA_F32 ? try_conv_dgrad_small_f32(s, dz, w, dx, mask, act, alpha)
+                                 : try_conv_dgrad_small_bf16(s, dz, w, dx, mask, act, alpha);
+    if (r < 0) return r;
+    if (r == 1) return DNNCA_OK;
+  }
+  return launch_conv_dgrad_generic(s, dz, w, dx, ksize, mask, act, alpha);
+}
+
+extern "C" int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dz, float* dw,
+                                  float* db, int ksize) {
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(dz) && dw, "conv2d_wgrad: bad tensor arguments");
+  DNNCA_CHECK_ARG(same_nhw(x, dz) && x->dtype == dz->dtype, "conv2d_wgrad: x and dz must share n,h,w and dtype");
+  if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_wgrad: kernel size %d", ksize);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!g_force_generic) {
+    int r = 0;
+    if (ksize == 3)
+      r = x->dtype == DNNCA_F32 ? try_conv_wgrad_small_f32(s, x, dz, dw, db) : try_conv_wgrad_small_bf16(s, x, dz, dw, db);
+    if (r < 0) return r;
+    if (r == 1) return DNNCA_OK;
+  }
+  return launch_conv_wgrad_generic(s, x, dz, dw, db, ksize);
+}
+
+extern "C" int dnnca_convtranspose2x2_fprop(void* stream, const dnnca_tensor_t* x, const float* k, const float* bias,
+                                            const dnnca_tensor_t* y, double* stats) {
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && k, "convtranspose2x2_fprop: bad tensor arguments");
+  DNNCA_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && x->dtype == y->dtype,
+                  "convtranspose2x2_fprop: y must be [n,2h,2w,cout] with x's dtype");
+  int r = launch_tconv_fprop_generic((cudaStream_t)stream, x, k, bias, y);
+  if (r != DNNCA_OK) return r;
+  if (stats) return dnnca_channel_stats(stream, y, stats);
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_convtranspose2x2_dgrad(void* stream, const dnnca_tensor_t* dy, const float* k,
+                                            const dnnca_tensor_t* dx, const dnnca_tensor_t* mask, int act,
+                                            float alpha) {
+  DNNCA_CHECK_ARG(view_ok(dy) && view_ok(dx) && k, "convtranspose2x2_dgrad: bad tensor arguments");
+  DNNCA_CHECK_ARG(dy->n == dx->n && dy->h == 2 * dx->h && dy->w == 2 * dx->w && dx->dtype == dy->dtype,
+                  "convtranspose2x2_dgrad: dy must be [n,2h,2w,cout]");
+  DNNCA_CHECK_ARG(!mask || (view_ok(mask) && same_shape(mask, dx) && mask->dtype == dx->dtype), "convtranspose2x2_dgrad: bad mask");
+  DNNCA_CHECK_ARG(act_ok(act), "convtranspose2x2_dgrad: unknown activation %d", act);
+  return launch_tconv_dgrad_generic((cudaStream_t)stream, dy, k, dx, mask, act, alpha);
+}
+
+extern "C" int dnnca_convtranspose2x2_wgrad(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dy,
+                                            float* dk, float* db) {
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(dy) && dk, "convtranspose2x2_wgrad: bad tensor arguments");
+  DNNCA_CHECK_ARG(dy->n == x->n && dy->h == 2 * x->h && dy->w == 2 * x->w && x->dtype == dy->dtype,
+                  "convtranspose2x2_wgrad: dy must be [n,2h,2w,cout]");
+  return launch_tconv_wgrad_generic((cudaStream_t)stream, x, dy, dk, db);
+}

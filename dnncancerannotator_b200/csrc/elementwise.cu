@@ -1,0 +1,415 @@
+// Memory-bound per-channel NHWC kernels: channel statistics, BatchNorm
+// (finalize / apply / backward), 2x2 max-pool forward/backward, the MultiRes
+// add-relu-affine tail, uint8->/255 input tail and dtype/slice conversion.
+//
+// Reference call sites: layers.BatchNormalization components.py:57,59,130,131;
+// layers.MaxPool2D components.py:54; multiresunet.py:120-124,148-150.
+// All kernels use the (pixel-lane, channel-lane) layout of common.cuh: coalesced
+// along the contiguous channel axis, per-channel parameters in registers,
+// fp64 block reductions -> one atomic per channel per CTA.
+#include "common.cuh"
+
+namespace dnnca {
+
+template <typename T>
+__device__ __forceinline__ const T* px_ptr(const View& v, long long p) {
+  return reinterpret_cast<const T*>(v.data) + p * v.cstride + v.coff;
+}
+template <typename T>
+__device__ __forceinline__ T* px_ptr_w(const View& v, long long p) {
+  return reinterpret_cast<T*>(v.data) + p * v.cstride + v.coff;
+}
+
+// reduce `val` over the pixel lanes (stride CL in thread index) of a 256-thread block
+__device__ __forceinline__ double block_reduce_pl(double val, double* sm, int CL, int PL) {
+  const int tid = threadIdx.x;
+  sm[tid] = val;
+  __syncthreads();
+  for (int s = PL >> 1; s > 0; s >>= 1) {
+    if (tid < s * CL) sm[tid] += sm[tid + s * CL];
+    __syncthreads();
+  }
+  double r = sm[tid % CL];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) channel_stats_kernel(View x, double* __restrict__ stats, int CL, int PL,
+                                                           long long P) {
+  __shared__ double sm[256];
+  const int cl = threadIdx.x & (CL - 1), pl = threadIdx.x / CL;
+  for (int c = cl; c < ((x.c + CL - 1) / CL) * CL; c += CL) {
+    double s = 0.0, ss = 0.0;
+    if (c < x.c) {
+      for (long long p = (long long)blockIdx.x * PL + pl; p < P; p += (long long)gridDim.x * PL) {
+        float v = ldf(px_ptr<T>(x, p) + c);
+        s += v;
+        ss += (double)v * v;
+      }
+    }
+    s = block_reduce_pl(s, sm, CL, PL);
+    ss = block_reduce_pl(ss, sm, CL, PL);
+    if (pl == 0 && c < x.c) {
+      atomicAdd(stats + c, s);
+      atomicAdd(stats + x.c + c, ss);
+    }
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, long long count, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float momentum,
+                                   float eps, float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float* __restrict__ scale_shift, float* __restrict__ mean_invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean = stats[c] / (double)count;
+  double var = stats[C + c] / (double)count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  float g = gamma ? gamma[c] : 1.f;
+  float scale = g * invstd;
+  scale_shift[c] = scale;
+  scale_shift[C + c] = beta[c] - (float)mean * scale;
+  mean_invstd[c] = (float)mean;
+  mean_invstd[C + c] = invstd;
+  if (moving_mean) {
+    double unbiased = count > 1 ? var * ((double)count / (double)(count - 1)) : var;
+    moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
+    moving_var[c] = moving_var[c] * momentum + (float)unbiased * (1.f - momentum);
+  }
+}
+
+__global__ void bn_inference_params_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           float eps, const float* __restrict__ mm, const float* __restrict__ mv,
+                                           float* __restrict__ scale_shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float scale = (gamma ? gamma[c] : 1.f) * rsqrtf(mv[c] + eps);
+  scale_shift[c] = scale;
+  scale_shift[C + c] = beta[c] - mm[c] * scale;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) bn_apply_kernel(View x, const float* __restrict__ ss, View y, int CL, int PL,
+                                                      long long P) {
+  const int cl = threadIdx.x & (CL - 1), pl = threadIdx.x / CL;
+  for (int c = cl; c < x.c; c += CL) {
+    const float scale = ss ? ss[c] : 1.f, shift = ss ? ss[x.c + c] : 0.f;
+    for (long long p = (long long)blockIdx.x * PL + pl; p < P; p += (long long)gridDim.x * PL)
+      stf(px_ptr_w<TO>(y, p) + c, ldf(px_ptr<TI>(x, p) + c) * scale + shift);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(View x, View dy, const float* __restrict__ mi,
+                                                           double* __restrict__ sums, int CL, int PL, long long P) {
+  __shared__ double sm[256];
+  const int cl = threadIdx.x & (CL - 1), pl = threadIdx.x / CL;
+  for (int c = cl; c < ((x.c + CL - 1) / CL) * CL; c += CL) {
+    double s0 = 0.0, s1 = 0.0;
+    if (c < x.c) {
+      const float mean = mi[c], invstd = mi[x.c + c];
+      for (long long p = (long long)blockIdx.x * PL + pl; p < P; p += (long long)gridDim.x * PL) {
+        float g = ldf(px_ptr<T>(dy, p) + c);
+        float xh = (ldf(px_ptr<T>(x, p) + c) - mean) * invstd;
+        s0 += g;
+        s1 += (double)g * xh;
+      }
+    }
+    s0 = block_reduce_pl(s0, sm, CL, PL);
+    s1 = block_reduce_pl(s1, sm, CL, PL);
+    if (pl == 0 && c < x.c) {
+      atomicAdd(sums + c, s0);
+      atomicAdd(sums + x.c + c, s1);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View x, View dy, const float* __restrict__ mi,
+                                                          const float* __restrict__ gamma,
+                                                          const double* __restrict__ sums, View dx, int act,
+                                                          float alpha, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, int CL, int PL, long long P) {
+  const int cl = threadIdx.x & (CL - 1), pl = threadIdx.x / CL;
+  const double invM = 1.0 / (double)P;
+  for (int c = cl; c < x.c; c += CL) {
+    const float mean = mi[c], invstd = mi[x.c + c];
+    const float a = (float)(sums[c] * invM), b = (float)(sums[x.c + c] * invM);
+    const float k = (gamma ? gamma[c] : 1.f) * invstd;
+    if (blockIdx.x == 0 && pl == 0) {
+      if (dgamma) dgamma[c] += (float)sums[x.c + c];
+      if (dbeta) dbeta[c] += (float)sums[c];
+    }
+    for (long long p = (long long)blockIdx.x * PL + pl; p < P; p += (long long)gridDim.x * PL) {
+      float xv = ldf(px_ptr<T>(x, p) + c);
+      float xh = (xv - mean) * invstd;
+      float g = k * (ldf(px_ptr<T>(dy, p) + c) - a - xh * b);
+      g *= act_grad(xv, act, alpha);
+      stf(px_ptr_w<T>(dx, p) + c, g);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// max-pool 2x2/2: thread (pl, cl) over OUTPUT pixels
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(View x, View y, uint8_t* __restrict__ idx,
+                                                         double* __restrict__ stats, int CL, int PL, long long PO) {
+  __shared__ double sm[256];
+  const int cl = threadIdx.x & (CL - 1), pl = threadIdx.x / CL;
+  const int ho = y.h, wo = y.w;
+  for (int c = cl; c < ((x.c + CL - 1) / CL) * CL; c += CL) {
+    double s = 0.0, ss = 0.0;
+    if (c < x.c) {
+      for (long long p = (long long)blockIdx.x * PL + pl; p < PO; p += (long long)gridDim.x * PL) {
+        int ox = (int)(p % wo);
+        long long t = p / wo;
+        int oy = (int)(t % ho);
+        long long n = t / ho;
+        long long p00 = (n * x.h + 2 * oy) * x.w + 2 * ox;
+        float best = ldf(px_ptr<T>(x, p00) + c);
+        int bi = 0;
+        float v = ldf(px_ptr<T>(x, p00 + 1) + c);
+        if (v > best) { best = v; bi = 1; }
+        v = ldf(px_ptr<T>(x, p00 + x.w) + c);
+        if (v > best) { best = v; bi = 2; }
+        v = ldf(px_ptr<T>(x, p00 + x.w + 1) + c);
+        if (v > best) { best = v; bi = 3; }
+        stf(px_ptr_w<T>(y, p) + c, best);
+        if (idx) idx[p * x.c + c] = (uint8_t)bi;
+        s += best;
+        ss += (double)best * best;
+      }
+    }
+    if (stats) {
+      s = block_reduce_pl(s, sm, CL, PL);
+      ss = block_reduce_pl(ss, sm, CL, PL);
+      if (pl == 0 && c < x.c) {
+        atomicAdd(stats + c, s);
+        atomicAdd(stats + x.c + c, ss);
+      }
+    }
+  }
+}
+
+// thread (pl, cl) over pooled pixels; writes the four input-gradient pixels of its window
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(View dy, const uint8_t* __restrict__ idx, View dskip,
+                                                         int has_skip, View dx, View mask, int has_mask, int act,
+                                                         float alpha, int CL, int PL, long long PO) {
+  const int cl = threadIdx.x & (CL - 1), pl = threadIdx.x / CL;
+  const int ho = dy.h, wo = dy.w;
+  for (int c = cl; c < dy.c; c += CL) {
+    for (long long p = (long long)blockIdx.x * PL + pl; p < PO; p += (long long)gridDim.x * PL) {
+      int ox = (int)(p % wo);
+      long long t = p / wo;
+      int oy = (int)(t % ho);
+      long long n = t / ho;
+      long long p00 = (n * dx.h + 2 * oy) * dx.w + 2 * ox;
+      float g = ldf(px_ptr<T>(dy, p) + c);
+      int bi = idx[p * dy.c + c];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        long long q = p00 + (k >> 1) * dx.w + (k & 1);
+        float v = (k == bi) ? g : 0.f;
+        if (has_skip) v += ldf(px_ptr<T>(dskip, q) + c);
+        if (has_mask) v *= act_grad(ldf(px_ptr<T>(mask, q) + c), act, alpha);
+        stf(px_ptr_w<T>(dx, q) + c, v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) add_relu_affine_kernel(View a, const float* __restrict__ fa, View b,
+                                                             const float* __restrict__ fb,
+                                                             const float* __restrict__ fo, View y, int CL, int PL,
+                                                             long long P) {
+  const int cl = threadIdx.x & (CL - 1), pl = threadIdx.x / CL;
+  for (int c = cl; c < a.c; c += CL) {
+    const float sa = fa ? fa[c] : 1.f, ta = fa ? fa[a.c + c] : 0.f;
+    const float sb = fb ? fb[c] : 1.f, tb = fb ? fb[a.c + c] : 0.f;
+    const float so = fo ? fo[c] : 1.f, to = fo ? fo[a.c + c] : 0.f;
+    for (long long p = (long long)blockIdx.x * PL + pl; p < P; p += (long long)gridDim.x * PL) {
+      float v = ldf(px_ptr<T>(a, p) + c) * sa + ta + ldf(px_ptr<T>(b, p) + c) * sb + tb;
+      v = v > 0.f ? v : 0.f;
+      stf(px_ptr_w<T>(y, p) + c, v * so + to);
+    }
+  }
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256) u8_to_unit_kernel(const uint8_t* __restrict__ src, long long count,
+                                                        TO* __restrict__ dst) {
+  // 16 source bytes per thread-iteration (128-bit load)
+  const long long nvec = count / 16;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    uint4 v = s4[i];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float f = (float)((w[k >> 2] >> ((k & 3) * 8)) & 0xffu) / 255.0f;
+      stf(dst + i * 16 + k, f);
+    }
+  }
+  for (long long i = nvec * 16 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    stf(dst + i, (float)src[i] / 255.0f);
+}
+
+}  // namespace dnnca
+
+using namespace dnnca;
+
+// ============================ C ABI =========================================
+extern "C" int dnnca_channel_stats(void* stream, const dnnca_tensor_t* x, double* stats) {
+  DNNCA_CHECK_ARG(view_ok(x) && stats, "channel_stats: bad arguments");
+  ChanLayout L = chan_layout(x->c);
+  long long P = (long long)x->n * x->h * x->w;
+  int grid = grid_for(P, L.pl * 8);
+  DNNCA_DISPATCH_DTYPE(x->dtype, channel_stats_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(mk(x), stats, L.cl, L.pl, P);)
+  DNNCA_LAUNCH_CHECK("channel_stats");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_bn_finalize(void* stream, const double* stats, int64_t count, int c, const float* gamma,
+                                 const float* beta, float momentum, float eps, float* moving_mean,
+                                 float* moving_var, float* scale_shift, float* mean_invstd) {
+  DNNCA_CHECK_ARG(stats && beta && scale_shift && mean_invstd && c > 0 && count > 0, "bn_finalize: bad arguments");
+  DNNCA_CHECK_ARG((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize: moving stats must come in pairs");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, count, c, gamma, beta, momentum, eps,
+                                                                         moving_mean, moving_var, scale_shift,
+                                                                         mean_invstd);
+  DNNCA_LAUNCH_CHECK("bn_finalize");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_bn_inference_params(void* stream, int c, const float* gamma, const float* beta, float eps,
+                                         const float* moving_mean, const float* moving_var, float* scale_shift) {
+  DNNCA_CHECK_ARG(c > 0 && beta && moving_mean && moving_var && scale_shift, "bn_inference_params: bad arguments");
+  bn_inference_params_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c, gamma, beta, eps, moving_mean,
+                                                                                 moving_var, scale_shift);
+  DNNCA_LAUNCH_CHECK("bn_inference_params");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_bn_apply(void* stream, const dnnca_tensor_t* x, const float* scale_shift,
+                              const dnnca_tensor_t* y) {
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && same_shape(x, y) && scale_shift, "bn_apply: bad arguments");
+  DNNCA_CHECK_ARG(x->dtype == y->dtype, "bn_apply: dtype mismatch");
+  ChanLayout L = chan_layout(x->c);
+  long long P = (long long)x->n * x->h * x->w;
+  int grid = grid_for(P, L.pl * 4);
+  DNNCA_DISPATCH_DTYPE(x->dtype, (bn_apply_kernel<T, T><<<grid, 256, 0, (cudaStream_t)stream>>>(mk(x), scale_shift, mk(y), L.cl, L.pl, P));)
+  DNNCA_LAUNCH_CHECK("bn_apply");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_convert(void* stream, const dnnca_tensor_t* src, const dnnca_tensor_t* dst) {
+  DNNCA_CHECK_ARG(view_ok(src) && view_ok(dst) && same_shape(src, dst), "convert: bad arguments");
+  ChanLayout L = chan_layout(src->c);
+  long long P = (long long)src->n * src->h * src->w;
+  int grid = grid_for(P, L.pl * 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (src->dtype == DNNCA_F32 && dst->dtype == DNNCA_F32)
+    bn_apply_kernel<float, float><<<grid, 256, 0, s>>>(mk(src), nullptr, mk(dst), L.cl, L.pl, P);
+  else if (src->dtype == DNNCA_F32)
+    bn_apply_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>(mk(src), nullptr, mk(dst), L.cl, L.pl, P);
+  else if (dst->dtype == DNNCA_F32)
+    bn_apply_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>(mk(src), nullptr, mk(dst), L.cl, L.pl, P);
+  else
+    bn_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>(mk(src), nullptr, mk(dst), L.cl, L.pl, P);
+  DNNCA_LAUNCH_CHECK("convert");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_bn_bwd_reduce(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dy,
+                                   const float* mean_invstd, double* sums) {
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(dy) && same_shape(x, dy) && mean_invstd && sums, "bn_bwd_reduce: bad arguments");
+  DNNCA_CHECK_ARG(x->dtype == dy->dtype, "bn_bwd_reduce: dtype mismatch");
+  ChanLayout L = chan_layout(x->c);
+  long long P = (long long)x->n * x->h * x->w;
+  int grid = grid_for(P, L.pl * 8);
+  DNNCA_DISPATCH_DTYPE(x->dtype, bn_bwd_reduce_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(mk(x), mk(dy), mean_invstd, sums, L.cl, L.pl, P);)
+  DNNCA_LAUNCH_CHECK("bn_bwd_reduce");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_bn_bwd_apply(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dy,
+                                  const float* mean_invstd, const float* gamma, const double* sums,
+                                  const dnnca_tensor_t* dx, int act, float alpha, float* dgamma, float* dbeta) {
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(dy) && view_ok(dx) && same_shape(x, dy) && same_shape(x, dx) && mean_invstd && sums,
+                  "bn_bwd_apply: bad arguments");
+  DNNCA_CHECK_ARG(x->dtype == dy->dtype && x->dtype == dx->dtype, "bn_bwd_apply: dtype mismatch");
+  ChanLayout L = chan_layout(x->c);
+  long long P = (long long)x->n * x->h * x->w;
+  int grid = grid_for(P, L.pl * 4);
+  DNNCA_DISPATCH_DTYPE(x->dtype, bn_bwd_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      mk(x), mk(dy), mean_invstd, gamma, sums, mk(dx), act, alpha, dgamma, dbeta, L.cl, L.pl, P);)
+  DNNCA_LAUNCH_CHECK("bn_bwd_apply");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_maxpool2x2_fwd(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* y, uint8_t* idx,
+                                    double* stats) {
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(y), "maxpool_fwd: bad arguments");
+  DNNCA_CHECK_ARG(x->h % 2 == 0 && x->w % 2 == 0 && y->h == x->h / 2 && y->w == x->w / 2 && y->n == x->n && y->c == x->c,
+                  "maxpool_fwd: y must be [n,h/2,w/2,c] of an even-sized x");
+  DNNCA_CHECK_ARG(x->dtype == y->dtype, "maxpool_fwd: dtype mismatch");
+  ChanLayout L = chan_layout(x->c);
+  long long PO = (long long)y->n * y->h * y->w;
+  int grid = grid_for(PO, L.pl * 4);
+  DNNCA_DISPATCH_DTYPE(x->dtype, maxpool_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(mk(x), mk(y), idx, stats, L.cl, L.pl, PO);)
+  DNNCA_LAUNCH_CHECK("maxpool_fwd");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_maxpool2x2_bwd(void* stream, const dnnca_tensor_t* dy, const uint8_t* idx,
+                                    const dnnca_tensor_t* dskip, const dnnca_tensor_t* dx,
+                                    const dnnca_tensor_t* mask, int act, float alpha) {
+  DNNCA_CHECK_ARG(view_ok(dy) && view_ok(dx) && idx, "maxpool_bwd: bad arguments");
+  DNNCA_CHECK_ARG(dx->h == 2 * dy->h && dx->w == 2 * dy->w && dx->n == dy->n && dx->c == dy->c, "maxpool_bwd: shape mismatch");
+  DNNCA_CHECK_ARG(!dskip || (view_ok(dskip) && same_shape(dskip, dx) && dskip->dtype == dx->dtype), "maxpool_bwd: bad dskip");
+  DNNCA_CHECK_ARG(!mask || (view_ok(mask) && same_shape(mask, dx) && mask->dtype == dx->dtype), "maxpool_bwd: bad mask");
+  DNNCA_CHECK_ARG(dy->dtype == dx->dtype, "maxpool_bwd: dtype mismatch");
+  ChanLayout L = chan_layout(dy->c);
+  long long PO = (long long)dy->n * dy->h * dy->w;
+  int grid = grid_for(PO, L.pl * 2);
+  View vs = dskip ? mk(dskip) : mk(dx), vm = mask ? mk(mask) : mk(dx);
+  DNNCA_DISPATCH_DTYPE(dy->dtype, maxpool_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      mk(dy), idx, vs, dskip != nullptr, mk(dx), vm, mask != nullptr, act, alpha, L.cl, L.pl, PO);)
+  DNNCA_LAUNCH_CHECK("maxpool_bwd");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_add_relu_affine(void* stream, const dnnca_tensor_t* a, const float* affine_a,
+                                     const dnnca_tensor_t* b, const float* affine_b, const float* affine_out,
+                                     const dnnca_tensor_t* y) {
+  DNNCA_CHECK_ARG(view_ok(a) && view_ok(b) && view_ok(y) && same_shape(a, b) && same_shape(a, y), "add_relu_affine: bad arguments");
+  DNNCA_CHECK_ARG(a->dtype == b->dtype && a->dtype == y->dtype, "add_relu_affine: dtype mismatch");
+  ChanLayout L = chan_layout(a->c);
+  long long P = (long long)a->n * a->h * a->w;
+  int grid = grid_for(P, L.pl * 4);
+  DNNCA_DISPATCH_DTYPE(a->dtype, add_relu_affine_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      mk(a), affine_a, mk(b), affine_b, affine_out, mk(y), L.cl, L.pl, P);)
+  DNNCA_LAUNCH_CHECK("add_relu_affine");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_u8_to_unit(void* stream, const uint8_t* src, int64_t count, void* dst, int dtype) {
+  DNNCA_CHECK_ARG(src && dst && count > 0 && (dtype == DNNCA_F32 || dtype == DNNCA_BF16), "u8_to_unit: bad arguments");
+  DNNCA_CHECK_ARG(((uintptr_t)src & 15) == 0, "u8_to_unit: src must be 16-byte aligned");
+  int grid = grid_for(count / 16 + 1, 256);
+  if (dtype == DNNCA_F32)
+    u8_to_unit_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(src, count, (float*)dst);
+  else
+    u8_to_unit_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, count, (__nv_bfloat16*)dst);
+  DNNCA_LAUNCH_CHECK("u8_to_unit");
+  return DNNCA_OK;
+}

@@ -1,0 +1,239 @@
+// Fused segmentation head + weighted binary cross-entropy.
+//
+// Replaces, in ONE pass over the feature map, what the reference runs as
+// Conv2D(1, k=1, 'sigmoid') (unet.py:241-244), tf_get_positive_rate
+// (losses.py:87-102), tf_weighted_crossentropy (losses.py:17-37) and their
+// gradients (~15 TF elementwise/reduce kernels + a 1x1 conv fwd/bwd):
+//   z = f.w + b ; p = sigmoid(z) ; loss ; dz ; df = dz*w (*act'(f)) ; dw ; db.
+// Memory-bound: reads f and the label once, writes df (and p/z) once.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dnnca {
+
+__device__ __forceinline__ uint32_t float_key(float f) {  // order-preserving
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void label_stats_init_kernel(dnnca_label_stats_t* s) {
+  s->sum = 0.0;
+  s->min_key = 0xffffffffu;
+  s->max_key = 0u;
+}
+
+__global__ void __launch_bounds__(256) label_stats_kernel(const float* __restrict__ label, long long count,
+                                                         dnnca_label_stats_t* __restrict__ out) {
+  double s = 0.0;
+  float mn = INFINITY, mx = -INFINITY;
+  const long long nvec = ((reinterpret_cast<uintptr_t>(label) & 15) == 0) ? count / 4 : 0;
+  const float4* l4 = reinterpret_cast<const float4*>(label);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = l4[i];
+    s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+    mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+    mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+  }
+  for (long long i = nvec * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = label[i];
+    s += v;
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ double ss[8];
+  __shared__ float smn[8], smx[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { ss[warp] = s; smn[warp] = mn; smx[warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) { s += ss[i]; mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+    atomicAdd(&out->sum, s);
+    if (mn <= mx) {
+      atomicMin(&out->min_key, float_key(mn));
+      atomicMax(&out->max_key, float_key(mx));
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_fwd_kernel(View f, const float* __restrict__ w,
+                                                      const float* __restrict__ b, float* __restrict__ logits,
+                                                      float* __restrict__ probs, long long P) {
+  const int F = f.c;
+  const float bias = b ? b[0] : 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P;
+       p += (long long)gridDim.x * blockDim.x) {
+    const T* fp = reinterpret_cast<const T*>(f.data) + p * f.cstride + f.coff;
+    float z = bias;
+    for (int c = 0; c < F; ++c) z = fmaf(ldf(fp + c), w[c], z);
+    if (logits) logits[p] = z;
+    if (probs) probs[p] = 1.f / (1.f + expf(-z));
+  }
+}
+
+// FMAX = compile-time bound on the feature count (register-resident dw partials)
+template <typename T, int FMAX>
+__global__ void __launch_bounds__(256) head_bce_kernel(View f, const float* __restrict__ w,
+                                                      const float* __restrict__ b, const float* __restrict__ label,
+                                                      const dnnca_label_stats_t* __restrict__ ls,
+                                                      dnnca_loss_config_t cfg, float* __restrict__ logits,
+                                                      float* __restrict__ probs, float* __restrict__ per_sample,
+                                                      View df, int has_df, int act, float alpha,
+                                                      float* __restrict__ dw, float* __restrict__ db) {
+  // grid = (chunks over H*W, B): every block stays inside one sample
+  const int F = f.c;
+  const long long HW = (long long)f.h * f.w;
+  const long long total = HW * f.n;
+  float weight;
+  if (cfg.has_weight) {
+    weight = cfg.weight;
+  } else {
+    const float r = (float)(ls->sum / (double)total);  // losses.py:95
+    weight = r > 0.f ? 1.f / r : 1.f;                  // losses.py:27
+  }
+  weight = cfg.weight_mul * weight + cfg.weight_add;    // losses.py:29
+  const float bias = b ? b[0] : 0.f;
+  float wr[FMAX];
+#pragma unroll
+  for (int c = 0; c < FMAX; ++c) wr[c] = c < F ? w[c] : 0.f;
+  float dwacc[FMAX];
+#pragma unroll
+  for (int c = 0; c < FMAX; ++c) dwacc[c] = 0.f;
+  float dbacc = 0.f, lossacc = 0.f;
+  const long long base = (long long)blockIdx.y * HW;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < HW;
+       q += (long long)gridDim.x * blockDim.x) {
+    const long long p = base + q;
+    const T* fp = reinterpret_cast<const T*>(f.data) + p * f.cstride + f.coff;
+    float fv[FMAX];
+    float z = bias;
+#pragma unroll
+    for (int c = 0; c < FMAX; ++c) {
+      fv[c] = c < F ? ldf(fp + c) : 0.f;
+      z = fmaf(fv[c], wr[c], z);
+    }
+    const float y = label[p];
+    const float mask = y * (weight - 1.f) + 1.f;                          // losses.py:31
+    const float bce = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));    // from_logits BCE
+    lossacc += bce * mask;
+    const float pr = 1.f / (1.f + expf(-z));
+    if (logits) logits[p] = z;
+    if (probs) probs[p] = pr;
+    const float dz = mask * (pr - y) * cfg.grad_scale;
+    dbacc += dz;
+    T* dp = has_df ? reinterpret_cast<T*>(df.data) + p * df.cstride + df.coff : nullptr;
+#pragma unroll
+    for (int c = 0; c < FMAX; ++c) {
+      if (c < F) {
+        dwacc[c] = fmaf(dz, fv[c], dwacc[c]);
+        if (has_df) stf(dp + c, dz * wr[c] * act_grad(fv[c], act, alpha));
+      }
+    }
+  }
+  // block reduction: warp shuffles then 8 partials through smem
+  __shared__ float sm[8][FMAX + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  lossacc = warp_sum(lossacc);
+  dbacc = warp_sum(dbacc);
+#pragma unroll
+  for (int c = 0; c < FMAX; ++c) dwacc[c] = warp_sum(dwacc[c]);
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < FMAX; ++c) sm[warp][c] = dwacc[c];
+    sm[warp][FMAX] = dbacc;
+    sm[warp][FMAX + 1] = lossacc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < FMAX + 2; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sm[i][c];
+    if (c < F) {
+      if (dw) atomicAdd(dw + c, s);
+    } else if (c == FMAX) {
+      if (db) atomicAdd(db, s);
+    } else if (c == FMAX + 1) {
+      atomicAdd(per_sample + blockIdx.y, s / (float)HW);                 // losses.py:36
+    }
+  }
+}
+
+}  // namespace dnnca
+
+using namespace dnnca;
+
+extern "C" int dnnca_label_stats_init(void* stream, dnnca_label_stats_t* lstats) {
+  DNNCA_CHECK_ARG(lstats, "label_stats_init: null");
+  label_stats_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(lstats);
+  DNNCA_LAUNCH_CHECK("label_stats_init");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_label_stats(void* stream, const float* label, int64_t count, dnnca_label_stats_t* lstats) {
+  DNNCA_CHECK_ARG(label && lstats && count > 0, "label_stats: bad arguments");
+  int grid = grid_for(count / 4 + 1, 256 * 4, 4);
+  label_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(label, count, lstats);
+  DNNCA_LAUNCH_CHECK("label_stats");
+  return DNNCA_OK;
+}
+
+extern "C" void dnnca_label_stats_decode(const dnnca_label_stats_t* h, double* sum, float* mn, float* mx) {
+  auto dec = [](uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  if (sum) *sum = h->sum;
+  if (mn) *mn = dec(h->min_key);
+  if (mx) *mx = dec(h->max_key);
+}
+
+extern "C" int dnnca_head_fwd(void* stream, const dnnca_tensor_t* f, const float* w, const float* b, float* logits,
+                              float* probs) {
+  DNNCA_CHECK_ARG(view_ok(f) && w && (logits || probs), "head_fwd: bad arguments");
+  long long P = (long long)f->n * f->h * f->w;
+  int grid = grid_for(P, 256, 8);
+  DNNCA_DISPATCH_DTYPE(f->dtype, head_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(mk(f), w, b, logits, probs, P);)
+  DNNCA_LAUNCH_CHECK("head_fwd");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_head_bce_fwd_bwd(void* stream, const dnnca_tensor_t* f, const float* w, const float* b,
+                                      const float* label, const dnnca_label_stats_t* lstats,
+                                      const dnnca_loss_config_t* cfg, float* logits, float* probs,
+                                      float* per_sample, const dnnca_tensor_t* df, int act, float alpha, float* dw,
+                                      float* db) {
+  DNNCA_CHECK_ARG(view_ok(f) && w && label && cfg && per_sample, "head_bce: bad arguments");
+  DNNCA_CHECK_ARG(cfg->has_weight || lstats, "head_bce: label stats needed when no explicit weight is given");
+  DNNCA_CHECK_ARG(!df || (view_ok(df) && same_shape(df, f) && df->dtype == f->dtype), "head_bce: bad df");
+  if (f->c > 64) DNNCA_UNSUPPORTED("head_bce: at most 64 head features supported (got %d)", f->c);
+  const long long HW = (long long)f->h * f->w;
+  int gx = (int)((HW + 256 * 4 - 1) / (256 * 4));
+  int cap = (sm_count() * 8 + f->n - 1) / f->n;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, f->n);
+  View vdf = df ? mk(df) : mk(f);
+  cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH_HEAD(FM)                                                                                          \
+  DNNCA_DISPATCH_DTYPE(f->dtype, (head_bce_kernel<T, FM><<<grid, 256, 0, s>>>(mk(f), w, b, label, lstats, *cfg, logits, \
+                                                                               probs, per_sample, vdf, df != nullptr, \
+                                                                               act, alpha, dw, db));)
+  if (f->c <= 4) { LAUNCH_HEAD(4) }
+  else if (f->c <= 16) { LAUNCH_HEAD(16) }
+  else if (f->c <= 32) { LAUNCH_HEAD(32) }
+  else { LAUNCH_HEAD(64) }
+#undef LAUNCH_HEAD
+  DNNCA_LAUNCH_CHECK("head_bce_fwd_bwd");
+  return DNNCA_OK;
+}

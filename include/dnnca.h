@@ -1,0 +1,224 @@
+/*
+ * dnnca.h -- C ABI of libdnnca.so: the B200 (sm_100a) kernels behind the
+ * DNNCancerAnnotator conv-stack hot path.
+ *
+ * The reference (yoshihikoueno/DNNCancerAnnotator) has no FFI of its own: it is
+ * pure Python on tf.keras, and every entry point below replaces the TensorFlow
+ * kernel(s) reached through one Keras call site of the reference.  Each
+ * declaration cites that call site (file:line under the reference root).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *  - Every function returns 0 on success or a negative dnnca_status_t;
+ *    dnnca_last_error() returns a thread-local message for the last failure.
+ *  - Every launch is asynchronous on the cudaStream_t passed as `stream`
+ *    (a void*; NULL = legacy default stream).  The library allocates no device
+ *    memory and never synchronises; the caller owns all buffers and workspaces.
+ *  - There is no CPU fallback and no backend dispatch: without a CUDA device the
+ *    launches fail with DNNCA_ERR_CUDA.
+ *  - Activations are NHWC.  A dnnca_tensor_t is a *channel-slice view* of an
+ *    NHWC buffer: element (n,y,x,ch) lives at
+ *        data + ((n*h + y)*w + x)*cstride + coff + ch     (in elements of dtype)
+ *    so a producer can write its channels straight into a concat buffer
+ *    (tf.concat at components.py:164 and unet.py:187 needs no copy kernel).
+ *  - Weights keep the reference's TensorFlow layouts, fp32 masters:
+ *    Conv2D kernel [kh,kw,Cin,Cout] (HWIO), Conv2DTranspose kernel [kh,kw,Cout,Cin].
+ *  - Parameter gradients, statistics and the loss are fp32 (fp64 accumulators
+ *    where noted); max-pool argmax is one uint8 (0..3, row-major in the window).
+ */
+#ifndef DNNCA_H_
+#define DNNCA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DNNCA_VERSION 100 /* 0.1.0 */
+#define DNNCA_API __attribute__((visibility("default")))
+
+typedef enum {
+  DNNCA_OK = 0,
+  DNNCA_ERR_BAD_ARG = -1,
+  DNNCA_ERR_UNSUPPORTED = -2,
+  DNNCA_ERR_CUDA = -3
+} dnnca_status_t;
+
+typedef enum { DNNCA_F32 = 0, DNNCA_BF16 = 1 } dnnca_dtype_t;
+
+/* components.py:323-335 solve_activation: 'relu' and LeakyReLU(alpha) (leakyReLU.yaml:1-4) */
+typedef enum { DNNCA_ACT_NONE = 0, DNNCA_ACT_RELU = 1, DNNCA_ACT_LEAKY = 2 } dnnca_act_t;
+
+typedef struct dnnca_tensor {
+  void* data;      /* device pointer to element (0,0,0, channel 0 of the buffer) */
+  int32_t n, h, w; /* logical extent of the view */
+  int32_t c;       /* channels in the view */
+  int32_t cstride; /* channels per pixel in the underlying buffer (>= coff + c) */
+  int32_t coff;    /* first channel of the view inside the buffer */
+  int32_t dtype;   /* dnnca_dtype_t */
+} dnnca_tensor_t;
+
+DNNCA_API int dnnca_version(void);
+DNNCA_API const char* dnnca_last_error(void);
+/* Number of SMs of the current device (grid sizing is a multiple of it). */
+DNNCA_API int dnnca_sm_count(int* out);
+/* test hook: non-zero routes every conv through the shape-generic kernels; returns the old value */
+DNNCA_API int dnnca_debug_force_generic(int on);
+
+/* ---------------------------------------------------------------------------
+ * Conv2D, stride 1, 'same' zero padding, k in {1,3}
+ *   replaces layers.Conv2D at components.py:47-50, components.py:123-126,
+ *   multiresunet.py:51-52 (use_bias=False -> bias == NULL).
+ * y = act(x (*) w + bias)  (cross-correlation).  If `stats` != NULL the per-
+ * channel sum and sum of squares of the *stored* output are ACCUMULATED into
+ * stats[0..C) and stats[C..2C) (fp64; caller zeroes) for the BatchNormalization
+ * that follows (components.py:57-58, 130-132).
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const float* w, const float* bias,
+                       const dnnca_tensor_t* y, int ksize, int act, float alpha, double* stats);
+
+/* Gradient w.r.t. the conv input (tf.GradientTape over the Conv2D above):
+ *   dx = dz (*) rot180(w)^T ; if `mask` != NULL, dx *= act'(mask) where `mask`
+ *   is the stored (post-activation) output of the layer that produced x --
+ *   so the kernel emits that layer's dz directly (ReLU/LeakyReLU preserve
+ *   sign, act'(y) is decided by y > 0). */
+DNNCA_API int dnnca_conv2d_dgrad(void* stream, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
+                       int ksize, const dnnca_tensor_t* mask, int act, float alpha);
+
+/* Gradient w.r.t. kernel and bias: dw[kh,kw,Cin,Cout] and db[Cout] are
+ * ACCUMULATED (+=) in fp32 (caller zeroes the flat gradient buffer once per
+ * step); db may be NULL. */
+DNNCA_API int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dz, float* dw, float* db,
+                       int ksize);
+
+/* ---------------------------------------------------------------------------
+ * Conv2DTranspose, k = s = 2 (non-overlapping), activation=None
+ *   replaces layers.Convolution2DTranspose at components.py:118-120 and
+ *   Conv2DTranspose at multiresunet.py:200-215.   kernel [2,2,Cout,Cin].
+ *   y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci]*k[a,b,co,ci] + bias[co]
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_convtranspose2x2_fprop(void* stream, const dnnca_tensor_t* x, const float* k, const float* bias,
+                                 const dnnca_tensor_t* y, double* stats);
+DNNCA_API int dnnca_convtranspose2x2_dgrad(void* stream, const dnnca_tensor_t* dy, const float* k, const dnnca_tensor_t* dx,
+                                 const dnnca_tensor_t* mask, int act, float alpha);
+DNNCA_API int dnnca_convtranspose2x2_wgrad(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dy, float* dk,
+                                 float* db);
+
+/* ---------------------------------------------------------------------------
+ * MaxPool2D([2,2], strides=2), VALID
+ *   replaces layers.MaxPool2D at components.py:54 / MaxPooling2D at
+ *   multiresunet.py:183-195.  First maximum in row-major window order wins.
+ *   idx: uint8 [n, h/2, w/2, c] dense (may be NULL for inference).
+ * bwd: dx = scatter(dy, idx) (+ dskip if != NULL: the gradient arriving over the
+ *   skip connection, components.py:162-164) and then (* act'(mask)) if mask != NULL.
+ *   dx may alias dskip (in-place accumulate into the concat-gradient slice).
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_maxpool2x2_fwd(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* y, uint8_t* idx,
+                         double* stats);
+DNNCA_API int dnnca_maxpool2x2_bwd(void* stream, const dnnca_tensor_t* dy, const uint8_t* idx, const dnnca_tensor_t* dskip,
+                         const dnnca_tensor_t* dx, const dnnca_tensor_t* mask, int act, float alpha);
+
+/* ---------------------------------------------------------------------------
+ * BatchNormalization(axis=-1), keras defaults momentum .99 / eps 1e-3
+ *   replaces layers.BatchNormalization at components.py:57,59,130,131 and
+ *   multiresunet.py:53,120,124,150,162.
+ * channel_stats : stats[0..C) += sum x ; stats[C..2C) += sum x^2   (fp64)
+ * bn_finalize   : training.  mean = S/M, var = SS/M - mean^2 (biased),
+ *                 scale_shift[0..C) = gamma*rsqrt(var+eps) (gamma NULL -> 1),
+ *                 scale_shift[C..2C) = beta - mean*scale,
+ *                 mean_invstd[0..C) = mean, [C..2C) = rsqrt(var+eps),
+ *                 moving_mean = moving_mean*momentum + mean*(1-momentum),
+ *                 moving_var  = moving_var*momentum + var*M/(M-1)*(1-momentum).
+ * bn_inference_params : scale/shift from the moving statistics (training=False).
+ * bn_apply      : y = x*scale + shift  (y may be a concat slice; may alias x)
+ * bn_bwd_reduce : sums[0..C) += sum dy ; sums[C..2C) += sum dy*xhat   (fp64)
+ * bn_bwd_apply  : dx = gamma*invstd*(dy - sums0/M - xhat*sums1/M), then
+ *                 (* act'(x)) if act != NONE (x is the activation output feeding
+ *                 the BN: Conv -> act -> BN order of components.py:46-61);
+ *                 dgamma += sums1 (if != NULL), dbeta += sums0.
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_channel_stats(void* stream, const dnnca_tensor_t* x, double* stats);
+DNNCA_API int dnnca_bn_finalize(void* stream, const double* stats, int64_t count, int c, const float* gamma,
+                      const float* beta, float momentum, float eps, float* moving_mean, float* moving_var,
+                      float* scale_shift, float* mean_invstd);
+DNNCA_API int dnnca_bn_inference_params(void* stream, int c, const float* gamma, const float* beta, float eps,
+                              const float* moving_mean, const float* moving_var, float* scale_shift);
+DNNCA_API int dnnca_bn_apply(void* stream, const dnnca_tensor_t* x, const float* scale_shift, const dnnca_tensor_t* y);
+DNNCA_API int dnnca_bn_bwd_reduce(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dy, const float* mean_invstd,
+                        double* sums);
+DNNCA_API int dnnca_bn_bwd_apply(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dy, const float* mean_invstd,
+                       const float* gamma, const double* sums, const dnnca_tensor_t* dx, int act, float alpha,
+                       float* dgamma, float* dbeta);
+
+/* ---------------------------------------------------------------------------
+ * Head Conv2D(filters=1, k=1, 'sigmoid') + WeightedCrossentropy
+ *   replaces layers.Conv2D at unet.py:241-244 and losses.py:17-37, 60-72, 87-102.
+ * label_stats: lstats = {sum(label) fp64, min, max} over the whole per-replica
+ *   batch (tf_get_positive_rate, losses.py:87-102); 16-byte device struct,
+ *   caller zero-fills it before the call (dnnca_label_stats_init does that).
+ * head_fwd: logits/probs only (training=False paths: evaluate, Visualizer).
+ * head_bce_fwd_bwd: z = f.w + b ; p = sigmoid(z) ; weight = cfg.weight if
+ *   cfg.has_weight else (1/r if r > 0 else 1) ; weight = weight_mul*weight +
+ *   weight_add ; mask = y*(weight-1)+1 ; per_sample[b] += mean_HW(mask *
+ *   (max(z,0) - z*y + log1p(exp(-|z|)))) ; dz = mask*(p - y)*grad_scale with
+ *   grad_scale = 1/(B*H*W*replicas) ; df = dz*w (* act'(f) if act != NONE) ;
+ *   dw += sum dz*f ; db += sum dz.   per_sample/dw/db are accumulated (caller zeroes).
+ * ------------------------------------------------------------------------- */
+typedef struct dnnca_label_stats {
+  double sum;
+  uint32_t min_key; /* order-preserving uint encoding of a float */
+  uint32_t max_key;
+} dnnca_label_stats_t;
+
+typedef struct dnnca_loss_config {
+  float weight; /* used when has_weight != 0 (losses.py:25) */
+  int32_t has_weight;
+  float weight_add; /* losses.py:29 */
+  float weight_mul;
+  float grad_scale; /* 1/(B*H*W*replicas) */
+} dnnca_loss_config_t;
+
+DNNCA_API int dnnca_label_stats_init(void* stream, dnnca_label_stats_t* lstats);
+DNNCA_API int dnnca_label_stats(void* stream, const float* label, int64_t count, dnnca_label_stats_t* lstats);
+/* host-side decode of a dnnca_label_stats_t copied back from the device */
+DNNCA_API void dnnca_label_stats_decode(const dnnca_label_stats_t* host_copy, double* sum, float* min, float* max);
+
+DNNCA_API int dnnca_head_fwd(void* stream, const dnnca_tensor_t* f, const float* w, const float* b, float* logits,
+                   float* probs);
+DNNCA_API int dnnca_head_bce_fwd_bwd(void* stream, const dnnca_tensor_t* f, const float* w, const float* b,
+                           const float* label, const dnnca_label_stats_t* lstats, const dnnca_loss_config_t* cfg,
+                           float* logits, float* probs, float* per_sample, const dnnca_tensor_t* df, int act,
+                           float alpha, float* dw, float* db);
+
+/* ---------------------------------------------------------------------------
+ * MultiResUnet elementwise tail (inference): y = s2*relu(a*sa+ta + b*sb+tb)+t2
+ *   replaces BatchNormalization -> add -> Activation('relu') -> BatchNormalization
+ *   at multiresunet.py:120-124 and add -> relu -> BN at :148-150, :160-162.
+ *   affine_a / affine_b / affine_out are [2C] scale|shift arrays (NULL = identity).
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_add_relu_affine(void* stream, const dnnca_tensor_t* a, const float* affine_a, const dnnca_tensor_t* b,
+                          const float* affine_b, const float* affine_out, const dnnca_tensor_t* y);
+
+/* ---------------------------------------------------------------------------
+ * Input tail: uint8 -> /255 -> activation dtype (data.py:193-206 `base`, 766-788)
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_u8_to_unit(void* stream, const uint8_t* src, int64_t count, void* dst, int dtype);
+/* dtype conversion between two views of equal logical shape (fp32 <-> bf16, slice copies) */
+DNNCA_API int dnnca_convert(void* stream, const dnnca_tensor_t* src, const dnnca_tensor_t* dst);
+
+/* ---------------------------------------------------------------------------
+ * Adam, keras form (engine.py:276-284), one launch over the flat parameter buffer.
+ *   hyper (device, fp32): {lr, beta1, beta2, eps}; step (device int64) is
+ *   incremented by the kernel (graph-replay safe).  l2 != NULL: per-element L2
+ *   coefficient added to the gradient as 2*l2*p (kernel_regularizer.yaml:1-4).
+ *   m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ;
+ *   p <- p - lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps)
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_adam_step(void* stream, float* params, const float* grads, float* m, float* v, int64_t count,
+                    const float* hyper, int64_t* step, const float* l2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNNCA_H_ */
