@@ -1,0 +1,376 @@
+"""The slice of the ``tf.keras.Model`` surface that the reference's engine and
+callbacks consume (``engine.py:93,126-135,198-203,222,286``;
+``callbacks.py:290-303``), implemented over a static ``runtime.Plan``.
+
+``Model.train_step`` is the hot path: H2D copy of the batch into static buffers,
+then ONE CUDA-graph replay of {zero grads/stats, forward, fused head+loss,
+backward, (gradient all-reduce), fused Adam}.
+"""
+from __future__ import annotations
+
+import os
+import re
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import native as N
+from . import runtime as R
+from .utils import losses as L
+
+
+class History:
+    """What ``Model.fit`` returns (``dump.py:68-73`` reads .epoch/.history/.params)."""
+
+    def __init__(self, model, params):
+        self.model, self.params = model, params
+        self.epoch, self.history = [], {}
+
+    def record(self, epoch, logs):
+        self.epoch.append(epoch)
+        for k, v in logs.items():
+            self.history.setdefault(k, []).append(float(v))
+
+
+def _to_device_f32(a, device):
+    if torch.is_tensor(a):
+        return a.to(device=device, dtype=torch.float32, non_blocking=True)
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device, non_blocking=True)
+
+
+class Model:
+    """Base of ``UNetAnnotator`` / ``MulmoUNetAnnotator`` / ``MultiResUnet``.
+
+    ``compute_dtype``: 'bf16' (default: bf16 activations, fp32 accumulate, fp32 master weights) or
+    'fp32' (bit-exact-mask mode).  Chosen with the ``dtype=`` constructor keyword or the
+    ``DNNCA_DTYPE`` environment variable; it is not part of the reference's config surface.
+    """
+
+    def __init__(self, dtype=None, seed=0, device=None, **kargs):
+        if kargs:
+            raise TypeError(f'unexpected keyword arguments {sorted(kargs)}')
+        dtype = dtype or os.environ.get('DNNCA_DTYPE', 'bf16')
+        self.compute_dtype = {'bf16': torch.bfloat16, 'bfloat16': torch.bfloat16, 'fp32': torch.float32,
+                              'float32': torch.float32}[dtype]
+        self.params = R.ParamStore()
+        self._ctx = dict(params=self.params, rng=np.random.default_rng(seed))
+        self._device = device
+        self._plans = {}
+        self.built = False
+        self.input_shape = None
+        self.loss = None
+        self.optimizer = None
+        self.metrics = []
+        self.stop_training = False
+        self.use_cuda_graph = os.environ.get('DNNCA_NO_GRAPH', '0') != '1'
+        self.trainable_model = True     # MultiResUnet (inference-only in this build) sets False
+        # data parallel (engine.py:260-263 MirroredStrategy): set by enable_data_parallel()
+        self._dp = None
+
+    # ---- to be provided by subclasses ------------------------------------------
+    def _build_variables(self, input_shape):
+        raise NotImplementedError
+
+    def _emit(self, plan):
+        raise NotImplementedError
+
+    # ---- keras surface ---------------------------------------------------------
+    @property
+    def device(self):
+        if self._device is None:
+            if not torch.cuda.is_available():
+                raise N.DnncaError('no CUDA device: dnncancerannotator_b200 has no CPU fallback')
+            self._device = torch.device('cuda', torch.cuda.current_device())
+        return self._device
+
+    def build(self, input_shape):
+        """engine.py:93 ``model.build((None, H, W, C))``: creates the variables."""
+        if self.built:
+            return
+        assert len(input_shape) == 4
+        self.input_shape = tuple(input_shape)
+        self._build_variables(self.input_shape)
+        self.built = True
+
+    def compile(self, optimizer='adam', loss=None, metrics=None, **kargs):
+        """engine.py:286.  ``loss``: a ``WeightedCrossentropy`` instance or its keras-style
+        dict/str identifier (deploy_options.yaml:4-7); ``optimizer``: 'adam' or a dict of
+        {learning_rate, beta_1, beta_2, epsilon} (engine.py:276-284)."""
+        self.loss = L.get(loss) if loss is not None else L.WeightedCrossentropy()
+        if isinstance(optimizer, str):
+            if optimizer.lower() != 'adam':
+                raise NotImplementedError(f'optimizer {optimizer!r}: the reference configs use adam only')
+            optimizer = {}
+        self.optimizer = dict(learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7)
+        self.optimizer.update(optimizer or {})
+        self.metrics = list(metrics or [])
+        self._hyper_dirty = True
+
+    def count_params(self, trainable=None):
+        return self.params.count(trainable)
+
+    def get_weights(self):
+        return self.params.get_weights()
+
+    def set_weights(self, weights):
+        self.params.set_weights(weights)
+
+    def get_grads(self):
+        return self.params.get_grads()
+
+    # checkpoints: own format (TF checkpoints need TF), same ckpt-<step> naming as engine.py:52
+    def save_weights(self, path):
+        os.makedirs(os.path.dirname(os.path.abspath(path)) or '.', exist_ok=True)
+        w = self.get_weights()
+        extra = {}
+        if self.params.device is not None:
+            extra = {'__adam_m': self.params.m.cpu().numpy(), '__adam_v': self.params.v.cpu().numpy(),
+                     '__step': self.params.step.cpu().numpy()}
+        np.savez(path + '.npz' if not path.endswith('.npz') else path, **w, **extra)
+
+    def load_weights(self, path):
+        p = path if path.endswith('.npz') else path + '.npz'
+        z = np.load(p)
+        self.set_weights({k: z[k] for k in z.files if not k.startswith('__')})
+        if '__step' in z.files and self.params.device is not None:
+            self.params.m.copy_(torch.from_numpy(z['__adam_m']))
+            self.params.v.copy_(torch.from_numpy(z['__adam_v']))
+            self.params.step.copy_(torch.from_numpy(z['__step']))
+        return self
+
+    @staticmethod
+    def list_checkpoints(save_dir):
+        """engine.py:55-65: {step: path} of ``checkpoints/ckpt-<step>`` files."""
+        out = {}
+        d = os.path.join(save_dir, 'checkpoints')
+        if os.path.isdir(d):
+            for f in os.listdir(d):
+                m = re.fullmatch(r'ckpt-(\d+)\.npz', f)
+                if m:
+                    out[int(m.group(1))] = os.path.join(d, f[:-4])
+        return OrderedDict(sorted(out.items()))
+
+    # ---- plans -----------------------------------------------------------------
+    def _plan(self, batch, height, width):
+        key = (batch, height, width)
+        if key not in self._plans:
+            if not self.built:
+                self.build((None, height, width, self.input_shape[-1] if self.input_shape else None))
+            self.params.materialize(self.device)
+            plan = R.Plan(self.params, batch, height, width, self.input_shape[-1], self.compute_dtype, self.device)
+            self._emit(plan)
+            self._plans[key] = plan
+        return self._plans[key]
+
+    def _run(self, plan, key, fn):
+        """Runs ``fn`` (a fixed launch sequence) eagerly twice (warm-up: lazy attribute setup,
+        allocator) and from then on as a CUDA graph replay."""
+        if not self.use_cuda_graph:
+            fn()
+            return
+        g = plan.graphs.get(key)
+        if g is None:
+            cnt = plan.graphs.get((key, 'warm'), 0)
+            if cnt < 2:
+                fn()
+                plan.graphs[(key, 'warm')] = cnt + 1
+                return
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            plan.graphs[key] = g
+        g.replay()
+
+    # ---- inference -------------------------------------------------------------
+    def __call__(self, x, training=False):
+        """``model(x)`` -> probabilities ``[B,H,W,1]`` (fp32 torch tensor on the device);
+        the logits of the same call are kept in ``self.last_logits`` (keras caches them as
+        ``_keras_logits``, losses.py:61)."""
+        if training:
+            raise NotImplementedError('use train_step for training-mode execution')
+        x = _to_device_f32(x, self.device)
+        plan = self._plan(*x.shape[:3])
+        plan.allocate(False)
+        plan.x_in.copy_(x, non_blocking=True)
+
+        def seq():
+            plan.forward(False)
+            plan.head_forward()
+        self._run(plan, 'infer', seq)
+        self.last_logits = plan.logits
+        return plan.probs
+
+    def predict(self, x, batch_size=None, verbose=0):
+        if isinstance(x, (np.ndarray, torch.Tensor)):
+            bs = batch_size or x.shape[0]
+            outs = [self(x[i:i + bs]).cpu().numpy().copy() for i in range(0, x.shape[0], bs)]
+            return np.concatenate(outs, 0)
+        outs = []
+        for batch in x:
+            xb = batch[0] if isinstance(batch, (tuple, list)) else batch.get('x', batch)
+            outs.append(self(xb).cpu().numpy().copy())
+        return np.concatenate(outs, 0)
+
+    # ---- training --------------------------------------------------------------
+    def enable_data_parallel(self, process_group=None, bucket_bytes=8 << 20):
+        """engine.py:260-263: synchronous data parallelism.  One process per GPU; gradients are
+        SUM-all-reduced over NCCL with the loss pre-scaled by 1/world (== averaging)."""
+        from . import parallel
+        self._dp = parallel.GradAllReduce(process_group, bucket_bytes)
+        return self
+
+    def _loss_cfg(self, plan):
+        world = self._dp.world_size if self._dp else 1
+        cfg = self.loss.native_config(plan.batch * plan.height * plan.width * world)
+        return cfg
+
+    def _sync_hyper(self, lr=None):
+        if lr is not None and lr != self.optimizer['learning_rate']:
+            self.optimizer['learning_rate'] = float(lr)
+            self._hyper_dirty = True
+        if getattr(self, '_hyper_dirty', True):
+            o = self.optimizer
+            self.params.hyper.copy_(torch.tensor([o['learning_rate'], o['beta_1'], o['beta_2'], o['epsilon']],
+                                                 dtype=torch.float32), non_blocking=True)
+            self._hyper_dirty = False
+
+    def _adam(self):
+        ps = self.params
+        N.call('dnnca_adam_step', N.stream_ptr(), N.ptr(ps.params), N.ptr(ps.grads), N.ptr(ps.m), N.ptr(ps.v),
+               ps.n_trainable, N.ptr(ps.hyper), N.ptr(ps.step), N.ptr(ps.l2))
+
+    def forward_backward(self, x, y):
+        """Forward + loss + backward WITHOUT the optimizer step: leaves the gradients in
+        ``get_grads()`` (parity tests, gradient inspection).  Returns the per-sample loss ``[B]``."""
+        if self.loss is None:
+            self.compile()
+        if not self.trainable_model:
+            raise NotImplementedError(f'{type(self).__name__} is forward/inference-only in this build')
+        x, y = _to_device_f32(x, self.device), _to_device_f32(y, self.device)
+        plan = self._plan(*x.shape[:3])
+        plan.allocate(True)
+        plan.x_in.copy_(x, non_blocking=True)
+        plan.y_in.copy_(self.loss.prepare_labels(y), non_blocking=True)
+        cfg = self._loss_cfg(plan)
+        plan._cfg = cfg   # keep the ctypes struct alive for graph capture
+
+        def seq():
+            plan.zero_step_state()
+            plan.forward(True)
+            plan.head_loss(cfg)
+            plan.backward()
+        self._run(plan, 'fwdbwd', seq)
+        self.last_logits = plan.logits
+        return plan.per_sample
+
+    def train_step(self, x, y, lr=None):
+        """One optimizer step (keras ``Model.train_step``): returns the scalar loss as a device
+        tensor (mean per-sample loss + L2 regulariser terms)."""
+        if self.loss is None:
+            self.compile()
+        if not self.trainable_model:
+            raise NotImplementedError(f'{type(self).__name__} is forward/inference-only in this build')
+        x, y = _to_device_f32(x, self.device), _to_device_f32(y, self.device)
+        plan = self._plan(*x.shape[:3])
+        plan.allocate(True)
+        self._sync_hyper(lr)
+        plan.x_in.copy_(x, non_blocking=True)
+        plan.y_in.copy_(self.loss.prepare_labels(y), non_blocking=True)
+        return self._train_on_static(plan)
+
+    def _train_on_static(self, plan):
+        """The hot path once the batch sits in ``plan.x_in`` / ``plan.y_in``."""
+        cfg = self._loss_cfg(plan)
+        plan._cfg = cfg
+
+        if self._dp is None:
+            def seq():
+                plan.zero_step_state()
+                plan.forward(True)
+                plan.head_loss(cfg)
+                plan.backward()
+                self._adam()
+            self._run(plan, 'train', seq)
+        else:
+            def seq_a():
+                plan.zero_step_state()
+                plan.forward(True)
+                plan.head_loss(cfg)
+                plan.backward()
+            self._run(plan, 'train_fb', seq_a)
+            self._dp.all_reduce(self.params.grads[:max(self.params.n_trainable, 1)])
+            self._run(plan, 'train_adam', self._adam)
+        self.last_logits = plan.logits
+        loss = plan.per_sample.mean()
+        if self.params.l2 is not None:
+            loss = loss + (self.params.l2 * self.params.params * self.params.params).sum()
+        return loss
+
+    def fit(self, x=None, y=None, validation_data=None, callbacks=None, steps_per_epoch=None, epochs=1,
+            validation_freq=1, initial_epoch=0, verbose=1, lr_schedule=None, **kargs):
+        """``Model.fit`` as the reference drives it (engine.py:126-135): ``x`` is an iterable of
+        ``(features, labels)`` batches, one "epoch" is ``steps_per_epoch`` optimizer steps.
+        ``lr_schedule(epoch, current_lr)`` reproduces the LearningRateScheduler callback
+        (engine.py:97-100)."""
+        callbacks = list(callbacks or [])
+        hist = History(self, dict(epochs=epochs, steps=steps_per_epoch, verbose=verbose))
+        for cb in callbacks:
+            if hasattr(cb, 'set_model'):
+                cb.set_model(self)
+            if hasattr(cb, 'on_train_begin'):
+                cb.on_train_begin({})
+        it = iter(x) if y is None else None
+        self.stop_training = False
+        for epoch in range(initial_epoch, epochs):
+            lr = lr_schedule(epoch, self.optimizer['learning_rate']) if lr_schedule else None
+            losses = []
+            n = steps_per_epoch or 1
+            for _ in range(n):
+                if it is not None:
+                    try:
+                        xb, yb = next(it)
+                    except StopIteration:
+                        it = iter(x)
+                        xb, yb = next(it)
+                else:
+                    xb, yb = x, y
+                losses.append(self.train_step(xb, yb, lr=lr))
+            logs = {'loss': float(torch.stack(losses).mean())}
+            if validation_data is not None and validation_freq and (epoch + 1) % validation_freq == 0:
+                logs.update({'val_' + k: v for k, v in self.evaluate(validation_data, return_dict=True).items()})
+            hist.record(epoch, logs)
+            for cb in callbacks:
+                if hasattr(cb, 'on_epoch_end'):
+                    cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            if hasattr(cb, 'on_train_end'):
+                cb.on_train_end({})
+        return hist
+
+    def evaluate(self, x, callbacks=None, verbose=0, return_dict=True):
+        """engine.py:198-203: forward with training=False + loss over a dataset of (features, labels)."""
+        if self.loss is None:
+            self.compile()
+        tot, cnt = 0.0, 0
+        for xb, yb in x:
+            xb, yb = _to_device_f32(xb, self.device), _to_device_f32(yb, self.device)
+            plan = self._plan(*xb.shape[:3])
+            plan.allocate(False)
+            plan.x_in.copy_(xb, non_blocking=True)
+            plan.y_in.copy_(self.loss.prepare_labels(yb), non_blocking=True)
+            cfg = self._loss_cfg(plan)
+            plan._cfg_eval = cfg
+
+            def seq():
+                plan.forward(False)
+                plan.head_loss(cfg, with_grads=False)
+            self._run(plan, 'eval', seq)
+            self.last_logits = plan.logits
+            tot += float(plan.per_sample.sum())
+            cnt += plan.batch
+        out = {'loss': tot / max(cnt, 1)}
+        return out if return_dict else out['loss']

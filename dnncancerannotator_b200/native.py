@@ -1,0 +1,140 @@
+"""ctypes binding of ``libdnnca.so`` (``include/dnnca.h``).
+
+This is the only door between the Python host code and the CUDA kernels.  There
+is **no CPU fallback**: if the shared library has not been built (run
+``python -m dnncancerannotator_b200.build``) importing :func:`lib` raises, and
+every call that returns a non-zero status raises ``DnncaError`` with the
+library's message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdnnca.so')
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+class DnncaError(RuntimeError):
+    pass
+
+
+class Tensor(C.Structure):
+    """``dnnca_tensor_t``: channel-slice view of an NHWC buffer."""
+    _fields_ = [('data', C.c_void_p), ('n', C.c_int32), ('h', C.c_int32), ('w', C.c_int32), ('c', C.c_int32),
+                ('cstride', C.c_int32), ('coff', C.c_int32), ('dtype', C.c_int32)]
+
+
+class LabelStats(C.Structure):
+    _fields_ = [('sum', C.c_double), ('min_key', C.c_uint32), ('max_key', C.c_uint32)]
+
+
+class LossConfig(C.Structure):
+    _fields_ = [('weight', C.c_float), ('has_weight', C.c_int32), ('weight_add', C.c_float),
+                ('weight_mul', C.c_float), ('grad_scale', C.c_float)]
+
+
+_TP = C.POINTER(Tensor)
+_vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+# name -> argtypes (all return int unless listed in _RESTYPES)
+_PROTOS = {
+    'dnnca_version': [],
+    'dnnca_last_error': [],
+    'dnnca_sm_count': [C.POINTER(C.c_int)],
+    'dnnca_debug_force_generic': [_i],
+    'dnnca_conv2d_fprop': [_vp, _TP, _vp, _vp, _TP, _i, _i, _f, _vp],
+    'dnnca_conv2d_dgrad': [_vp, _TP, _vp, _TP, _i, _TP, _i, _f],
+    'dnnca_conv2d_wgrad': [_vp, _TP, _TP, _vp, _vp, _i],
+    'dnnca_convtranspose2x2_fprop': [_vp, _TP, _vp, _vp, _TP, _vp],
+    'dnnca_convtranspose2x2_dgrad': [_vp, _TP, _vp, _TP, _TP, _i, _f],
+    'dnnca_convtranspose2x2_wgrad': [_vp, _TP, _TP, _vp, _vp],
+    'dnnca_maxpool2x2_fwd': [_vp, _TP, _TP, _vp, _vp],
+    'dnnca_maxpool2x2_bwd': [_vp, _TP, _vp, _TP, _TP, _TP, _i, _f],
+    'dnnca_channel_stats': [_vp, _TP, _vp],
+    'dnnca_bn_finalize': [_vp, _vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp],
+    'dnnca_bn_inference_params': [_vp, _i, _vp, _vp, _f, _vp, _vp, _vp],
+    'dnnca_bn_apply': [_vp, _TP, _vp, _TP],
+    'dnnca_bn_bwd_reduce': [_vp, _TP, _TP, _vp, _vp],
+    'dnnca_bn_bwd_apply': [_vp, _TP, _TP, _vp, _vp, _vp, _TP, _i, _f, _vp, _vp],
+    'dnnca_label_stats_init': [_vp, _vp],
+    'dnnca_label_stats': [_vp, _vp, _i64, _vp],
+    'dnnca_label_stats_decode': [C.POINTER(LabelStats), C.POINTER(C.c_double), C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float)],
+    'dnnca_head_fwd': [_vp, _TP, _vp, _vp, _vp, _vp],
+    'dnnca_head_bce_fwd_bwd': [_vp, _TP, _vp, _vp, _vp, _vp, C.POINTER(LossConfig), _vp, _vp, _vp, _TP, _i, _f,
+                               _vp, _vp],
+    'dnnca_add_relu_affine': [_vp, _TP, _vp, _TP, _vp, _vp, _TP],
+    'dnnca_u8_to_unit': [_vp, _vp, _i64, _vp, _i],
+    'dnnca_convert': [_vp, _TP, _TP],
+    'dnnca_adam_step': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+}
+_RESTYPES = {'dnnca_last_error': C.c_char_p, 'dnnca_label_stats_decode': None}
+
+_lib = None
+
+
+def exported_symbols():
+    """Every symbol ``include/dnnca.h`` declares (used by the CPU-side ABI test)."""
+    return sorted(_PROTOS)
+
+
+def lib():
+    """Loads libdnnca.so once; raises if it is missing (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DnncaError(
+                f'{LIB_PATH} is missing: build it with `python -m dnncancerannotator_b200.build` '
+                '(nvcc, sm_100a). dnncancerannotator_b200 has no CPU or PyTorch fallback.')
+        handle = C.CDLL(LIB_PATH)
+        for name, argtypes in _PROTOS.items():
+            fn = getattr(handle, name)          # AttributeError = ABI mismatch, fail loudly
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().dnnca_last_error()
+        raise DnncaError(f'{what or "dnnca call"} failed ({rc}): {msg.decode() if msg else "?"}')
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)
+
+
+def stream_ptr():
+    """cudaStream_t of torch's current stream (all launches go there)."""
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(dt):
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise DnncaError(f'unsupported activation dtype {dt}')
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None) as c_void_p."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def tensor_view(buf: torch.Tensor, coff=0, c=None) -> Tensor:
+    """``dnnca_tensor_t`` for channels [coff, coff+c) of a contiguous NHWC torch buffer."""
+    assert buf.dim() == 4 and buf.is_contiguous(), 'NHWC contiguous buffer expected'
+    n, h, w, cs = buf.shape
+    c = cs - coff if c is None else c
+    assert 0 <= coff and coff + c <= cs
+    return Tensor(buf.data_ptr(), n, h, w, c, cs, coff, dtype_code(buf.dtype))

@@ -1,0 +1,458 @@
+"""Static execution plan for the conv-stack hot path.
+
+The reference runs its Keras layers through TensorFlow's tracing compiler
+(``@tf.function`` on every ``call``, components.py:77,158,235,314) and
+``tf.GradientTape``.  Here a model is lowered ONCE per (batch, H, W) into a flat
+list of ops over pre-allocated NHWC buffers in HBM:
+
+* every activation lives in a ``Buf``; a ``TRef`` is a channel-slice view of one
+  (``dnnca_tensor_t``), so ``tf.concat`` (components.py:164, unet.py:187) is just
+  two producers writing disjoint channel ranges of the same buffer;
+* gradients mirror the activation buffers; each op knows the C-ABI calls of its
+  forward and of its backward (forward list reversed = the tape);
+* all parameters sit in one flat fp32 buffer (+ one flat gradient buffer, which
+  is what the data-parallel all-reduce and the fused Adam see);
+* the whole training step (zeroing, forward, loss, backward, Adam) is a fixed
+  launch sequence on one stream -> captured in a CUDA graph and replayed.
+
+Only libdnnca kernels do arithmetic; torch supplies device memory, streams and
+graph capture.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import native as N
+
+BN_MOMENTUM = 0.99   # keras BatchNormalization defaults (components.py:57 passes none)
+BN_EPSILON = 1e-3
+
+
+# ----------------------------------------------------------------------------
+# parameters
+# ----------------------------------------------------------------------------
+class ParamStore:
+    """Named variables packed into flat fp32 device buffers.
+
+    trainable -> ``params`` (+ ``grads``, Adam ``m``/``v``); non-trainable (BN moving
+    statistics) -> ``state``.  Names follow the oracle's convention so weights can be
+    exchanged with ``get_weights`` / ``set_weights``.
+    """
+
+    def __init__(self):
+        self.specs: 'OrderedDict[str, dict]' = OrderedDict()
+        self.device = None
+        self.params = self.grads = self.m = self.v = self.state = self.l2 = None
+        self._views = {}
+        self._gviews = {}
+        self.n_trainable = 0
+        self.n_state = 0
+
+    def add(self, name, array, trainable=True, l2=0.0):
+        assert self.device is None, 'variables must be created before the store is materialised'
+        assert name not in self.specs, f'duplicate variable {name}'
+        array = np.ascontiguousarray(array, dtype=np.float32)
+        self.specs[name] = dict(shape=array.shape, trainable=trainable, init=array, l2=float(l2 or 0.0))
+
+    def __contains__(self, name):
+        return name in self.specs
+
+    def materialize(self, device):
+        if self.device is not None:
+            return
+        self.device = device
+        off_t = off_s = 0
+        for name, s in self.specs.items():
+            n = int(np.prod(s['shape'])) if len(s['shape']) else 1
+            # 4-float (16 B) alignment of every variable inside the flat buffers
+            if s['trainable']:
+                s['offset'] = off_t
+                off_t += (n + 3) // 4 * 4
+            else:
+                s['offset'] = off_s
+                off_s += (n + 3) // 4 * 4
+            s['numel'] = n
+        self.n_trainable, self.n_state = off_t, off_s
+        self.params = torch.zeros(max(off_t, 4), dtype=torch.float32, device=device)
+        self.grads = torch.zeros_like(self.params)
+        self.m = torch.zeros_like(self.params)
+        self.v = torch.zeros_like(self.params)
+        self.state = torch.zeros(max(off_s, 4), dtype=torch.float32, device=device)
+        any_l2 = any(s['l2'] for s in self.specs.values())
+        self.l2 = torch.zeros_like(self.params) if any_l2 else None
+        for name, s in self.specs.items():
+            flat = self.params if s['trainable'] else self.state
+            v = flat[s['offset']:s['offset'] + s['numel']].view(s['shape'])
+            v.copy_(torch.from_numpy(s['init']))
+            self._views[name] = v
+            if s['trainable']:
+                self._gviews[name] = self.grads[s['offset']:s['offset'] + s['numel']].view(s['shape'])
+                if s['l2']:
+                    self.l2[s['offset']:s['offset'] + s['numel']] = s['l2']
+            s['init'] = None
+        # Adam hyper-parameters and step counter live on the device (graph replay)
+        self.hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-7], dtype=torch.float32, device=device)
+        self.step = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def view(self, name):
+        return self._views[name]
+
+    def gview(self, name):
+        return self._gviews[name]
+
+    def ptr(self, name):
+        return C.c_void_p(self._views[name].data_ptr()) if name in self._views else None
+
+    def gptr(self, name):
+        return C.c_void_p(self._gviews[name].data_ptr()) if name in self._gviews else None
+
+    def names(self, trainable=None):
+        return [k for k, s in self.specs.items() if trainable is None or s['trainable'] == trainable]
+
+    def get_weights(self):
+        out = OrderedDict()
+        for name, s in self.specs.items():
+            out[name] = self._views[name].detach().cpu().numpy().copy() if self.device is not None else s['init'].copy()
+        return out
+
+    def set_weights(self, weights):
+        for name, arr in weights.items():
+            if name not in self.specs:
+                raise KeyError(f'unknown variable {name}')
+            s = self.specs[name]
+            arr = np.ascontiguousarray(arr, dtype=np.float32)
+            if tuple(arr.shape) != tuple(s['shape']):
+                raise ValueError(f'{name}: shape {arr.shape} != {s["shape"]}')
+            if self.device is None:
+                s['init'] = arr
+            else:
+                self._views[name].copy_(torch.from_numpy(arr))
+
+    def get_grads(self):
+        return OrderedDict((k, self._gviews[k].detach().cpu().numpy().copy()) for k in self._gviews)
+
+    def count(self, trainable=None):
+        return int(sum(int(np.prod(s['shape'])) for s in self.specs.values()
+                       if trainable is None or s['trainable'] == trainable))
+
+
+# ----------------------------------------------------------------------------
+# buffers and views
+# ----------------------------------------------------------------------------
+class Buf:
+    def __init__(self, plan, n, h, w, c, name, dtype=None, external=None):
+        self.plan, self.n, self.h, self.w, self.c, self.name = plan, n, h, w, c, name
+        self.dtype = dtype or plan.dtype
+        self.data = external
+        self.grad = None
+        self.want_grad = False
+        plan.bufs.append(self)
+
+    def allocate(self, training):
+        dev = self.plan.device
+        if self.data is None:
+            self.data = torch.empty(self.n, self.h, self.w, self.c, dtype=self.dtype, device=dev)
+        if training and self.want_grad and self.grad is None:
+            self.grad = torch.empty(self.n, self.h, self.w, self.c, dtype=self.dtype, device=dev)
+
+    def nbytes(self):
+        return self.n * self.h * self.w * self.c * (2 if self.dtype == torch.bfloat16 else 4)
+
+
+class TRef:
+    """Channels [coff, coff+c) of a Buf (= one logical tensor of the model)."""
+
+    def __init__(self, buf: Buf, coff=0, c=None):
+        self.buf, self.coff = buf, coff
+        self.c = buf.c - coff if c is None else c
+        self.act = None            # (code, alpha) when this tensor IS the output of conv+activation
+        self.skip_consumed = False  # a second consumer (skip concat) adds into its gradient first
+        self.needs_grad = True
+        self._ct = self._gct = None
+
+    n = property(lambda s: s.buf.n)
+    h = property(lambda s: s.buf.h)
+    w = property(lambda s: s.buf.w)
+    shape = property(lambda s: (s.buf.n, s.buf.h, s.buf.w, s.c))
+
+    def ct(self):
+        if self._ct is None:
+            self._ct = N.tensor_view(self.buf.data, self.coff, self.c)
+        return C.byref(self._ct)
+
+    def gct(self):
+        if self._gct is None:
+            assert self.buf.grad is not None, f'no gradient buffer for {self.buf.name}'
+            self._gct = N.tensor_view(self.buf.grad, self.coff, self.c)
+        return C.byref(self._gct)
+
+    def mask_args(self):
+        """(mask view or None, act code, alpha) for kernels that write this tensor's gradient."""
+        if self.act is None:
+            return None, N.ACT_NONE, 0.0
+        return self.ct(), self.act[0], self.act[1]
+
+    def torch_view(self):
+        return self.buf.data[..., self.coff:self.coff + self.c]
+
+    def torch_grad(self):
+        return self.buf.grad[..., self.coff:self.coff + self.c]
+
+
+# ----------------------------------------------------------------------------
+# ops
+# ----------------------------------------------------------------------------
+class Op:
+    def fwd(self, train):
+        raise NotImplementedError
+
+    def bwd(self):
+        pass
+
+
+class ConvOp(Op):
+    """layers.Conv2D (components.py:47-50,123-126; multiresunet.py:51-52)."""
+
+    def __init__(self, plan, x: TRef, y: TRef, kernel, bias, ksize, act, stats=None):
+        self.p, self.x, self.y, self.kernel, self.bias, self.k = plan, x, y, kernel, bias, ksize
+        self.act = act or (N.ACT_NONE, 0.0)
+        self.stats = stats
+        if act and act[0] != N.ACT_NONE:
+            y.act = act
+
+    def fwd(self, train):
+        ps = self.p.params
+        N.call('dnnca_conv2d_fprop', N.stream_ptr(), self.x.ct(), ps.ptr(self.kernel), ps.ptr(self.bias), self.y.ct(),
+               self.k, self.act[0], self.act[1], self.stats.fwd_ptr() if (self.stats and train) else None)
+
+    def bwd(self):
+        ps = self.p.params
+        s = N.stream_ptr()
+        N.call('dnnca_conv2d_wgrad', s, self.x.ct(), self.y.gct(), ps.gptr(self.kernel), ps.gptr(self.bias), self.k)
+        if self.x.needs_grad:
+            m, a, al = self.x.mask_args()
+            N.call('dnnca_conv2d_dgrad', s, self.y.gct(), ps.ptr(self.kernel), self.x.gct(), self.k, m, a, al)
+
+
+class TConvOp(Op):
+    """layers.Convolution2DTranspose k=s=2 (components.py:118-120; multiresunet.py:200-215)."""
+
+    def __init__(self, plan, x, y, kernel, bias, stats=None):
+        self.p, self.x, self.y, self.kernel, self.bias, self.stats = plan, x, y, kernel, bias, stats
+
+    def fwd(self, train):
+        ps = self.p.params
+        N.call('dnnca_convtranspose2x2_fprop', N.stream_ptr(), self.x.ct(), ps.ptr(self.kernel), ps.ptr(self.bias),
+               self.y.ct(), self.stats.fwd_ptr() if (self.stats and train) else None)
+
+    def bwd(self):
+        ps = self.p.params
+        s = N.stream_ptr()
+        N.call('dnnca_convtranspose2x2_wgrad', s, self.x.ct(), self.y.gct(), ps.gptr(self.kernel), ps.gptr(self.bias))
+        if self.x.needs_grad:
+            m, a, al = self.x.mask_args()
+            N.call('dnnca_convtranspose2x2_dgrad', s, self.y.gct(), ps.ptr(self.kernel), self.x.gct(), m, a, al)
+
+
+class PoolOp(Op):
+    """layers.MaxPool2D([2,2], strides=2) (components.py:54)."""
+
+    def __init__(self, plan, x, y, stats=None):
+        self.p, self.x, self.y, self.stats = plan, x, y, stats
+        self.idx = None
+
+    def allocate(self, training):
+        if training and self.idx is None:
+            self.idx = torch.empty(self.y.n, self.y.h, self.y.w, self.y.c, dtype=torch.uint8, device=self.p.device)
+
+    def fwd(self, train):
+        N.call('dnnca_maxpool2x2_fwd', N.stream_ptr(), self.x.ct(), self.y.ct(), N.ptr(self.idx) if train else None,
+               self.stats.fwd_ptr() if (self.stats and train) else None)
+
+    def bwd(self):
+        if not self.x.needs_grad:
+            return
+        m, a, al = self.x.mask_args()
+        dskip = self.x.gct() if self.x.skip_consumed else None
+        N.call('dnnca_maxpool2x2_bwd', N.stream_ptr(), self.y.gct(), N.ptr(self.idx), dskip, self.x.gct(), m, a, al)
+
+
+class BNStats:
+    """fp64 accumulators of one BatchNormalization: forward (sum, sumsq) and backward (sum dy, sum dy*xhat)."""
+
+    def __init__(self, plan, c):
+        self.p, self.c = plan, c
+        self.off = plan.stats_len
+        plan.stats_len += 4 * c
+
+    def fwd_ptr(self):
+        return C.c_void_p(self.p.stats.data_ptr() + 8 * self.off)
+
+    def bwd_ptr(self):
+        return C.c_void_p(self.p.stats.data_ptr() + 8 * (self.off + 2 * self.c))
+
+
+class BNOp(Op):
+    """layers.BatchNormalization (components.py:57,59,130,131).  Training statistics arrive
+    in ``stats`` (filled by the producer's epilogue or a channel_stats pass)."""
+
+    def __init__(self, plan, x, y, prefix, stats: BNStats, scale=True, fused_stats=True):
+        self.p, self.x, self.y, self.prefix, self.stats = plan, x, y, prefix, stats
+        self.gamma = f'{prefix}/gamma' if scale else None
+        self.fused_stats = fused_stats
+        self.ss = self.mi = None   # scale|shift and mean|invstd, fp32 [2C] each
+
+    def allocate(self, training):
+        if self.ss is None:
+            self.ss = torch.empty(2 * self.x.c, dtype=torch.float32, device=self.p.device)
+            self.mi = torch.empty(2 * self.x.c, dtype=torch.float32, device=self.p.device)
+
+    def fwd(self, train):
+        ps, s, c = self.p.params, N.stream_ptr(), self.x.c
+        g = ps.ptr(self.gamma) if self.gamma else None
+        if train:
+            if not self.fused_stats:
+                N.call('dnnca_channel_stats', s, self.x.ct(), self.stats.fwd_ptr())
+            N.call('dnnca_bn_finalize', s, self.stats.fwd_ptr(), self.x.n * self.x.h * self.x.w, c, g,
+                   ps.ptr(f'{self.prefix}/beta'), BN_MOMENTUM, BN_EPSILON, ps.ptr(f'{self.prefix}/moving_mean'),
+                   ps.ptr(f'{self.prefix}/moving_var'), N.ptr(self.ss), N.ptr(self.mi))
+        else:
+            N.call('dnnca_bn_inference_params', s, c, g, ps.ptr(f'{self.prefix}/beta'), BN_EPSILON,
+                   ps.ptr(f'{self.prefix}/moving_mean'), ps.ptr(f'{self.prefix}/moving_var'), N.ptr(self.ss))
+        N.call('dnnca_bn_apply', s, self.x.ct(), N.ptr(self.ss), self.y.ct())
+
+    def bwd(self):
+        ps, s = self.p.params, N.stream_ptr()
+        N.call('dnnca_bn_bwd_reduce', s, self.x.ct(), self.y.gct(), N.ptr(self.mi), self.stats.bwd_ptr())
+        act = self.x.act or (N.ACT_NONE, 0.0)
+        N.call('dnnca_bn_bwd_apply', s, self.x.ct(), self.y.gct(), N.ptr(self.mi),
+               ps.ptr(self.gamma) if self.gamma else None, self.stats.bwd_ptr(), self.x.gct(), act[0], act[1],
+               ps.gptr(self.gamma) if self.gamma else None, ps.gptr(f'{self.prefix}/beta'))
+
+
+class ConvertOp(Op):
+    """fp32 network input -> activation dtype (the tail of data.py:193-206 on the device)."""
+
+    def __init__(self, plan, x, y):
+        self.x, self.y = x, y
+
+    def fwd(self, train):
+        N.call('dnnca_convert', N.stream_ptr(), self.x.ct(), self.y.ct())
+
+
+class AddReluAffineOp(Op):
+    """BN -> add -> relu -> BN tail of MultiResBlock / ResPath (multiresunet.py:120-124,148-150), inference."""
+
+    def __init__(self, plan, a, fa, b, fb, fo, y):
+        self.p, self.a, self.fa, self.b, self.fb, self.fo, self.y = plan, a, fa, b, fb, fo, y
+
+    def fwd(self, train):
+        assert not train, 'MultiResUnet is forward/inference only in this build'
+        N.call('dnnca_add_relu_affine', N.stream_ptr(), self.a.ct(), N.ptr(self.fa() if self.fa else None),
+               self.b.ct(), N.ptr(self.fb() if self.fb else None), N.ptr(self.fo() if self.fo else None), self.y.ct())
+
+
+class CallbackOp(Op):
+    """Host-side closure run at this point of the forward sequence (e.g. folding BN into weights)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def fwd(self, train):
+        self.fn(train)
+
+
+# ----------------------------------------------------------------------------
+# plan
+# ----------------------------------------------------------------------------
+class Plan:
+    def __init__(self, params: ParamStore, batch, height, width, channels, dtype, device):
+        self.params, self.dtype, self.device = params, dtype, device
+        self.bufs: list[Buf] = []
+        self.ops: list[Op] = []
+        self.stats_len = 0
+        self.stats = None
+        self.batch, self.height, self.width, self.channels = batch, height, width, channels
+        # static fp32 input / label / output buffers (the H2D copies of a step land here)
+        self.x_in = torch.zeros(batch, height, width, channels, dtype=torch.float32, device=device)
+        self.y_in = torch.zeros(batch, height, width, dtype=torch.float32, device=device)
+        self.input = TRef(Buf(self, batch, height, width, channels, 'input', torch.float32, external=self.x_in))
+        self.input.needs_grad = False
+        self.features = None          # TRef feeding the head
+        self.head = None              # (kernel name, bias name)
+        self.allocated_training = None
+        self.graphs = {}
+
+    def new_buf(self, h, w, c, name, n=None):
+        return Buf(self, n or self.batch, h, w, c, name)
+
+    def add(self, op):
+        self.ops.append(op)
+        return op
+
+    def allocate(self, training):
+        if self.allocated_training is not None and (self.allocated_training or not training):
+            return
+        for op in self.ops:
+            for t in (getattr(op, 'x', None), getattr(op, 'y', None)):
+                if training and isinstance(t, TRef) and t.needs_grad:
+                    t.buf.want_grad = True
+        if training and self.features is not None:
+            self.features.buf.want_grad = True
+        for b in self.bufs:
+            b.allocate(training)
+        for op in self.ops:
+            if hasattr(op, 'allocate'):
+                op.allocate(training)
+        if self.stats is None:
+            self.stats = torch.zeros(max(self.stats_len, 1), dtype=torch.float64, device=self.device)
+        B, H, W = self.batch, self.height, self.width
+        if getattr(self, 'logits', None) is None:
+            self.logits = torch.empty(B, H, W, 1, dtype=torch.float32, device=self.device)
+            self.probs = torch.empty(B, H, W, 1, dtype=torch.float32, device=self.device)
+        if training and getattr(self, 'per_sample', None) is None:
+            self.per_sample = torch.zeros(B, dtype=torch.float32, device=self.device)
+            self.lstats = torch.zeros(16, dtype=torch.uint8, device=self.device)
+        self.allocated_training = training or bool(self.allocated_training)
+
+    def activation_bytes(self):
+        return sum(b.nbytes() * (2 if b.grad is not None else 1) for b in self.bufs)
+
+    # ---- launch sequences ----------------------------------------------------
+    def forward(self, train=False):
+        for op in self.ops:
+            op.fwd(train)
+
+    def head_forward(self):
+        ps = self.params
+        N.call('dnnca_head_fwd', N.stream_ptr(), self.features.ct(), ps.ptr(self.head[0]), ps.ptr(self.head[1]),
+               N.ptr(self.logits), N.ptr(self.probs))
+
+    def head_loss(self, loss_cfg: N.LossConfig, with_grads=True):
+        ps, s = self.params, N.stream_ptr()
+        if getattr(self, 'per_sample', None) is None:
+            self.per_sample = torch.zeros(self.batch, dtype=torch.float32, device=self.device)
+            self.lstats = torch.zeros(16, dtype=torch.uint8, device=self.device)
+        self.per_sample.zero_()
+        if not loss_cfg.has_weight:
+            N.call('dnnca_label_stats_init', s, N.ptr(self.lstats))
+            N.call('dnnca_label_stats', s, N.ptr(self.y_in), self.y_in.numel(), N.ptr(self.lstats))
+        f = self.features
+        act = f.act or (N.ACT_NONE, 0.0)
+        N.call('dnnca_head_bce_fwd_bwd', s, f.ct(), ps.ptr(self.head[0]), ps.ptr(self.head[1]), N.ptr(self.y_in),
+               N.ptr(self.lstats), C.byref(loss_cfg), N.ptr(self.logits), N.ptr(self.probs), N.ptr(self.per_sample),
+               f.gct() if with_grads else None, act[0], act[1], ps.gptr(self.head[0]) if with_grads else None,
+               ps.gptr(self.head[1]) if with_grads else None)
+
+    def backward(self):
+        for op in reversed(self.ops):
+            op.bwd()
+
+    def zero_step_state(self):
+        self.params.grads.zero_()
+        if self.stats_len:
+            self.stats.zero_()
