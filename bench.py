@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- train slices/s of configs/unet.yaml on N B200s (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W            # this build (CUDA path)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...                      # oracle port of the reference on host cores
+
+A "step" = one optimizer step (zero grads, forward, fused head+loss, backward, gradient all-reduce
+when N>1, fused Adam) of UNetAnnotator(configs/unet.yaml) on a per-GPU batch of synthetic
+256x256x3 slices.  ``value`` is measured with the batch already resident in HBM (CUDA-graph replay,
+CUDA events, max over ranks); ``e2e`` goes through the public ``Model.train_step`` with pinned HOST
+buffers (H2D of the inputs and D2H of the loss inside the timed region).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'train_slices_per_sec'
+UNIT = 'slices/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='unet')
+    ap.add_argument('--batch', type=int, default=256, help='per-GPU batch (weak scaling)')
+    ap.add_argument('--size', type=int, default=256)
+    ap.add_argument('--channels', type=int, default=3)
+    ap.add_argument('--dtype', default='bf16')
+    ap.add_argument('--cpu-batch', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-profile', action='store_true')
+    return ap.parse_args()
+
+
+def load_cfg(name):
+    from dnncancerannotator_b200.utils.load import load_config
+    return load_config([os.path.join(ROOT, 'configs', name + '.yaml'),
+                        os.path.join(ROOT, 'configs', 'additionals', 'deploy_options.yaml')])
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU comparator: the oracle port of the reference (TensorFlow itself is not installable here)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_rate(cfg, args, steps, warmup, budget_s=25.0):
+    """torch-CPU restatement of the reference train step (forward + weighted BCE + backward +
+    keras Adam) on all host threads; a bounded sample of the same workload (batch ``cpu_batch``)."""
+    import torch
+    from oracle import ref_models as rm
+    from oracle import ref_ops as ops
+    from dnncancerannotator_b200.synthetic import make_slices
+    B = args.cpu_batch
+    ref = rm.build_model(cfg['model'], cfg['model_options'], (None, args.size, args.size, args.channels), seed=0)
+    x, y = make_slices(B, args.size, args.size, args.channels, seed=1234)
+    loss_cfg = cfg['deploy_options']['loss']['config']
+    mom = {k: (torch.zeros_like(ref.weights[k]), torch.zeros_like(ref.weights[k])) for k in ref.trainable}
+
+    def step(t):
+        r = ref.train_step_grads(x, y, loss_cfg)
+        for k in ref.trainable:
+            ref.weights[k], m_, v_ = ops.adam_step(ref.weights[k], r['grads'][k], mom[k][0], mom[k][1], t + 1)
+            mom[k] = (m_, v_)
+        for k, v in r['new_moving'].items():
+            ref.weights[k] = v
+    for t in range(warmup):
+        step(t)
+    times = []
+    t_begin = time.perf_counter()
+    for t in range(steps):
+        t0 = time.perf_counter()
+        step(warmup + t)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    ms = 1e3 * statistics.median(times)
+    return dict(value=B / (ms / 1e3), ms_per_step=ms, steps=len(times), cores=torch.get_num_threads(),
+                sample=f'{len(times)} steps of batch {B} ({args.size}x{args.size}x{args.channels} fp32), median')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cfg = load_cfg(args.config)
+    r = cpu_reference_rate(cfg, args, steps=args.steps, warmup=max(args.warmup, 1), budget_s=120.0)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': r['steps'], 'warmup': max(args.warmup, 1), 'ms_per_step': r['ms_per_step'],
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'configs/{args.config}.yaml train step, batch {args.cpu_batch} of '
+                               f'{args.size}x{args.size}x{args.channels} slices, host CPU'},
+        'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                         'sample': r['sample'] + '; torch-CPU restatement of the reference (TensorFlow unavailable)'},
+        'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        # under load = the upper half of the samples (idle samples before/after the region are excluded)
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {'sm_mhz': statistics.median(load) if load else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dnncancerannotator_b200 import native as N
+    from dnncancerannotator_b200.models import tf_models
+    from dnncancerannotator_b200.synthetic import make_slices
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+
+    cfg = load_cfg(args.config)
+    B, S, Cc = args.batch, args.size, args.channels
+    m = getattr(tf_models, cfg['model'])(**cfg['model_options'], dtype=args.dtype)
+    m.build((None, S, S, Cc))
+    m.compile(optimizer=cfg['deploy_options']['optimizer'], loss=cfg['deploy_options']['loss'])
+    if world > 1:
+        m.enable_data_parallel()
+    x, y = make_slices(B, S, S, Cc, seed=1234 + rank)
+    xh = torch.from_numpy(x).pin_memory()
+    yh = torch.from_numpy(y).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident measurement (value) ------------------------------------------------
+    loss0 = float(m.train_step(xh, yh))            # builds the plan, uploads the batch
+    plan = m._plan(B, S, S)
+    for _ in range(max(args.warmup, 3)):           # eager warm-ups + graph capture happen here
+        m._train_on_static(plan)
+    barrier()
+    lib = N.lib()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        loss = m._train_on_static(plan)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms], device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t) / args.steps
+    value = B * world / (ms_per_step / 1e3)
+    final_loss = float(loss)
+
+    # ---- end-to-end through the public API with host buffers ----------------------------------
+    for _ in range(2):
+        float(m.train_step(xh, yh))
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        l = m.train_step(xh, yh)                   # H2D of x,y from pinned memory ...
+        _ = l.item()                                # ... and D2H of the step's loss, every step
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t) / args.steps
+    e2e = {'value': B * world / (e2e_ms / 1e3), 'unit': UNIT, 'ms_per_step': e2e_ms,
+           'h2d_bytes_per_step': int(xh.numel() * 4 + yh.numel() * 4), 'd2h_bytes_per_step': 4}
+
+    # ---- launches per step and per-kernel roofline (eager pass, CUDA events per C-ABI call) ---
+    m.use_cuda_graph = False
+    lib.dnnca_debug_launch_count(1)
+    m._train_on_static(plan)
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.dnnca_debug_launch_count(1))
+    roofline, breakdown = None, None
+    if not args.no_profile and rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        with N.Profiler() as prof:
+            for _ in range(3):
+                m._train_on_static(plan)
+        agg = prof.summary()
+        tot = sum(d['ms'] for d in agg.values())
+        rows = sorted(agg.items(), key=lambda kv: -kv[1]['ms'])
+        breakdown = [{'kernel': k, 'share': round(d['ms'] / tot, 4), 'ms': round(d['ms'] / 3, 4),
+                      'gbs': round(d['bytes'] / d['ms'] / 1e6, 1) if d['ms'] else None,
+                      'tflops': round(d['flops'] / d['ms'] / 1e9, 2) if d['ms'] else None} for k, d in rows[:12]]
+        k, d = rows[0]
+        ach = d['bytes'] / d['ms'] / 1e6
+        roofline = {'bound': 'hbm', 'kernel': k, 'achieved': round(ach, 1), 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': round(ach / hbm_peak, 4), 'traffic': None, 'share_of_step': round(d['ms'] / tot, 4),
+                    'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback (B200_PROFILING.md)',
+                    'step_algorithmic_gbs': round(sum(v['bytes'] for v in agg.values()) / tot / 1e6, 1),
+                    'note': 'CUDA events around each C-ABI call in an eager pass after the timed region'}
+    m.use_cuda_graph = True
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_rate(cfg, args, steps=10, warmup=3)
+        cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+               'sample': r['sample'] + '; torch-CPU restatement of the reference (TensorFlow unavailable)'}
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3) + 1, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+        'config': {'workload': f'configs/{args.config}.yaml UNetAnnotator training step, per-GPU batch {B} of '
+                               f'{S}x{S}x{Cc} slices ({args.dtype} activations, fp32 accumulate/master weights)',
+                   'global_batch': B * world, 'parallelism': f'dp{world}',
+                   'l2': 'working set per step (>1 GB of activations) exceeds the 126 MB L2; no flush needed',
+                   'cuda_graph': True},
+        'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
+        'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'breakdown': breakdown,
+        'loss_first': loss0, 'loss_last': final_loss, 'wall_s_timed_region': wall,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

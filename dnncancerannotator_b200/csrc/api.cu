@@ -20,6 +20,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   return DNNCA_ERR_CUDA;
 }
 
+static long long g_launches = 0;
+void note_launch(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static int cached = 0;
   if (cached == 0) {
@@ -60,6 +63,12 @@ extern "C" int dnnca_sm_count(int* out) {
   if (!out) return DNNCA_ERR_BAD_ARG;
   *out = sm_count();
   return DNNCA_OK;
+}
+// kernels launched by this library since load (or since the last reset)
+extern "C" long long dnnca_debug_launch_count(int reset) {
+  long long v = __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+  if (reset) __atomic_store_n(&g_launches, 0LL, __ATOMIC_RELAXED);
+  return v;
 }
 // test hook: route every conv through the shape-generic kernels
 extern "C" int dnnca_debug_force_generic(int on) {

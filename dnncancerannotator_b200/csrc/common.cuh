@@ -27,8 +27,12 @@ int cuda_fail(cudaError_t e, const char* what);
     return DNNCA_ERR_UNSUPPORTED;               \
   } while (0)
 
+void note_launch(int n);
+
+// placed after every kernel launch: counts it and surfaces launch errors
 #define DNNCA_LAUNCH_CHECK(what)                                 \
   do {                                                           \
+    ::dnnca::note_launch(1);                                     \
     cudaError_t e__ = cudaGetLastError();                        \
     if (e__ != cudaSuccess) return ::dnnca::cuda_fail(e__, what); \
   } while (0)

@@ -38,6 +38,7 @@ extern "C" int dnnca_adam_step(void* stream, float* params, const float* grads, 
   DNNCA_CHECK_ARG(params && grads && m && v && hyper && step && count > 0, "adam_step: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   adam_tick_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(step));
+  note_launch(1);
   int grid = grid_for(count, 256 * 4, 4);
   adam_kernel<<<grid, 256, 0, s>>>(params, grads, m, v, count, hyper, reinterpret_cast<const long long*>(step), l2);
   DNNCA_LAUNCH_CHECK("adam_step");

@@ -48,6 +48,7 @@ _PROTOS = {
     'dnnca_last_error': [],
     'dnnca_sm_count': [C.POINTER(C.c_int)],
     'dnnca_debug_force_generic': [_i],
+    'dnnca_debug_launch_count': [_i],
     'dnnca_conv2d_fprop': [_vp, _TP, _vp, _vp, _TP, _i, _i, _f, _vp],
     'dnnca_conv2d_dgrad': [_vp, _TP, _vp, _TP, _i, _TP, _i, _f],
     'dnnca_conv2d_wgrad': [_vp, _TP, _TP, _vp, _vp, _i],
@@ -74,7 +75,8 @@ _PROTOS = {
     'dnnca_convert': [_vp, _TP, _TP],
     'dnnca_adam_step': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
 }
-_RESTYPES = {'dnnca_last_error': C.c_char_p, 'dnnca_label_stats_decode': None}
+_RESTYPES = {'dnnca_last_error': C.c_char_p, 'dnnca_label_stats_decode': None,
+             'dnnca_debug_launch_count': C.c_longlong}
 
 _lib = None
 
@@ -107,8 +109,99 @@ def check(rc, what=''):
         raise DnncaError(f'{what or "dnnca call"} failed ({rc}): {msg.decode() if msg else "?"}')
 
 
+_profiler = None   # set by Profiler: records (name, args, start event, end event) per C-ABI call
+
+
 def call(name, *args):
+    if _profiler is not None:
+        _profiler.before(name, args)
+        check(getattr(lib(), name)(*args), name)
+        _profiler.after()
+        return
     check(getattr(lib(), name)(*args), name)
+
+
+class Profiler:
+    """Times every C-ABI call of an eager (non-graph) pass with CUDA events on the launching
+    stream and estimates its algorithmic bytes / conv FLOPs from the tensor arguments
+    (each activation read once per consumer and written once at its storage dtype)."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _profiler
+        _profiler = self
+        return self
+
+    def __exit__(self, *a):
+        global _profiler
+        _profiler = None
+
+    def before(self, name, args):
+        self._cur = (name, self._cost(name, args), torch.cuda.Event(enable_timing=True),
+                     torch.cuda.Event(enable_timing=True))
+        self._cur[2].record(torch.cuda.current_stream())
+
+    def after(self):
+        self._cur[3].record(torch.cuda.current_stream())
+        self.records.append(self._cur)
+
+    @staticmethod
+    def _views(args):
+        out = []
+        for a in args:
+            obj = getattr(a, '_obj', None)
+            if isinstance(obj, Tensor):
+                out.append(obj)
+        return out
+
+    def _cost(self, name, args):
+        vs = self._views(args)
+        esz = lambda v: 4 if v.dtype == F32 else 2
+        byt = sum(v.n * v.h * v.w * v.c * esz(v) for v in vs)
+        flops = 0
+        label = name.replace('dnnca_', '')
+        if name.startswith('dnnca_conv2d_') and len(vs) >= 2:
+            k = [a for a in args if isinstance(a, int)][0]
+            a, b = vs[0], vs[1]
+            flops = 2 * a.n * a.h * a.w * a.c * b.c * k * k
+            byt += 4 * k * k * a.c * b.c
+            label += f'[{a.c}->{b.c}@{a.h}]'
+        elif name.startswith('dnnca_convtranspose2x2_') and len(vs) >= 2:
+            a, b = vs[0], vs[1]
+            small = a if a.h < b.h else b
+            flops = 2 * small.n * small.h * small.w * a.c * b.c * 4
+            byt += 16 * a.c * b.c
+            label += f'[{a.c}->{b.c}@{small.h}]'
+        elif name == 'dnnca_maxpool2x2_fwd' and vs:
+            byt += vs[1].n * vs[1].h * vs[1].w * vs[1].c
+            label += f'[{vs[0].c}@{vs[0].h}]'
+        elif name == 'dnnca_maxpool2x2_bwd' and vs:
+            byt += vs[0].n * vs[0].h * vs[0].w * vs[0].c
+            label += f'[{vs[0].c}@{vs[0].h}]'
+        elif name in ('dnnca_head_bce_fwd_bwd', 'dnnca_head_fwd') and vs:
+            f = vs[0]
+            byt += f.n * f.h * f.w * 4 * (3 if name.endswith('bwd') else 2)
+            label += f'[{f.c}@{f.h}]'
+        elif name == 'dnnca_label_stats':
+            byt = 4 * [a for a in args if isinstance(a, int)][0]
+        elif name == 'dnnca_adam_step':
+            byt = 28 * [a for a in args if isinstance(a, int)][0]
+        elif vs:
+            label += f'[{vs[0].c}@{vs[0].h}]'
+        return dict(label=label, bytes=byt, flops=flops)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, cost, e0, e1 in self.records:
+            d = agg.setdefault(cost['label'], dict(ms=0.0, calls=0, bytes=0, flops=0))
+            d['ms'] += e0.elapsed_time(e1)
+            d['calls'] += 1
+            d['bytes'] += cost['bytes']
+            d['flops'] += cost['flops']
+        return agg
 
 
 def stream_ptr():

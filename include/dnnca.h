@@ -65,6 +65,8 @@ DNNCA_API const char* dnnca_last_error(void);
 DNNCA_API int dnnca_sm_count(int* out);
 /* test hook: non-zero routes every conv through the shape-generic kernels; returns the old value */
 DNNCA_API int dnnca_debug_force_generic(int on);
+/* number of kernels this library has launched since load (reset != 0 zeroes the counter afterwards) */
+DNNCA_API long long dnnca_debug_launch_count(int reset);
 
 /* ---------------------------------------------------------------------------
  * Conv2D, stride 1, 'same' zero padding, k in {1,3}

@@ -1,0 +1,205 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/dnnca.h
+declares, and the host-side lowering (model classes -> static plan) has the structure of
+the reference graphs.  No kernels are launched here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def libpath():
+    from dnncancerannotator_b200 import build
+    return build.build()          # nvcc cross-compiles sm_100a without a GPU
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'dnnca.h')).read()
+    return sorted(set(re.findall(r'DNNCA_API\s+[\w\s\*]+?\b(dnnca_\w+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    declared = header_symbols()
+    assert len(declared) >= 27
+    out = subprocess.run(['nm', '-D', '--defined-only', libpath], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r' T (dnnca_\w+)', out))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    # nothing but the C ABI leaks out of the library
+    assert all(s.startswith('dnnca_') for s in re.findall(r' T (\w+)', out))
+
+
+def test_ctypes_binding_covers_the_header(libpath):
+    from dnncancerannotator_b200 import native
+    assert sorted(native.exported_symbols()) == header_symbols()
+    lib = native.lib()
+    assert lib.dnnca_version() == 100
+    assert ctypes.sizeof(native.Tensor) == 40 and ctypes.sizeof(native.LabelStats) == 16
+    assert ctypes.sizeof(native.LossConfig) == 20
+
+
+def test_sass_is_sm100a(libpath):
+    out = subprocess.run(['cuobjdump', '-lelf', libpath], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from dnncancerannotator_b200 import native
+    monkeypatch.setattr(native, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    monkeypatch.setattr(native, '_lib', None)
+    with pytest.raises(native.DnncaError, match='no CPU or PyTorch fallback'):
+        native.lib()
+
+
+def test_no_cuda_device_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip('needs a CPU-only host')
+    from dnncancerannotator_b200 import native
+    from dnncancerannotator_b200.models import tf_models
+    m = tf_models.UNetAnnotator(3, 2, 2, 3, 1, padding='same')
+    with pytest.raises(native.DnncaError, match='no CPU fallback'):
+        m(np.zeros((1, 16, 16, 3), np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, 'dnncancerannotator_b200')):
+        for f in files:
+            if f.endswith('.py') and re.search(r'^\s*(from|import)\s+oracle\b', open(os.path.join(d, f)).read(), re.M):
+                bad.append(f)
+    assert not bad, bad
+
+
+# ---- config surface -------------------------------------------------------------------
+def test_layered_config_loading_matches_reference_semantics():
+    from dnncancerannotator_b200.utils.load import load_config
+    c = os.path.join(ROOT, 'configs')
+    cfg = load_config([f'{c}/unet.yaml', f'{c}/additionals/data_options.yaml', f'{c}/additionals/deploy_options.yaml',
+                       f'{c}/additionals/multigpu.yaml', f'{c}/additionals/train_batch28.yaml',
+                       f'{c}/additionals/leakyReLU.yaml', f'{c}/additionals/kernel_regularizer.yaml'])
+    assert cfg['model'] == 'UNetAnnotator' and cfg['model_options']['n_filters_first'] == 3
+    assert cfg['deploy_options']['enable_multigpu'] is True              # dotted-key overlay (load.py:44-57)
+    assert cfg['data_options']['train'] == {'batch_size': 28}           # whole-value overwrite like the reference
+    assert cfg['model_options']['activation']['config']['alpha'] == 0.3
+    assert cfg['deploy_options']['loss']['config']['weight_mul'] == 3.0
+    assert cfg['data_options']['eval']['batch_size'] == 64
+
+
+def test_loss_registry_and_config_keys():
+    from dnncancerannotator_b200.utils import losses
+    l = losses.get({'class_name': 'WeightedCrossentropy', 'config': {'weight_mul': 3.0}})
+    assert l.get_config() == dict(weight=None, weight_add=0.0, weight_mul=3.0, label_smoothing=False,
+                                  label_smoothing_filter_size=6, label_smoothing_sigma=3)
+    cfg = l.native_config(1000)
+    assert cfg.has_weight == 0 and cfg.weight_mul == 3.0 and abs(cfg.grad_scale - 1e-3) < 1e-9
+    assert losses.get('WeightedCrossentropy').weight_mul == 1.0
+    with pytest.raises(NotImplementedError):
+        losses.WeightedCrossentropy(label_smoothing=True)
+    with pytest.raises(ValueError):
+        losses.get('mse')
+
+
+# ---- lowering --------------------------------------------------------------------------
+def cpu_plan(model, B, H, C, dtype=torch.bfloat16, training=True):
+    from dnncancerannotator_b200 import runtime as R
+    model.build((None, H, H, C))
+    model.params.materialize(torch.device('cpu'))
+    plan = R.Plan(model.params, B, H, H, C, dtype, torch.device('cpu'))
+    model._emit(plan)
+    plan.allocate(training)
+    return plan
+
+
+def op_counts(plan):
+    out = {}
+    for op in plan.ops:
+        out[type(op).__name__] = out.get(type(op).__name__, 0) + 1
+    return out
+
+
+def test_unet_yaml_lowering_structure():
+    from dnncancerannotator_b200.models import tf_models
+    from dnncancerannotator_b200 import runtime as R
+    from dnncancerannotator_b200.utils.load import load_config
+    cfg = load_config(os.path.join(ROOT, 'configs', 'unet.yaml'))
+    m = getattr(tf_models, cfg['model'])(**cfg['model_options'])
+    plan = cpu_plan(m, 2, 64, 3)
+    assert m.count_params() == 8740
+    assert op_counts(plan) == {'ConvertOp': 1, 'ConvOp': 12, 'PoolOp': 3, 'TConvOp': 3}
+    convs = [op for op in plan.ops if isinstance(op, R.ConvOp)]
+    assert [(o.x.c, o.y.c) for o in convs] == [(3, 3), (3, 3), (3, 6), (6, 6), (6, 12), (12, 12),
+                                               (24, 12), (12, 12), (12, 6), (6, 6), (6, 3), (3, 3)]
+    assert not convs[0].x.needs_grad                          # input gets no gradient (first dgrad skipped)
+    # skip tensors live in the upper half of the decoder concat buffers; tconv writes the lower half
+    pools = [op for op in plan.ops if isinstance(op, R.PoolOp)]
+    tconvs = [op for op in plan.ops if isinstance(op, R.TConvOp)]
+    for pool, tconv in zip(pools, reversed(tconvs)):
+        res = pool.x
+        assert res.skip_consumed and res.buf is tconv.y.buf
+        assert tconv.y.coff == 0 and res.coff == tconv.y.c and res.buf.c == 2 * res.c
+    assert plan.features.shape == (2, 64, 64, 3) and plan.features.act is not None
+    assert plan.head == ('head/kernel', 'head/bias')
+
+
+def test_unet_big_and_mulmo_lowering_structure():
+    from dnncancerannotator_b200.models import tf_models
+    from dnncancerannotator_b200 import runtime as R
+    from dnncancerannotator_b200.utils.load import load_config
+    cfg = load_config(os.path.join(ROOT, 'configs', 'unet_big.yaml'))
+    m = getattr(tf_models, cfg['model'])(**cfg['model_options'])
+    plan = cpu_plan(m, 1, 32, 3, training=False)
+    assert m.count_params() == 15848385 and m.count_params(True) == 15836865
+    assert op_counts(plan) == {'ConvertOp': 1, 'ConvOp': 16, 'BNOp': 24, 'PoolOp': 4, 'TConvOp': 4}
+    cfg = load_config(os.path.join(ROOT, 'configs', 'mulmo_unet.yaml'))
+    m = getattr(tf_models, cfg['model'])(**cfg['model_options'])
+    plan = cpu_plan(m, 1, 32, 3, training=False)
+    assert m.count_params() == 1719089 and m.count_params(True) == 1713329
+    assert op_counts(plan) == {'ConvertOp': 1, 'ConvOp': 32, 'BNOp': 48, 'PoolOp': 12, 'TConvOp': 4}
+    first = [op for op in plan.ops if isinstance(op, R.ConvOp)][0]
+    assert first.x.c == 1 and first.x.buf.c == 3                 # inputs[..., m:m+1] is a channel-slice view
+    bott = [b for b in plan.bufs if b.name == 'bottleneck'][0]
+    assert (bott.h, bott.w, bott.c) == (2, 2, 384)               # concat of the three 128-channel encoders
+
+
+def test_multiresunet_lowering_structure():
+    from dnncancerannotator_b200.models import tf_models
+    m = tf_models.MultiResUnet(None, None, 5)
+    plan = cpu_plan(m, 1, 32, 5, training=False)
+    assert m.count_params() == 7262996
+    c = op_counts(plan)
+    assert c['_FoldedConv'] == 56 and c['TConvOp'] == 4 and c['PoolOp'] == 4 and c['AddReluAffineOp'] == 19
+
+
+def test_unsupported_geometry_is_rejected():
+    from dnncancerannotator_b200.models import tf_models
+    with pytest.raises(NotImplementedError, match="padding='valid'"):
+        tf_models.UNetAnnotator(3, 2, 2, 3, 1)                   # reference default padding
+    with pytest.raises(NotImplementedError):
+        tf_models.UNetAnnotator(3, 2, 3, 3, 1, padding='same')   # rate 3
+
+
+def test_weights_roundtrip_and_checkpoint_naming(tmp_path):
+    from dnncancerannotator_b200.models import tf_models
+    m = tf_models.UNetAnnotator(4, 2, 2, 3, 1, bn=True, padding='same')
+    m.build((None, 32, 32, 3))
+    w = m.get_weights()
+    w['head/bias'] = np.array([0.5], np.float32)
+    m.set_weights(w)
+    os.makedirs(tmp_path / 'checkpoints')
+    m.save_weights(str(tmp_path / 'checkpoints' / 'ckpt-5000'))
+    m.save_weights(str(tmp_path / 'checkpoints' / 'ckpt-10000'))
+    assert list(m.list_checkpoints(str(tmp_path))) == [5000, 10000]
+    m2 = tf_models.UNetAnnotator(4, 2, 2, 3, 1, bn=True, padding='same', seed=9)
+    m2.build((None, 32, 32, 3))
+    m2.load_weights(m.list_checkpoints(str(tmp_path))[10000])
+    for k, v in m.get_weights().items():
+        np.testing.assert_array_equal(v, m2.get_weights()[k])
+    with pytest.raises(KeyError):
+        m2.set_weights({'nope': np.zeros(1)})
+    with pytest.raises(ValueError):
+        m2.set_weights({'head/bias': np.zeros(2)})

@@ -1,0 +1,211 @@
+"""End-to-end parity of the CUDA path (model classes -> static plan -> C ABI) against the
+oracle and the committed golden vectors, at the tolerances BASELINE.json states:
+logits <= 1e-2 relative, loss <= 1e-3 relative, parameter gradients <= 2e-2 relative L2 in
+bf16 mode; fp32 mode is held to much tighter bounds plus bit-exact thresholded masks (p>0.5 and
+p>=0.8) and max-pool indices away from numerical ties.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_models as rm
+from oracle import ref_ops as ops
+from tests.golden.make_golden import CASES
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+# BASELINE.json tolerances (bf16) and the tighter fp32-mode bounds
+TOL = {'bf16': dict(logits=1e-2, loss=1e-3, grad=2e-2), 'fp32': dict(logits=2e-4, loss=2e-5, grad=1e-3)}
+
+
+def product_model(name, opts, dtype):
+    from dnncancerannotator_b200.models import tf_models
+    return getattr(tf_models, name)(**opts, dtype=dtype)
+
+
+def rel_inf(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64).ravel() - np.asarray(b, np.float64).ravel()) /
+                 max(np.linalg.norm(np.asarray(b, np.float64).ravel()), 1e-12))
+
+
+def check_masks(logits, ref_logits, exact):
+    """thresholded masks at p>0.5 (logit>0) and p>=0.8 (logit>=ln4)."""
+    for thr in (0.0, float(np.log(4.0))):
+        a, b = logits > thr, ref_logits > thr
+        near = np.abs(ref_logits - thr) < (1e-4 if exact else 5e-2)
+        assert np.array_equal(a[~near], b[~near]), f'mask mismatch away from the threshold {thr}'
+        if exact:
+            assert (a != b).mean() < 1e-3
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('case', list(CASES))
+def test_golden_forward_backward(case, mode):
+    model, opts, B, H, C, loss_cfg, _ = CASES[case]
+    z = np.load(os.path.join(GOLDEN, case + '.npz'))
+    m = product_model(model, opts, mode)
+    m.build((None, H, H, C))
+    m.set_weights({k[2:]: z[k] for k in z.files if k.startswith('w:')})
+    m.compile(loss=dict(class_name='WeightedCrossentropy', config=loss_cfg))
+    tol = TOL[mode]
+    for rep in range(4):      # eager warm-up runs, then the captured CUDA graph: all must agree
+        per = m.forward_backward(z['x'], z['y']).cpu().numpy()
+        logits = m.last_logits.cpu().numpy()
+        assert rel_inf(logits, z['logits']) <= tol['logits'], (rep, rel_inf(logits, z['logits']))
+        np.testing.assert_allclose(per, z['per_sample'], rtol=tol['loss'] * 3)
+        assert abs(per.mean() - z['data_loss']) <= tol['loss'] * abs(z['data_loss']), (per.mean(), z['data_loss'])
+        grads = m.get_grads()
+        l2 = None
+        worst = 0.0
+        for k in z.files:
+            if not k.startswith('g:'):
+                continue
+            name = k[2:]
+            g = grads[name]
+            ref = z[k].astype(np.float64)
+            if m.params.specs[name]['l2']:          # golden grads include d(l2*sum w^2)/dw; the kernels add it in Adam
+                ref = ref - 2 * m.params.specs[name]['l2'] * z['w:' + name]
+            if np.linalg.norm(ref) < 1e-7:
+                assert np.linalg.norm(g) < 1e-5, name
+                continue
+            worst = max(worst, rel_l2(g, ref))
+            assert rel_l2(g, ref) <= tol['grad'], (name, rel_l2(g, ref))
+        # all gradients together
+        names = [k[2:] for k in z.files if k.startswith('g:')]
+        allg = np.concatenate([grads[n].ravel() for n in names])
+        allr = np.concatenate([(z['g:' + n] - (2 * m.params.specs[n]['l2'] * z['w:' + n] if m.params.specs[n]['l2'] else 0)).ravel() for n in names])
+        assert rel_l2(allg, allr) <= tol['grad']
+    check_masks(logits, z['logits'], exact=(mode == 'fp32'))
+    # BN moving statistics after the 4 training-mode passes == 4 momentum updates with the same batch stats
+    if opts.get('bn'):
+        w = m.get_weights()
+        for k in z.files:
+            if k.startswith('m:'):
+                name = k[2:]
+                init = z['w:' + name]
+                batch = (z[k] - 0.99 * init) / 0.01              # oracle's batch statistic
+                expect = init * 0.99 ** 4 + batch * (1 - 0.99 ** 4)
+                np.testing.assert_allclose(w[name], expect, rtol=2e-2 if mode == 'bf16' else 2e-3, atol=2e-3 if mode == 'bf16' else 1e-4)
+
+
+@pytest.mark.parametrize('case', ['unet_tiny', 'unet_bn_tiny'])
+def test_pool_indices_fp32_bit_exact(case):
+    model, opts, B, H, C, loss_cfg, _ = CASES[case]
+    z = np.load(os.path.join(GOLDEN, case + '.npz'))
+    m = product_model(model, opts, 'fp32')
+    m.build((None, H, H, C))
+    m.set_weights({k[2:]: z[k] for k in z.files if k.startswith('w:')})
+    m.compile(loss=dict(class_name='WeightedCrossentropy', config=loss_cfg))
+    m.use_cuda_graph = False
+    m.forward_backward(z['x'], z['y'])
+    plan = m._plan(B, H, H)
+    from dnncancerannotator_b200 import runtime as R
+    pools = [op for op in plan.ops if isinstance(op, R.PoolOp)]
+    assert len(pools) == opts['n_downsample']
+    for i, op in enumerate(pools):
+        got, ref = op.idx.cpu().numpy(), z[f'pool_idx:{i}']
+        x = op.x.torch_view().float().cpu().numpy()
+        # windows whose two largest values are closer than fp32 summation noise may legitimately differ
+        win = x.reshape(B, x.shape[1] // 2, 2, x.shape[2] // 2, 2, -1).transpose(0, 1, 3, 5, 2, 4).reshape(*got.shape, 4)
+        s = np.sort(win, -1)
+        clear = (s[..., 3] - s[..., 2] > 1e-5 * np.maximum(np.abs(s[..., 3]), 1e-3)) | (s[..., 3] == s[..., 2])
+        assert np.array_equal(got[clear], ref[clear])
+        assert (got != ref).mean() < 2e-3
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_inference_matches_oracle_eval_mode(mode):
+    for case in ('unet_bn_tiny', 'mulmo_tiny'):
+        model, opts, B, H, C, _, _ = CASES[case]
+        z = np.load(os.path.join(GOLDEN, case + '.npz'))
+        m = product_model(model, opts, mode)
+        m.build((None, H, H, C))
+        m.set_weights({k[2:]: z[k] for k in z.files if k.startswith('w:')})
+        for _ in range(4):
+            p = m(z['x']).cpu().numpy()
+        logits = m.last_logits.cpu().numpy()
+        assert rel_inf(logits, z['eval_logits']) <= TOL[mode]['logits']
+        np.testing.assert_allclose(p, 1 / (1 + np.exp(-z['eval_logits'].astype(np.float64))), atol=2e-2 if mode == 'bf16' else 1e-4)
+        assert p.shape == (B, H, H, 1)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_multiresunet_forward(mode):
+    z = np.load(os.path.join(GOLDEN, 'multires_fwd_tiny.npz'))
+    ref = rm.build_model('MultiResUnet', dict(height=None, width=None, n_channels=5), None, seed=0)
+    ref.randomize_bn(seed=1)
+    m = product_model('MultiResUnet', dict(height=None, width=None, n_channels=5), mode)
+    m.build((None, 32, 32, 5))
+    assert m.count_params() == 7262996
+    m.set_weights(ref.get_weights())
+    for _ in range(3):
+        m(z['x'])
+    logits = m.last_logits.cpu().numpy()
+    assert rel_inf(logits, z['eval_logits']) <= (3e-2 if mode == 'bf16' else 5e-4), rel_inf(logits, z['eval_logits'])
+    with pytest.raises(NotImplementedError):
+        m.train_step(z['x'], np.zeros((1, 32, 32), np.float32))
+
+
+@pytest.mark.parametrize('case', ['unet_tiny', 'unet_bn_tiny', 'unet_leaky_l2_tiny'])
+def test_training_trajectory_fp32(case):
+    """5 optimizer steps (fused Adam, keras form, LR schedule, L2) vs the oracle's autograd + adam_step."""
+    model, opts, B, H, C, loss_cfg, _ = CASES[case]
+    z = np.load(os.path.join(GOLDEN, case + '.npz'))
+    weights = {k[2:]: z[k] for k in z.files if k.startswith('w:')}
+    m = product_model(model, opts, 'fp32')
+    m.build((None, H, H, C))
+    m.set_weights(weights)
+    m.compile(optimizer='adam', loss=dict(class_name='WeightedCrossentropy', config=loss_cfg))
+    ref = rm.build_model(model, opts, (None, H, H, C), seed=0, dtype=torch.float64)
+    ref.set_weights(weights)
+    mom = {k: (torch.zeros_like(ref.weights[k]), torch.zeros_like(ref.weights[k])) for k in ref.trainable}
+    losses, rlosses = [], []
+    for step in range(5):
+        lr = ops.lr_schedule(step)
+        losses.append(float(m.train_step(z['x'], z['y'], lr=lr)))
+        r = ref.train_step_grads(z['x'], z['y'], loss_cfg)
+        rlosses.append(r['loss'])
+        for k in ref.trainable:
+            ref.weights[k], m_, v_ = ops.adam_step(ref.weights[k], r['grads'][k], mom[k][0], mom[k][1], step + 1, lr=lr)
+            mom[k] = (m_, v_)
+        for k, v in r['new_moving'].items():
+            ref.weights[k] = v
+    np.testing.assert_allclose(losses, rlosses, rtol=2e-3)
+    w = m.get_weights()
+    for k in ref.trainable:
+        assert rel_l2(w[k], ref.weights[k].numpy()) < 5e-3 or np.abs(w[k] - ref.weights[k].numpy()).max() < 2e-4, k
+
+
+def test_unet_yaml_config_full_size_bf16():
+    """configs/unet.yaml at its real input size (256x256, C=3): bf16 CUDA path vs the fp32 oracle."""
+    from dnncancerannotator_b200.utils.load import load_config
+    from dnncancerannotator_b200.synthetic import make_slices
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = load_config([os.path.join(root, 'configs', 'unet.yaml'),
+                       os.path.join(root, 'configs', 'additionals', 'deploy_options.yaml')])
+    m = product_model(cfg['model'], cfg['model_options'], 'bf16')
+    m.build((None, 256, 256, 3))
+    m.compile(loss=cfg['deploy_options']['loss'])
+    ref = rm.build_model(cfg['model'], cfg['model_options'], (None, 256, 256, 3), seed=3)
+    rng = np.random.default_rng(5)
+    for k in ref.weights:
+        if k.endswith('/bias'):
+            ref.weights[k] = torch.tensor(rng.normal(0, 0.05, ref.weights[k].shape), dtype=torch.float32)
+    m.set_weights(ref.get_weights())
+    x, y = make_slices(4, 256, 256, 3, seed=1234)
+    r = ref.train_step_grads(x, y, cfg['deploy_options']['loss']['config'])
+    per = m.forward_backward(x, y).cpu().numpy()
+    logits = m.last_logits.cpu().numpy()
+    assert rel_inf(logits, r['logits'].numpy()) <= 1e-2
+    assert abs(per.mean() - r['data_loss']) <= 1e-3 * abs(r['data_loss'])
+    g = m.get_grads()
+    allg = np.concatenate([g[k].ravel() for k in ref.trainable])
+    allr = np.concatenate([r['grads'][k].numpy().ravel() for k in ref.trainable])
+    assert rel_l2(allg, allr) <= 2e-2, rel_l2(allg, allr)

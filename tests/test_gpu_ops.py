@@ -1,0 +1,366 @@
+"""Per-op parity of the CUDA kernels (called through the C ABI) against the oracle.
+
+Every case runs in fp32 (tight tolerance: same arithmetic, different summation order) and
+bf16 (inputs rounded to bf16 first, so the only differences are the kernel's bf16 output
+rounding and fp32 accumulation order).  Tensors are embedded as channel slices of wider
+buffers to exercise the concat-slice views.  Conv shapes cover both the specialised
+small-channel kernels and the shape-generic kernels (also forced via the debug hook).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops as ops
+from oracle import ref_numpy as rn
+
+pytestmark = pytest.mark.gpu
+
+DT = {'fp32': torch.float32, 'bf16': torch.bfloat16}
+TOL = {'fp32': dict(rtol=2e-5, atol=2e-5), 'bf16': dict(rtol=1.2e-2, atol=1.2e-2)}
+
+
+@pytest.fixture(scope='module')
+def N():
+    from dnncancerannotator_b200 import native
+    native.lib()
+    return native
+
+
+def sync():
+    torch.cuda.synchronize()
+
+
+def embed(a, dtype, pad_lo=0, pad_hi=0, fill=7.0):
+    """numpy NHWC array -> (torch buffer on GPU with extra channels, coff, c)."""
+    n, h, w, c = a.shape
+    buf = torch.full((n, h, w, pad_lo + c + pad_hi), fill, dtype=dtype, device='cuda')
+    buf[..., pad_lo:pad_lo + c] = torch.from_numpy(a).to('cuda').to(dtype)
+    return buf, pad_lo, c
+
+
+def view(N, buf, coff, c):
+    return N.tensor_view(buf, coff, c)
+
+
+def q(a, dtype):
+    """quantise a numpy array like the device storage does."""
+    return torch.from_numpy(a).to(dtype).to(torch.float32).numpy()
+
+
+def dev(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to('cuda').to(dtype)
+
+
+def close(got, ref, mode, scale=None):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    tol = TOL[mode]
+    s = scale if scale is not None else max(np.abs(ref).max(), 1e-6)
+    err = np.abs(got - ref).max()
+    assert err <= tol['atol'] * s + 1e-12, f'max abs err {err:.3e} vs scale {s:.3e} (tol {tol["atol"]})'
+
+
+CONV_SHAPES = [  # (n, h, w, cin, cout, k)
+    (2, 16, 16, 3, 3, 3), (1, 40, 72, 3, 6, 3), (2, 8, 136, 6, 6, 3), (1, 16, 16, 24, 12, 3),
+    (1, 12, 20, 12, 12, 3), (2, 16, 16, 1, 16, 3), (1, 16, 16, 5, 3, 3),
+    (1, 10, 14, 7, 9, 3), (1, 8, 8, 20, 33, 3), (2, 9, 11, 17, 8, 1), (1, 8, 8, 64, 64, 3),
+]
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('force_generic', [0, 1])
+@pytest.mark.parametrize('shape', CONV_SHAPES)
+def test_conv_fprop_dgrad_wgrad(N, mode, force_generic, shape):
+    n, h, w, cin, cout, k = shape
+    dt = DT[mode]
+    rng = np.random.default_rng(hash(shape) % 2 ** 31)
+    x = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), dt)
+    wt = (rng.normal(size=(k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    b = rng.normal(size=cout).astype(np.float32)
+    lib = N.lib()
+    old = lib.dnnca_debug_force_generic(force_generic)
+    try:
+        for act, alpha, tact in [(N.ACT_RELU, 0.0, 'relu'), (N.ACT_LEAKY, 0.3, ('leaky', 0.3)), (N.ACT_NONE, 0.0, None)]:
+            xb, xo, _ = embed(x, dt, 2, 1)
+            yb = torch.full((n, h, w, cout + 3), 5.0, dtype=dt, device='cuda')
+            stats = torch.zeros(2 * cout, dtype=torch.float64, device='cuda')
+            xv, yv = view(N, xb, xo, cin), view(N, yb, 1, cout)
+            N.call('dnnca_conv2d_fprop', None, C.byref(xv), N.ptr(dev(wt)), N.ptr(dev(b)), C.byref(yv), k, act, alpha,
+                   N.ptr(stats))
+            sync()
+            ref = ops.activation(ops.conv2d(torch.from_numpy(x), torch.from_numpy(wt), torch.from_numpy(b)), tact).numpy()
+            got = yb[..., 1:1 + cout].float().cpu().numpy()
+            close(got, ref, mode)
+            assert (yb[..., 0].float() == 5.0).all() and (yb[..., 1 + cout:].float() == 5.0).all(), 'wrote outside the slice'
+            st = stats.cpu().numpy()
+            np.testing.assert_allclose(st[:cout], got.astype(np.float64).sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
+            np.testing.assert_allclose(st[cout:], (got.astype(np.float64) ** 2).sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
+        # backward: dz arrives as a slice, dx is masked by relu'(mask)
+        dz = q(rng.normal(size=(n, h, w, cout)).astype(np.float32), dt)
+        mask = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), dt)
+        dzb, dzo, _ = embed(dz, dt, 1, 2)
+        mb, mo, _ = embed(mask, dt, 0, 1)
+        dxb = torch.full((n, h, w, cin + 2), 3.0, dtype=dt, device='cuda')
+        dzv, mv, dxv = view(N, dzb, dzo, cout), view(N, mb, mo, cin), view(N, dxb, 2, cin)
+        N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(dev(wt)), C.byref(dxv), k, C.byref(mv), N.ACT_RELU, 0.0)
+        dw = torch.zeros(k, k, cin, cout, dtype=torch.float32, device='cuda')
+        db = torch.zeros(cout, dtype=torch.float32, device='cuda')
+        xb, xo, _ = embed(x, dt, 2, 1)
+        xv = view(N, xb, xo, cin)
+        N.call('dnnca_conv2d_wgrad', None, C.byref(xv), C.byref(dzv), N.ptr(dw), N.ptr(db), k)
+        sync()
+        rdx, rdw, rdb = rn.conv2d_same_bwd(x, wt, dz)
+        rdx = rdx * (mask > 0)
+        close(dxb[..., 2:].float().cpu().numpy(), rdx, mode)
+        assert (dxb[..., :2].float() == 3.0).all()
+        close(dw.cpu().numpy(), rdw, 'fp32', scale=np.abs(rdw).max() * (1 if mode == 'fp32' else 50))
+        close(db.cpu().numpy(), rdb, 'fp32', scale=np.abs(rdb).max() * (1 if mode == 'fp32' else 50))
+        # unmasked dgrad
+        N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(dev(wt)), C.byref(dxv), k, None, N.ACT_NONE, 0.0)
+        sync()
+        close(dxb[..., 2:].float().cpu().numpy(), rn.conv2d_same_bwd(x, wt, dz)[0], mode)
+    finally:
+        lib.dnnca_debug_force_generic(old)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('shape', [(2, 8, 8, 12, 12), (1, 6, 10, 24, 8), (2, 5, 7, 6, 3), (1, 4, 4, 40, 70)])
+def test_tconv(N, mode, shape):
+    n, h, w, cin, cout = shape
+    dt = DT[mode]
+    rng = np.random.default_rng(sum(shape))
+    x = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), dt)
+    kt = (rng.normal(size=(2, 2, cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.normal(size=cout).astype(np.float32)
+    xb, xo, _ = embed(x, dt, 1, 1)
+    yb = torch.full((n, 2 * h, 2 * w, 2 * cout), 5.0, dtype=dt, device='cuda')   # concat buffer, tconv half first
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device='cuda')
+    xv, yv = view(N, xb, xo, cin), view(N, yb, 0, cout)
+    N.call('dnnca_convtranspose2x2_fprop', None, C.byref(xv), N.ptr(dev(kt)), N.ptr(dev(b)), C.byref(yv), N.ptr(stats))
+    sync()
+    ref = rn.tconv2x2_fwd(x, kt, b)
+    got = yb[..., :cout].float().cpu().numpy()
+    close(got, ref, mode)
+    assert (yb[..., cout:].float() == 5.0).all()
+    np.testing.assert_allclose(stats.cpu().numpy()[:cout], got.astype(np.float64).sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
+    dy = q(rng.normal(size=(n, 2 * h, 2 * w, cout)).astype(np.float32), dt)
+    mask = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), dt)
+    dyb, dyo, _ = embed(dy, dt, 0, cout)
+    mb, mo, _ = embed(mask, dt)
+    dxb = torch.zeros(n, h, w, cin, dtype=dt, device='cuda')
+    dyv, mv, dxv = view(N, dyb, dyo, cout), view(N, mb, mo, cin), view(N, dxb, 0, cin)
+    N.call('dnnca_convtranspose2x2_dgrad', None, C.byref(dyv), N.ptr(dev(kt)), C.byref(dxv), C.byref(mv), N.ACT_LEAKY, 0.3)
+    dk = torch.zeros(2, 2, cout, cin, dtype=torch.float32, device='cuda')
+    db = torch.zeros(cout, dtype=torch.float32, device='cuda')
+    N.call('dnnca_convtranspose2x2_wgrad', None, C.byref(xv), C.byref(dyv), N.ptr(dk), N.ptr(db))
+    sync()
+    rdx, rdk, rdb = rn.tconv2x2_bwd(x, kt, dy)
+    rdx = rn.act_bwd(mask, rdx, ('leaky', 0.3))
+    close(dxb.float().cpu().numpy(), rdx, mode)
+    close(dk.cpu().numpy(), rdk, 'fp32', scale=np.abs(rdk).max() * (1 if mode == 'fp32' else 50))
+    close(db.cpu().numpy(), rdb, 'fp32', scale=np.abs(rdb).max() * (1 if mode == 'fp32' else 50))
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('c', [1, 3, 12, 64, 300])
+def test_maxpool_fwd_bwd_bit_exact(N, mode, c):
+    dt = DT[mode]
+    rng = np.random.default_rng(c)
+    n, h, w = 2, 12, 20
+    x = q(np.maximum(rng.normal(size=(n, h, w, c)), 0).astype(np.float32), dt)   # relu output: many exact ties at 0
+    xb, xo, _ = embed(x, dt, 1, 2)
+    yb = torch.zeros(n, h // 2, w // 2, c + 1, dtype=dt, device='cuda')
+    idx = torch.zeros(n, h // 2, w // 2, c, dtype=torch.uint8, device='cuda')
+    stats = torch.zeros(2 * c, dtype=torch.float64, device='cuda')
+    xv, yv = view(N, xb, xo, c), view(N, yb, 1, c)
+    N.call('dnnca_maxpool2x2_fwd', None, C.byref(xv), C.byref(yv), N.ptr(idx), N.ptr(stats))
+    sync()
+    ry, ridx = rn.maxpool2x2_fwd(x)
+    np.testing.assert_array_equal(yb[..., 1:].float().cpu().numpy(), ry)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ridx)          # first-max-wins, bit exact
+    ty, tidx = ops.maxpool(torch.from_numpy(x), 2, return_indices=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), tidx.numpy())
+    np.testing.assert_allclose(stats.cpu().numpy()[:c], ry.astype(np.float64).sum((0, 1, 2)), rtol=1e-6, atol=1e-4)
+    # backward with skip gradient added in place and relu mask from x
+    dy = q(rng.normal(size=ry.shape).astype(np.float32), dt)
+    dskip = q(rng.normal(size=x.shape).astype(np.float32), dt)
+    dyb, dyo, _ = embed(dy, dt)
+    dxb, dxo, _ = embed(dskip, dt, 3, 0)
+    dyv, dxv = view(N, dyb, dyo, c), view(N, dxb, dxo, c)
+    N.call('dnnca_maxpool2x2_bwd', None, C.byref(dyv), N.ptr(idx), C.byref(dxv), C.byref(dxv), C.byref(xv), N.ACT_RELU, 0.0)
+    sync()
+    ref = (rn.maxpool2x2_bwd(dy, ridx) + dskip) * (x > 0)
+    close(dxb[..., 3:].float().cpu().numpy(), ref, mode)
+    # plain scatter
+    N.call('dnnca_maxpool2x2_bwd', None, C.byref(dyv), N.ptr(idx), None, C.byref(dxv), None, N.ACT_NONE, 0.0)
+    sync()
+    np.testing.assert_array_equal(dxb[..., 3:].float().cpu().numpy(), rn.maxpool2x2_bwd(dy, ridx))
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('c,scale', [(3, True), (16, True), (64, False), (130, True), (600, True)])
+def test_batchnorm_train_fwd_bwd_and_inference(N, mode, c, scale):
+    dt = DT[mode]
+    rng = np.random.default_rng(c)
+    n, h, w = 2, 10, 12
+    x = q(np.maximum(rng.normal(0.3, 1.0, size=(n, h, w, c)), 0).astype(np.float32), dt)
+    gamma = rng.uniform(.5, 1.5, c).astype(np.float32) if scale else None
+    beta = rng.normal(0, .1, c).astype(np.float32)
+    mm0, mv0 = rng.normal(0, .1, c).astype(np.float32), rng.uniform(.5, 1.5, c).astype(np.float32)
+    xb, xo, _ = embed(x, dt, 1, 1)
+    xv = view(N, xb, xo, c)
+    stats = torch.zeros(4 * c, dtype=torch.float64, device='cuda')
+    N.call('dnnca_channel_stats', None, C.byref(xv), N.ptr(stats))
+    ss = torch.zeros(2 * c, device='cuda')
+    mi = torch.zeros(2 * c, device='cuda')
+    mm, mv = dev(mm0), dev(mv0)
+    g = dev(gamma) if scale else None
+    N.call('dnnca_bn_finalize', None, N.ptr(stats), n * h * w, c, N.ptr(g), N.ptr(dev(beta)), 0.99, 1e-3, N.ptr(mm),
+           N.ptr(mv), N.ptr(ss), N.ptr(mi))
+    yb = torch.zeros(n, h, w, c + 2, dtype=dt, device='cuda')
+    yv = view(N, yb, 2, c)
+    N.call('dnnca_bn_apply', None, C.byref(xv), N.ptr(ss), C.byref(yv))
+    sync()
+    T = lambda a: torch.tensor(a, dtype=torch.float64)
+    ry, rmm, rmv = ops.batchnorm(T(x), T(gamma) if scale else None, T(beta), T(mm0), T(mv0), True)
+    close(yb[..., 2:].float().cpu().numpy(), ry.numpy(), mode)
+    np.testing.assert_allclose(mm.cpu().numpy(), rmm.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(mv.cpu().numpy(), rmv.numpy(), rtol=1e-5, atol=1e-6)
+    # backward (x is a relu output feeding the BN -> fused relu mask)
+    dy = q(rng.normal(size=x.shape).astype(np.float32), dt)
+    dyb, dyo, _ = embed(dy, dt, 0, 3)
+    dyv = view(N, dyb, dyo, c)
+    dxb = torch.zeros(n, h, w, c, dtype=dt, device='cuda')
+    dxv = view(N, dxb, 0, c)
+    sums = stats[2 * c:]
+    N.call('dnnca_bn_bwd_reduce', None, C.byref(xv), C.byref(dyv), N.ptr(mi), N.ptr(sums))
+    dg, dbt = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+    N.call('dnnca_bn_bwd_apply', None, C.byref(xv), C.byref(dyv), N.ptr(mi), N.ptr(g), N.ptr(sums), C.byref(dxv),
+           N.ACT_RELU, 0.0, N.ptr(dg) if scale else None, N.ptr(dbt))
+    sync()
+    _, mean, var, invstd = rn.bn_train_fwd(x, gamma, beta)
+    rdx, rdg, rdb = rn.bn_train_bwd(x, gamma, dy, mean, invstd)
+    close(dxb.float().cpu().numpy(), rdx * (x > 0), mode)
+    np.testing.assert_allclose(dbt.cpu().numpy(), rdb, rtol=1e-4, atol=1e-4)
+    if scale:
+        np.testing.assert_allclose(dg.cpu().numpy(), rdg, rtol=1e-4, atol=1e-3)
+    # inference parameters from the moving statistics
+    N.call('dnnca_bn_inference_params', None, c, N.ptr(g), N.ptr(dev(beta)), 1e-3, N.ptr(dev(mm0)), N.ptr(dev(mv0)), N.ptr(ss))
+    N.call('dnnca_bn_apply', None, C.byref(xv), N.ptr(ss), C.byref(yv))
+    sync()
+    ry, _, _ = ops.batchnorm(T(x), T(gamma) if scale else None, T(beta), T(mm0), T(mv0), False)
+    close(yb[..., 2:].float().cpu().numpy(), ry.numpy(), mode)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('F,healthy,weight', [(3, False, None), (16, False, None), (64, True, None), (3, False, 5.0)])
+def test_head_bce_fused(N, mode, F, healthy, weight):
+    dt = DT[mode]
+    rng = np.random.default_rng(F)
+    n, h, w = 3, 16, 24
+    f = q(np.maximum(rng.normal(size=(n, h, w, F)), 0).astype(np.float32), dt)
+    wt = rng.normal(size=F).astype(np.float32)
+    b = np.array([0.1], np.float32)
+    y = (rng.uniform(size=(n, h, w)) < (0.0 if healthy else 0.05)).astype(np.float32)
+    fb, fo, _ = embed(f, dt, 1, 0)
+    fv = view(N, fb, fo, F)
+    ls = torch.zeros(16, dtype=torch.uint8, device='cuda')
+    yd = dev(y)
+    N.call('dnnca_label_stats_init', None, N.ptr(ls))
+    N.call('dnnca_label_stats', None, N.ptr(yd), y.size, N.ptr(ls))
+    cfg = N.LossConfig(weight or 0.0, 1 if weight is not None else 0, 0.0, 3.0, 1.0 / (y.size * 2))
+    logits, probs = torch.zeros(n, h, w, device='cuda'), torch.zeros(n, h, w, device='cuda')
+    per = torch.zeros(n, device='cuda')
+    dfb = torch.zeros(n, h, w, F, dtype=dt, device='cuda')
+    dfv = view(N, dfb, 0, F)
+    dw, db = torch.zeros(F, device='cuda'), torch.zeros(1, device='cuda')
+    N.call('dnnca_head_bce_fwd_bwd', None, C.byref(fv), N.ptr(dev(wt)), N.ptr(dev(b)), N.ptr(yd), N.ptr(ls),
+           C.byref(cfg), N.ptr(logits), N.ptr(probs), N.ptr(per), C.byref(dfv), N.ACT_RELU, 0.0, N.ptr(dw), N.ptr(db))
+    sync()
+    host = N.LabelStats.from_buffer_copy(ls.cpu().numpy().tobytes())
+    s, mn, mx = C.c_double(), C.c_float(), C.c_float()
+    N.lib().dnnca_label_stats_decode(C.byref(host), C.byref(s), C.byref(mn), C.byref(mx))
+    assert abs(s.value - y.sum()) < 1e-6 and mn.value == y.min() and mx.value == y.max()
+    z = f.astype(np.float64) @ wt.astype(np.float64) + b[0]
+    rper, rdz = rn.weighted_bce_fwd_bwd(y, z, weight=weight, weight_mul=3.0, n_replicas=2)
+    np.testing.assert_allclose(logits.cpu().numpy(), z, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(probs.cpu().numpy(), 1 / (1 + np.exp(-z)), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(per.cpu().numpy(), rper, rtol=1e-4)
+    rdf = rdz[..., None] * wt * (f > 0)
+    close(dfb.float().cpu().numpy(), rdf, mode)
+    np.testing.assert_allclose(dw.cpu().numpy(), np.einsum('nhw,nhwf->f', rdz, f.astype(np.float64)), rtol=1e-3, atol=1e-7)
+    np.testing.assert_allclose(db.cpu().numpy()[0], rdz.sum(), rtol=1e-3, atol=1e-8)
+    # forward-only head
+    l2, p2 = torch.zeros_like(logits), torch.zeros_like(probs)
+    N.call('dnnca_head_fwd', None, C.byref(fv), N.ptr(dev(wt)), N.ptr(dev(b)), N.ptr(l2), N.ptr(p2))
+    sync()
+    np.testing.assert_allclose(l2.cpu().numpy(), z, rtol=1e-5, atol=1e-5)
+
+
+def test_adam_matches_keras_form(N):
+    rng = np.random.default_rng(0)
+    n = 1000
+    p0, g = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
+    p, m, v = dev(p0), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    hyper = dev(np.array([1e-3, 0.9, 0.999, 1e-7], np.float32))
+    step = torch.zeros(1, dtype=torch.int64, device='cuda')
+    rp, rm, rv = torch.tensor(p0, dtype=torch.float64), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    for t in range(1, 4):
+        N.call('dnnca_adam_step', None, N.ptr(p), N.ptr(dev(g)), N.ptr(m), N.ptr(v), n, N.ptr(hyper), N.ptr(step), None)
+        rp, rm, rv = ops.adam_step(rp, torch.tensor(g, dtype=torch.float64), rm, rv, t)
+    sync()
+    assert int(step) == 3
+    np.testing.assert_allclose(p.cpu().numpy(), rp.numpy(), rtol=1e-5, atol=1e-6)
+    # L2 term: g + 2*l2*p
+    l2 = dev(np.full(n, 0.01, np.float32))
+    p2, m2, v2 = dev(p0), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    step.zero_()
+    N.call('dnnca_adam_step', None, N.ptr(p2), N.ptr(dev(g)), N.ptr(m2), N.ptr(v2), n, N.ptr(hyper), N.ptr(step), N.ptr(l2))
+    sync()
+    rp2, _, _ = ops.adam_step(torch.tensor(p0, dtype=torch.float64), torch.tensor(g + 0.02 * p0, dtype=torch.float64),
+                              torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64), 1)
+    np.testing.assert_allclose(p2.cpu().numpy(), rp2.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_u8_to_unit_and_convert_bit_exact(N):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, 10007, dtype=np.uint8)
+    src = torch.from_numpy(a).cuda()
+    dst = torch.zeros(a.size, device='cuda')
+    N.call('dnnca_u8_to_unit', None, N.ptr(src), a.size, N.ptr(dst), N.F32)
+    sync()
+    np.testing.assert_array_equal(dst.cpu().numpy(), a.astype(np.float32) / np.float32(255.0))   # data.py:206
+    x = rng.normal(size=(2, 5, 7, 6)).astype(np.float32)
+    xb, xo, _ = embed(x, torch.float32, 1, 1)
+    yb = torch.zeros(2, 5, 7, 9, dtype=torch.bfloat16, device='cuda')
+    xv, yv = view(N, xb, xo, 6), view(N, yb, 3, 6)
+    N.call('dnnca_convert', None, C.byref(xv), C.byref(yv))
+    sync()
+    np.testing.assert_array_equal(yb[..., 3:].float().cpu().numpy(), q(x, torch.bfloat16))
+
+
+def test_add_relu_affine(N):
+    rng = np.random.default_rng(1)
+    c = 51
+    a, b = rng.normal(size=(2, 6, 6, c)).astype(np.float32), rng.normal(size=(2, 6, 6, c)).astype(np.float32)
+    fb, fo = rng.normal(size=2 * c).astype(np.float32), rng.normal(size=2 * c).astype(np.float32)
+    ab, ao, _ = embed(a, torch.float32, 1, 0)
+    bb, bo, _ = embed(b, torch.float32)
+    yb = torch.zeros(2, 6, 6, c, device='cuda')
+    av, bv, yv = view(N, ab, ao, c), view(N, bb, bo, c), view(N, yb, 0, c)
+    N.call('dnnca_add_relu_affine', None, C.byref(av), None, C.byref(bv), N.ptr(dev(fb)), N.ptr(dev(fo)), C.byref(yv))
+    sync()
+    ref = np.maximum(a + b * fb[:c] + fb[c:], 0) * fo[:c] + fo[c:]
+    np.testing.assert_allclose(yb.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_bad_arguments_fail_loudly(N):
+    x = torch.zeros(1, 4, 4, 3, device='cuda')
+    xv = N.tensor_view(x)
+    yv = N.tensor_view(torch.zeros(1, 4, 4, 3, device='cuda'))
+    with pytest.raises(N.DnncaError, match='kernel size'):
+        N.call('dnnca_conv2d_fprop', None, C.byref(xv), N.ptr(x), None, C.byref(yv), 5, 0, 0.0, None)
+    yv2 = N.tensor_view(torch.zeros(1, 5, 4, 3, device='cuda'))
+    with pytest.raises(N.DnncaError):
+        N.call('dnnca_conv2d_fprop', None, C.byref(xv), N.ptr(x), None, C.byref(yv2), 3, 0, 0.0, None)
