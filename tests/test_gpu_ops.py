@@ -49,8 +49,22 @@ def q(a, dtype):
     return torch.from_numpy(a).to(dtype).to(torch.float32).numpy()
 
 
+_KEEP = []
+
+
+@pytest.fixture(autouse=True)
+def _keep_alive():
+    """The C ABI sees raw pointers only: every device tensor made by dev() must outlive the launch."""
+    _KEEP.clear()
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
 def dev(a, dtype=torch.float32):
-    return torch.from_numpy(np.ascontiguousarray(a)).to('cuda').to(dtype)
+    t = torch.from_numpy(np.ascontiguousarray(a)).to('cuda').to(dtype)
+    _KEEP.append(t)
+    return t
 
 
 def close(got, ref, mode, scale=None):
