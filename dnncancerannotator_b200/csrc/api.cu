@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace dnnca {
 
@@ -36,20 +37,50 @@ int sm_count() {
   return cached;
 }
 
+// ---- TMA tensor maps ----------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+bool make_row_map(CUtensorMap* map, const dnnca_tensor_t* t, int box_chunks, int box_rows) {
+  if (!t || !tma_row_ok(t) || box_chunks < 1 || box_chunks > 256 || box_rows < 1 || box_rows > 256) return false;
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  const int es = t->dtype == DNNCA_F32 ? 4 : 2;
+  const cuuint64_t epc = 16 / es;
+  const cuuint64_t row_bytes = (cuuint64_t)t->w * t->c * es;
+  cuuint64_t dims[4] = {epc, row_bytes / 16, (cuuint64_t)t->h, (cuuint64_t)t->n};
+  cuuint64_t strides[3] = {16, row_bytes, row_bytes * t->h};
+  cuuint32_t box[4] = {(cuuint32_t)epc, (cuuint32_t)box_chunks, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // kernel families (conv_generic.cu / conv_small.cu)
-int launch_conv_fprop_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, int, float);
-int launch_conv_dgrad_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, int, const dnnca_tensor_t*, int, float);
-int launch_conv_wgrad_generic(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*, int);
+int launch_conv_fprop_generic(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, int, float);
+int launch_conv_dgrad_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, const dnnca_tensor_t*, int, float);
+int launch_conv_wgrad_generic(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*, int);
 int launch_tconv_fprop_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*);
 int launch_tconv_dgrad_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
 int launch_tconv_wgrad_generic(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
 // return 1 when the shape was handled, 0 when not covered, <0 on error
-int try_conv_fprop_small_f32(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
-int try_conv_fprop_small_bf16(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
-int try_conv_dgrad_small_f32(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
-int try_conv_dgrad_small_bf16(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
-int try_conv_wgrad_small_f32(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
-int try_conv_wgrad_small_bf16(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
+int try_conv_fprop_small_f32(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
+int try_conv_fprop_small_bf16(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
+int try_conv_dgrad_small_f32(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
+int try_conv_dgrad_small_bf16(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
+int try_conv_wgrad_small_f32(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
+int try_conv_wgrad_small_bf16(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
 
 }  // namespace dnnca
 
@@ -79,60 +110,65 @@ extern "C" int dnnca_debug_force_generic(int on) {
 
 static bool act_ok(int act) { return act == DNNCA_ACT_NONE || act == DNNCA_ACT_RELU || act == DNNCA_ACT_LEAKY; }
 
-extern "C" int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const float* w, const float* bias,
-                                  const dnnca_tensor_t* y, int ksize, int act, float alpha, double* stats) {
+static bool second_ok(const dnnca_tensor_t* a, const dnnca_tensor_t* b) {
+  return b == nullptr || (view_ok(b) && same_nhw(a, b) && a->dtype == b->dtype);
+}
+
+extern "C" int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w,
+                                  const float* bias, const dnnca_tensor_t* y, int ksize, int act, float alpha,
+                                  double* stats) {
   DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && w, "conv2d_fprop: bad tensor arguments");
   DNNCA_CHECK_ARG(same_nhw(x, y) && x->dtype == y->dtype, "conv2d_fprop: x and y must share n,h,w and dtype ('same' padding, stride 1)");
+  DNNCA_CHECK_ARG(second_ok(x, x2), "conv2d_fprop: x2 must share n,h,w and dtype with x");
   DNNCA_CHECK_ARG(act_ok(act), "conv2d_fprop: unknown activation %d", act);
   if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_fprop: kernel size %d (only 1 and 3 are used by the reference models)", ksize);
   cudaStream_t s = (cudaStream_t)stream;
   int r = 0;
-  if (!g_force_generic) {
-    if (ksize == 3)
-      r = x->dtype == DNNCA_F32 ? try_conv_fprop_small_f32(s, x, w, bias, y, act, alpha, stats)
-                                : try_conv_fprop_small_bf16(s, x, w, bias, y, act, alpha, stats);
+  if (!g_force_generic && ksize == 3) {
+    r = x->dtype == DNNCA_F32 ? try_conv_fprop_small_f32(s, x, x2, w, bias, y, act, alpha, stats)
+                              : try_conv_fprop_small_bf16(s, x, x2, w, bias, y, act, alpha, stats);
     if (r < 0) return r;
     if (r == 1) return DNNCA_OK;
   }
-  r = launch_conv_fprop_generic(s, x, w, bias, y, ksize, act, alpha);
+  r = launch_conv_fprop_generic(s, x, x2, w, bias, y, ksize, act, alpha);
   if (r != DNNCA_OK) return r;
   if (stats) return dnnca_channel_stats(stream, y, stats);
   return DNNCA_OK;
 }
 
 extern "C" int dnnca_conv2d_dgrad(void* stream, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
-                                  int ksize, const dnnca_tensor_t* mask, int act, float alpha) {
+                                  const dnnca_tensor_t* dx2, int ksize, const dnnca_tensor_t* mask, int act,
+                                  float alpha) {
   DNNCA_CHECK_ARG(view_ok(dz) && view_ok(dx) && w, "conv2d_dgrad: bad tensor arguments");
   DNNCA_CHECK_ARG(same_nhw(dz, dx) && dz->dtype == dx->dtype, "conv2d_dgrad: dz and dx must share n,h,w and dtype");
+  DNNCA_CHECK_ARG(second_ok(dx, dx2), "conv2d_dgrad: dx2 must share n,h,w and dtype with dx");
   DNNCA_CHECK_ARG(!mask || (view_ok(mask) && same_shape(mask, dx) && mask->dtype == dx->dtype), "conv2d_dgrad: bad mask");
   DNNCA_CHECK_ARG(act_ok(act), "conv2d_dgrad: unknown activation %d", act);
   if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_dgrad: kernel size %d", ksize);
   cudaStream_t s = (cudaStream_t)stream;
-  if (!g_force_generic) {
-    int r = 0;
-    if (ksize == 3)
-      r = dx->dtype == DNNCA_F32 ? try_conv_dgrad_small_f32(s, dz, w, dx, mask, act, alpha)
-                                 : try_conv_dgrad_small_bf16(s, dz, w, dx, mask, act, alpha);
+  if (!g_force_generic && ksize == 3) {
+    int r = dx->dtype == DNNCA_F32 ? try_conv_dgrad_small_f32(s, dz, w, dx, dx2, mask, act, alpha)
+                                   : try_conv_dgrad_small_bf16(s, dz, w, dx, dx2, mask, act, alpha);
     if (r < 0) return r;
     if (r == 1) return DNNCA_OK;
   }
-  return launch_conv_dgrad_generic(s, dz, w, dx, ksize, mask, act, alpha);
+  return launch_conv_dgrad_generic(s, dz, w, dx, dx2, ksize, mask, act, alpha);
 }
 
-extern "C" int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dz, float* dw,
-                                  float* db, int ksize) {
+extern "C" int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2,
+                                  const dnnca_tensor_t* dz, float* dw, float* db, int ksize) {
   DNNCA_CHECK_ARG(view_ok(x) && view_ok(dz) && dw, "conv2d_wgrad: bad tensor arguments");
   DNNCA_CHECK_ARG(same_nhw(x, dz) && x->dtype == dz->dtype, "conv2d_wgrad: x and dz must share n,h,w and dtype");
+  DNNCA_CHECK_ARG(second_ok(x, x2), "conv2d_wgrad: x2 must share n,h,w and dtype with x");
   if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_wgrad: kernel size %d", ksize);
   cudaStream_t s = (cudaStream_t)stream;
-  if (!g_force_generic) {
-    int r = 0;
-    if (ksize == 3)
-      r = x->dtype == DNNCA_F32 ? try_conv_wgrad_small_f32(s, x, dz, dw, db) : try_conv_wgrad_small_bf16(s, x, dz, dw, db);
+  if (!g_force_generic && ksize == 3) {
+    int r = x->dtype == DNNCA_F32 ? try_conv_wgrad_small_f32(s, x, x2, dz, dw, db)
+                                  : try_conv_wgrad_small_bf16(s, x, x2, dz, dw, db);
     if (r < 0) return r;
     if (r == 1) return DNNCA_OK;
   }
-  return launch_conv_wgrad_generic(s, x, dz, dw, db, ksize);
+  return launch_conv_wgrad_generic(s, x, x2, dz, dw, db, ksize);
 }
 
 extern "C" int dnnca_convtranspose2x2_fprop(void* stream, const dnnca_tensor_t* x, const float* k, const float* bias,

@@ -20,10 +20,10 @@ __device__ __forceinline__ T* pxw(const View& v, long long p) {
 // ------------------------------------------------------------------ fprop ---
 // one thread = one output pixel x 4 output channels
 template <typename T>
-__global__ void __launch_bounds__(256) conv_fprop_generic_kernel(View x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) conv_fprop_generic_kernel(View x, View x2, int c2, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, View y, int k,
                                                                 int act, float alpha, long long total, int ncb) {
-  const int H = x.h, W = x.w, Cin = x.c, Cout = y.c, ph = k / 2;
+  const int H = x.h, W = x.w, C1 = x.c, Cin = x.c + c2, Cout = y.c, ph = k / 2;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const int cb = (int)(t % ncb);
@@ -42,9 +42,10 @@ __global__ void __launch_bounds__(256) conv_fprop_generic_kernel(View x, const f
         const int xx = px + c - ph;
         if (xx < 0 || xx >= W) continue;
         const T* xp = pxp<T>(x, (n * H + yy) * W + xx);
+        const T* xp2 = c2 ? pxp<T>(x2, (n * H + yy) * W + xx) : nullptr;
         const float* wp = w + (size_t)((a * k + c) * Cin) * Cout + co0;
         for (int ci = 0; ci < Cin; ++ci) {
-          const float xv = ldf(xp + ci);
+          const float xv = ci < C1 ? ldf(xp + ci) : ldf(xp2 + (ci - C1));
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (j < nco) acc[j] = fmaf(xv, wp[(size_t)ci * Cout + j], acc[j]);
@@ -62,9 +63,9 @@ __global__ void __launch_bounds__(256) conv_fprop_generic_kernel(View x, const f
 // dx[n,p,q,ci] = sum_{a,c,co} dz[n,p-a+ph,q-c+ph,co] * w[a,c,ci,co]
 template <typename T>
 __global__ void __launch_bounds__(256) conv_dgrad_generic_kernel(View dz, const float* __restrict__ w, View dx,
-                                                                int k, View mask, int has_mask, int act,
-                                                                float alpha, long long total, int ncb) {
-  const int H = dx.h, W = dx.w, Cin = dx.c, Cout = dz.c, ph = k / 2;
+                                                                View dx2, int c2, int k, View mask, int has_mask,
+                                                                int act, float alpha, long long total, int ncb) {
+  const int H = dx.h, W = dx.w, C1 = dx.c, Cin = dx.c + c2, Cout = dz.c, ph = k / 2;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const int cb = (int)(t % ncb);
@@ -92,11 +93,17 @@ __global__ void __launch_bounds__(256) conv_dgrad_generic_kernel(View dz, const 
         }
       }
     }
-    T* dp = pxw<T>(dx, p) + ci0;
-    const T* mp = has_mask ? pxp<T>(mask, p) + ci0 : nullptr;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < nci) stf(dp + j, has_mask ? acc[j] * act_grad(ldf(mp + j), act, alpha) : acc[j]);
+    for (int j = 0; j < 4; ++j) {
+      if (j >= nci) continue;
+      const int ci = ci0 + j;
+      if (ci < C1) {
+        const float m = has_mask ? act_grad(ldf(pxp<T>(mask, p) + ci), act, alpha) : 1.f;
+        stf(pxw<T>(dx, p) + ci, acc[j] * m);
+      } else {
+        stf(pxw<T>(dx2, p) + (ci - C1), acc[j]);
+      }
+    }
   }
 }
 
@@ -105,8 +112,8 @@ __global__ void __launch_bounds__(256) conv_dgrad_generic_kernel(View dz, const 
 //                               MODE 1 (ConvT2x2): out[tap][co][ci] += sum_p dy[2i+a,2j+b][co] * x[i,j][ci]
 // grid = (M tiles, N tiles, taps * ksplit); block 16x16, 2x2 outputs per thread, 32-pixel smem stages.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256) wgrad_generic_kernel(View xa, View gb, float* __restrict__ out, int k,
-                                                           int ksplit, long long P) {
+__global__ void __launch_bounds__(256) wgrad_generic_kernel(View xa, View xa2, int c2, View gb,
+                                                           float* __restrict__ out, int k, int ksplit, long long P) {
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int tap = blockIdx.z / ksplit, ks = blockIdx.z % ksplit;
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(256) wgrad_generic_kernel(View xa, View gb, fl
   // rows (M) come from the first view for MODE 0 (x), from the second (dy) for MODE 1
   const View& vm = MODE == 0 ? xa : gb;
   const View& vn = MODE == 0 ? gb : xa;
-  const int M = vm.c, N = vn.c;
+  const int M = vm.c + (MODE == 0 ? c2 : 0), N = vn.c;
   const int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int H = xa.h, W = xa.w;  // pixel grid the reduction runs over (= x's grid in both modes)
   const long long chunk = (P + ksplit - 1) / ksplit;
@@ -136,8 +143,10 @@ __global__ void __launch_bounds__(256) wgrad_generic_kernel(View xa, View gb, fl
         const long long n = r / H;
         if (MODE == 0) {
           const int yy = py + a - k / 2, xx = px + c - k / 2;
-          if (m0 + ch < M && yy >= 0 && yy < H && xx >= 0 && xx < W)
-            va = ldf(pxp<T>(xa, (n * H + yy) * W + xx) + m0 + ch);
+          if (m0 + ch < M && yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const int m = m0 + ch;
+            va = m < xa.c ? ldf(pxp<T>(xa, (n * H + yy) * W + xx) + m) : ldf(pxp<T>(xa2, (n * H + yy) * W + xx) + (m - xa.c));
+          }
           if (n0 + ch < N) vb = ldf(pxp<T>(gb, p) + n0 + ch);
         } else {
           const long long q = (n * gb.h + 2 * py + a) * gb.w + 2 * px + c;
@@ -260,23 +269,27 @@ __global__ void __launch_bounds__(256) tconv_dgrad_generic_kernel(View dy, const
 }
 
 // ----------------------------------------------------------- host launchers --
-int launch_conv_fprop_generic(cudaStream_t s, const dnnca_tensor_t* x, const float* w, const float* bias,
-                              const dnnca_tensor_t* y, int k, int act, float alpha) {
+int launch_conv_fprop_generic(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w,
+                              const float* bias, const dnnca_tensor_t* y, int k, int act, float alpha) {
   const int ncb = (y->c + 3) / 4;
   const long long total = (long long)x->n * x->h * x->w * ncb;
   const int grid = grid_for(total, 256, 16);
-  DNNCA_DISPATCH_DTYPE(x->dtype, conv_fprop_generic_kernel<T><<<grid, 256, 0, s>>>(mk(x), w, bias, mk(y), k, act, alpha, total, ncb);)
+  View v2 = x2 ? mk(x2) : mk(x);
+  const int c2 = x2 ? x2->c : 0;
+  DNNCA_DISPATCH_DTYPE(x->dtype, conv_fprop_generic_kernel<T><<<grid, 256, 0, s>>>(mk(x), v2, c2, w, bias, mk(y), k, act, alpha, total, ncb);)
   DNNCA_LAUNCH_CHECK("conv_fprop_generic");
   return DNNCA_OK;
 }
 
 int launch_conv_dgrad_generic(cudaStream_t s, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
-                              int k, const dnnca_tensor_t* mask, int act, float alpha) {
-  const int ncb = (dx->c + 3) / 4;
+                              const dnnca_tensor_t* dx2, int k, const dnnca_tensor_t* mask, int act, float alpha) {
+  const int c2 = dx2 ? dx2->c : 0;
+  const int ncb = (dx->c + c2 + 3) / 4;
   const long long total = (long long)dx->n * dx->h * dx->w * ncb;
   const int grid = grid_for(total, 256, 16);
   View vm = mask ? mk(mask) : mk(dx);
-  DNNCA_DISPATCH_DTYPE(dx->dtype, conv_dgrad_generic_kernel<T><<<grid, 256, 0, s>>>(mk(dz), w, mk(dx), k, vm, mask != nullptr, act, alpha, total, ncb);)
+  View v2 = dx2 ? mk(dx2) : mk(dx);
+  DNNCA_DISPATCH_DTYPE(dx->dtype, conv_dgrad_generic_kernel<T><<<grid, 256, 0, s>>>(mk(dz), w, mk(dx), v2, c2, k, vm, mask != nullptr, act, alpha, total, ncb);)
   DNNCA_LAUNCH_CHECK("conv_dgrad_generic");
   return DNNCA_OK;
 }
@@ -299,13 +312,15 @@ int launch_channel_sum(cudaStream_t s, const dnnca_tensor_t* g, float* out) {
   return DNNCA_OK;
 }
 
-int launch_conv_wgrad_generic(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* dz, float* dw,
-                              float* db, int k) {
+int launch_conv_wgrad_generic(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2,
+                              const dnnca_tensor_t* dz, float* dw, float* db, int k) {
   const long long P = (long long)x->n * x->h * x->w;
-  dim3 grid((x->c + 31) / 32, (dz->c + 31) / 32, 1);
+  const int c2 = x2 ? x2->c : 0;
+  dim3 grid((x->c + c2 + 31) / 32, (dz->c + 31) / 32, 1);
   const int ksplit = pick_ksplit(grid.x * grid.y * k * k, P);
   grid.z = k * k * ksplit;
-  DNNCA_DISPATCH_DTYPE(x->dtype, (wgrad_generic_kernel<T, 0><<<grid, 256, 0, s>>>(mk(x), mk(dz), dw, k, ksplit, P));)
+  View v2 = x2 ? mk(x2) : mk(x);
+  DNNCA_DISPATCH_DTYPE(x->dtype, (wgrad_generic_kernel<T, 0><<<grid, 256, 0, s>>>(mk(x), v2, c2, mk(dz), dw, k, ksplit, P));)
   DNNCA_LAUNCH_CHECK("conv_wgrad_generic");
   if (db) return launch_channel_sum(s, dz, db);
   return DNNCA_OK;
@@ -338,7 +353,7 @@ int launch_tconv_wgrad_generic(cudaStream_t s, const dnnca_tensor_t* x, const dn
   dim3 grid((dy->c + 31) / 32, (x->c + 31) / 32, 1);
   const int ksplit = pick_ksplit(grid.x * grid.y * 4, P);
   grid.z = 4 * ksplit;
-  DNNCA_DISPATCH_DTYPE(x->dtype, (wgrad_generic_kernel<T, 1><<<grid, 256, 0, s>>>(mk(x), mk(dy), dk, 2, ksplit, P));)
+  DNNCA_DISPATCH_DTYPE(x->dtype, (wgrad_generic_kernel<T, 1><<<grid, 256, 0, s>>>(mk(x), mk(x), 0, mk(dy), dk, 2, ksplit, P));)
   DNNCA_LAUNCH_CHECK("tconv_wgrad_generic");
   if (db) return launch_channel_sum(s, dy, db);
   return DNNCA_OK;

@@ -1,25 +1,33 @@
-// Direct 3x3 convolution for tiny channel counts (configs/unet.yaml: 3/6/12/24
-// channels; first layers of every model: Cin = 1/3/5).  These layers sit far
-// below the tensor-core ridge (4-72 flop/B vs ~258), so they run on the FP32
-// pipe from shared-memory tiles instead of being padded into a GEMM:
-//   * the input tile (+1-pixel halo = the conv's 'same' zero padding) is staged
-//     once per CTA as fp32 planes xs[ci][row][col]; every thread owns 4 adjacent
-//     pixels x ALL output channels, so one 6-float window (LDS.128 + LDS.64) and
-//     3*COUT broadcast weights (LDS.128) feed 12*COUT FMAs;
-//   * fprop and dgrad are the same kernel: dgrad stages rot180/transposed
-//     weights and swaps the bias+activation epilogue for the act'(mask) product;
-//   * outputs go back through shared memory so global stores are coalesced
-//     along NHWC rows even for 3-channel (6-byte) pixels; BatchNorm statistics
-//     (sum, sum of squares of the stored values) are reduced per CTA -> fp64 atomics;
-//   * wgrad: thread = (4-pixel group, ci); keeps the 3x6 input window of its
-//     channel in registers and streams dz (LDS.128): 36 FMAs per load,
-//     9*COUT register accumulators, one smem/atomic reduction per CTA.
-// Reference call sites: layers.Conv2D components.py:47-50,123-126 and their
-// tf.GradientTape gradients.
+// Direct 3x3 convolution for tiny channel counts (configs/unet.yaml: 3/6/12 channels and the
+// 12+12 / 6+6 / 3+3 decoder concats; first layers of the other models: Cin = 1/3/5).
+// These layers sit far below the tensor-core ridge (4-72 flop/B vs ~258) and their im2col rows
+// (6-byte pixels) cannot form UMMA/TMA-im2col operands, so they run on the FP32 pipe:
+//
+//   * TMA-staged NHWC tiles: a dense NHWC tensor is described to the TMA as rows of 16-byte
+//     chunks (tma.cuh); ONE cp.async.bulk.tensor box brings a (rows+halo) x (pixels+halo) tile
+//     into shared memory, zero-filling everything outside the image = the conv's 'same' padding.
+//     No per-element address arithmetic is spent on staging.
+//   * the raw tile is de-interleaved once per CTA into fp32 channel planes xs[ci][row][col];
+//     every thread owns 4 adjacent pixels x ALL output channels.
+//   * packed FFMA2 (fma.rn.f32x2): accumulators are pixel pairs, weights sit in shared memory
+//     as duplicated (w,w) pairs -> one LDS.128 feeds 4 FFMA2 = 8 FMA.  Measured on B200: FFMA2
+//     does not raise the FMA-pipe peak (71 TFLOP/s either way) but halves the issue slots the
+//     FMAs need, so the LDS / address / unpack instructions issue in their shadow.
+//   * a second input tensor (x2) is consumed in the same K loop: tf.concat([tconv, skip])
+//     (components.py:164) is never materialised; dgrad symmetrically writes two outputs.
+//   * fprop and dgrad are the same kernel: dgrad stages rot180/transposed weights and swaps
+//     the bias+activation epilogue for the act'(mask) product.
+//   * results leave through shared memory + one TMA store per output tensor (coalesced even
+//     for 6-byte pixels); BatchNorm statistics of the stored values are reduced per CTA into
+//     fp64 atomics.
+//   * wgrad: persistent CTAs; thread = (4-pixel group slot, ci, co-block) keeps the 3x6 input
+//     window of its channel as register pairs and streams dz pairs: 18 FFMA2 per LDS.128.
 //
 // Compiled once per (dtype, kind) with -DSMALL_DT=0|1 (f32|bf16) and -DSMALL_KIND=0|1|2
 // (fprop|dgrad|wgrad) so the template instantiations build in parallel.
+// Reference call sites: layers.Conv2D components.py:47-50,123-126 and their gradients.
 #include "common.cuh"
+#include "tma.cuh"
 
 #ifndef SMALL_DT
 #error "compile with -DSMALL_DT=0|1 -DSMALL_KIND=0|1|2"
@@ -34,357 +42,527 @@
 
 namespace dnnca {
 
-constexpr int PX = 4;  // pixels per thread along x
+typedef unsigned long long u64;
 
-template <int COUT> struct CoPad { static constexpr int v = (COUT + 3) / 4 * 4; };
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float lo32(u64 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi32(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
 
-// ----------------------------------------------------------------------------
-// shared staging helpers
-// ----------------------------------------------------------------------------
-// xs[ck][rows][pitch] <- channels [c0, c0+ck) of the (rows x cols) window whose top-left
-// image coordinate is (gy0, gx0); out-of-image -> 0.  Global order (row, col, ci) keeps
-// the reads contiguous along NHWC rows.
-template <typename T>
-__device__ __forceinline__ void stage_planes(float* __restrict__ xs, const View& v, long long n, int gy0, int gx0,
-                                             int rows, int cols, int pitch, int c0, int ck) {
-  const int total = rows * cols * ck;
-  const T* base = reinterpret_cast<const T*>(v.data) + v.coff + c0;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int ci = e % ck;
-    const int t = e / ck;
-    const int col = t % cols, row = t / cols;
-    const int gy = gy0 + row, gx = gx0 + col;
-    float val = 0.f;
-    if (gy >= 0 && gy < v.h && gx >= 0 && gx < v.w)
-      val = ldf(base + ((n * v.h + gy) * v.w + gx) * (long long)v.cstride + ci);
-    xs[(ci * rows + row) * pitch + col] = val;
+constexpr int PX = 4;  // pixels per thread along x (two FFMA2 pixel pairs)
+constexpr int ru(int a, int b) { return (a + b - 1) / b * b; }
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// geometry of one raw TMA tile row: C interleaved channels, TW pixels + HALO pixels each side
+template <typename T, int C, int TW, int HALO>
+struct Raw {
+  static constexpr int EPC = 16 / (int)sizeof(T);                         // elements per 16-byte chunk
+  static constexpr int OFF = HALO ? (((-C) % EPC + EPC) % EPC) : 0;       // (x0-1)*C mod EPC, x0 % EPC == 0
+  static constexpr int NCH = C ? (OFF + (TW + 2 * HALO) * C + EPC - 1) / EPC : 0;
+  __device__ static int chunk_start(int x0) { return ((x0 - HALO) * C - OFF) / EPC; }
+};
+
+// raw tile [rows][NCH*EPC] (T, interleaved) -> planes dst[ci][rows][pitch] (fp32); one thread per pixel
+template <typename T, int C, int TW, int HALO>
+__device__ __forceinline__ void deinterleave(const T* __restrict__ raw, float* __restrict__ dst, int rows, int pitch) {
+  using G = Raw<T, C, TW, HALO>;
+  constexpr int COLS = TW + 2 * HALO;
+  constexpr int RP = G::NCH * G::EPC;
+  constexpr bool WORDS = sizeof(T) == 2 && (G::OFF % 2 == 0) && (C % 2 == 0);
+  for (int e = threadIdx.x; e < rows * COLS; e += 256) {
+    const int row = e / COLS, col = e - row * COLS;
+    const T* src = raw + row * RP + G::OFF + col * C;
+    float* d = dst + row * pitch + col;
+    if (WORDS) {                                     // bf16 pairs: one 32-bit LDS per two channels
+      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+      for (int j = 0; j < C / 2; ++j) {
+        const uint32_t wd = s32[j];
+        d[(2 * j) * rows * pitch] = __uint_as_float(wd << 16);
+        d[(2 * j + 1) * rows * pitch] = __uint_as_float(wd & 0xffff0000u);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < C; ++j) d[j * rows * pitch] = ldf(src + j);
+    }
   }
 }
 
 // ----------------------------------------------------------------------------
 // fprop / dgrad
 // ----------------------------------------------------------------------------
-template <typename T, int CIN, int COUT, int TXN, bool DGRAD>
-__global__ void __launch_bounds__(256) conv3x3_small_kernel(View x, const float* __restrict__ w,
-                                                           const float* __restrict__ bias, View y, View mask,
-                                                           int has_mask, int act, float alpha,
-                                                           double* __restrict__ stats, int tiles_x, int tiles_y) {
-  constexpr int TYN = 256 / TXN;
-  constexpr int TW = TXN * PX;
-  constexpr int CK = CIN < 12 ? CIN : 12;           // channels per smem stage
-  constexpr int NST = (CIN + CK - 1) / CK;
-  constexpr int ROWS = TYN + 2, COLS = TW + 2, PITCH = TW + 4;
-  constexpr int COP = CoPad<COUT>::v;
-  extern __shared__ __align__(16) float smem[];
-  float* ws = smem;                                  // [CIN][3][3][COP]
-  float* xs = smem + CIN * 9 * COP;                  // [CK][ROWS][PITCH]   (re-used as the output tile)
+template <typename T, int CA, int CB, int OA, int OB, int TXN>
+struct FGeom {
+  static constexpr int TYN = 256 / TXN, TW = TXN * PX;
+  static constexpr int ROWS = TYN + 2, PITCH = TW + 4;
+  static constexpr int CIN = CA + CB, COT = OA + OB, COTP = ru(COT, 2);
+  static constexpr int NCH = cmax(Raw<T, CA, TW, 1>::NCH, Raw<T, CB, TW, 1>::NCH);
+  static constexpr int CK = cmax(CA, CB);
+  static constexpr int RAW_BYTES = ru(ROWS * NCH * 16, 128);
+  static constexpr int WS_BYTES = ru(CIN * 9 * COTP * 8, 128);
+  static constexpr int OSA_BYTES = ru(TYN * TW * OA * (int)sizeof(T), 128);
+  static constexpr int OSB_BYTES = ru(TYN * TW * OB * (int)sizeof(T), 128);
+  static constexpr int XS_BYTES = cmax(ru(CK * ROWS * PITCH * 4, 128), OSA_BYTES + OSB_BYTES);
+  static constexpr int OFF_RAW = 128, OFF_WS = OFF_RAW + RAW_BYTES, OFF_XS = OFF_WS + WS_BYTES;
+  static constexpr int SMEM = OFF_XS + XS_BYTES;
+  static constexpr int EPC = 16 / (int)sizeof(T);
+  static constexpr bool FITS = NCH <= 256 && TW * OA / EPC <= 256 && TW * OB / EPC <= 256 && SMEM <= 200 * 1024;
+};
+
+struct FArgs {
+  const float* w;
+  const float* bias;
+  View ya, yb, mask;       // outputs (manual-store fallback / geometry) and the dgrad mask
+  int has_mask, act;
+  float alpha;
+  double* stats;
+  int tiles_x, tiles_y, tma_out;
+};
+
+template <typename T, int CA, int CB, int OA, int OB, int TXN, bool DGRAD>
+__global__ void __launch_bounds__(256) conv3x3_small_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                           const __grid_constant__ CUtensorMap mapB,
+                                                           const __grid_constant__ CUtensorMap mapOA,
+                                                           const __grid_constant__ CUtensorMap mapOB, FArgs a) {
+  using G = FGeom<T, CA, CB, OA, OB, TXN>;
+  constexpr int TYN = G::TYN, TW = G::TW, ROWS = G::ROWS, PITCH = G::PITCH;
+  constexpr int CIN = G::CIN, COT = G::COT, COTP = G::COTP;
+  constexpr int CBS = CB ? CB : 1;                            // keeps dead template arguments well-formed
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  T* raw = reinterpret_cast<T*>(smem + G::OFF_RAW);
+  float* ws2 = reinterpret_cast<float*>(smem + G::OFF_WS);   // [CIN][3][3][COTP] of (w,w) pairs
+  float* xs = reinterpret_cast<float*>(smem + G::OFF_XS);    // [CK][ROWS][PITCH], later the output tiles
 
   int b = blockIdx.x;
-  const int tix = b % tiles_x; b /= tiles_x;
-  const int tiy = b % tiles_y;
-  const long long n = b / tiles_y;
+  const int tix = b % a.tiles_x; b /= a.tiles_x;
+  const int tiy = b % a.tiles_y;
+  const int n = b / a.tiles_y;
   const int x0 = tix * TW, y0 = tiy * TYN;
   const int tx = threadIdx.x % TXN, ty = threadIdx.x / TXN;
 
-  // weights -> smem in [ci][dy][dx][co] order (dgrad: rot180 + in/out transpose)
-  for (int e = threadIdx.x; e < CIN * 9 * COP; e += 256) {
-    const int co = e % COP;
-    int t = e / COP;
-    const int dx = t % 3; t /= 3;
-    const int dy = t % 3;
-    const int ci = t / 3;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, ROWS * Raw<T, CA, TW, 1>::NCH * 16);
+    tma_load_4d(raw, &mapA, bar, 0, Raw<T, CA, TW, 1>::chunk_start(x0), y0 - 1, n);
+  }
+  // weights -> smem as duplicated pairs, [ci][dy][dx][co] (dgrad: rot180 + in/out transpose)
+  for (int e = threadIdx.x; e < CIN * 9 * COTP; e += 256) {
+    const int co = e % COTP;
+    const int t = e / COTP;
+    const int tap = t % 9;
+    const int ci = t / 9;
+    const int dy = tap / 3, dx = tap % 3;
     float v = 0.f;
-    if (co < COUT) {
-      if (!DGRAD) v = w[((dy * 3 + dx) * CIN + ci) * COUT + co];
-      else        v = w[(((2 - dy) * 3 + (2 - dx)) * COUT + co) * CIN + ci];  // layer Cin = COUT, layer Cout = CIN
+    if (co < COT) {
+      if (!DGRAD) v = a.w[((dy * 3 + dx) * CIN + ci) * COT + co];
+      else        v = a.w[(((2 - dy) * 3 + (2 - dx)) * COT + co) * CIN + ci];  // layer Cin = COT, layer Cout = CIN
     }
-    ws[e] = v;
+    ws2[2 * e] = v;
+    ws2[2 * e + 1] = v;
   }
 
-  float acc[COUT][PX];
+  u64 acc[COTP][2];
 #pragma unroll
-  for (int co = 0; co < COUT; ++co)
-#pragma unroll
-    for (int p = 0; p < PX; ++p) acc[co][p] = 0.f;
+  for (int co = 0; co < COTP; ++co) acc[co][0] = acc[co][1] = 0ull;
 
+#pragma unroll
+  for (int s = 0; s < (CB ? 2 : 1); ++s) {
+    const int cs = s == 0 ? CA : CB;
+    const int cbase = s == 0 ? 0 : CA;
+    mbar_wait(bar, s);
+    if (s == 0) deinterleave<T, CA, TW, 1>(raw, xs, ROWS, PITCH);
+    else        deinterleave<T, CBS, TW, 1>(raw, xs, ROWS, PITCH);
+    __syncthreads();                                   // planes ready, raw buffer free, weights visible
+    if (CB && s == 0 && threadIdx.x == 0) {            // second input streams in behind the first one's math
+      mbar_expect_tx(bar, ROWS * Raw<T, CBS, TW, 1>::NCH * 16);
+      tma_load_4d(raw, &mapB, bar, 0, Raw<T, CBS, TW, 1>::chunk_start(x0), y0 - 1, n);
+    }
 #pragma unroll 1
-  for (int st = 0; st < NST; ++st) {
-    const int c0 = st * CK;
-    const int ck = (CIN - c0) < CK ? (CIN - c0) : CK;
-    if (st > 0) __syncthreads();
-    stage_planes<T>(xs, x, n, y0 - 1, x0 - 1, ROWS, COLS, PITCH, c0, ck);
-    __syncthreads();
-#pragma unroll 1
-    for (int ci = 0; ci < ck; ++ci) {
-      const float* wrow = ws + (c0 + ci) * 9 * COP;
+    for (int ci = 0; ci < cs; ++ci) {
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) {
         const float* xr = xs + (ci * ROWS + ty + dy) * PITCH + tx * PX;
-        const float4 w0 = *reinterpret_cast<const float4*>(xr);
-        const float2 w1 = *reinterpret_cast<const float2*>(xr + 4);
-        const float win[6] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
+        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(xr);
+        const u64 p45 = *reinterpret_cast<const u64*>(xr + 4);
+        const u64 p01 = q.x, p23 = q.y;
+        const u64 p12 = pack2(hi32(p01), lo32(p23)), p34 = pack2(hi32(p23), lo32(p45));
+        const float* wrow = ws2 + ((cbase + ci) * 9 + dy * 3) * COTP * 2;
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const float* wp = wrow + (dy * 3 + dx) * COP;
+          const u64 lo = dx == 0 ? p01 : (dx == 1 ? p12 : p23);
+          const u64 hi = dx == 0 ? p23 : (dx == 1 ? p34 : p45);
 #pragma unroll
-          for (int c4 = 0; c4 < COP / 4; ++c4) {
-            const float4 wv = *reinterpret_cast<const float4*>(wp + c4 * 4);
-            const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int co = c4 * 4 + j;
-              if (co < COUT) {
-#pragma unroll
-                for (int p = 0; p < PX; ++p) acc[co][p] = fmaf(win[p + dx], wa[j], acc[co][p]);
-              }
-            }
+          for (int cp = 0; cp < COTP / 2; ++cp) {
+            const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(wrow + (dx * COTP + 2 * cp) * 2);
+            acc[2 * cp][0] = ffma2(lo, wv.x, acc[2 * cp][0]);
+            acc[2 * cp][1] = ffma2(hi, wv.x, acc[2 * cp][1]);
+            acc[2 * cp + 1][0] = ffma2(lo, wv.y, acc[2 * cp + 1][0]);
+            acc[2 * cp + 1][1] = ffma2(hi, wv.y, acc[2 * cp + 1][1]);
           }
         }
       }
     }
+    __syncthreads();                                   // everyone done with the planes
   }
-  __syncthreads();  // everyone is done reading xs -> reuse it as the output tile
 
-  // epilogue into smem tile os[row][col][co] (T), then coalesced row stores
-  T* os = reinterpret_cast<T*>(xs);
+  // ---- epilogue: output tile(s) [row][col][c] in T, then TMA store (or guarded manual store) ----
+  T* osA = reinterpret_cast<T*>(xs);
+  T* osB = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(xs) + G::OSA_BYTES);
   const int gy = y0 + ty;
-  float ssum[COUT], ssq[COUT];
+  float ssum[COT], ssq[COT];
 #pragma unroll
-  for (int co = 0; co < COUT; ++co) { ssum[co] = 0.f; ssq[co] = 0.f; }
+  for (int co = 0; co < COT; ++co) { ssum[co] = 0.f; ssq[co] = 0.f; }
 #pragma unroll
   for (int p = 0; p < PX; ++p) {
     const int gx = x0 + tx * PX + p;
-    const bool inside = gy < y.h && gx < y.w;
+    const bool inside = gy < a.ya.h && gx < a.ya.w;
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) {
-      float v = acc[co][p];
+    for (int co = 0; co < COT; ++co) {
+      float v = (p & 1) ? hi32(acc[co][p >> 1]) : lo32(acc[co][p >> 1]);
       if (!DGRAD) {
-        v = apply_act(v + (bias ? bias[co] : 0.f), act, alpha);
-      } else if (has_mask && inside) {
-        const T* mp = reinterpret_cast<const T*>(mask.data) + ((n * mask.h + gy) * mask.w + gx) * (long long)mask.cstride + mask.coff;
-        v *= act_grad(ldf(mp + co), act, alpha);
+        v = apply_act(v + (a.bias ? a.bias[co] : 0.f), a.act, a.alpha);
+      } else if (a.has_mask && co < OA && inside) {
+        const T* mp = reinterpret_cast<const T*>(a.mask.data) +
+                      (((long long)n * a.mask.h + gy) * a.mask.w + gx) * a.mask.cstride + a.mask.coff;
+        v *= act_grad(ldf(mp + co), a.act, a.alpha);
       }
-      const float r = rnd<T>(v);
-      if (inside) { ssum[co] += r; ssq[co] += r * r; }
-      stf(os + ((ty * TW) + tx * PX + p) * COUT + co, v);
+      if (!DGRAD && inside) {
+        const float r = rnd<T>(v);
+        ssum[co] += r;
+        ssq[co] += r * r;
+      }
+      if (co < OA) stf(osA + (ty * TW + tx * PX + p) * OA + co, v);
+      else         stf(osB + (ty * TW + tx * PX + p) * (OB ? OB : 1) + (co - OA), v);
     }
   }
-  __syncthreads();
-  {
-    // cooperative store: tile row = contiguous TW*COUT elements when the view is dense
-    const int wv = min(TW, y.w - x0);                    // valid columns
-    const int hv = min(TYN, y.h - y0);
-    T* ybase = reinterpret_cast<T*>(y.data) + y.coff;
-    const int row_elems = wv * COUT;
-    for (int e = threadIdx.x; e < hv * row_elems; e += 256) {
-      const int row = e / row_elems, r = e % row_elems;
-      const int col = r / COUT, co = r % COUT;
-      ybase[((n * y.h + y0 + row) * y.w + x0 + col) * (long long)y.cstride + co] = os[(row * TW + col) * COUT + co];
+  if (a.tma_out) {
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      constexpr int EPC = 16 / (int)sizeof(T);
+      tma_store_4d(&mapOA, osA, 0, x0 * OA / EPC, y0, n);
+      if (OB) tma_store_4d(&mapOB, osB, 0, x0 * OB / EPC, y0, n);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  } else {
+    __syncthreads();
+    const int wv = min(TW, a.ya.w - x0), hv = min(TYN, a.ya.h - y0);
+#pragma unroll
+    for (int o = 0; o < (OB ? 2 : 1); ++o) {
+      const View& yv = o ? a.yb : a.ya;
+      const T* os = o ? osB : osA;
+      const int oc = o ? OB : OA;
+      T* ybase = reinterpret_cast<T*>(yv.data) + yv.coff;
+      const int row_elems = wv * oc;
+      for (int e = threadIdx.x; e < hv * row_elems; e += 256) {
+        const int row = e / row_elems, r = e % row_elems;
+        const int col = r / oc, co = r % oc;
+        ybase[(((long long)n * yv.h + y0 + row) * yv.w + x0 + col) * yv.cstride + co] = os[(row * TW + col) * oc + co];
+      }
     }
   }
-  if (!DGRAD && stats) {
-    __shared__ float red[8][2 * COUT];
+  if (!DGRAD && a.stats) {
+    __shared__ float red[8][2 * COT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) {
+    for (int co = 0; co < COT; ++co) {
       const float s = warp_sum(ssum[co]), q = warp_sum(ssq[co]);
-      if (lane == 0) { red[warp][co] = s; red[warp][COUT + co] = q; }
+      if (lane == 0) { red[warp][co] = s; red[warp][COT + co] = q; }
     }
     __syncthreads();
-    if (threadIdx.x < 2 * COUT) {
+    if (threadIdx.x < 2 * COT) {
       double s = 0.0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-      atomicAdd(stats + threadIdx.x, s);
+      atomicAdd(a.stats + threadIdx.x, s);
     }
   }
 }
 
 // ----------------------------------------------------------------------------
-// wgrad: dw[a][c][ci][co] += sum_p x[p+(a-1,c-1)][ci] * dz[p][co] ; db[co] += sum_p dz[p][co]
-// persistent CTAs loop over tiles; thread = (pixel-group slot, ci)
+// wgrad: dw[a][c][ci][co] += sum_p [x|x2][p+(a-1,c-1)][ci] * dz[p][co] ; db[co] += sum_p dz[p][co]
 // ----------------------------------------------------------------------------
-template <typename T, int CIN, int COUT>
-__global__ void __launch_bounds__(256) conv3x3_small_wgrad_kernel(View x, View dz, float* __restrict__ dw,
-                                                                 float* __restrict__ db, int tiles_x, int tiles_y,
-                                                                 long long ntiles) {
-  constexpr int TYN = 4, TXN = 16, TW = TXN * PX;      // 4 x 64 pixel tiles
-  constexpr int ROWS = TYN + 2, COLS = TW + 2, PITCH = TW + 4;
-  constexpr int COP = CoPad<COUT>::v;
-  constexpr int G = 256 / CIN;                          // pixel-group slots processed concurrently
-  constexpr int NGRP = TYN * TXN;                       // 4-pixel groups per tile
-  extern __shared__ __align__(16) float smem[];
-  float* xs = smem;                                     // [CIN][ROWS][PITCH]
-  float* gs = smem + CIN * ROWS * PITCH;                // [COUT][TYN][TW]
-  float* red = gs + COUT * TYN * TW;                    // [9*CIN*COUT + COUT] block accumulators
+template <typename T, int CA, int CB, int COUT>
+struct WGeom {
+  static constexpr int TYN = 4, TXN = 16, TW = TXN * PX, ROWS = TYN + 2, PITCH = TW + 4;
+  static constexpr int CIN = CA + CB;
+  static constexpr int COB = COUT <= 6 ? COUT : (COUT % 6 == 0 ? 6 : 4);  // output channels per thread
+  static constexpr int NCB = COUT / COB;
+  static constexpr int TPS = CIN * NCB;                                    // threads per pixel-group slot
+  static constexpr int G = 256 / TPS;
+  static constexpr int NCHA = Raw<T, CA, TW, 1>::NCH, NCHB = Raw<T, CB, TW, 1>::NCH, NCHG = Raw<T, COUT, TW, 0>::NCH;
+  static constexpr int RAWA = ru(ROWS * NCHA * 16, 128), RAWB = ru(ROWS * NCHB * 16, 128), RAWG = ru(TYN * NCHG * 16, 128);
+  static constexpr int XS = ru(CIN * ROWS * PITCH * 4, 128), GS = ru(COUT * TYN * TW * 4, 128);
+  static constexpr int RED = ru((9 * CIN * COUT + COUT) * 4, 128);
+  static constexpr int OFF_RA = 128, OFF_RB = OFF_RA + RAWA, OFF_RG = OFF_RB + RAWB, OFF_XS = OFF_RG + RAWG,
+                       OFF_GS = OFF_XS + XS, OFF_RED = OFF_GS + GS, SMEM = OFF_RED + RED;
+  static constexpr bool FITS = COUT % COB == 0 && TPS <= 256 && NCHA <= 256 && NCHB <= 256 && NCHG <= 256 && SMEM <= 200 * 1024;
+};
 
-  const int slot = threadIdx.x / CIN, ci = threadIdx.x % CIN;
-  const bool active = slot < G;
+template <typename T, int CA, int CB, int COUT>
+__global__ void __launch_bounds__(256) conv3x3_small_wgrad_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                 const __grid_constant__ CUtensorMap mapB,
+                                                                 const __grid_constant__ CUtensorMap mapG,
+                                                                 float* __restrict__ dw, float* __restrict__ db,
+                                                                 int tiles_x, int tiles_y, int ntiles) {
+  using G = WGeom<T, CA, CB, COUT>;
+  constexpr int TYN = G::TYN, TXN = G::TXN, TW = G::TW, ROWS = G::ROWS, PITCH = G::PITCH;
+  constexpr int CIN = G::CIN, COB = G::COB, NCB = G::NCB;
+  constexpr int NGRP = TYN * TXN;
+  constexpr int CBS = CB ? CB : 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  T* rawA = reinterpret_cast<T*>(smem + G::OFF_RA);
+  T* rawB = reinterpret_cast<T*>(smem + G::OFF_RB);
+  T* rawG = reinterpret_cast<T*>(smem + G::OFF_RG);
+  float* xs = reinterpret_cast<float*>(smem + G::OFF_XS);   // [CIN][ROWS][PITCH]
+  float* gs = reinterpret_cast<float*>(smem + G::OFF_GS);   // [COUT][TYN][TW]
+  float* red = reinterpret_cast<float*>(smem + G::OFF_RED);
 
-  float acc[9][COUT];
-  float dbacc[COUT];
+  const int slot = threadIdx.x / G::TPS;
+  const int rem = threadIdx.x % G::TPS;
+  const int ci = rem / NCB, cb = rem % NCB;
+  const bool active = slot < G::G;
+
+  u64 acc[9][COB];
+  float dbacc[COB];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[t][co] = 0.f;
+    for (int c = 0; c < COB; ++c) acc[t][c] = 0ull;
 #pragma unroll
-  for (int co = 0; co < COUT; ++co) dbacc[co] = 0.f;
-
+  for (int c = 0; c < COB; ++c) dbacc[c] = 0.f;
   for (int e = threadIdx.x; e < 9 * CIN * COUT + COUT; e += 256) red[e] = 0.f;
 
-#pragma unroll 1
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    long long b = tile;
-    const int tix = (int)(b % tiles_x); b /= tiles_x;
-    const int tiy = (int)(b % tiles_y);
-    const long long n = b / tiles_y;
+  constexpr uint32_t TX_BYTES = ROWS * G::NCHA * 16 + ROWS * G::NCHB * 16 + TYN * G::NCHG * 16;
+  auto issue = [&](int tile) {
+    int b = tile;
+    const int tix = b % tiles_x; b /= tiles_x;
+    const int tiy = b % tiles_y;
+    const int n = b / tiles_y;
     const int x0 = tix * TW, y0 = tiy * TYN;
-    __syncthreads();
-    stage_planes<T>(xs, x, n, y0 - 1, x0 - 1, ROWS, COLS, PITCH, 0, CIN);
-    stage_planes<T>(gs, dz, n, y0, x0, TYN, TW, TW, 0, COUT);
-    __syncthreads();
+    mbar_expect_tx(bar, TX_BYTES);
+    tma_load_4d(rawA, &mapA, bar, 0, Raw<T, CA, TW, 1>::chunk_start(x0), y0 - 1, n);
+    if (CB) tma_load_4d(rawB, &mapB, bar, 0, Raw<T, CBS, TW, 1>::chunk_start(x0), y0 - 1, n);
+    tma_load_4d(rawG, &mapG, bar, 0, Raw<T, COUT, TW, 0>::chunk_start(x0), y0, n);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    issue(blockIdx.x);
+  }
+  __syncthreads();
+
+  uint32_t phase = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    deinterleave<T, CA, TW, 1>(rawA, xs, ROWS, PITCH);
+    if (CB) deinterleave<T, CBS, TW, 1>(rawB, xs + CA * ROWS * PITCH, ROWS, PITCH);
+    deinterleave<T, COUT, TW, 0>(rawG, gs, TYN, TW);
+    __syncthreads();                                       // planes ready, raw buffers free
+    if (threadIdx.x == 0 && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);   // overlaps the math below
     if (active) {
 #pragma unroll 1
-      for (int g = slot; g < NGRP; g += G) {
+      for (int g = slot; g < NGRP; g += G::G) {
         const int ty = g / TXN, tx = g % TXN;
-        float win[3][6];
+        u64 pr[3][5];                                       // per dy: (0,1) (1,2) (2,3) (3,4) (4,5)
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
           const float* xr = xs + (ci * ROWS + ty + dy) * PITCH + tx * PX;
-          const float4 a = *reinterpret_cast<const float4*>(xr);
-          const float2 c = *reinterpret_cast<const float2*>(xr + 4);
-          win[dy][0] = a.x; win[dy][1] = a.y; win[dy][2] = a.z; win[dy][3] = a.w; win[dy][4] = c.x; win[dy][5] = c.y;
+          const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(xr);
+          const u64 p45 = *reinterpret_cast<const u64*>(xr + 4);
+          pr[dy][0] = q.x;
+          pr[dy][2] = q.y;
+          pr[dy][4] = p45;
+          pr[dy][1] = pack2(hi32(q.x), lo32(q.y));
+          pr[dy][3] = pack2(hi32(q.y), lo32(p45));
         }
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) {
-          const float4 gv = *reinterpret_cast<const float4*>(gs + (co * TYN + ty) * TW + tx * PX);
-          const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
-          if (ci == 0) dbacc[co] += (ga[0] + ga[1]) + (ga[2] + ga[3]);
+        for (int c = 0; c < COB; ++c) {
+          const int co = cb * COB + c;
+          const ulonglong2 gv = *reinterpret_cast<const ulonglong2*>(gs + (co * TYN + ty) * TW + tx * PX);
+          if (ci == 0) dbacc[c] += (lo32(gv.x) + hi32(gv.x)) + (lo32(gv.y) + hi32(gv.y));
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-              for (int p = 0; p < PX; ++p) acc[dy * 3 + dx][co] = fmaf(win[dy][p + dx], ga[p], acc[dy * 3 + dx][co]);
+            for (int dx = 0; dx < 3; ++dx) {
+              acc[dy * 3 + dx][c] = ffma2(pr[dy][dx], gv.x, acc[dy * 3 + dx][c]);
+              acc[dy * 3 + dx][c] = ffma2(pr[dy][dx + 2], gv.y, acc[dy * 3 + dx][c]);
+            }
         }
       }
     }
+    __syncthreads();                                       // before the next tile overwrites the planes
   }
-  __syncthreads();
   // CTA reduction in shared memory, then one global atomic per output per CTA
   if (active) {
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int co = 0; co < COUT; ++co) atomicAdd(red + (t * CIN + ci) * COUT + co, acc[t][co]);
+      for (int c = 0; c < COB; ++c)
+        atomicAdd(red + (t * CIN + ci) * COUT + cb * COB + c, lo32(acc[t][c]) + hi32(acc[t][c]));
     if (ci == 0) {
 #pragma unroll
-      for (int co = 0; co < COUT; ++co) atomicAdd(red + 9 * CIN * COUT + co, dbacc[co]);
+      for (int c = 0; c < COB; ++c) atomicAdd(red + 9 * CIN * COUT + cb * COB + c, dbacc[c]);
     }
   }
   __syncthreads();
   for (int e = threadIdx.x; e < 9 * CIN * COUT; e += 256) atomicAdd(dw + e, red[e]);
   if (db)
     for (int e = threadIdx.x; e < COUT; e += 256) atomicAdd(db + e, red[9 * CIN * COUT + e]);
-  (void)COP;
 }
 
 // ----------------------------------------------------------------------------
 // host dispatch
 // ----------------------------------------------------------------------------
-template <typename T, int CIN, int COUT, int TXN, bool DGRAD>
-static int launch_small(cudaStream_t s, const dnnca_tensor_t* x, const float* w, const float* bias,
-                        const dnnca_tensor_t* y, const dnnca_tensor_t* mask, int act, float alpha, double* stats) {
-  constexpr int TYN = 256 / TXN, TW = TXN * PX;
-  constexpr int CK = CIN < 12 ? CIN : 12;
-  constexpr int COP = CoPad<COUT>::v;
-  constexpr size_t xs_bytes = (size_t)CK * (TYN + 2) * (TW + 4) * 4;
-  constexpr size_t os_bytes = (size_t)TYN * TW * COUT * sizeof(T);
-  constexpr size_t smem = (size_t)CIN * 9 * COP * 4 + (xs_bytes > os_bytes ? xs_bytes : os_bytes);
-  auto kern = conv3x3_small_kernel<T, CIN, COUT, TXN, DGRAD>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "conv3x3_small: cudaFuncSetAttribute");
-    attr_done = true;
+static bool views_ok(const dnnca_tensor_t* t) { return t == nullptr || tma_row_ok(t); }
+
+template <typename T, int CA, int CB, int OA, int OB, int TXN, bool DGRAD>
+static int launch_small(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tensor_t* xb, const float* w,
+                        const float* bias, const dnnca_tensor_t* ya, const dnnca_tensor_t* yb,
+                        const dnnca_tensor_t* mask, int act, float alpha, double* stats) {
+  using G = FGeom<T, CA, CB, OA, OB, TXN>;
+  if constexpr (!G::FITS) {
+    return 0;
+  } else {
+    constexpr int EPC = 16 / (int)sizeof(T);
+    constexpr int CBS = CB ? CB : 1;
+    auto kern = conv3x3_small_kernel<T, CA, CB, OA, OB, TXN, DGRAD>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+      if (e != cudaSuccess) return cuda_fail(e, "conv3x3_small: cudaFuncSetAttribute");
+      attr_done = true;
+    }
+    CUtensorMap mA, mB, mOA, mOB;
+    if (!make_row_map(&mA, xa, Raw<T, CA, G::TW, 1>::NCH, G::ROWS)) return 0;
+    mB = mA;
+    if (CB && !make_row_map(&mB, xb, Raw<T, CBS, G::TW, 1>::NCH, G::ROWS)) return 0;
+    const bool tma_out = tma_row_ok(ya) && (!OB || tma_row_ok(yb));
+    mOA = mA;
+    mOB = mA;
+    if (tma_out) {
+      if (!make_row_map(&mOA, ya, G::TW * OA / EPC, G::TYN)) return 0;
+      if (OB && !make_row_map(&mOB, yb, G::TW * OB / EPC, G::TYN)) return 0;
+    }
+    FArgs a;
+    a.w = w; a.bias = bias; a.ya = mk(ya); a.yb = yb ? mk(yb) : mk(ya); a.mask = mask ? mk(mask) : mk(ya);
+    a.has_mask = mask != nullptr; a.act = act; a.alpha = alpha; a.stats = stats;
+    a.tiles_x = (xa->w + G::TW - 1) / G::TW; a.tiles_y = (xa->h + G::TYN - 1) / G::TYN; a.tma_out = tma_out;
+    const long long nblk = (long long)a.tiles_x * a.tiles_y * xa->n;
+    if (nblk > 0x7fffffffLL) return 0;
+    kern<<<(unsigned)nblk, 256, G::SMEM, s>>>(mA, mB, mOA, mOB, a);
+    DNNCA_LAUNCH_CHECK("conv3x3_small");
+    return 1;
   }
-  const int tiles_x = (x->w + TW - 1) / TW, tiles_y = (x->h + TYN - 1) / TYN;
-  const long long nblk = (long long)tiles_x * tiles_y * x->n;
-  if (nblk > 0x7fffffffLL) { set_error("conv3x3_small: grid too large"); return DNNCA_ERR_UNSUPPORTED; }
-  View vm = mask ? mk(mask) : mk(y);
-  kern<<<(unsigned)nblk, 256, smem, s>>>(mk(x), w, bias, mk(y), vm, mask != nullptr, act, alpha, stats, tiles_x, tiles_y);
-  DNNCA_LAUNCH_CHECK("conv3x3_small");
-  return 1;
 }
 
-template <typename T, int CIN, int COUT, bool DGRAD>
-static int launch_small_w(cudaStream_t s, const dnnca_tensor_t* x, const float* w, const float* bias,
-                          const dnnca_tensor_t* y, const dnnca_tensor_t* mask, int act, float alpha, double* stats) {
-  if (x->w > 64) return launch_small<T, CIN, COUT, 32, DGRAD>(s, x, w, bias, y, mask, act, alpha, stats);
-  if (x->w > 32) return launch_small<T, CIN, COUT, 16, DGRAD>(s, x, w, bias, y, mask, act, alpha, stats);
-  return launch_small<T, CIN, COUT, 8, DGRAD>(s, x, w, bias, y, mask, act, alpha, stats);
+template <typename T, int CA, int CB, int OA, int OB, bool DGRAD>
+static int launch_small_w(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tensor_t* xb, const float* w,
+                          const float* bias, const dnnca_tensor_t* ya, const dnnca_tensor_t* yb,
+                          const dnnca_tensor_t* mask, int act, float alpha, double* stats) {
+  // widest tile that fits the image width and the TMA box limits
+  int r = 0;
+  if (xa->w > 64) r = launch_small<T, CA, CB, OA, OB, 32, DGRAD>(s, xa, xb, w, bias, ya, yb, mask, act, alpha, stats);
+  if (r == 0 && xa->w > 32) r = launch_small<T, CA, CB, OA, OB, 16, DGRAD>(s, xa, xb, w, bias, ya, yb, mask, act, alpha, stats);
+  if (r == 0) r = launch_small<T, CA, CB, OA, OB, 8, DGRAD>(s, xa, xb, w, bias, ya, yb, mask, act, alpha, stats);
+  return r;
 }
 
-// (kernel-input channels, kernel-output channels) pairs that occur in configs/unet.yaml
-// (C = 3 or 5 modalities), the first layers of mulmo_unet.yaml (1 -> 16) and unet_big.yaml (3 -> 64 is
-// left to the generic/tensor path), for fprop and -- with the roles swapped -- dgrad.
+// (input channels of x, of x2, output channels) occurring in configs/unet.yaml (C = 3 or 5 modalities), the
+// first layers of mulmo_unet.yaml (1 -> 16) and the small golden-test nets (F = 4)
 #define DNNCA_SMALL_FPROP_SHAPES(X) \
-  X(1, 4) X(1, 16) X(3, 3) X(5, 3) X(3, 6) X(6, 3) X(6, 6) X(6, 12) X(12, 6) X(12, 12) X(24, 12) \
-  X(3, 4) X(4, 4) X(4, 8) X(8, 8) X(8, 4) X(16, 8)
-// dgrad: kernel input = layer Cout, kernel output = layer Cin (first-layer dgrads fall to the generic kernel)
+  X(1, 0, 4) X(1, 0, 16) X(3, 0, 3) X(5, 0, 3) X(3, 0, 6) X(6, 0, 6) X(6, 0, 12) X(12, 0, 12) X(3, 3, 3) X(6, 6, 6) \
+  X(12, 12, 12) X(3, 0, 4) X(4, 0, 4) X(4, 0, 8) X(8, 0, 8) X(4, 4, 4) X(8, 8, 8)
+// dgrad: kernel input = dz (layer Cout); outputs = dx (+ dx2); first-layer dgrads go to the generic kernel
 #define DNNCA_SMALL_DGRAD_SHAPES(X) \
-  X(3, 3) X(6, 3) X(3, 6) X(6, 6) X(12, 6) X(6, 12) X(12, 12) X(12, 24) X(4, 4) X(8, 4) X(4, 8) X(8, 8) X(8, 16)
+  X(3, 3, 0) X(6, 3, 0) X(6, 6, 0) X(12, 6, 0) X(12, 12, 0) X(3, 3, 3) X(6, 6, 6) X(12, 12, 12) X(4, 4, 0) X(8, 4, 0) \
+  X(8, 8, 0) X(4, 4, 4) X(8, 8, 8)
 
 #if SMALL_KIND == 0
-int SMALL_FN(try_conv_fprop_small)(cudaStream_t s, const dnnca_tensor_t* x, const float* w, const float* bias,
-                                   const dnnca_tensor_t* y, int act, float alpha, double* stats) {
-#define X(CI, CO) \
-  if (x->c == CI && y->c == CO) return launch_small_w<SMALL_T, CI, CO, false>(s, x, w, bias, y, nullptr, act, alpha, stats);
+int SMALL_FN(try_conv_fprop_small)(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w,
+                                   const float* bias, const dnnca_tensor_t* y, int act, float alpha, double* stats) {
+  if (!tma_row_ok(x) || !views_ok(x2)) return 0;
+  const int c2 = x2 ? x2->c : 0;
+#define X(CA, CB, CO) \
+  if (x->c == CA && c2 == CB && y->c == CO) \
+    return launch_small_w<SMALL_T, CA, CB, CO, 0, false>(s, x, x2, w, bias, y, nullptr, nullptr, act, alpha, stats);
   DNNCA_SMALL_FPROP_SHAPES(X)
 #undef X
   return 0;
 }
 #elif SMALL_KIND == 1
 int SMALL_FN(try_conv_dgrad_small)(cudaStream_t s, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
-                                   const dnnca_tensor_t* mask, int act, float alpha) {
-#define X(CI, CO) \
-  if (dz->c == CI && dx->c == CO) return launch_small_w<SMALL_T, CI, CO, true>(s, dz, w, nullptr, dx, mask, act, alpha, nullptr);
+                                   const dnnca_tensor_t* dx2, const dnnca_tensor_t* mask, int act, float alpha) {
+  if (!tma_row_ok(dz)) return 0;
+  const int c2 = dx2 ? dx2->c : 0;
+#define X(CI, OA, OB) \
+  if (dz->c == CI && dx->c == OA && c2 == OB) \
+    return launch_small_w<SMALL_T, CI, 0, OA, OB, true>(s, dz, nullptr, w, nullptr, dx, dx2, mask, act, alpha, nullptr);
   DNNCA_SMALL_DGRAD_SHAPES(X)
 #undef X
   return 0;
 }
 #endif
 
-template <typename T, int CIN, int COUT>
-static int launch_small_wgrad(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* dz, float* dw, float* db) {
-  constexpr int TYN = 4, TXN = 16, TW = TXN * PX;
-  constexpr size_t smem = ((size_t)CIN * (TYN + 2) * (TW + 4) + (size_t)COUT * TYN * TW + 9 * CIN * COUT + COUT) * 4;
-  auto kern = conv3x3_small_wgrad_kernel<T, CIN, COUT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "conv3x3_small_wgrad: cudaFuncSetAttribute");
-    attr_done = true;
+template <typename T, int CA, int CB, int COUT>
+static int launch_small_wgrad(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2,
+                              const dnnca_tensor_t* dz, float* dw, float* db) {
+  using G = WGeom<T, CA, CB, COUT>;
+  if constexpr (!G::FITS) {
+    return 0;
+  } else {
+    auto kern = conv3x3_small_wgrad_kernel<T, CA, CB, COUT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+      if (e != cudaSuccess) return cuda_fail(e, "conv3x3_small_wgrad: cudaFuncSetAttribute");
+      attr_done = true;
+    }
+    CUtensorMap mA, mB, mG;
+    if (!make_row_map(&mA, x, G::NCHA, G::ROWS)) return 0;
+    mB = mA;
+    if (CB && !make_row_map(&mB, x2, G::NCHB, G::ROWS)) return 0;
+    if (!make_row_map(&mG, dz, G::NCHG, G::TYN)) return 0;
+    const int tiles_x = (x->w + G::TW - 1) / G::TW, tiles_y = (x->h + G::TYN - 1) / G::TYN;
+    const long long ntiles = (long long)tiles_x * tiles_y * x->n;
+    if (ntiles > 0x7fffffffLL) return 0;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, G::SMEM) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    long long grid = (long long)sm_count() * per_sm;     // persistent: one resident wave
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, 256, G::SMEM, s>>>(mA, mB, mG, dw, db, tiles_x, tiles_y, (int)ntiles);
+    DNNCA_LAUNCH_CHECK("conv3x3_small_wgrad");
+    return 1;
   }
-  const int tiles_x = (x->w + TW - 1) / TW, tiles_y = (x->h + TYN - 1) / TYN;
-  const long long ntiles = (long long)tiles_x * tiles_y * x->n;
-  long long grid = (long long)sm_count() * 2;
-  if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, 256, smem, s>>>(mk(x), mk(dz), dw, db, tiles_x, tiles_y, ntiles);
-  DNNCA_LAUNCH_CHECK("conv3x3_small_wgrad");
-  return 1;
 }
 
-#define DNNCA_SMALL_WGRAD_SHAPES(X) \
-  X(1, 3) X(1, 4) X(1, 16) X(3, 3) X(5, 3) X(3, 6) X(6, 6) X(6, 12) X(12, 12) X(24, 12) X(12, 6) X(6, 3) X(3, 4) \
-  X(4, 4) X(4, 8) X(8, 8) X(16, 8) X(8, 4) X(5, 4)
-
 #if SMALL_KIND == 2
-int SMALL_FN(try_conv_wgrad_small)(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* dz, float* dw,
-                                   float* db) {
-#define X(CI, CO) \
-  if (x->c == CI && dz->c == CO) return launch_small_wgrad<SMALL_T, CI, CO>(s, x, dz, dw, db);
-  DNNCA_SMALL_WGRAD_SHAPES(X)
+int SMALL_FN(try_conv_wgrad_small)(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2,
+                                   const dnnca_tensor_t* dz, float* dw, float* db) {
+  if (!tma_row_ok(x) || !views_ok(x2) || !tma_row_ok(dz)) return 0;
+  const int c2 = x2 ? x2->c : 0;
+#define X(CA, CB, CO) \
+  if (x->c == CA && c2 == CB && dz->c == CO) return launch_small_wgrad<SMALL_T, CA, CB, CO>(s, x, x2, dz, dw, db);
+  DNNCA_SMALL_FPROP_SHAPES(X)
 #undef X
   return 0;
 }

@@ -100,7 +100,7 @@ def _check_supported(rate, kernel_size, conv_stride, padding):
             'the reference configs (rate 2, 3x3 stride-1 convs)')
 
 
-def conv_act_bn(layer, plan, x, dst, prefix, bnprefix, ksize, act, bn, bias=True):
+def conv_act_bn(layer, plan, x, dst, prefix, bnprefix, ksize, act, bn, bias=True, x2=None):
     """Conv2D(+bias, activation) [-> BatchNormalization]   (components.py:46-61, 122-134).
 
     Without BN the conv writes straight into ``dst``; with BN the conv writes its
@@ -108,11 +108,11 @@ def conv_act_bn(layer, plan, x, dst, prefix, bnprefix, ksize, act, bn, bias=True
     epilogue, and the BN apply pass writes ``dst``."""
     kernel, b = f'{prefix}/kernel', (f'{prefix}/bias' if bias else None)
     if not bn:
-        plan.add(R.ConvOp(plan, x, dst, kernel, b, ksize, act))
+        plan.add(R.ConvOp(plan, x, dst, kernel, b, ksize, act, x2=x2))
         return dst
     a = R.TRef(plan.new_buf(x.h, x.w, dst.c, prefix + ':a'))
     st = R.BNStats(plan, dst.c)
-    plan.add(R.ConvOp(plan, x, a, kernel, b, ksize, act, stats=st))
+    plan.add(R.ConvOp(plan, x, a, kernel, b, ksize, act, stats=st, x2=x2))
     plan.add(R.BNOp(plan, a, dst, bnprefix, st))
     return dst
 
@@ -150,7 +150,7 @@ class Downsample(Layer):
 
     def emit(self, plan, x, res_dst=None, half_dst=None):
         """-> (conv, half) like ``call`` (components.py:77-81).  ``res_dst`` / ``half_dst`` let the
-        caller place the two outputs inside concat buffers."""
+        caller place an output inside a concat buffer (MulmoUNet's bottleneck, unet.py:187)."""
         f = self.filters
         if x.h % 2 or x.w % 2:
             raise ValueError(f'{self.name}: spatial size {x.h}x{x.w} is not divisible by the pool rate')
@@ -204,26 +204,28 @@ class Upsample(Layer):
     def compute_output_shape(self, input_shape, ref_shape):
         return [input_shape[0], input_shape[1] * self.rate, input_shape[2] * self.rate, self.filters]
 
-    def emit(self, plan, x, concat_buf, reference):
-        """``concat_buf`` holds [tconv | reference] (components.py:164: tconv first, skip second);
-        ``reference`` already lives in its upper channels, so concat and the centre crop
-        (identity under padding='same', components.py:161-163) cost nothing."""
+    def emit(self, plan, x, reference):
+        """``tf.concat([tconv0, cropped], -1)`` (components.py:164: tconv first, skip second) is
+        virtual: the first conv reads the transposed-conv output and the skip tensor as two inputs.
+        The centre crop (components.py:161-163) is the identity under padding='same'."""
         f = self.filters
-        assert reference.buf is concat_buf and reference.coff == f and concat_buf.c == f + reference.c
-        tdst = R.TRef(concat_buf, 0, f)
+        assert (reference.h, reference.w) == (x.h * self.rate, x.w * self.rate)
+        t = R.TRef(plan.new_buf(reference.h, reference.w, f, f'{self.name}/tconv'))
         if not self.bn:
-            plan.add(R.TConvOp(plan, x, tdst, f'{self.name}/tconv/kernel', f'{self.name}/tconv/bias'))
+            plan.add(R.TConvOp(plan, x, t, f'{self.name}/tconv/kernel', f'{self.name}/tconv/bias'))
         else:
-            t = R.TRef(plan.new_buf(concat_buf.h, concat_buf.w, f, f'{self.name}/tconv'))
             st = R.BNStats(plan, f)
             plan.add(R.TConvOp(plan, x, t, f'{self.name}/tconv/kernel', f'{self.name}/tconv/bias', stats=st))
-            plan.add(R.BNOp(plan, t, tdst, f'{self.name}/tconv_bn', st))
-        reference.skip_consumed = True
-        x = R.TRef(concat_buf)            # whole concat: no single producer -> no activation mask on its gradient
+            tb = R.TRef(plan.new_buf(reference.h, reference.w, f, f'{self.name}/tconv_bn'))
+            plan.add(R.BNOp(plan, t, tb, f'{self.name}/tconv_bn', st))
+            t = tb
+        reference.skip_consumed = True       # its gradient arrives from this conv AND from its max-pool
+        x, x2 = t, reference
         for k in range(self.n_conv):
             dst = R.TRef(plan.new_buf(x.h, x.w, f, f'{self.name}/conv{k}'))
             x = conv_act_bn(self, plan, x, dst, f'{self.name}/conv{k}', f'{self.name}/bn{k}', self.kernel_size,
-                            self.act, self.bn)
+                            self.act, self.bn, x2=x2)
+            x2 = None
         return x
 
 
@@ -300,9 +302,9 @@ class Decoder(Layer):
         self.built = True
         return inputs_shape
 
-    def emit(self, plan, x, concat_bufs, res_list):
+    def emit(self, plan, x, res_list):
         assert len(res_list) == len(self.upsamples), \
             f'#References {len(res_list)} != #upsamples {len(self.upsamples)}'
-        for reference, cbuf, up in zip(reversed(res_list), reversed(concat_bufs), self.upsamples):
-            x = up.emit(plan, x, cbuf, reference)
+        for reference, up in zip(reversed(res_list), self.upsamples):
+            x = up.emit(plan, x, reference)
         return x

@@ -43,7 +43,7 @@ class _FoldedConv(R.Op):
         s = torch.rsqrt(ps.view(f'{self.bn}/moving_var') + R.BN_EPSILON)
         torch.mul(ps.view(f'{self.conv}/kernel'), s, out=self.wf)
         torch.addcmul(ps.view(f'{self.bn}/beta'), ps.view(f'{self.bn}/moving_mean'), s, value=-1.0, out=self.bf)
-        N.call('dnnca_conv2d_fprop', N.stream_ptr(), self.x.ct(), N.ptr(self.wf), N.ptr(self.bf), self.y.ct(),
+        N.call('dnnca_conv2d_fprop', N.stream_ptr(), self.x.ct(), None, N.ptr(self.wf), N.ptr(self.bf), self.y.ct(),
                self.k, self.act, 0.0, None)
 
 

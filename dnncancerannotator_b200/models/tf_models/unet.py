@@ -43,16 +43,8 @@ class UNet(Layer):
         return decoder_out
 
     def emit(self, plan, x):
-        # one concat buffer per level: [tconv (rc) | skip (rc)]; the encoder writes its skip output
-        # straight into the upper half (components.py:164 order: tconv first, reference second)
-        cbufs, res_dsts = [], []
-        for i, ref in enumerate(self.ref_shapes):
-            rc = ref[-1]
-            cb = plan.new_buf(x.h >> i, x.w >> i, 2 * rc, f'dec/concat{i}')
-            cbufs.append(cb)
-            res_dsts.append(R.TRef(cb, rc, rc))
-        res_list, down = self.encoder.emit(plan, x, res_dsts=res_dsts)
-        return self.decoder.emit(plan, down, cbufs, res_list)
+        res_list, down = self.encoder.emit(plan, x)
+        return self.decoder.emit(plan, down, res_list)
 
 
 class MulmoUNet(Layer):
@@ -96,12 +88,6 @@ class MulmoUNet(Layer):
         return decoder_out
 
     def emit(self, plan, x):
-        cbufs, res_dsts = [], []
-        for i, ref in enumerate(self.ref_shapes):
-            rc = ref[-1]
-            cb = plan.new_buf(x.h >> i, x.w >> i, 2 * rc, f'dec/concat{i}')
-            cbufs.append(cb)
-            res_dsts.append(R.TRef(cb, rc, rc))
         fb = self.encoder_output_shape_list[0][-1]
         n = len(self.ref_shapes)
         bott = plan.new_buf(x.h >> n, x.w >> n, fb * self.channel_len, 'bottleneck')     # tf.concat, unet.py:187
@@ -109,11 +95,10 @@ class MulmoUNet(Layer):
         for m, enc in enumerate(self.encoders):
             xin = R.TRef(x.buf, x.coff + m, 1)                                            # inputs[..., m:m+1]
             xin.needs_grad = False
-            res_list, _ = enc.emit(plan, xin, res_dsts=res_dsts if m == self.reference_index else None,
-                                   out_dst=R.TRef(bott, m * fb, fb))
+            res_list, _ = enc.emit(plan, xin, out_dst=R.TRef(bott, m * fb, fb))
             if m == self.reference_index:
                 res_ref = res_list
-        return self.decoder.emit(plan, R.TRef(bott), cbufs, res_ref)
+        return self.decoder.emit(plan, R.TRef(bott), res_ref)
 
 
 class UNetAnnotator(Model):

@@ -49,9 +49,9 @@ _PROTOS = {
     'dnnca_sm_count': [C.POINTER(C.c_int)],
     'dnnca_debug_force_generic': [_i],
     'dnnca_debug_launch_count': [_i],
-    'dnnca_conv2d_fprop': [_vp, _TP, _vp, _vp, _TP, _i, _i, _f, _vp],
-    'dnnca_conv2d_dgrad': [_vp, _TP, _vp, _TP, _i, _TP, _i, _f],
-    'dnnca_conv2d_wgrad': [_vp, _TP, _TP, _vp, _vp, _i],
+    'dnnca_conv2d_fprop': [_vp, _TP, _TP, _vp, _vp, _TP, _i, _i, _f, _vp],
+    'dnnca_conv2d_dgrad': [_vp, _TP, _vp, _TP, _TP, _i, _TP, _i, _f],
+    'dnnca_conv2d_wgrad': [_vp, _TP, _TP, _TP, _vp, _vp, _i],
     'dnnca_convtranspose2x2_fprop': [_vp, _TP, _vp, _vp, _TP, _vp],
     'dnnca_convtranspose2x2_dgrad': [_vp, _TP, _vp, _TP, _TP, _i, _f],
     'dnnca_convtranspose2x2_wgrad': [_vp, _TP, _TP, _vp, _vp],
@@ -164,10 +164,17 @@ class Profiler:
         label = name.replace('dnnca_', '')
         if name.startswith('dnnca_conv2d_') and len(vs) >= 2:
             k = [a for a in args if isinstance(a, int)][0]
-            a, b = vs[0], vs[1]
-            flops = 2 * a.n * a.h * a.w * a.c * b.c * k * k
-            byt += 4 * k * k * a.c * b.c
-            label += f'[{a.c}->{b.c}@{a.h}]'
+            a = vs[0]
+            if name.endswith('fprop'):      # x [x2] y
+                cin, cout = sum(v.c for v in vs[:-1]), vs[-1].c
+            elif name.endswith('wgrad'):    # x [x2] dz
+                cin, cout = sum(v.c for v in vs[:-1]), vs[-1].c
+            else:                            # dz dx [dx2] [mask]: kernel-input = dz, kernel-output = dx (+dx2)
+                nout = 2 if (len(args) > 4 and getattr(args[4], '_obj', None) is not None) else 1
+                cin, cout = vs[0].c, sum(v.c for v in vs[1:1 + nout])
+            flops = 2 * a.n * a.h * a.w * cin * cout * k * k
+            byt += 4 * k * k * cin * cout
+            label += f'[{cin}->{cout}@{a.h}]'
         elif name.startswith('dnnca_convtranspose2x2_') and len(vs) >= 2:
             a, b = vs[0], vs[1]
             small = a if a.h < b.h else b

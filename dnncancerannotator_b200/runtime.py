@@ -215,10 +215,14 @@ class Op:
 
 
 class ConvOp(Op):
-    """layers.Conv2D (components.py:47-50,123-126; multiresunet.py:51-52)."""
+    """layers.Conv2D (components.py:47-50,123-126; multiresunet.py:51-52).
 
-    def __init__(self, plan, x: TRef, y: TRef, kernel, bias, ksize, act, stats=None):
-        self.p, self.x, self.y, self.kernel, self.bias, self.k = plan, x, y, kernel, bias, ksize
+    ``x2``: second input whose channels follow x's -- the conv reads both producers of
+    ``tf.concat([tconv0, cropped], -1)`` (components.py:164), the concat is never materialised;
+    backward writes the two gradients to their own tensors."""
+
+    def __init__(self, plan, x: TRef, y: TRef, kernel, bias, ksize, act, stats=None, x2: TRef = None):
+        self.p, self.x, self.x2, self.y, self.kernel, self.bias, self.k = plan, x, x2, y, kernel, bias, ksize
         self.act = act or (N.ACT_NONE, 0.0)
         self.stats = stats
         if act and act[0] != N.ACT_NONE:
@@ -226,16 +230,19 @@ class ConvOp(Op):
 
     def fwd(self, train):
         ps = self.p.params
-        N.call('dnnca_conv2d_fprop', N.stream_ptr(), self.x.ct(), ps.ptr(self.kernel), ps.ptr(self.bias), self.y.ct(),
-               self.k, self.act[0], self.act[1], self.stats.fwd_ptr() if (self.stats and train) else None)
+        N.call('dnnca_conv2d_fprop', N.stream_ptr(), self.x.ct(), self.x2.ct() if self.x2 else None,
+               ps.ptr(self.kernel), ps.ptr(self.bias), self.y.ct(), self.k, self.act[0], self.act[1],
+               self.stats.fwd_ptr() if (self.stats and train) else None)
 
     def bwd(self):
         ps = self.p.params
         s = N.stream_ptr()
-        N.call('dnnca_conv2d_wgrad', s, self.x.ct(), self.y.gct(), ps.gptr(self.kernel), ps.gptr(self.bias), self.k)
+        N.call('dnnca_conv2d_wgrad', s, self.x.ct(), self.x2.ct() if self.x2 else None, self.y.gct(),
+               ps.gptr(self.kernel), ps.gptr(self.bias), self.k)
         if self.x.needs_grad:
             m, a, al = self.x.mask_args()
-            N.call('dnnca_conv2d_dgrad', s, self.y.gct(), ps.ptr(self.kernel), self.x.gct(), self.k, m, a, al)
+            N.call('dnnca_conv2d_dgrad', s, self.y.gct(), ps.ptr(self.kernel), self.x.gct(),
+                   self.x2.gct() if self.x2 else None, self.k, m, a, al)
 
 
 class TConvOp(Op):
@@ -398,7 +405,7 @@ class Plan:
         if self.allocated_training is not None and (self.allocated_training or not training):
             return
         for op in self.ops:
-            for t in (getattr(op, 'x', None), getattr(op, 'y', None)):
+            for t in (getattr(op, 'x', None), getattr(op, 'x2', None), getattr(op, 'y', None)):
                 if training and isinstance(t, TRef) and t.needs_grad:
                     t.buf.want_grad = True
         if training and self.features is not None:

@@ -72,27 +72,34 @@ DNNCA_API long long dnnca_debug_launch_count(int reset);
  * Conv2D, stride 1, 'same' zero padding, k in {1,3}
  *   replaces layers.Conv2D at components.py:47-50, components.py:123-126,
  *   multiresunet.py:51-52 (use_bias=False -> bias == NULL).
- * y = act(x (*) w + bias)  (cross-correlation).  If `stats` != NULL the per-
- * channel sum and sum of squares of the *stored* output are ACCUMULATED into
+ * y = act([x | x2] (*) w + bias)  (cross-correlation).  `x2` (may be NULL) is a
+ * second input whose channels follow x's: the kernel reads the two producers of
+ * tf.concat([tconv0, cropped], -1) (components.py:164) directly, so the concat is
+ * never materialised; w is [k,k,Cx+Cx2,Cout].  If `stats` != NULL the per-channel
+ * sum and sum of squares of the *stored* output are ACCUMULATED into
  * stats[0..C) and stats[C..2C) (fp64; caller zeroes) for the BatchNormalization
  * that follows (components.py:57-58, 130-132).
  * ------------------------------------------------------------------------- */
-DNNCA_API int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const float* w, const float* bias,
-                       const dnnca_tensor_t* y, int ksize, int act, float alpha, double* stats);
+DNNCA_API int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w,
+                                 const float* bias, const dnnca_tensor_t* y, int ksize, int act, float alpha,
+                                 double* stats);
 
-/* Gradient w.r.t. the conv input (tf.GradientTape over the Conv2D above):
- *   dx = dz (*) rot180(w)^T ; if `mask` != NULL, dx *= act'(mask) where `mask`
- *   is the stored (post-activation) output of the layer that produced x --
- *   so the kernel emits that layer's dz directly (ReLU/LeakyReLU preserve
- *   sign, act'(y) is decided by y > 0). */
+/* Gradient w.r.t. the conv input(s) (tf.GradientTape over the Conv2D above):
+ *   [dx | dx2] = dz (*) rot180(w)^T ; dx2 (may be NULL) receives the channels of the
+ *   second input.  If `mask` != NULL, dx *= act'(mask) where `mask` is the stored
+ *   (post-activation) output of the layer that produced x -- so the kernel emits
+ *   that layer's dz directly (ReLU/LeakyReLU preserve sign: act'(y) is decided by
+ *   y > 0).  dx2 is never masked (it is a skip gradient that max-pool backward
+ *   merges and masks). */
 DNNCA_API int dnnca_conv2d_dgrad(void* stream, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
-                       int ksize, const dnnca_tensor_t* mask, int act, float alpha);
+                                 const dnnca_tensor_t* dx2, int ksize, const dnnca_tensor_t* mask, int act,
+                                 float alpha);
 
-/* Gradient w.r.t. kernel and bias: dw[kh,kw,Cin,Cout] and db[Cout] are
+/* Gradient w.r.t. kernel and bias: dw[k,k,Cx+Cx2,Cout] and db[Cout] are
  * ACCUMULATED (+=) in fp32 (caller zeroes the flat gradient buffer once per
- * step); db may be NULL. */
-DNNCA_API int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dz, float* dw, float* db,
-                       int ksize);
+ * step); x2 and db may be NULL. */
+DNNCA_API int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2,
+                                 const dnnca_tensor_t* dz, float* dw, float* db, int ksize);
 
 /* ---------------------------------------------------------------------------
  * Conv2DTranspose, k = s = 2 (non-overlapping), activation=None

@@ -132,16 +132,18 @@ def test_unet_yaml_lowering_structure():
     assert m.count_params() == 8740
     assert op_counts(plan) == {'ConvertOp': 1, 'ConvOp': 12, 'PoolOp': 3, 'TConvOp': 3}
     convs = [op for op in plan.ops if isinstance(op, R.ConvOp)]
-    assert [(o.x.c, o.y.c) for o in convs] == [(3, 3), (3, 3), (3, 6), (6, 6), (6, 12), (12, 12),
-                                               (24, 12), (12, 12), (12, 6), (6, 6), (6, 3), (3, 3)]
+    assert [(o.x.c, o.x2.c if o.x2 else 0, o.y.c) for o in convs] == [
+        (3, 0, 3), (3, 0, 3), (3, 0, 6), (6, 0, 6), (6, 0, 12), (12, 0, 12),
+        (12, 12, 12), (12, 0, 12), (6, 6, 6), (6, 0, 6), (3, 3, 3), (3, 0, 3)]
     assert not convs[0].x.needs_grad                          # input gets no gradient (first dgrad skipped)
-    # skip tensors live in the upper half of the decoder concat buffers; tconv writes the lower half
+    # tf.concat([tconv, skip]) is virtual: the first decoder conv of a level reads the transposed-conv
+    # output (x) and the encoder's skip tensor (x2); the skip tensor is also the max-pool's input
     pools = [op for op in plan.ops if isinstance(op, R.PoolOp)]
     tconvs = [op for op in plan.ops if isinstance(op, R.TConvOp)]
-    for pool, tconv in zip(pools, reversed(tconvs)):
-        res = pool.x
-        assert res.skip_consumed and res.buf is tconv.y.buf
-        assert tconv.y.coff == 0 and res.coff == tconv.y.c and res.buf.c == 2 * res.c
+    dec0 = [o for o in convs if o.x2 is not None]
+    for pool, tconv, conv in zip(reversed(pools), tconvs, dec0):
+        assert pool.x.skip_consumed and conv.x2 is pool.x and conv.x is tconv.y
+        assert all(t.coff == 0 and t.buf.c == t.c for t in (conv.x, conv.x2, conv.y))   # every tensor is dense
     assert plan.features.shape == (2, 64, 64, 3) and plan.features.act is not None
     assert plan.head == ('head/kernel', 'head/bias')
 

@@ -75,65 +75,84 @@ def close(got, ref, mode, scale=None):
     assert err <= tol['atol'] * s + 1e-12, f'max abs err {err:.3e} vs scale {s:.3e} (tol {tol["atol"]})'
 
 
-CONV_SHAPES = [  # (n, h, w, cin, cout, k)
-    (2, 16, 16, 3, 3, 3), (1, 40, 72, 3, 6, 3), (2, 8, 136, 6, 6, 3), (1, 16, 16, 24, 12, 3),
-    (1, 12, 20, 12, 12, 3), (2, 16, 16, 1, 16, 3), (1, 16, 16, 5, 3, 3),
-    (1, 10, 14, 7, 9, 3), (1, 8, 8, 20, 33, 3), (2, 9, 11, 17, 8, 1), (1, 8, 8, 64, 64, 3),
+CONV_SHAPES = [  # (n, h, w, c_x, c_x2, cout, k)
+    (2, 16, 16, 3, 0, 3, 3), (1, 40, 72, 3, 0, 6, 3), (2, 8, 136, 6, 0, 6, 3), (1, 16, 16, 12, 12, 12, 3),
+    (1, 12, 24, 12, 0, 12, 3), (2, 16, 16, 1, 0, 16, 3), (1, 16, 16, 5, 0, 3, 3), (1, 20, 264, 3, 3, 3, 3),
+    (2, 24, 48, 6, 6, 6, 3), (1, 36, 40, 6, 0, 12, 3), (1, 16, 32, 8, 8, 8, 3), (2, 16, 16, 4, 0, 8, 3),
+    (1, 10, 14, 7, 0, 9, 3), (1, 8, 8, 20, 0, 33, 3), (2, 9, 11, 17, 0, 8, 1), (1, 8, 8, 64, 0, 64, 3),
+    (1, 10, 12, 7, 5, 9, 3),
 ]
 
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
-@pytest.mark.parametrize('force_generic', [0, 1])
+@pytest.mark.parametrize('variant', ['dense', 'sliced', 'generic'])
 @pytest.mark.parametrize('shape', CONV_SHAPES)
-def test_conv_fprop_dgrad_wgrad(N, mode, force_generic, shape):
-    n, h, w, cin, cout, k = shape
+def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
+    """dense: tensors are whole buffers (the TMA-staged small-channel kernels take the shapes they cover);
+    sliced: every tensor is a channel slice of a wider buffer; generic: shape-generic kernels forced."""
+    n, h, w, ca, cb, cout, k = shape
+    cin = ca + cb
     dt = DT[mode]
     rng = np.random.default_rng(hash(shape) % 2 ** 31)
     x = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), dt)
     wt = (rng.normal(size=(k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
     b = rng.normal(size=cout).astype(np.float32)
     lib = N.lib()
-    old = lib.dnnca_debug_force_generic(force_generic)
+    old = lib.dnnca_debug_force_generic(1 if variant == 'generic' else 0)
+    P = (lambda lo, hi: (lo, hi)) if variant == 'sliced' else (lambda lo, hi: (0, 0))
     try:
+        wd, bd = dev(wt), dev(b)
+        xa_b, xa_o, _ = embed(x[..., :ca], dt, *P(2, 1))
+        xav = view(N, xa_b, xa_o, ca)
+        xbv = None
+        if cb:
+            xb_b, xb_o, _ = embed(x[..., ca:], dt, *P(0, 3))
+            xbv = view(N, xb_b, xb_o, cb)
+        xbp = C.byref(xbv) if cb else None
         for act, alpha, tact in [(N.ACT_RELU, 0.0, 'relu'), (N.ACT_LEAKY, 0.3, ('leaky', 0.3)), (N.ACT_NONE, 0.0, None)]:
-            xb, xo, _ = embed(x, dt, 2, 1)
-            yb = torch.full((n, h, w, cout + 3), 5.0, dtype=dt, device='cuda')
+            lo, hi = P(1, 2)
+            yb = torch.full((n, h, w, lo + cout + hi), 5.0, dtype=dt, device='cuda')
             stats = torch.zeros(2 * cout, dtype=torch.float64, device='cuda')
-            xv, yv = view(N, xb, xo, cin), view(N, yb, 1, cout)
-            N.call('dnnca_conv2d_fprop', None, C.byref(xv), N.ptr(dev(wt)), N.ptr(dev(b)), C.byref(yv), k, act, alpha,
+            yv = view(N, yb, lo, cout)
+            N.call('dnnca_conv2d_fprop', None, C.byref(xav), xbp, N.ptr(wd), N.ptr(bd), C.byref(yv), k, act, alpha,
                    N.ptr(stats))
             sync()
             ref = ops.activation(ops.conv2d(torch.from_numpy(x), torch.from_numpy(wt), torch.from_numpy(b)), tact).numpy()
-            got = yb[..., 1:1 + cout].float().cpu().numpy()
+            got = yb[..., lo:lo + cout].float().cpu().numpy()
             close(got, ref, mode)
-            assert (yb[..., 0].float() == 5.0).all() and (yb[..., 1 + cout:].float() == 5.0).all(), 'wrote outside the slice'
+            if variant == 'sliced':
+                assert (yb[..., :lo].float() == 5.0).all() and (yb[..., lo + cout:].float() == 5.0).all(), 'wrote outside the slice'
             st = stats.cpu().numpy()
             np.testing.assert_allclose(st[:cout], got.astype(np.float64).sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
             np.testing.assert_allclose(st[cout:], (got.astype(np.float64) ** 2).sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
-        # backward: dz arrives as a slice, dx is masked by relu'(mask)
+        # backward: dx is masked by relu'(mask); dx2 (skip gradient) is never masked
         dz = q(rng.normal(size=(n, h, w, cout)).astype(np.float32), dt)
-        mask = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), dt)
-        dzb, dzo, _ = embed(dz, dt, 1, 2)
-        mb, mo, _ = embed(mask, dt, 0, 1)
-        dxb = torch.full((n, h, w, cin + 2), 3.0, dtype=dt, device='cuda')
-        dzv, mv, dxv = view(N, dzb, dzo, cout), view(N, mb, mo, cin), view(N, dxb, 2, cin)
-        N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(dev(wt)), C.byref(dxv), k, C.byref(mv), N.ACT_RELU, 0.0)
+        mask = q(rng.normal(size=(n, h, w, ca)).astype(np.float32), dt)
+        dzb, dzo, _ = embed(dz, dt, *P(1, 2))
+        mb, mo, _ = embed(mask, dt, *P(0, 1))
+        lo, hi = P(2, 0)
+        dxb = torch.full((n, h, w, lo + ca + hi), 3.0, dtype=dt, device='cuda')
+        dx2b = torch.full((n, h, w, max(cb, 1) + lo), 3.0, dtype=dt, device='cuda')
+        dzv, mv, dxv = view(N, dzb, dzo, cout), view(N, mb, mo, ca), view(N, dxb, lo, ca)
+        dx2v = view(N, dx2b, lo, max(cb, 1))
+        dx2p = C.byref(dx2v) if cb else None
+        N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(wd), C.byref(dxv), dx2p, k, C.byref(mv), N.ACT_RELU, 0.0)
         dw = torch.zeros(k, k, cin, cout, dtype=torch.float32, device='cuda')
         db = torch.zeros(cout, dtype=torch.float32, device='cuda')
-        xb, xo, _ = embed(x, dt, 2, 1)
-        xv = view(N, xb, xo, cin)
-        N.call('dnnca_conv2d_wgrad', None, C.byref(xv), C.byref(dzv), N.ptr(dw), N.ptr(db), k)
+        N.call('dnnca_conv2d_wgrad', None, C.byref(xav), xbp, C.byref(dzv), N.ptr(dw), N.ptr(db), k)
         sync()
         rdx, rdw, rdb = rn.conv2d_same_bwd(x, wt, dz)
-        rdx = rdx * (mask > 0)
-        close(dxb[..., 2:].float().cpu().numpy(), rdx, mode)
-        assert (dxb[..., :2].float() == 3.0).all()
+        close(dxb[..., lo:lo + ca].float().cpu().numpy(), rdx[..., :ca] * (mask > 0), mode, scale=np.abs(rdx).max())
+        if cb:
+            close(dx2b[..., lo:].float().cpu().numpy(), rdx[..., ca:], mode, scale=np.abs(rdx).max())
+        if variant == 'sliced':
+            assert (dxb[..., :lo].float() == 3.0).all()
         close(dw.cpu().numpy(), rdw, 'fp32', scale=np.abs(rdw).max() * (1 if mode == 'fp32' else 50))
         close(db.cpu().numpy(), rdb, 'fp32', scale=np.abs(rdb).max() * (1 if mode == 'fp32' else 50))
         # unmasked dgrad
-        N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(dev(wt)), C.byref(dxv), k, None, N.ACT_NONE, 0.0)
+        N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(wd), C.byref(dxv), dx2p, k, None, N.ACT_NONE, 0.0)
         sync()
-        close(dxb[..., 2:].float().cpu().numpy(), rn.conv2d_same_bwd(x, wt, dz)[0], mode)
+        close(dxb[..., lo:lo + ca].float().cpu().numpy(), rdx[..., :ca], mode, scale=np.abs(rdx).max())
     finally:
         lib.dnnca_debug_force_generic(old)
 
@@ -374,7 +393,7 @@ def test_bad_arguments_fail_loudly(N):
     xv = N.tensor_view(x)
     yv = N.tensor_view(torch.zeros(1, 4, 4, 3, device='cuda'))
     with pytest.raises(N.DnncaError, match='kernel size'):
-        N.call('dnnca_conv2d_fprop', None, C.byref(xv), N.ptr(x), None, C.byref(yv), 5, 0, 0.0, None)
+        N.call('dnnca_conv2d_fprop', None, C.byref(xv), None, N.ptr(x), None, C.byref(yv), 5, 0, 0.0, None)
     yv2 = N.tensor_view(torch.zeros(1, 5, 4, 3, device='cuda'))
     with pytest.raises(N.DnncaError):
-        N.call('dnnca_conv2d_fprop', None, C.byref(xv), N.ptr(x), None, C.byref(yv2), 3, 0, 0.0, None)
+        N.call('dnnca_conv2d_fprop', None, C.byref(xv), None, N.ptr(x), None, C.byref(yv2), 3, 0, 0.0, None)
