@@ -74,6 +74,9 @@ int launch_conv_wgrad_generic(cudaStream_t, const dnnca_tensor_t*, const dnnca_t
 int launch_tconv_fprop_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*);
 int launch_tconv_dgrad_generic(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
 int launch_tconv_wgrad_generic(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
+int try_tconv_fprop_small(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*);
+int try_tconv_dgrad_small(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
+int try_tconv_wgrad_small(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
 // return 1 when the shape was handled, 0 when not covered, <0 on error
 int try_conv_fprop_small_f32(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
 int try_conv_fprop_small_bf16(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
@@ -176,7 +179,10 @@ extern "C" int dnnca_convtranspose2x2_fprop(void* stream, const dnnca_tensor_t* 
   DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && k, "convtranspose2x2_fprop: bad tensor arguments");
   DNNCA_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && x->dtype == y->dtype,
                   "convtranspose2x2_fprop: y must be [n,2h,2w,cout] with x's dtype");
-  int r = launch_tconv_fprop_generic((cudaStream_t)stream, x, k, bias, y);
+  int r = g_force_generic ? 0 : try_tconv_fprop_small((cudaStream_t)stream, x, k, bias, y);
+  if (r < 0) return r;
+  if (r == 0) r = launch_tconv_fprop_generic((cudaStream_t)stream, x, k, bias, y);
+  else r = DNNCA_OK;
   if (r != DNNCA_OK) return r;
   if (stats) return dnnca_channel_stats(stream, y, stats);
   return DNNCA_OK;
@@ -190,6 +196,11 @@ extern "C" int dnnca_convtranspose2x2_dgrad(void* stream, const dnnca_tensor_t* 
                   "convtranspose2x2_dgrad: dy must be [n,2h,2w,cout]");
   DNNCA_CHECK_ARG(!mask || (view_ok(mask) && same_shape(mask, dx) && mask->dtype == dx->dtype), "convtranspose2x2_dgrad: bad mask");
   DNNCA_CHECK_ARG(act_ok(act), "convtranspose2x2_dgrad: unknown activation %d", act);
+  if (!g_force_generic) {
+    int r = try_tconv_dgrad_small((cudaStream_t)stream, dy, k, dx, mask, act, alpha);
+    if (r < 0) return r;
+    if (r == 1) return DNNCA_OK;
+  }
   return launch_tconv_dgrad_generic((cudaStream_t)stream, dy, k, dx, mask, act, alpha);
 }
 
@@ -198,5 +209,10 @@ extern "C" int dnnca_convtranspose2x2_wgrad(void* stream, const dnnca_tensor_t* 
   DNNCA_CHECK_ARG(view_ok(x) && view_ok(dy) && dk, "convtranspose2x2_wgrad: bad tensor arguments");
   DNNCA_CHECK_ARG(dy->n == x->n && dy->h == 2 * x->h && dy->w == 2 * x->w && x->dtype == dy->dtype,
                   "convtranspose2x2_wgrad: dy must be [n,2h,2w,cout]");
+  if (!g_force_generic) {
+    int r = try_tconv_wgrad_small((cudaStream_t)stream, x, dy, dk, db);
+    if (r < 0) return r;
+    if (r == 1) return DNNCA_OK;
+  }
   return launch_tconv_wgrad_generic((cudaStream_t)stream, x, dy, dk, db);
 }

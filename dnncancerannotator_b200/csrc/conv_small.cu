@@ -26,8 +26,7 @@
 // Compiled once per (dtype, kind) with -DSMALL_DT=0|1 (f32|bf16) and -DSMALL_KIND=0|1|2
 // (fprop|dgrad|wgrad) so the template instantiations build in parallel.
 // Reference call sites: layers.Conv2D components.py:47-50,123-126 and their gradients.
-#include "common.cuh"
-#include "tma.cuh"
+#include "small_common.cuh"
 
 #ifndef SMALL_DT
 #error "compile with -DSMALL_DT=0|1 -DSMALL_KIND=0|1|2"
@@ -41,60 +40,6 @@
 #endif
 
 namespace dnnca {
-
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ u64 pack2(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ float lo32(u64 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
-__device__ __forceinline__ float hi32(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
-
-constexpr int PX = 4;  // pixels per thread along x (two FFMA2 pixel pairs)
-constexpr int ru(int a, int b) { return (a + b - 1) / b * b; }
-constexpr int cmax(int a, int b) { return a > b ? a : b; }
-
-// geometry of one raw TMA tile row: C interleaved channels, TW pixels + HALO pixels each side
-template <typename T, int C, int TW, int HALO>
-struct Raw {
-  static constexpr int EPC = 16 / (int)sizeof(T);                         // elements per 16-byte chunk
-  static constexpr int OFF = HALO ? (((-C) % EPC + EPC) % EPC) : 0;       // (x0-1)*C mod EPC, x0 % EPC == 0
-  static constexpr int NCH = C ? (OFF + (TW + 2 * HALO) * C + EPC - 1) / EPC : 0;
-  __device__ static int chunk_start(int x0) { return ((x0 - HALO) * C - OFF) / EPC; }
-};
-
-// raw tile [rows][NCH*EPC] (T, interleaved) -> planes dst[ci][rows][pitch] (fp32); one thread per pixel
-template <typename T, int C, int TW, int HALO>
-__device__ __forceinline__ void deinterleave(const T* __restrict__ raw, float* __restrict__ dst, int rows, int pitch) {
-  using G = Raw<T, C, TW, HALO>;
-  constexpr int COLS = TW + 2 * HALO;
-  constexpr int RP = G::NCH * G::EPC;
-  constexpr bool WORDS = sizeof(T) == 2 && (G::OFF % 2 == 0) && (C % 2 == 0);
-  for (int e = threadIdx.x; e < rows * COLS; e += 256) {
-    const int row = e / COLS, col = e - row * COLS;
-    const T* src = raw + row * RP + G::OFF + col * C;
-    float* d = dst + row * pitch + col;
-    if (WORDS) {                                     // bf16 pairs: one 32-bit LDS per two channels
-      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-#pragma unroll
-      for (int j = 0; j < C / 2; ++j) {
-        const uint32_t wd = s32[j];
-        d[(2 * j) * rows * pitch] = __uint_as_float(wd << 16);
-        d[(2 * j + 1) * rows * pitch] = __uint_as_float(wd & 0xffff0000u);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < C; ++j) d[j * rows * pitch] = ldf(src + j);
-    }
-  }
-}
 
 // ----------------------------------------------------------------------------
 // fprop / dgrad

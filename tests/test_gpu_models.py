@@ -105,8 +105,9 @@ def test_golden_forward_backward(case, mode):
         total = np.linalg.norm(allr)
         worst = ('', 0.0)
         for n in names:
-            if bn and n.endswith('/bias') and not n.startswith('head'):
-                # a bias that feeds a BatchNormalization has an exactly-zero gradient; both sides hold noise
+            if bn and n.endswith('/tconv/bias'):
+                # ConvT -> BN with no activation in between (components.py:131): the bias gradient is exactly
+                # zero in exact arithmetic; both sides hold rounding noise only
                 assert np.linalg.norm(grads[n]) < 2e-2 * total, n
                 continue
             # per-tensor error, measured against the tensor's own norm but not below 5 % of the total gradient

@@ -158,11 +158,15 @@ def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
 
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
-@pytest.mark.parametrize('shape', [(2, 8, 8, 12, 12), (1, 6, 10, 24, 8), (2, 5, 7, 6, 3), (1, 4, 4, 40, 70)])
-def test_tconv(N, mode, shape):
+@pytest.mark.parametrize('variant', ['dense', 'sliced'])
+@pytest.mark.parametrize('shape', [(2, 8, 8, 12, 12), (1, 6, 16, 24, 8), (2, 5, 7, 6, 3), (1, 4, 4, 40, 70),
+                                   (1, 20, 72, 12, 6), (2, 12, 40, 6, 3), (1, 36, 32, 8, 8)])
+def test_tconv(N, mode, variant, shape):
     n, h, w, cin, cout = shape
     dt = DT[mode]
     rng = np.random.default_rng(sum(shape))
+    if variant == 'dense':
+        return _tconv_dense(N, mode, shape, rng)
     x = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), dt)
     kt = (rng.normal(size=(2, 2, cout, cin)) / np.sqrt(cin)).astype(np.float32)
     b = rng.normal(size=cout).astype(np.float32)
@@ -193,6 +197,40 @@ def test_tconv(N, mode, shape):
     close(dxb.float().cpu().numpy(), rdx, mode)
     close(dk.cpu().numpy(), rdk, 'fp32', scale=np.abs(rdk).max() * (1 if mode == 'fp32' else 50))
     close(db.cpu().numpy(), rdb, 'fp32', scale=np.abs(rdb).max() * (1 if mode == 'fp32' else 50))
+
+
+def _tconv_dense(N, mode, shape, rng):
+    """every tensor a whole dense buffer: the TMA-staged small-channel kernels take the shapes they cover"""
+    n, h, w, cin, cout = shape
+    dt = DT[mode]
+    x = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), dt)
+    kt = (rng.normal(size=(2, 2, cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.normal(size=cout).astype(np.float32)
+    kd, bd = dev(kt), dev(b)
+    xb, _, _ = embed(x, dt)
+    yb = torch.full((n, 2 * h, 2 * w, cout), 5.0, dtype=dt, device='cuda')
+    xv, yv = view(N, xb, 0, cin), view(N, yb, 0, cout)
+    N.call('dnnca_convtranspose2x2_fprop', None, C.byref(xv), N.ptr(kd), N.ptr(bd), C.byref(yv), None)
+    sync()
+    close(yb.float().cpu().numpy(), rn.tconv2x2_fwd(x, kt, b), mode)
+    dy = q(rng.normal(size=(n, 2 * h, 2 * w, cout)).astype(np.float32), dt)
+    mask = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), dt)
+    dyb, _, _ = embed(dy, dt)
+    mb, _, _ = embed(mask, dt)
+    dxb = torch.full((n, h, w, cin), 9.0, dtype=dt, device='cuda')
+    dyv, mv, dxv = view(N, dyb, 0, cout), view(N, mb, 0, cin), view(N, dxb, 0, cin)
+    N.call('dnnca_convtranspose2x2_dgrad', None, C.byref(dyv), N.ptr(kd), C.byref(dxv), C.byref(mv), N.ACT_RELU, 0.0)
+    dk = torch.zeros(2, 2, cout, cin, dtype=torch.float32, device='cuda')
+    db = torch.zeros(cout, dtype=torch.float32, device='cuda')
+    N.call('dnnca_convtranspose2x2_wgrad', None, C.byref(xv), C.byref(dyv), N.ptr(dk), N.ptr(db))
+    sync()
+    rdx, rdk, rdb = rn.tconv2x2_bwd(x, kt, dy)
+    close(dxb.float().cpu().numpy(), rdx * (mask > 0), mode, scale=np.abs(rdx).max())
+    close(dk.cpu().numpy(), rdk, 'fp32', scale=np.abs(rdk).max() * (1 if mode == 'fp32' else 50))
+    close(db.cpu().numpy(), rdb, 'fp32', scale=np.abs(rdb).max() * (1 if mode == 'fp32' else 50))
+    N.call('dnnca_convtranspose2x2_dgrad', None, C.byref(dyv), N.ptr(kd), C.byref(dxv), None, N.ACT_NONE, 0.0)
+    sync()
+    close(dxb.float().cpu().numpy(), rdx, mode)
 
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
