@@ -77,6 +77,12 @@ int launch_tconv_wgrad_generic(cudaStream_t, const dnnca_tensor_t*, const dnnca_
 int try_tconv_fprop_small(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*);
 int try_tconv_dgrad_small(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
 int try_tconv_wgrad_small(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
+// tcgen05 implicit-GEMM family (conv_umma.cu)
+size_t umma_pack_bytes(int taps, int cin, int cout);
+int try_conv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, int, float, void*, size_t);
+int try_conv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, const dnnca_tensor_t*, int, float, void*, size_t);
+int try_tconv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, void*, size_t);
+int try_tconv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float, void*, size_t);
 // return 1 when the shape was handled, 0 when not covered, <0 on error
 int try_conv_fprop_small_f32(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
 int try_conv_fprop_small_bf16(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
@@ -117,9 +123,14 @@ static bool second_ok(const dnnca_tensor_t* a, const dnnca_tensor_t* b) {
   return b == nullptr || (view_ok(b) && same_nhw(a, b) && a->dtype == b->dtype);
 }
 
+extern "C" size_t dnnca_conv_workspace_bytes(int taps, int cin, int cout) {
+  if (taps <= 0 || cin <= 0 || cout <= 0) return 0;
+  return (umma_pack_bytes(taps, cin, cout) + 255) / 256 * 256;
+}
+
 extern "C" int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w,
                                   const float* bias, const dnnca_tensor_t* y, int ksize, int act, float alpha,
-                                  double* stats) {
+                                  double* stats, void* workspace, size_t workspace_bytes) {
   DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && w, "conv2d_fprop: bad tensor arguments");
   DNNCA_CHECK_ARG(same_nhw(x, y) && x->dtype == y->dtype, "conv2d_fprop: x and y must share n,h,w and dtype ('same' padding, stride 1)");
   DNNCA_CHECK_ARG(second_ok(x, x2), "conv2d_fprop: x2 must share n,h,w and dtype with x");
@@ -133,6 +144,11 @@ extern "C" int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const d
     if (r < 0) return r;
     if (r == 1) return DNNCA_OK;
   }
+  if (!g_force_generic) {
+    r = try_conv_fprop_umma(s, x, x2, w, bias, y, ksize, act, alpha, workspace, workspace_bytes);
+    if (r < 0) return r;
+    if (r == 1) return stats ? dnnca_channel_stats(stream, y, stats) : DNNCA_OK;
+  }
   r = launch_conv_fprop_generic(s, x, x2, w, bias, y, ksize, act, alpha);
   if (r != DNNCA_OK) return r;
   if (stats) return dnnca_channel_stats(stream, y, stats);
@@ -141,7 +157,7 @@ extern "C" int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const d
 
 extern "C" int dnnca_conv2d_dgrad(void* stream, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
                                   const dnnca_tensor_t* dx2, int ksize, const dnnca_tensor_t* mask, int act,
-                                  float alpha) {
+                                  float alpha, void* workspace, size_t workspace_bytes) {
   DNNCA_CHECK_ARG(view_ok(dz) && view_ok(dx) && w, "conv2d_dgrad: bad tensor arguments");
   DNNCA_CHECK_ARG(same_nhw(dz, dx) && dz->dtype == dx->dtype, "conv2d_dgrad: dz and dx must share n,h,w and dtype");
   DNNCA_CHECK_ARG(second_ok(dx, dx2), "conv2d_dgrad: dx2 must share n,h,w and dtype with dx");
@@ -152,6 +168,11 @@ extern "C" int dnnca_conv2d_dgrad(void* stream, const dnnca_tensor_t* dz, const 
   if (!g_force_generic && ksize == 3) {
     int r = dx->dtype == DNNCA_F32 ? try_conv_dgrad_small_f32(s, dz, w, dx, dx2, mask, act, alpha)
                                    : try_conv_dgrad_small_bf16(s, dz, w, dx, dx2, mask, act, alpha);
+    if (r < 0) return r;
+    if (r == 1) return DNNCA_OK;
+  }
+  if (!g_force_generic) {
+    int r = try_conv_dgrad_umma(s, dz, w, dx, dx2, ksize, mask, act, alpha, workspace, workspace_bytes);
     if (r < 0) return r;
     if (r == 1) return DNNCA_OK;
   }
@@ -175,11 +196,13 @@ extern "C" int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const d
 }
 
 extern "C" int dnnca_convtranspose2x2_fprop(void* stream, const dnnca_tensor_t* x, const float* k, const float* bias,
-                                            const dnnca_tensor_t* y, double* stats) {
+                                            const dnnca_tensor_t* y, double* stats, void* workspace,
+                                            size_t workspace_bytes) {
   DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && k, "convtranspose2x2_fprop: bad tensor arguments");
   DNNCA_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && x->dtype == y->dtype,
                   "convtranspose2x2_fprop: y must be [n,2h,2w,cout] with x's dtype");
   int r = g_force_generic ? 0 : try_tconv_fprop_small((cudaStream_t)stream, x, k, bias, y);
+  if (r == 0 && !g_force_generic) r = try_tconv_fprop_umma((cudaStream_t)stream, x, k, bias, y, workspace, workspace_bytes);
   if (r < 0) return r;
   if (r == 0) r = launch_tconv_fprop_generic((cudaStream_t)stream, x, k, bias, y);
   else r = DNNCA_OK;
@@ -190,7 +213,7 @@ extern "C" int dnnca_convtranspose2x2_fprop(void* stream, const dnnca_tensor_t* 
 
 extern "C" int dnnca_convtranspose2x2_dgrad(void* stream, const dnnca_tensor_t* dy, const float* k,
                                             const dnnca_tensor_t* dx, const dnnca_tensor_t* mask, int act,
-                                            float alpha) {
+                                            float alpha, void* workspace, size_t workspace_bytes) {
   DNNCA_CHECK_ARG(view_ok(dy) && view_ok(dx) && k, "convtranspose2x2_dgrad: bad tensor arguments");
   DNNCA_CHECK_ARG(dy->n == dx->n && dy->h == 2 * dx->h && dy->w == 2 * dx->w && dx->dtype == dy->dtype,
                   "convtranspose2x2_dgrad: dy must be [n,2h,2w,cout]");
@@ -198,6 +221,7 @@ extern "C" int dnnca_convtranspose2x2_dgrad(void* stream, const dnnca_tensor_t* 
   DNNCA_CHECK_ARG(act_ok(act), "convtranspose2x2_dgrad: unknown activation %d", act);
   if (!g_force_generic) {
     int r = try_tconv_dgrad_small((cudaStream_t)stream, dy, k, dx, mask, act, alpha);
+    if (r == 0) r = try_tconv_dgrad_umma((cudaStream_t)stream, dy, k, dx, mask, act, alpha, workspace, workspace_bytes);
     if (r < 0) return r;
     if (r == 1) return DNNCA_OK;
   }

@@ -243,9 +243,11 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const __grid_constan
 // ----------------------------------------------------------------------------
 template <typename T, int CA, int CB, int COUT>
 struct WGeom {
-  static constexpr int TYN = 4, TXN = 16, TW = TXN * PX, ROWS = TYN + 2, PITCH = TW + 4;
   static constexpr int CIN = CA + CB;
-  static constexpr int COB = COUT <= 6 ? COUT : (COUT % 6 == 0 ? 6 : 4);  // output channels per thread
+  // 8-row tiles halve the per-tile fixed cost; 4 rows when the planes of a wide layer would not let 2 CTAs share an SM
+  static constexpr int TYN = (CIN + COUT <= 24) ? 8 : 4, TXN = 16, TW = TXN * PX, ROWS = TYN + 2, PITCH = TW + 4;
+  // output channels per thread: 9*COB accumulator pairs must leave room for 2 CTAs (<= 128 registers/thread)
+  static constexpr int COB = COUT % 3 == 0 ? 3 : (COUT % 4 == 0 ? 4 : COUT);
   static constexpr int NCB = COUT / COB;
   static constexpr int TPS = CIN * NCB;                                    // threads per pixel-group slot
   static constexpr int G = 256 / TPS;
@@ -259,7 +261,7 @@ struct WGeom {
 };
 
 template <typename T, int CA, int CB, int COUT>
-__global__ void __launch_bounds__(256) conv3x3_small_wgrad_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(256, 2) conv3x3_small_wgrad_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapB,
                                                                  const __grid_constant__ CUtensorMap mapG,
                                                                  float* __restrict__ dw, float* __restrict__ db,

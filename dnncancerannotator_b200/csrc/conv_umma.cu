@@ -1,0 +1,495 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// One kernel serves Conv2D fprop, Conv2D dgrad, ConvTranspose2x2 fprop and ConvTranspose2x2 dgrad:
+//     D[128 pixels, BN channels] = sum over (tap, channel chunk)  A_tap[128 px, KC] * Wp_tap[BN, KC]^T
+//   * A tile  : an 8x16 pixel rectangle of the NHWC activation (4-D TMA box {KC, 16, 8, 1}); a filter tap
+//               is the same box at shifted coordinates and the TMA's out-of-bounds zero fill IS the
+//               'same' padding.  ConvT dgrad uses traversal stride 2 (one 2x2 tap per box).
+//               A second input tensor continues the K loop (virtual tf.concat, components.py:164).
+//   * B tile  : bf16 weights pre-packed K-major [tap][N][K] by pack_weights_kernel (3-D TMA box).
+//   * both land in 128/64/32-byte swizzled K-major shared memory = the canonical UMMA operand layout,
+//     so the shared-memory matrix descriptors need only (start address, SBO, swizzle mode).
+//   * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane) + TMEM allocator,
+//     warps 2..5 = epilogue: tcgen05.ld 32 lanes x 32 columns -> bias/activation (fprop) or act'(mask)
+//     (dgrad) -> bf16 -> 16-byte global stores straight into the (possibly channel-sliced) NHWC output;
+//     ConvT fprop scatters each 2x2 tap to its pixel-shuffled position.
+//   * full/empty mbarrier ring between TMA and MMA (tcgen05.commit frees a stage), one mbarrier hands
+//     the finished accumulator to the epilogue.
+// wgrad (both operands pixel-major = MN-major) is wgrad_umma_kernel below.
+// Reference call sites: layers.Conv2D components.py:47-50,123-126; Convolution2DTranspose :118-120.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace dnnca {
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t gets row (lane) t, v[j] = column j
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major swizzled operand: rows of SWB bytes, 8-row groups SBO = 8*SWB apart (mma_sm100_desc.hpp SmemDescriptor)
+template <int SWB>
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t saddr) {
+  constexpr uint64_t layout = SWB == 128 ? 2 : (SWB == 64 ? 4 : 6);   // SWIZZLE_128B / 64B / 32B
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((8 * SWB) >> 4) << 32;                   // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
+  d |= layout << 61;                                       // layout type, bits [61,64)
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);                       // F32 accum, BF16 A/B
+}
+
+// ---------------------------------------------------------------- weight packing
+// Conv2D  w[k,k,Cin,Cout] (HWIO) -> fprop pack  [tap][Cout][Cin]           (MODE 0)
+//                                 -> dgrad pack  [tap'][Cin][Cout], tap' = rot180(tap)   (MODE 1)
+// ConvT   k[2,2,Cout,Cin]        -> fprop pack  [1][tap*Cout + co][Cin]    (MODE 2: plain bf16 cast)
+//                                 -> dgrad pack  [tap][Cin][Cout]           (MODE 3)
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                          int mode, int taps, int cin, int cout) {
+  const long long total = (long long)taps * cin * cout;
+  const int kk = taps == 9 ? 3 : (taps == 4 ? 2 : 1);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    float v;
+    if (mode == 0) {            // e = (tap, co, ci)
+      const int ci = (int)(e % cin);
+      const long long t = e / cin;
+      const int co = (int)(t % cout), tap = (int)(t / cout);
+      v = w[((long long)tap * cin + ci) * cout + co];
+    } else if (mode == 1) {     // e = (tap', ci, co), source tap = rot180
+      const int co = (int)(e % cout);
+      const long long t = e / cout;
+      const int ci = (int)(t % cin), tp = (int)(t / cin);
+      const int a = kk - 1 - tp / kk, c = kk - 1 - tp % kk;
+      v = w[((long long)(a * kk + c) * cin + ci) * cout + co];
+    } else if (mode == 2) {
+      v = w[e];
+    } else {                    // e = (tap, ci, co) from k[tap][co][ci]
+      const int co = (int)(e % cout);
+      const long long t = e / cout;
+      const int ci = (int)(t % cin), tap = (int)(t / cin);
+      v = w[((long long)tap * cout + co) * cin + ci];
+    }
+    out[e] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------- the kernel
+enum { EPI_FPROP = 0, EPI_DGRAD = 1, EPI_TCONV = 2 };
+
+struct UArgs {
+  int taps, ktap;            // filter taps; ktap = sqrt(taps)
+  int sx, offbase;           // A coordinate = pixel*sx + (tap offset) + offbase   (conv: sx 1, offbase -pad)
+  int c_a, c_b;              // channels of input A / B (K extents)
+  int H, W;                  // pixel grid of the A tile space (= output grid except for ConvT fprop)
+  int tiles_x, tiles_y;
+  int epi, act;
+  float alpha;
+  const float* bias;
+  // outputs: channel-slice views (bf16).  ya: columns [0, split); yb: columns [split, N)
+  __nv_bfloat16* ya; long long ya_cs; int split;
+  __nv_bfloat16* yb; long long yb_cs;
+  const __nv_bfloat16* mask; long long mask_cs;   // dgrad: post-activation output of the layer that produced dx
+  int n_total;               // total GEMM N
+  int cout_t;                // ConvT fprop: channels per tap
+};
+
+template <int BN, int KC>
+struct UGeom {
+  static constexpr int SWB = KC * 2;
+  static constexpr int A_BYTES = 128 * SWB, B_BYTES = BN * SWB, STAGE = A_BYTES + B_BYTES;
+  static constexpr int BUDGET = BN > 128 ? 196 * 1024 : 100 * 1024;
+  static constexpr int STAGES_ = (BUDGET - 2048) / STAGE;
+  static constexpr int STAGES = STAGES_ > 8 ? 8 : STAGES_;
+  static constexpr int SMEM = 1024 + STAGES * STAGE + 1024;     // + alignment slack
+  static constexpr int TCOLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                       const __grid_constant__ CUtensorMap mapB,
+                                                       const __grid_constant__ CUtensorMap mapW, UArgs a) {
+  using G = UGeom<BN, KC>;
+  constexpr int SWB = G::SWB, STAGES = G::STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte aligned stage ring (128B swizzle atoms), control block in the first 1024 bytes
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [STAGES]
+  uint64_t* empty = full + STAGES;                               // [STAGES]
+  uint64_t* accum = empty + STAGES;                              // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  unsigned char* ring = smem + 1024;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int b = blockIdx.x;
+  const int tix = b % a.tiles_x; b /= a.tiles_x;
+  const int tiy = b % a.tiles_y;
+  const int n = b / a.tiles_y;
+  const int x0 = tix * 16, y0 = tiy * 8;
+  const int n0 = blockIdx.y * BN;
+
+  const int kca = a.c_a / KC, kcb = a.c_b / KC;
+  const int kiters = a.taps * (kca + kcb);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, G::TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&mapA);
+      tma_prefetch_desc(&mapW);
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(empty + s, ((it / STAGES) - 1) & 1);
+        // iteration order: input (A then B) -> tap -> channel chunk
+        int r = it;
+        const bool second = r >= a.taps * kca;
+        if (second) r -= a.taps * kca;
+        const int kcn = second ? kcb : kca;
+        const int tap = r / kcn, kc = r % kcn;
+        const int ox = (tap % a.ktap) + a.offbase, oy = (tap / a.ktap) + a.offbase;
+        unsigned char* sa = ring + s * G::STAGE;
+        mbar_expect_tx(full + s, G::STAGE);
+        tma_load_4d(sa, second ? &mapB : &mapA, full + s, kc * KC, x0 * a.sx + ox, y0 * a.sx + oy, n);
+        // weights: {K (all inputs), N, tap}
+        const int kglob = (second ? a.c_a : 0) + kc * KC;
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(sa + G::A_BYTES)), "l"(reinterpret_cast<uint64_t>(&mapW)), "r"(smem_u32(full + s)), "r"(kglob),
+            "r"(n0), "r"(tap)
+            : "memory");
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN < 16 ? 16 : BN, 0, 0);
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full + s, (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + s * G::STAGE), sb = sa + G::A_BYTES;
+        const uint64_t da = kmajor_desc<SWB>(sa), db = kmajor_desc<SWB>(sb);
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k)   // +32 bytes per K=16 step inside the swizzle row (start-address field is >>4)
+          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+        umma_commit(empty + s);             // frees the stage when these MMAs retire
+      }
+      umma_commit(accum);                   // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4).. =====
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;           // row of the 128-pixel tile
+    const int ty = r >> 4, tx = r & 15;
+    const int gy = y0 + ty, gx = x0 + tx;
+    const bool inside = gy < a.H && gx < a.W;
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    constexpr int CH = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += CH) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+      if (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+      tmem_ld_wait();
+      const int ncol = n0 + c0;               // first GEMM column of this chunk
+      if (!inside || ncol >= a.n_total) continue;
+      __nv_bfloat16* dst;
+      int ch;                                  // channel inside the destination view
+      long long pix;
+      if (a.epi == EPI_TCONV) {
+        const int tap = ncol / a.cout_t;
+        ch = ncol - tap * a.cout_t;
+        pix = ((long long)n * (2 * a.H) + 2 * gy + (tap >> 1)) * (2 * a.W) + 2 * gx + (tap & 1);
+        dst = a.ya + pix * a.ya_cs + ch;
+      } else {
+        pix = ((long long)n * a.H + gy) * a.W + gx;
+        if (ncol < a.split) { ch = ncol; dst = a.ya + pix * a.ya_cs + ch; }
+        else { ch = ncol - a.split; dst = a.yb + pix * a.yb_cs + ch; }
+      }
+      float f[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+      if (a.epi == EPI_DGRAD) {
+        if (a.mask && ncol < a.split) {
+          const uint4* mp = reinterpret_cast<const uint4*>(a.mask + pix * a.mask_cs + ch);
+#pragma unroll
+          for (int q = 0; q < CH / 8; ++q) {
+            const uint4 m = mp[q];
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[q * 8 + 2 * j] *= act_grad(__uint_as_float(mw[j] << 16), a.act, a.alpha);
+              f[q * 8 + 2 * j + 1] *= act_grad(__uint_as_float(mw[j] & 0xffff0000u), a.act, a.alpha);
+            }
+          }
+        }
+      } else {
+        const int bch = a.epi == EPI_TCONV ? ch : ncol;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j] + (a.bias ? __ldg(a.bias + bch + j) : 0.f), a.act, a.alpha);
+      }
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int q = 0; q < CH / 8; ++q) {
+        uint4 o;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(f[q * 8 + 0], f[q * 8 + 1]);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(f[q * 8 + 2], f[q * 8 + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(f[q * 8 + 4], f[q * 8 + 5]);
+        __nv_bfloat162 p3 = __floats2bfloat162_rn(f[q * 8 + 6], f[q * 8 + 7]);
+        o.x = *reinterpret_cast<uint32_t*>(&p0);
+        o.y = *reinterpret_cast<uint32_t*>(&p1);
+        o.z = *reinterpret_cast<uint32_t*>(&p2);
+        o.w = *reinterpret_cast<uint32_t*>(&p3);
+        d4[q] = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, G::TCOLS);
+}
+
+// ---------------------------------------------------------------- host side
+static bool act_map(CUtensorMap* m, const dnnca_tensor_t* t, int kc, int estride) {
+  // 4-D {C, W, H, N} view of a (channel-sliced) NHWC bf16 tensor; box {kc, 16, 8, 1}
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  char* base = reinterpret_cast<char*>(t->data) + (size_t)t->coff * 2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (t->cstride * 2) % 16) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
+  cuuint64_t strides[3] = {(cuuint64_t)t->cstride * 2, (cuuint64_t)t->w * t->cstride * 2, (cuuint64_t)t->h * t->w * t->cstride * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, 16, 8, 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  // with a traversal stride the box extent is given in tensor elements (16 px * stride)
+  box[1] = 16 * estride;
+  box[2] = 8 * estride;
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool weight_map(CUtensorMap* m, const void* wp, int ktot, int ntot, int taps, int kc, int bn) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)ntot, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)ktot * ntot * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)bn, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int KC>
+static int launch_umma(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mW, const UArgs& a,
+                       int nimg) {
+  using G = UGeom<BN, KC>;
+  auto kern = conv_umma_kernel<BN, KC>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_umma: cudaFuncSetAttribute");
+    done = true;
+  }
+  dim3 grid((unsigned)((long long)a.tiles_x * a.tiles_y * nimg), (unsigned)((a.n_total + BN - 1) / BN));
+  kern<<<grid, 192, G::SMEM, s>>>(mA, mB, mW, a);
+  DNNCA_LAUNCH_CHECK("conv_umma");
+  return 1;
+}
+
+static int pick_kc(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
+static int gcd_kc(int a, int b) { return a < b ? a : b; }
+
+template <int KC>
+static int dispatch_bn(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mW, const UArgs& a,
+                       int nimg, int bn) {
+  switch (bn) {
+    case 256: return launch_umma<256, KC>(s, mA, mB, mW, a, nimg);
+    case 128: return launch_umma<128, KC>(s, mA, mB, mW, a, nimg);
+    case 64: return launch_umma<64, KC>(s, mA, mB, mW, a, nimg);
+    case 32: return launch_umma<32, KC>(s, mA, mB, mW, a, nimg);
+    case 16: return launch_umma<16, KC>(s, mA, mB, mW, a, nimg);
+  }
+  return 0;
+}
+
+// N tile: the largest of 256/128/64/32/16 dividing `unit` (columns that must not straddle a destination boundary)
+static int pick_bn(int unit, int ntotal) {
+  for (int bn : {256, 128, 64, 32, 16})
+    if (unit % bn == 0 && bn <= ntotal) return bn;
+  return 0;
+}
+
+size_t umma_pack_bytes(int taps, int cin, int cout) { return (size_t)taps * cin * cout * 2; }
+
+static int pack(cudaStream_t s, const float* w, void* out, int mode, int taps, int cin, int cout) {
+  const long long total = (long long)taps * cin * cout;
+  pack_weights_kernel<<<grid_for(total, 256 * 4, 4), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(out), mode, taps, cin, cout);
+  DNNCA_LAUNCH_CHECK("pack_weights");
+  return DNNCA_OK;
+}
+
+static bool bf16_view16(const dnnca_tensor_t* t) {
+  return t && t->dtype == DNNCA_BF16 && t->c % 16 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
+}
+
+// returns 1 handled / 0 not covered / <0 error
+int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w, const float* bias,
+                        const dnnca_tensor_t* y, int k, int act, float alpha, void* ws, size_t ws_bytes) {
+  if (!ws || !bf16_view16(x) || (x2 && !bf16_view16(x2)) || !bf16_view16(y)) return 0;
+  const int ca = x->c, cb = x2 ? x2->c : 0, cin = ca + cb, cout = y->c, taps = k * k;
+  if (ws_bytes < umma_pack_bytes(taps, cin, cout)) return 0;
+  const int kc = cb ? gcd_kc(pick_kc(ca), pick_kc(cb)) : pick_kc(ca);
+  const int bn = pick_bn(cout, cout);
+  if (!kc || !bn) return 0;
+  int r = pack(s, w, ws, 0, taps, cin, cout);
+  if (r != DNNCA_OK) return r;
+  CUtensorMap mA, mB, mW;
+  if (!act_map(&mA, x, kc, 1)) return 0;
+  mB = mA;
+  if (x2 && !act_map(&mB, x2, kc, 1)) return 0;
+  if (!weight_map(&mW, ws, cin, cout, taps, kc, bn)) return 0;
+  UArgs a{};
+  a.taps = taps; a.ktap = k; a.sx = 1; a.offbase = -(k / 2); a.c_a = ca; a.c_b = cb; a.H = x->h; a.W = x->w;
+  a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + 7) / 8; a.epi = EPI_FPROP; a.act = act; a.alpha = alpha; a.bias = bias;
+  a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
+  a.mask = nullptr; a.n_total = cout; a.cout_t = cout;
+  if (kc == 64) return dispatch_bn<64>(s, mA, mB, mW, a, x->n, bn);
+  if (kc == 32) return dispatch_bn<32>(s, mA, mB, mW, a, x->n, bn);
+  return dispatch_bn<16>(s, mA, mB, mW, a, x->n, bn);
+}
+
+int try_conv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
+                        const dnnca_tensor_t* dx2, int k, const dnnca_tensor_t* mask, int act, float alpha, void* ws,
+                        size_t ws_bytes) {
+  if (!ws || !bf16_view16(dz) || !bf16_view16(dx) || (dx2 && !bf16_view16(dx2)) || (mask && !bf16_view16(mask))) return 0;
+  const int cout = dz->c, ca = dx->c, cb = dx2 ? dx2->c : 0, cin = ca + cb, taps = k * k;
+  if (ws_bytes < umma_pack_bytes(taps, cin, cout)) return 0;
+  const int kc = pick_kc(cout);
+  const int bn = pick_bn(cb ? (ca < cb ? ca : cb) : ca, cin);
+  if (!kc || !bn || (cb && (ca % bn || cb % bn))) return 0;
+  int r = pack(s, w, ws, 1, taps, cin, cout);     // [tap'][Cin][Cout]: GEMM N = layer Cin, K = layer Cout
+  if (r != DNNCA_OK) return r;
+  CUtensorMap mA, mW;
+  if (!act_map(&mA, dz, kc, 1)) return 0;
+  if (!weight_map(&mW, ws, cout, cin, taps, kc, bn)) return 0;
+  UArgs a{};
+  a.taps = taps; a.ktap = k; a.sx = 1; a.offbase = -(k / 2); a.c_a = cout; a.c_b = 0; a.H = dx->h; a.W = dx->w;
+  a.tiles_x = (dx->w + 15) / 16; a.tiles_y = (dx->h + 7) / 8; a.epi = EPI_DGRAD; a.act = act; a.alpha = alpha; a.bias = nullptr;
+  a.ya = reinterpret_cast<__nv_bfloat16*>(dx->data) + dx->coff; a.ya_cs = dx->cstride; a.split = ca;
+  a.yb = dx2 ? reinterpret_cast<__nv_bfloat16*>(dx2->data) + dx2->coff : a.ya; a.yb_cs = dx2 ? dx2->cstride : a.ya_cs;
+  a.mask = mask ? reinterpret_cast<const __nv_bfloat16*>(mask->data) + mask->coff : nullptr; a.mask_cs = mask ? mask->cstride : 0;
+  a.n_total = cin; a.cout_t = cin;
+  if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, dx->n, bn);
+  if (kc == 32) return dispatch_bn<32>(s, mA, mA, mW, a, dx->n, bn);
+  return dispatch_bn<16>(s, mA, mA, mW, a, dx->n, bn);
+}
+
+int try_tconv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const float* kw, const float* bias, const dnnca_tensor_t* y,
+                         void* ws, size_t ws_bytes) {
+  if (!ws || !bf16_view16(x) || !bf16_view16(y)) return 0;
+  const int cin = x->c, cout = y->c;
+  if (ws_bytes < umma_pack_bytes(4, cin, cout)) return 0;
+  const int kc = pick_kc(cin);
+  const int bn = pick_bn(cout, 4 * cout);
+  if (!kc || !bn) return 0;
+  int r = pack(s, kw, ws, 2, 4, cin, cout);       // [tap*Cout + co][Cin]: one GEMM with N = 4*Cout
+  if (r != DNNCA_OK) return r;
+  CUtensorMap mA, mW;
+  if (!act_map(&mA, x, kc, 1)) return 0;
+  if (!weight_map(&mW, ws, cin, 4 * cout, 1, kc, bn)) return 0;
+  UArgs a{};
+  a.taps = 1; a.ktap = 1; a.sx = 1; a.offbase = 0; a.c_a = cin; a.c_b = 0; a.H = x->h; a.W = x->w;
+  a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + 7) / 8; a.epi = EPI_TCONV; a.act = DNNCA_ACT_NONE; a.alpha = 0.f; a.bias = bias;
+  a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = 4 * cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
+  a.mask = nullptr; a.n_total = 4 * cout; a.cout_t = cout;
+  if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, x->n, bn);
+  if (kc == 32) return dispatch_bn<32>(s, mA, mA, mW, a, x->n, bn);
+  return dispatch_bn<16>(s, mA, mA, mW, a, x->n, bn);
+}
+
+int try_tconv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dy, const float* kw, const dnnca_tensor_t* dx,
+                         const dnnca_tensor_t* mask, int act, float alpha, void* ws, size_t ws_bytes) {
+  if (!ws || !bf16_view16(dy) || !bf16_view16(dx) || (mask && !bf16_view16(mask))) return 0;
+  const int cout = dy->c, cin = dx->c;
+  if (ws_bytes < umma_pack_bytes(4, cin, cout)) return 0;
+  const int kc = pick_kc(cout);
+  const int bn = pick_bn(cin, cin);
+  if (!kc || !bn) return 0;
+  int r = pack(s, kw, ws, 3, 4, cin, cout);       // [tap][Cin][Cout]
+  if (r != DNNCA_OK) return r;
+  CUtensorMap mA, mW;
+  if (!act_map(&mA, dy, kc, 2)) return 0;          // traversal stride 2: one 2x2 tap of dy per box
+  if (!weight_map(&mW, ws, cout, cin, 4, kc, bn)) return 0;
+  UArgs a{};
+  a.taps = 4; a.ktap = 2; a.sx = 2; a.offbase = 0; a.c_a = cout; a.c_b = 0; a.H = dx->h; a.W = dx->w;
+  a.tiles_x = (dx->w + 15) / 16; a.tiles_y = (dx->h + 7) / 8; a.epi = EPI_DGRAD; a.act = act; a.alpha = alpha; a.bias = nullptr;
+  a.ya = reinterpret_cast<__nv_bfloat16*>(dx->data) + dx->coff; a.ya_cs = dx->cstride; a.split = cin; a.yb = a.ya; a.yb_cs = a.ya_cs;
+  a.mask = mask ? reinterpret_cast<const __nv_bfloat16*>(mask->data) + mask->coff : nullptr; a.mask_cs = mask ? mask->cstride : 0;
+  a.n_total = cin; a.cout_t = cin;
+  if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, dx->n, bn);
+  if (kc == 32) return dispatch_bn<32>(s, mA, mA, mW, a, dx->n, bn);
+  return dispatch_bn<16>(s, mA, mA, mW, a, dx->n, bn);
+}
+
+}  // namespace dnnca

@@ -44,7 +44,7 @@ class _FoldedConv(R.Op):
         torch.mul(ps.view(f'{self.conv}/kernel'), s, out=self.wf)
         torch.addcmul(ps.view(f'{self.bn}/beta'), ps.view(f'{self.bn}/moving_mean'), s, value=-1.0, out=self.bf)
         N.call('dnnca_conv2d_fprop', N.stream_ptr(), self.x.ct(), None, N.ptr(self.wf), N.ptr(self.bf), self.y.ct(),
-               self.k, self.act, 0.0, None)
+               self.k, self.act, 0.0, None, None, 0)
 
 
 class _Affine:

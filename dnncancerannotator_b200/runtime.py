@@ -206,6 +206,20 @@ class TRef:
 # ----------------------------------------------------------------------------
 # ops
 # ----------------------------------------------------------------------------
+def conv_workspace(plan, taps, inputs, y):
+    """bf16 weight-repack workspace of the tcgen05 kernels (dnnca_conv_workspace_bytes), or None when the layer
+    cannot take the tensor-core path (fp32 mode, channel counts that are not multiples of 16)."""
+    ins = [t for t in inputs if t is not None]
+    if plan.dtype != torch.bfloat16 or any(t.c % 16 for t in ins) or y.c % 16:
+        return None
+    nbytes = N.lib().dnnca_conv_workspace_bytes(taps, sum(t.c for t in ins), y.c)
+    return torch.empty(nbytes, dtype=torch.uint8, device=plan.device)
+
+
+def ws_args(ws):
+    return (N.ptr(ws), ws.numel()) if ws is not None else (None, 0)
+
+
 class Op:
     def fwd(self, train):
         raise NotImplementedError
@@ -225,14 +239,18 @@ class ConvOp(Op):
         self.p, self.x, self.x2, self.y, self.kernel, self.bias, self.k = plan, x, x2, y, kernel, bias, ksize
         self.act = act or (N.ACT_NONE, 0.0)
         self.stats = stats
+        self.ws = None
         if act and act[0] != N.ACT_NONE:
             y.act = act
+
+    def allocate(self, training):
+        self.ws = conv_workspace(self.p, self.k * self.k, [self.x, self.x2], self.y) if self.ws is None else self.ws
 
     def fwd(self, train):
         ps = self.p.params
         N.call('dnnca_conv2d_fprop', N.stream_ptr(), self.x.ct(), self.x2.ct() if self.x2 else None,
                ps.ptr(self.kernel), ps.ptr(self.bias), self.y.ct(), self.k, self.act[0], self.act[1],
-               self.stats.fwd_ptr() if (self.stats and train) else None)
+               self.stats.fwd_ptr() if (self.stats and train) else None, *ws_args(self.ws))
 
     def bwd(self):
         ps = self.p.params
@@ -242,7 +260,7 @@ class ConvOp(Op):
         if self.x.needs_grad:
             m, a, al = self.x.mask_args()
             N.call('dnnca_conv2d_dgrad', s, self.y.gct(), ps.ptr(self.kernel), self.x.gct(),
-                   self.x2.gct() if self.x2 else None, self.k, m, a, al)
+                   self.x2.gct() if self.x2 else None, self.k, m, a, al, *ws_args(self.ws))
 
 
 class TConvOp(Op):
@@ -250,11 +268,15 @@ class TConvOp(Op):
 
     def __init__(self, plan, x, y, kernel, bias, stats=None):
         self.p, self.x, self.y, self.kernel, self.bias, self.stats = plan, x, y, kernel, bias, stats
+        self.ws = None
+
+    def allocate(self, training):
+        self.ws = conv_workspace(self.p, 4, [self.x], self.y) if self.ws is None else self.ws
 
     def fwd(self, train):
         ps = self.p.params
         N.call('dnnca_convtranspose2x2_fprop', N.stream_ptr(), self.x.ct(), ps.ptr(self.kernel), ps.ptr(self.bias),
-               self.y.ct(), self.stats.fwd_ptr() if (self.stats and train) else None)
+               self.y.ct(), self.stats.fwd_ptr() if (self.stats and train) else None, *ws_args(self.ws))
 
     def bwd(self):
         ps = self.p.params
@@ -262,7 +284,8 @@ class TConvOp(Op):
         N.call('dnnca_convtranspose2x2_wgrad', s, self.x.ct(), self.y.gct(), ps.gptr(self.kernel), ps.gptr(self.bias))
         if self.x.needs_grad:
             m, a, al = self.x.mask_args()
-            N.call('dnnca_convtranspose2x2_dgrad', s, self.y.gct(), ps.ptr(self.kernel), self.x.gct(), m, a, al)
+            N.call('dnnca_convtranspose2x2_dgrad', s, self.y.gct(), ps.ptr(self.kernel), self.x.gct(), m, a, al,
+                   *ws_args(self.ws))
 
 
 class PoolOp(Op):

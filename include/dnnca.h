@@ -29,6 +29,7 @@
 #ifndef DNNCA_H_
 #define DNNCA_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -69,6 +70,14 @@ DNNCA_API int dnnca_debug_force_generic(int on);
 DNNCA_API long long dnnca_debug_launch_count(int reset);
 
 /* ---------------------------------------------------------------------------
+ * Workspace of the tensor-core (tcgen05) kernels: room for the bf16 K-major repack of one layer's
+ * weights, `taps * cin * cout * 2` bytes (taps = k*k, or 4 for ConvT).  The caller owns it (one per
+ * layer or one shared scratch on a single stream); every fprop/dgrad call re-packs from the fp32
+ * masters, so nothing in it is state.  workspace == NULL selects the CUDA-core kernels.
+ * ------------------------------------------------------------------------- */
+DNNCA_API size_t dnnca_conv_workspace_bytes(int taps, int cin, int cout);
+
+/* ---------------------------------------------------------------------------
  * Conv2D, stride 1, 'same' zero padding, k in {1,3}
  *   replaces layers.Conv2D at components.py:47-50, components.py:123-126,
  *   multiresunet.py:51-52 (use_bias=False -> bias == NULL).
@@ -82,7 +91,7 @@ DNNCA_API long long dnnca_debug_launch_count(int reset);
  * ------------------------------------------------------------------------- */
 DNNCA_API int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w,
                                  const float* bias, const dnnca_tensor_t* y, int ksize, int act, float alpha,
-                                 double* stats);
+                                 double* stats, void* workspace, size_t workspace_bytes);
 
 /* Gradient w.r.t. the conv input(s) (tf.GradientTape over the Conv2D above):
  *   [dx | dx2] = dz (*) rot180(w)^T ; dx2 (may be NULL) receives the channels of the
@@ -93,7 +102,7 @@ DNNCA_API int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const dn
  *   merges and masks). */
 DNNCA_API int dnnca_conv2d_dgrad(void* stream, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
                                  const dnnca_tensor_t* dx2, int ksize, const dnnca_tensor_t* mask, int act,
-                                 float alpha);
+                                 float alpha, void* workspace, size_t workspace_bytes);
 
 /* Gradient w.r.t. kernel and bias: dw[k,k,Cx+Cx2,Cout] and db[Cout] are
  * ACCUMULATED (+=) in fp32 (caller zeroes the flat gradient buffer once per
@@ -108,9 +117,10 @@ DNNCA_API int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const dn
  *   y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci]*k[a,b,co,ci] + bias[co]
  * ------------------------------------------------------------------------- */
 DNNCA_API int dnnca_convtranspose2x2_fprop(void* stream, const dnnca_tensor_t* x, const float* k, const float* bias,
-                                 const dnnca_tensor_t* y, double* stats);
+                                 const dnnca_tensor_t* y, double* stats, void* workspace, size_t workspace_bytes);
 DNNCA_API int dnnca_convtranspose2x2_dgrad(void* stream, const dnnca_tensor_t* dy, const float* k, const dnnca_tensor_t* dx,
-                                 const dnnca_tensor_t* mask, int act, float alpha);
+                                 const dnnca_tensor_t* mask, int act, float alpha, void* workspace,
+                                 size_t workspace_bytes);
 DNNCA_API int dnnca_convtranspose2x2_wgrad(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* dy, float* dk,
                                  float* db);
 

@@ -90,6 +90,10 @@ CONV_SHAPES = [  # (n, h, w, c_x, c_x2, cout, k)
 def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
     """dense: tensors are whole buffers (the TMA-staged small-channel kernels take the shapes they cover);
     sliced: every tensor is a channel slice of a wider buffer; generic: shape-generic kernels forced."""
+    _conv_case(N, mode, variant, shape)
+
+
+def _conv_case(N, mode, variant, shape):
     n, h, w, ca, cb, cout, k = shape
     cin = ca + cb
     dt = DT[mode]
@@ -99,7 +103,17 @@ def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
     b = rng.normal(size=cout).astype(np.float32)
     lib = N.lib()
     old = lib.dnnca_debug_force_generic(1 if variant == 'generic' else 0)
-    P = (lambda lo, hi: (lo, hi)) if variant == 'sliced' else (lambda lo, hi: (0, 0))
+    P = (lambda lo, hi: (lo, hi)) if variant == 'sliced' else ((lambda lo, hi: (8 * lo, 8 * hi)) if variant == 'umma_sliced' else (lambda lo, hi: (0, 0)))
+    if variant == 'umma_sliced':
+        variant = 'umma'
+        sliced = True
+    else:
+        sliced = variant == 'sliced'
+    WS = (None, 0)
+    if variant == 'umma':
+        ws = torch.zeros(int(lib.dnnca_conv_workspace_bytes(k * k, cin, cout)), dtype=torch.uint8, device='cuda')
+        _KEEP.append(ws)
+        WS = (N.ptr(ws), ws.numel())
     try:
         wd, bd = dev(wt), dev(b)
         xa_b, xa_o, _ = embed(x[..., :ca], dt, *P(2, 1))
@@ -115,12 +129,12 @@ def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
             stats = torch.zeros(2 * cout, dtype=torch.float64, device='cuda')
             yv = view(N, yb, lo, cout)
             N.call('dnnca_conv2d_fprop', None, C.byref(xav), xbp, N.ptr(wd), N.ptr(bd), C.byref(yv), k, act, alpha,
-                   N.ptr(stats))
+                   N.ptr(stats), *WS)
             sync()
             ref = ops.activation(ops.conv2d(torch.from_numpy(x), torch.from_numpy(wt), torch.from_numpy(b)), tact).numpy()
             got = yb[..., lo:lo + cout].float().cpu().numpy()
             close(got, ref, mode)
-            if variant == 'sliced':
+            if sliced:
                 assert (yb[..., :lo].float() == 5.0).all() and (yb[..., lo + cout:].float() == 5.0).all(), 'wrote outside the slice'
             st = stats.cpu().numpy()
             np.testing.assert_allclose(st[:cout], got.astype(np.float64).sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
@@ -136,7 +150,7 @@ def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
         dzv, mv, dxv = view(N, dzb, dzo, cout), view(N, mb, mo, ca), view(N, dxb, lo, ca)
         dx2v = view(N, dx2b, lo, max(cb, 1))
         dx2p = C.byref(dx2v) if cb else None
-        N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(wd), C.byref(dxv), dx2p, k, C.byref(mv), N.ACT_RELU, 0.0)
+        N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(wd), C.byref(dxv), dx2p, k, C.byref(mv), N.ACT_RELU, 0.0, *WS)
         dw = torch.zeros(k, k, cin, cout, dtype=torch.float32, device='cuda')
         db = torch.zeros(cout, dtype=torch.float32, device='cuda')
         N.call('dnnca_conv2d_wgrad', None, C.byref(xav), xbp, C.byref(dzv), N.ptr(dw), N.ptr(db), k)
@@ -145,12 +159,12 @@ def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
         close(dxb[..., lo:lo + ca].float().cpu().numpy(), rdx[..., :ca] * (mask > 0), mode, scale=np.abs(rdx).max())
         if cb:
             close(dx2b[..., lo:].float().cpu().numpy(), rdx[..., ca:], mode, scale=np.abs(rdx).max())
-        if variant == 'sliced':
+        if sliced:
             assert (dxb[..., :lo].float() == 3.0).all()
         close(dw.cpu().numpy(), rdw, 'fp32', scale=np.abs(rdw).max() * (1 if mode == 'fp32' else 50))
         close(db.cpu().numpy(), rdb, 'fp32', scale=np.abs(rdb).max() * (1 if mode == 'fp32' else 50))
         # unmasked dgrad
-        N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(wd), C.byref(dxv), dx2p, k, None, N.ACT_NONE, 0.0)
+        N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(wd), C.byref(dxv), dx2p, k, None, N.ACT_NONE, 0.0, *WS)
         sync()
         close(dxb[..., lo:lo + ca].float().cpu().numpy(), rdx[..., :ca], mode, scale=np.abs(rdx).max())
     finally:
@@ -160,7 +174,8 @@ def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
 @pytest.mark.parametrize('variant', ['dense', 'sliced'])
 @pytest.mark.parametrize('shape', [(2, 8, 8, 12, 12), (1, 6, 16, 24, 8), (2, 5, 7, 6, 3), (1, 4, 4, 40, 70),
-                                   (1, 20, 72, 12, 6), (2, 12, 40, 6, 3), (1, 36, 32, 8, 8)])
+                                   (1, 20, 72, 12, 6), (2, 12, 40, 6, 3), (1, 36, 32, 8, 8),
+                                   (1, 8, 16, 64, 32), (2, 16, 16, 128, 64), (1, 8, 32, 32, 16), (1, 8, 16, 384, 128)])
 def test_tconv(N, mode, variant, shape):
     n, h, w, cin, cout = shape
     dt = DT[mode]
@@ -174,7 +189,7 @@ def test_tconv(N, mode, variant, shape):
     yb = torch.full((n, 2 * h, 2 * w, 2 * cout), 5.0, dtype=dt, device='cuda')   # concat buffer, tconv half first
     stats = torch.zeros(2 * cout, dtype=torch.float64, device='cuda')
     xv, yv = view(N, xb, xo, cin), view(N, yb, 0, cout)
-    N.call('dnnca_convtranspose2x2_fprop', None, C.byref(xv), N.ptr(dev(kt)), N.ptr(dev(b)), C.byref(yv), N.ptr(stats))
+    N.call('dnnca_convtranspose2x2_fprop', None, C.byref(xv), N.ptr(dev(kt)), N.ptr(dev(b)), C.byref(yv), N.ptr(stats), None, 0)
     sync()
     ref = rn.tconv2x2_fwd(x, kt, b)
     got = yb[..., :cout].float().cpu().numpy()
@@ -187,7 +202,7 @@ def test_tconv(N, mode, variant, shape):
     mb, mo, _ = embed(mask, dt)
     dxb = torch.zeros(n, h, w, cin, dtype=dt, device='cuda')
     dyv, mv, dxv = view(N, dyb, dyo, cout), view(N, mb, mo, cin), view(N, dxb, 0, cin)
-    N.call('dnnca_convtranspose2x2_dgrad', None, C.byref(dyv), N.ptr(dev(kt)), C.byref(dxv), C.byref(mv), N.ACT_LEAKY, 0.3)
+    N.call('dnnca_convtranspose2x2_dgrad', None, C.byref(dyv), N.ptr(dev(kt)), C.byref(dxv), C.byref(mv), N.ACT_LEAKY, 0.3, None, 0)
     dk = torch.zeros(2, 2, cout, cin, dtype=torch.float32, device='cuda')
     db = torch.zeros(cout, dtype=torch.float32, device='cuda')
     N.call('dnnca_convtranspose2x2_wgrad', None, C.byref(xv), C.byref(dyv), N.ptr(dk), N.ptr(db))
@@ -199,6 +214,20 @@ def test_tconv(N, mode, variant, shape):
     close(db.cpu().numpy(), rdb, 'fp32', scale=np.abs(rdb).max() * (1 if mode == 'fp32' else 50))
 
 
+UMMA_SHAPES = [  # (n, h, w, c_x, c_x2, cout, k): channel counts the tcgen05 implicit-GEMM kernels take
+    (1, 16, 32, 64, 0, 64, 3), (2, 8, 16, 16, 0, 32, 3), (1, 16, 16, 64, 64, 64, 3), (1, 8, 16, 128, 0, 256, 3),
+    (1, 24, 48, 32, 32, 32, 3), (2, 16, 16, 16, 16, 16, 3), (1, 8, 32, 256, 0, 128, 3), (1, 12, 20, 64, 0, 48, 3),
+    (1, 16, 16, 64, 0, 64, 1), (1, 8, 16, 512, 512, 512, 3),
+]
+
+
+@pytest.mark.parametrize('variant', ['umma', 'umma_sliced'])
+@pytest.mark.parametrize('shape', UMMA_SHAPES)
+def test_conv_umma(N, variant, shape):
+    """tcgen05/TMEM/TMA implicit-GEMM fprop + dgrad (bf16), dense and channel-sliced views; wgrad rides along."""
+    _conv_case(N, 'bf16', variant, shape)
+
+
 def _tconv_dense(N, mode, shape, rng):
     """every tensor a whole dense buffer: the TMA-staged small-channel kernels take the shapes they cover"""
     n, h, w, cin, cout = shape
@@ -207,10 +236,15 @@ def _tconv_dense(N, mode, shape, rng):
     kt = (rng.normal(size=(2, 2, cout, cin)) / np.sqrt(cin)).astype(np.float32)
     b = rng.normal(size=cout).astype(np.float32)
     kd, bd = dev(kt), dev(b)
+    WS = (None, 0)
+    if mode == 'bf16' and cin % 16 == 0 and cout % 16 == 0:      # tensor-core path
+        ws = torch.zeros(int(N.lib().dnnca_conv_workspace_bytes(4, cin, cout)), dtype=torch.uint8, device='cuda')
+        _KEEP.append(ws)
+        WS = (N.ptr(ws), ws.numel())
     xb, _, _ = embed(x, dt)
     yb = torch.full((n, 2 * h, 2 * w, cout), 5.0, dtype=dt, device='cuda')
     xv, yv = view(N, xb, 0, cin), view(N, yb, 0, cout)
-    N.call('dnnca_convtranspose2x2_fprop', None, C.byref(xv), N.ptr(kd), N.ptr(bd), C.byref(yv), None)
+    N.call('dnnca_convtranspose2x2_fprop', None, C.byref(xv), N.ptr(kd), N.ptr(bd), C.byref(yv), None, *WS)
     sync()
     close(yb.float().cpu().numpy(), rn.tconv2x2_fwd(x, kt, b), mode)
     dy = q(rng.normal(size=(n, 2 * h, 2 * w, cout)).astype(np.float32), dt)
@@ -219,7 +253,7 @@ def _tconv_dense(N, mode, shape, rng):
     mb, _, _ = embed(mask, dt)
     dxb = torch.full((n, h, w, cin), 9.0, dtype=dt, device='cuda')
     dyv, mv, dxv = view(N, dyb, 0, cout), view(N, mb, 0, cin), view(N, dxb, 0, cin)
-    N.call('dnnca_convtranspose2x2_dgrad', None, C.byref(dyv), N.ptr(kd), C.byref(dxv), C.byref(mv), N.ACT_RELU, 0.0)
+    N.call('dnnca_convtranspose2x2_dgrad', None, C.byref(dyv), N.ptr(kd), C.byref(dxv), C.byref(mv), N.ACT_RELU, 0.0, *WS)
     dk = torch.zeros(2, 2, cout, cin, dtype=torch.float32, device='cuda')
     db = torch.zeros(cout, dtype=torch.float32, device='cuda')
     N.call('dnnca_convtranspose2x2_wgrad', None, C.byref(xv), C.byref(dyv), N.ptr(dk), N.ptr(db))
@@ -228,7 +262,7 @@ def _tconv_dense(N, mode, shape, rng):
     close(dxb.float().cpu().numpy(), rdx * (mask > 0), mode, scale=np.abs(rdx).max())
     close(dk.cpu().numpy(), rdk, 'fp32', scale=np.abs(rdk).max() * (1 if mode == 'fp32' else 50))
     close(db.cpu().numpy(), rdb, 'fp32', scale=np.abs(rdb).max() * (1 if mode == 'fp32' else 50))
-    N.call('dnnca_convtranspose2x2_dgrad', None, C.byref(dyv), N.ptr(kd), C.byref(dxv), None, N.ACT_NONE, 0.0)
+    N.call('dnnca_convtranspose2x2_dgrad', None, C.byref(dyv), N.ptr(kd), C.byref(dxv), None, N.ACT_NONE, 0.0, *WS)
     sync()
     close(dxb.float().cpu().numpy(), rdx, mode)
 
@@ -431,7 +465,7 @@ def test_bad_arguments_fail_loudly(N):
     xv = N.tensor_view(x)
     yv = N.tensor_view(torch.zeros(1, 4, 4, 3, device='cuda'))
     with pytest.raises(N.DnncaError, match='kernel size'):
-        N.call('dnnca_conv2d_fprop', None, C.byref(xv), None, N.ptr(x), None, C.byref(yv), 5, 0, 0.0, None)
+        N.call('dnnca_conv2d_fprop', None, C.byref(xv), None, N.ptr(x), None, C.byref(yv), 5, 0, 0.0, None, None, 0)
     yv2 = N.tensor_view(torch.zeros(1, 5, 4, 3, device='cuda'))
     with pytest.raises(N.DnncaError):
-        N.call('dnnca_conv2d_fprop', None, C.byref(xv), None, N.ptr(x), None, C.byref(yv2), 3, 0, 0.0, None)
+        N.call('dnnca_conv2d_fprop', None, C.byref(xv), None, N.ptr(x), None, C.byref(yv2), 3, 0, 0.0, None, None, 0)
