@@ -23,6 +23,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 static long long g_launches = 0;
 void note_launch(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
+static long long g_family[3] = {0, 0, 0};
+void note_family(int f) { __atomic_fetch_add(&g_family[f], 1LL, __ATOMIC_RELAXED); }
 
 int sm_count() {
   static int cached = 0;
@@ -83,6 +85,8 @@ int try_conv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_
 int try_conv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, const dnnca_tensor_t*, int, float, void*, size_t);
 int try_tconv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, void*, size_t);
 int try_tconv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float, void*, size_t);
+int try_conv_wgrad_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*, int);
+int try_tconv_wgrad_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
 // return 1 when the shape was handled, 0 when not covered, <0 on error
 int try_conv_fprop_small_f32(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
 int try_conv_fprop_small_bf16(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
@@ -96,6 +100,7 @@ int try_conv_wgrad_small_bf16(cudaStream_t, const dnnca_tensor_t*, const dnnca_t
 using namespace dnnca;
 
 static int g_force_generic = 0;
+static int g_no_umma = 0;          // test hook: keep wgrad off the tensor cores (it needs no workspace to opt in)
 
 extern "C" int dnnca_version(void) { return DNNCA_VERSION; }
 extern "C" const char* dnnca_last_error(void) { return g_err; }
@@ -115,6 +120,13 @@ extern "C" int dnnca_debug_force_generic(int on) {
   int old = g_force_generic;
   g_force_generic = on;
   return old;
+}
+// per-family launch counters: 0 = shape-generic, 1 = small-channel TMA/FFMA2, 2 = tcgen05
+extern "C" long long dnnca_debug_family_count(int family, int reset) {
+  if (family < 0 || family > 2) return -1;
+  long long v = __atomic_load_n(&g_family[family], __ATOMIC_RELAXED);
+  if (reset) __atomic_store_n(&g_family[family], 0LL, __ATOMIC_RELAXED);
+  return v;
 }
 
 static bool act_ok(int act) { return act == DNNCA_ACT_NONE || act == DNNCA_ACT_RELU || act == DNNCA_ACT_LEAKY; }
@@ -192,6 +204,11 @@ extern "C" int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const d
     if (r < 0) return r;
     if (r == 1) return DNNCA_OK;
   }
+  if (!g_force_generic && !g_no_umma) {
+    int r = try_conv_wgrad_umma(s, x, x2, dz, dw, db, ksize);
+    if (r < 0) return r;
+    if (r == 1) return DNNCA_OK;
+  }
   return launch_conv_wgrad_generic(s, x, x2, dz, dw, db, ksize);
 }
 
@@ -235,6 +252,7 @@ extern "C" int dnnca_convtranspose2x2_wgrad(void* stream, const dnnca_tensor_t* 
                   "convtranspose2x2_wgrad: dy must be [n,2h,2w,cout]");
   if (!g_force_generic) {
     int r = try_tconv_wgrad_small((cudaStream_t)stream, x, dy, dk, db);
+    if (r == 0 && !g_no_umma) r = try_tconv_wgrad_umma((cudaStream_t)stream, x, dy, dk, db);
     if (r < 0) return r;
     if (r == 1) return DNNCA_OK;
   }

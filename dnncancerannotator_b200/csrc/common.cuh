@@ -28,6 +28,7 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 void note_launch(int n);
+void note_family(int f);   // 0 generic, 1 small-channel TMA/FFMA2, 2 tcgen05 (conv/ConvT kernels only)
 
 // placed after every kernel launch: counts it and surfaces launch errors
 #define DNNCA_LAUNCH_CHECK(what)                                 \

@@ -278,6 +278,7 @@ int launch_conv_fprop_generic(cudaStream_t s, const dnnca_tensor_t* x, const dnn
   const int c2 = x2 ? x2->c : 0;
   DNNCA_DISPATCH_DTYPE(x->dtype, conv_fprop_generic_kernel<T><<<grid, 256, 0, s>>>(mk(x), v2, c2, w, bias, mk(y), k, act, alpha, total, ncb);)
   DNNCA_LAUNCH_CHECK("conv_fprop_generic");
+  note_family(0);
   return DNNCA_OK;
 }
 
@@ -291,6 +292,7 @@ int launch_conv_dgrad_generic(cudaStream_t s, const dnnca_tensor_t* dz, const fl
   View v2 = dx2 ? mk(dx2) : mk(dx);
   DNNCA_DISPATCH_DTYPE(dx->dtype, conv_dgrad_generic_kernel<T><<<grid, 256, 0, s>>>(mk(dz), w, mk(dx), v2, c2, k, vm, mask != nullptr, act, alpha, total, ncb);)
   DNNCA_LAUNCH_CHECK("conv_dgrad_generic");
+  note_family(0);
   return DNNCA_OK;
 }
 
@@ -322,6 +324,7 @@ int launch_conv_wgrad_generic(cudaStream_t s, const dnnca_tensor_t* x, const dnn
   View v2 = x2 ? mk(x2) : mk(x);
   DNNCA_DISPATCH_DTYPE(x->dtype, (wgrad_generic_kernel<T, 0><<<grid, 256, 0, s>>>(mk(x), v2, c2, mk(dz), dw, k, ksplit, P));)
   DNNCA_LAUNCH_CHECK("conv_wgrad_generic");
+  note_family(0);
   if (db) return launch_channel_sum(s, dz, db);
   return DNNCA_OK;
 }
@@ -333,6 +336,7 @@ int launch_tconv_fprop_generic(cudaStream_t s, const dnnca_tensor_t* x, const fl
   const int grid = grid_for(total, 256, 16);
   DNNCA_DISPATCH_DTYPE(x->dtype, tconv_fprop_generic_kernel<T><<<grid, 256, 0, s>>>(mk(x), kw, bias, mk(y), total, ncb);)
   DNNCA_LAUNCH_CHECK("tconv_fprop_generic");
+  note_family(0);
   return DNNCA_OK;
 }
 
@@ -344,6 +348,7 @@ int launch_tconv_dgrad_generic(cudaStream_t s, const dnnca_tensor_t* dy, const f
   View vm = mask ? mk(mask) : mk(dx);
   DNNCA_DISPATCH_DTYPE(dx->dtype, tconv_dgrad_generic_kernel<T><<<grid, 256, 0, s>>>(mk(dy), kw, mk(dx), vm, mask != nullptr, act, alpha, total, ncb);)
   DNNCA_LAUNCH_CHECK("tconv_dgrad_generic");
+  note_family(0);
   return DNNCA_OK;
 }
 
@@ -355,6 +360,7 @@ int launch_tconv_wgrad_generic(cudaStream_t s, const dnnca_tensor_t* x, const dn
   grid.z = 4 * ksplit;
   DNNCA_DISPATCH_DTYPE(x->dtype, (wgrad_generic_kernel<T, 1><<<grid, 256, 0, s>>>(mk(x), mk(x), 0, mk(dy), dk, 2, ksplit, P));)
   DNNCA_LAUNCH_CHECK("tconv_wgrad_generic");
+  note_family(0);
   if (db) return launch_channel_sum(s, dy, db);
   return DNNCA_OK;
 }

@@ -416,6 +416,7 @@ static int launch_small(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_te
     if (nblk > 0x7fffffffLL) return 0;
     kern<<<(unsigned)nblk, 256, G::SMEM, s>>>(mA, mB, mOA, mOB, a);
     DNNCA_LAUNCH_CHECK("conv3x3_small");
+    note_family(1);
     return 1;
   }
 }
@@ -498,6 +499,7 @@ static int launch_small_wgrad(cudaStream_t s, const dnnca_tensor_t* x, const dnn
     if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, 256, G::SMEM, s>>>(mA, mB, mG, dw, db, tiles_x, tiles_y, (int)ntiles);
     DNNCA_LAUNCH_CHECK("conv3x3_small_wgrad");
+    note_family(1);
     return 1;
   }
 }

@@ -307,6 +307,217 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, G::TCOLS);
 }
 
+static bool bf16_view16(const dnnca_tensor_t* t);
+
+// ---------------------------------------------------------------- wgrad
+// dW[tap][ci][co] += sum_pixels xs_tap[p][ci] * dz[p][co]        (Conv2D, MODE 0; ConvT uses xs = x, dz at 2p+tap)
+// GEMM with M = 128 input channels, N = BN output channels, K = pixels.  Both operands are "MN-major":
+// a TMA box {64 channels, 16 px, 4 rows} lands as 64 pixel rows of 128 bytes = eight 1024-byte SWIZZLE_128B
+// atoms (8 pixels x 64 channels), exactly the canonical MN-major UMMA layout with SBO = 1024 (next 8 pixels)
+// and LBO = 8192 (next 64 channels).  Channels beyond the tensor are zero-filled by the TMA, so any channel
+// count that is a multiple of 16 works (at the price of idle MMA rows).  A CTA owns one (M tile, N tile, tap)
+// and a slice of the pixel tiles; partial sums are added to the fp32 gradient with red.global.add.
+struct WArgs {
+  int taps, ktap, offbase, sx;     // conv: 9,3,-1,1 ; ConvT: 4,2,0,2 (dz sampled with traversal stride 2)
+  int c_a, c_b, cout;              // channels of x, x2; output channels
+  int tiles_x, tiles_y, nimg;      // 16x4 pixel tiles over the x grid
+  int ksplit;
+  int tconv;                       // output index order: conv [tap][ci][co], ConvT [tap][co][ci]
+  float* dw;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192) wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                        const __grid_constant__ CUtensorMap mapB,
+                                                        const __grid_constant__ CUtensorMap mapG, WArgs a) {
+  constexpr int ATOM = 8192;                       // 64 px x 128 B
+  constexpr int NB = BN / 64;
+  constexpr int STAGE = (2 + NB) * ATOM;
+  constexpr int STAGES = BN > 128 ? 4 : 3;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  unsigned char* ring = smem + 1024;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const int tap = blockIdx.z / a.ksplit, ks = blockIdx.z % a.ksplit;
+  const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
+  const int per = (ntiles + a.ksplit - 1) / a.ksplit;
+  const int t_beg = ks * per, t_end = min(ntiles, t_beg + per);
+  const int kiters = t_end - t_beg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (kiters > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const int ox = (tap % a.ktap) + a.offbase, oy = (tap / a.ktap) + a.offbase;
+        for (int it = 0; it < kiters; ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(empty + s, ((it / STAGES) - 1) & 1);
+          int b = t_beg + it;
+          const int tix = b % a.tiles_x; b /= a.tiles_x;
+          const int tiy = b % a.tiles_y;
+          const int n = b / a.tiles_y;
+          const int x0 = tix * 16, y0 = tiy * 4;
+          unsigned char* st = ring + s * STAGE;
+          mbar_expect_tx(full + s, STAGE);
+          // A: two 64-channel atoms of the (virtually concatenated) input, shifted by the tap for Conv2D
+          const int xa = a.tconv ? x0 : x0 + ox, ya = a.tconv ? y0 : y0 + oy;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = m0 + 64 * h;
+            if (c < a.c_a || a.c_b == 0) tma_load_4d(st + h * ATOM, &mapA, full + s, c, xa, ya, n);   // c >= C reads zeros
+            else                         tma_load_4d(st + h * ATOM, &mapB, full + s, c - a.c_a, xa, ya, n);
+          }
+          const int xg = a.tconv ? 2 * x0 + ox : x0, yg = a.tconv ? 2 * y0 + oy : y0;
+#pragma unroll
+          for (int h = 0; h < NB; ++h) tma_load_4d(st + (2 + h) * ATOM, &mapG, full + s, n0 + 64 * h, xg, yg, n);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+        for (int it = 0; it < kiters; ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full + s, (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + s * STAGE), sb = sa + 2 * ATOM;
+          // MN-major SWIZZLE_128B: LBO = next 64-channel atom, SBO = next 8 pixels
+          auto mn_desc = [](uint32_t addr) {
+            uint64_t d = 0;
+            d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+            d |= (uint64_t)(ATOM >> 4) << 16;
+            d |= (uint64_t)(1024 >> 4) << 32;
+            d |= (uint64_t)1 << 46;
+            d |= (uint64_t)2 << 61;
+            return d;
+          };
+#pragma unroll
+          for (int k = 0; k < 4; ++k)       // 16 pixels (2 atoms along K) per MMA: +2048 bytes
+            umma_bf16(tmem_base, mn_desc(sa + k * 2048), mn_desc(sb + k * 2048), idesc, (it | k) ? 1u : 0u);
+          umma_commit(empty + s);
+        }
+        umma_commit(accum);
+      }
+    } else {
+      const int lg = warp & 3;
+      const int m = m0 + lg * 32 + lane;        // input channel (row of the accumulator)
+      mbar_wait(accum, 0);
+      tc_fence_after();
+      const int cin = a.c_a + a.c_b;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (m >= cin) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = n0 + c0 + j;
+          if (co < a.cout) {
+            float* dst = a.tconv ? a.dw + ((size_t)tap * a.cout + co) * cin + m : a.dw + ((size_t)tap * cin + m) * a.cout + co;
+            atomicAdd(dst, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+static bool act_map64(CUtensorMap* m, const dnnca_tensor_t* t, int estride) {
+  // 4-D {C, W, H, N}; box {64 channels, 16 px, 4 rows, 1}, SWIZZLE_128B; channels >= C read as zero
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  char* base = reinterpret_cast<char*>(t->data) + (size_t)t->coff * 2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (t->cstride * 2) % 16) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
+  cuuint64_t strides[3] = {(cuuint64_t)t->cstride * 2, (cuuint64_t)t->w * t->cstride * 2, (cuuint64_t)t->h * t->w * t->cstride * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(16 * estride), (cuuint32_t)(4 * estride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+static int launch_wgrad_umma(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mG, WArgs a) {
+  constexpr int STAGE = (2 + BN / 64) * 8192, STAGES = BN > 128 ? 4 : 3, SMEM = 1024 + STAGES * STAGE + 1024;
+  auto kern = wgrad_umma_kernel<BN>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "wgrad_umma: cudaFuncSetAttribute");
+    done = true;
+  }
+  const int cin = a.c_a + a.c_b;
+  const int mt = (cin + 127) / 128, nt = (a.cout + BN - 1) / BN;
+  const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
+  long long want = (3LL * sm_count() + (long long)mt * nt * a.taps - 1) / ((long long)mt * nt * a.taps);
+  if (want > ntiles / 4) want = ntiles / 4;
+  if (want < 1) want = 1;
+  if ((long long)a.taps * want > 65535) want = 65535 / a.taps;
+  a.ksplit = (int)want;
+  dim3 grid(mt, nt, a.taps * a.ksplit);
+  kern<<<grid, 192, SMEM, s>>>(mA, mB, mG, a);
+  DNNCA_LAUNCH_CHECK("wgrad_umma");
+  note_family(2);
+  return 1;
+}
+
+int launch_channel_sum(cudaStream_t s, const dnnca_tensor_t* g, float* out);
+
+static int wgrad_umma_common(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g,
+                             float* dw, float* db, int k, int tconv) {
+  if (!bf16_view16(x) || (x2 && !bf16_view16(x2)) || !bf16_view16(g)) return 0;
+  const int ca = x->c, cb = x2 ? x2->c : 0;
+  if (cb && ca % 64) return 0;                      // the second tensor must start on an atom boundary
+  if (x->w % 16 || x->h % 4) return 0;              // whole 16x4 pixel tiles only (partial tiles would double count nothing,
+                                                    // but keep the fast path simple; other sizes use the generic kernel)
+  CUtensorMap mA, mB, mG;
+  if (!act_map64(&mA, x, 1)) return 0;
+  mB = mA;
+  if (x2 && !act_map64(&mB, x2, 1)) return 0;
+  if (!act_map64(&mG, g, tconv ? 2 : 1)) return 0;
+  WArgs a{};
+  a.taps = tconv ? 4 : k * k; a.ktap = tconv ? 2 : k; a.offbase = tconv ? 0 : -(k / 2); a.sx = tconv ? 2 : 1;
+  a.c_a = ca; a.c_b = cb; a.cout = g->c; a.tiles_x = x->w / 16; a.tiles_y = x->h / 4; a.nimg = x->n; a.tconv = tconv; a.dw = dw;
+  int r;
+  const int cout = g->c;
+  if (cout > 128) r = launch_wgrad_umma<256>(s, mA, mB, mG, a);
+  else if (cout > 64) r = launch_wgrad_umma<128>(s, mA, mB, mG, a);
+  else r = launch_wgrad_umma<64>(s, mA, mB, mG, a);
+  if (r != 1) return r;
+  if (db) {
+    int e = launch_channel_sum(s, g, db);
+    if (e != DNNCA_OK) return e;
+  }
+  return 1;
+}
+
+int try_conv_wgrad_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* dz,
+                        float* dw, float* db, int k) {
+  return wgrad_umma_common(s, x, x2, dz, dw, db, k, 0);
+}
+int try_tconv_wgrad_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* dy, float* dk, float* db) {
+  return wgrad_umma_common(s, x, nullptr, dy, dk, db, 2, 1);
+}
+
 // ---------------------------------------------------------------- host side
 static bool act_map(CUtensorMap* m, const dnnca_tensor_t* t, int kc, int estride) {
   // 4-D {C, W, H, N} view of a (channel-sliced) NHWC bf16 tensor; box {kc, 16, 8, 1}
@@ -353,6 +564,7 @@ static int launch_umma(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap&
   dim3 grid((unsigned)((long long)a.tiles_x * a.tiles_y * nimg), (unsigned)((a.n_total + BN - 1) / BN));
   kern<<<grid, 192, G::SMEM, s>>>(mA, mB, mW, a);
   DNNCA_LAUNCH_CHECK("conv_umma");
+  note_family(2);
   return 1;
 }
 

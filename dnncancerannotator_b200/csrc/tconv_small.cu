@@ -328,6 +328,7 @@ static int launch_tconv_fprop(cudaStream_t s, const dnnca_tensor_t* x, const flo
     const int tiles_x = (x->w + G::TWI - 1) / G::TWI, tiles_y = (x->h + G::TIY - 1) / G::TIY;
     kern<<<(unsigned)((long long)tiles_x * tiles_y * x->n), 256, SMEM, s>>>(mx, my, kw, bias, tiles_x, tiles_y);
     DNNCA_LAUNCH_CHECK("tconv_small_fprop");
+    note_family(1);
     return 1;
   }
 }
@@ -354,6 +355,7 @@ static int launch_tconv_dgrad(cudaStream_t s, const dnnca_tensor_t* dy, const fl
     kern<<<(unsigned)((long long)tiles_x * tiles_y * dx->n), 256, SMEM, s>>>(my, mx, kw, vm, mask != nullptr, act, alpha,
                                                                              dx->h, dx->w, tiles_x, tiles_y);
     DNNCA_LAUNCH_CHECK("tconv_small_dgrad");
+    note_family(1);
     return 1;
   }
 }
@@ -382,6 +384,7 @@ static int launch_tconv_wgrad(cudaStream_t s, const dnnca_tensor_t* x, const dnn
     if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, 256, SMEM, s>>>(mx, my, dk, db, tiles_x, tiles_y, (int)ntiles);
     DNNCA_LAUNCH_CHECK("tconv_small_wgrad");
+    note_family(1);
     return 1;
   }
 }

@@ -49,6 +49,7 @@ _PROTOS = {
     'dnnca_sm_count': [C.POINTER(C.c_int)],
     'dnnca_debug_force_generic': [_i],
     'dnnca_debug_launch_count': [_i],
+    'dnnca_debug_family_count': [_i, _i],
     'dnnca_conv_workspace_bytes': [_i, _i, _i],
     'dnnca_conv2d_fprop': [_vp, _TP, _TP, _vp, _vp, _TP, _i, _i, _f, _vp, _vp, C.c_size_t],
     'dnnca_conv2d_dgrad': [_vp, _TP, _vp, _TP, _TP, _i, _TP, _i, _f, _vp, C.c_size_t],
@@ -77,7 +78,8 @@ _PROTOS = {
     'dnnca_adam_step': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
 }
 _RESTYPES = {'dnnca_last_error': C.c_char_p, 'dnnca_label_stats_decode': None,
-             'dnnca_debug_launch_count': C.c_longlong, 'dnnca_conv_workspace_bytes': C.c_size_t}
+             'dnnca_debug_launch_count': C.c_longlong, 'dnnca_debug_family_count': C.c_longlong,
+             'dnnca_conv_workspace_bytes': C.c_size_t}
 
 _lib = None
 

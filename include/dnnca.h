@@ -68,6 +68,9 @@ DNNCA_API int dnnca_sm_count(int* out);
 DNNCA_API int dnnca_debug_force_generic(int on);
 /* number of kernels this library has launched since load (reset != 0 zeroes the counter afterwards) */
 DNNCA_API long long dnnca_debug_launch_count(int reset);
+/* conv / ConvT launches per kernel family since load: 0 = shape-generic CUDA-core, 1 = small-channel
+ * TMA + FFMA2, 2 = tcgen05 implicit GEMM (tests assert which family served a shape) */
+DNNCA_API long long dnnca_debug_family_count(int family, int reset);
 
 /* ---------------------------------------------------------------------------
  * Workspace of the tensor-core (tcgen05) kernels: room for the bf16 K-major repack of one layer's

@@ -248,3 +248,45 @@ def test_unet_yaml_config_full_size_bf16():
     allr = np.concatenate([r['grads'][k].numpy().ravel() for k in ref.trainable])
     REPORT['unet.yaml@256/bf16/train'].update(grad_rel_l2=rel_l2(allg, allr), loss_rel=abs(per.mean() - r['data_loss']) / abs(r['data_loss']))
     assert rel_l2(allg, allr) <= 2e-2, rel_l2(allg, allr)
+
+
+@pytest.mark.parametrize('cfgname,C,size,B', [('unet_big', 3, 64, 2), ('mulmo_unet', 3, 64, 2)])
+def test_wide_configs_run_on_tensor_cores_bf16(cfgname, C, size, B):
+    """configs/unet_big.yaml and configs/mulmo_unet.yaml (BN, 16..1024 channels): the convs must be served by
+    the tcgen05 implicit-GEMM kernels, and one training-mode pass must agree with the fp32 oracle."""
+    from dnncancerannotator_b200 import native as N
+    from dnncancerannotator_b200.utils.load import load_config
+    from dnncancerannotator_b200.synthetic import make_slices
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = load_config([os.path.join(root, 'configs', cfgname + '.yaml'),
+                       os.path.join(root, 'configs', 'additionals', 'deploy_options.yaml')])
+    m = product_model(cfg['model'], cfg['model_options'], 'bf16')
+    m.build((None, size, size, C))
+    m.compile(loss=cfg['deploy_options']['loss'])
+    ref = rm.build_model(cfg['model'], cfg['model_options'], (None, size, size, C), seed=3)
+    ref.randomize_bn(seed=2)
+    m.set_weights(ref.get_weights())
+    x, y = make_slices(B, size, size, C, seed=77)
+    r = ref.train_step_grads(x, y, cfg['deploy_options']['loss']['config'])
+    lib = N.lib()
+    m.use_cuda_graph = False
+    for f in range(3):
+        lib.dnnca_debug_family_count(f, 1)
+    per = m.forward_backward(x, y).cpu().numpy()
+    fam = [int(lib.dnnca_debug_family_count(f, 0)) for f in range(3)]
+    logits = m.last_logits.cpu().numpy()
+    g = m.get_grads()
+    allg = np.concatenate([g[k].ravel() for k in ref.trainable])
+    allr = np.concatenate([r['grads'][k].numpy().ravel() for k in ref.trainable])
+    tag = f'{cfgname}@{size}/bf16/train'
+    REPORT[tag] = dict(logits_rel_l2=rel_l2(logits, r['logits'].numpy()), logits_rel_max=rel_inf(logits, r['logits'].numpy()),
+                       grad_rel_l2=rel_l2(allg, allr), loss_rel=abs(per.mean() - r['data_loss']) / abs(r['data_loss']),
+                       launches_generic=fam[0], launches_small=fam[1], launches_tcgen05=fam[2])
+    # every conv / ConvT with >= 16 channels on both sides runs on tcgen05; only first-layer convs
+    # (Cin = 1 or 3) may use the CUDA-core kernels
+    assert fam[2] >= 3 * 16, fam
+    assert fam[0] <= (2 if cfgname == 'unet_big' else 0) + 1, fam
+    assert np.isfinite(logits).all() and np.isfinite(allg).all()
+    assert rel_l2(logits, r['logits'].numpy()) <= TOL['bf16']['logits_bn_train'], REPORT[tag]
+    assert abs(per.mean() - r['data_loss']) <= TOL['bf16']['loss_bn'] * abs(r['data_loss']), REPORT[tag]
+    assert rel_l2(allg, allr) <= TOL['bf16']['grad_bn'], REPORT[tag]

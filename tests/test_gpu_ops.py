@@ -90,7 +90,17 @@ CONV_SHAPES = [  # (n, h, w, c_x, c_x2, cout, k)
 def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
     """dense: tensors are whole buffers (the TMA-staged small-channel kernels take the shapes they cover);
     sliced: every tensor is a channel slice of a wider buffer; generic: shape-generic kernels forced."""
+    lib = N.lib()
+    lib.dnnca_debug_family_count(1, 1)
     _conv_case(N, mode, variant, shape)
+    n, h, w, ca, cb, cout, k = shape
+    small = {(3, 0, 3), (3, 0, 6), (6, 0, 6), (12, 12, 12), (12, 0, 12), (1, 0, 16), (5, 0, 3), (3, 3, 3), (6, 6, 6),
+             (6, 0, 12), (8, 8, 8), (4, 0, 8)}
+    if variant == 'dense' and (ca, cb, cout) in small:
+        es = 4 if mode == 'fp32' else 2
+        assert all((w * c * es) % 16 == 0 for c in (ca, cb, cout) if c)
+        # 3 fprop + wgrad + 2 dgrad, except first-layer style shapes whose dgrad is not instantiated
+        assert lib.dnnca_debug_family_count(1, 0) >= 4, 'the TMA/FFMA2 small-channel kernels did not take this shape'
 
 
 def _conv_case(N, mode, variant, shape):
@@ -225,7 +235,15 @@ UMMA_SHAPES = [  # (n, h, w, c_x, c_x2, cout, k): channel counts the tcgen05 imp
 @pytest.mark.parametrize('shape', UMMA_SHAPES)
 def test_conv_umma(N, variant, shape):
     """tcgen05/TMEM/TMA implicit-GEMM fprop + dgrad (bf16), dense and channel-sliced views; wgrad rides along."""
+    lib = N.lib()
+    lib.dnnca_debug_family_count(2, 1)
+    lib.dnnca_debug_family_count(0, 1)
     _conv_case(N, 'bf16', variant, shape)
+    n, h, w = shape[:3]
+    wgrad_tc = (w % 16 == 0 and h % 4 == 0)
+    # 3 fprop + 2 dgrad (+ wgrad when the image tiles evenly) ran on the tensor cores, nothing fell back
+    assert lib.dnnca_debug_family_count(2, 0) == 5 + (1 if wgrad_tc else 0)
+    assert lib.dnnca_debug_family_count(0, 0) == (0 if wgrad_tc else 1)
 
 
 def _tconv_dense(N, mode, shape, rng):
