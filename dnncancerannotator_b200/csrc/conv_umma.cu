@@ -487,8 +487,7 @@ static int wgrad_umma_common(cudaStream_t s, const dnnca_tensor_t* x, const dnnc
   if (!bf16_view16(x) || (x2 && !bf16_view16(x2)) || !bf16_view16(g)) return 0;
   const int ca = x->c, cb = x2 ? x2->c : 0;
   if (cb && ca % 64) return 0;                      // the second tensor must start on an atom boundary
-  if (x->w % 16 || x->h % 4) return 0;              // whole 16x4 pixel tiles only (partial tiles would double count nothing,
-                                                    // but keep the fast path simple; other sizes use the generic kernel)
+  // partial 16x4 pixel tiles are fine: the TMA zero-fills x and dz outside the image, so they add nothing
   CUtensorMap mA, mB, mG;
   if (!act_map64(&mA, x, 1)) return 0;
   mB = mA;
@@ -496,7 +495,7 @@ static int wgrad_umma_common(cudaStream_t s, const dnnca_tensor_t* x, const dnnc
   if (!act_map64(&mG, g, tconv ? 2 : 1)) return 0;
   WArgs a{};
   a.taps = tconv ? 4 : k * k; a.ktap = tconv ? 2 : k; a.offbase = tconv ? 0 : -(k / 2); a.sx = tconv ? 2 : 1;
-  a.c_a = ca; a.c_b = cb; a.cout = g->c; a.tiles_x = x->w / 16; a.tiles_y = x->h / 4; a.nimg = x->n; a.tconv = tconv; a.dw = dw;
+  a.c_a = ca; a.c_b = cb; a.cout = g->c; a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + 3) / 4; a.nimg = x->n; a.tconv = tconv; a.dw = dw;
   int r;
   const int cout = g->c;
   if (cout > 128) r = launch_wgrad_umma<256>(s, mA, mB, mG, a);
