@@ -92,25 +92,29 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_
 //                                 -> dgrad pack  [tap'][Cin][Cout], tap' = rot180(tap)   (MODE 1)
 // ConvT   k[2,2,Cout,Cin]        -> fprop pack  [1][tap*Cout + co][Cin]    (MODE 2: plain bf16 cast)
 //                                 -> dgrad pack  [tap][Cin][Cout]           (MODE 3)
+// K (the contiguous axis) is padded to a multiple of 16 with zeros in modes 0/2 (`kp` >= cin): layers whose input
+// has fewer than 16 channels (first convs: 1, 3 or 5 modalities) still feed whole K=16 MMAs.
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                                          int mode, int taps, int cin, int cout) {
-  const long long total = (long long)taps * cin * cout;
+                                                          int mode, int taps, int cin, int cout, int kp) {
+  const long long total = (mode == 0 || mode == 2) ? (long long)taps * cout * kp : (long long)taps * cin * cout;
   const int kk = taps == 9 ? 3 : (taps == 4 ? 2 : 1);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     float v;
-    if (mode == 0) {            // e = (tap, co, ci)
-      const int ci = (int)(e % cin);
-      const long long t = e / cin;
+    if (mode == 0) {            // e = (tap, co, ci padded)
+      const int ci = (int)(e % kp);
+      const long long t = e / kp;
       const int co = (int)(t % cout), tap = (int)(t / cout);
-      v = w[((long long)tap * cin + ci) * cout + co];
+      v = ci < cin ? w[((long long)tap * cin + ci) * cout + co] : 0.f;
     } else if (mode == 1) {     // e = (tap', ci, co), source tap = rot180
       const int co = (int)(e % cout);
       const long long t = e / cout;
       const int ci = (int)(t % cin), tp = (int)(t / cin);
       const int a = kk - 1 - tp / kk, c = kk - 1 - tp % kk;
       v = w[((long long)(a * kk + c) * cin + ci) * cout + co];
-    } else if (mode == 2) {
-      v = w[e];
+    } else if (mode == 2) {     // e = (tap*cout + co, ci padded) from k[tap][co][ci]
+      const int ci = (int)(e % kp);
+      const long long t = e / kp;
+      v = ci < cin ? w[t * cin + ci] : 0.f;
     } else {                    // e = (tap, ci, co) from k[tap][co][ci]
       const int co = (int)(e % cout);
       const long long t = e / cout;
@@ -308,6 +312,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
 }
 
 static bool bf16_view16(const dnnca_tensor_t* t);
+static bool bf16_view_in(const dnnca_tensor_t* t);
 
 // ---------------------------------------------------------------- wgrad
 // dW[tap][ci][co] += sum_pixels xs_tap[p][ci] * dz[p][co]        (Conv2D, MODE 0; ConvT uses xs = x, dz at 2p+tap)
@@ -343,7 +348,10 @@ __global__ void __launch_bounds__(192) wgrad_umma_kernel(const __grid_constant__
   unsigned char* ring = smem + 1024;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  // M tiles cover x first, then x2 (each tensor padded to whole 128-row tiles by the TMA's zero fill)
+  const int mta = (a.c_a + 127) / 128;
+  const bool second = (int)blockIdx.x >= mta;
+  const int m0 = (second ? (int)blockIdx.x - mta : (int)blockIdx.x) * 128, n0 = blockIdx.y * BN;
   const int tap = blockIdx.z / a.ksplit, ks = blockIdx.z % a.ksplit;
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
   const int per = (ntiles + a.ksplit - 1) / a.ksplit;
@@ -378,11 +386,8 @@ __global__ void __launch_bounds__(192) wgrad_umma_kernel(const __grid_constant__
           // A: two 64-channel atoms of the (virtually concatenated) input, shifted by the tap for Conv2D
           const int xa = a.tconv ? x0 : x0 + ox, ya = a.tconv ? y0 : y0 + oy;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c = m0 + 64 * h;
-            if (c < a.c_a || a.c_b == 0) tma_load_4d(st + h * ATOM, &mapA, full + s, c, xa, ya, n);   // c >= C reads zeros
-            else                         tma_load_4d(st + h * ATOM, &mapB, full + s, c - a.c_a, xa, ya, n);
-          }
+          for (int h = 0; h < 2; ++h)      // channels >= C read zeros
+            tma_load_4d(st + h * ATOM, second ? &mapB : &mapA, full + s, m0 + 64 * h, xa, ya, n);
           const int xg = a.tconv ? 2 * x0 + ox : x0, yg = a.tconv ? 2 * y0 + oy : y0;
 #pragma unroll
           for (int h = 0; h < NB; ++h) tma_load_4d(st + (2 + h) * ATOM, &mapG, full + s, n0 + 64 * h, xg, yg, n);
@@ -415,7 +420,9 @@ __global__ void __launch_bounds__(192) wgrad_umma_kernel(const __grid_constant__
       }
     } else {
       const int lg = warp & 3;
-      const int m = m0 + lg * 32 + lane;        // input channel (row of the accumulator)
+      const int row = m0 + lg * 32 + lane;      // channel inside its tensor (row of the accumulator)
+      const bool live = row < (second ? a.c_b : a.c_a);
+      const int m = row + (second ? a.c_a : 0); // input channel of the (virtually concatenated) layer
       mbar_wait(accum, 0);
       tc_fence_after();
       const int cin = a.c_a + a.c_b;
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(192) wgrad_umma_kernel(const __grid_constant__
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (m >= cin) continue;
+        if (!live) continue;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int co = n0 + c0 + j;
@@ -465,8 +472,7 @@ static int launch_wgrad_umma(cudaStream_t s, const CUtensorMap& mA, const CUtens
     if (e != cudaSuccess) return cuda_fail(e, "wgrad_umma: cudaFuncSetAttribute");
     done = true;
   }
-  const int cin = a.c_a + a.c_b;
-  const int mt = (cin + 127) / 128, nt = (a.cout + BN - 1) / BN;
+  const int mt = (a.c_a + 127) / 128 + (a.c_b + 127) / 128, nt = (a.cout + BN - 1) / BN;
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
   long long want = (3LL * sm_count() + (long long)mt * nt * a.taps - 1) / ((long long)mt * nt * a.taps);
   if (want > ntiles / 4) want = ntiles / 4;
@@ -484,9 +490,8 @@ int launch_channel_sum(cudaStream_t s, const dnnca_tensor_t* g, float* out);
 
 static int wgrad_umma_common(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g,
                              float* dw, float* db, int k, int tconv) {
-  if (!bf16_view16(x) || (x2 && !bf16_view16(x2)) || !bf16_view16(g)) return 0;
+  if (!bf16_view_in(x) || (x2 && !bf16_view_in(x2)) || !bf16_view_in(g)) return 0;
   const int ca = x->c, cb = x2 ? x2->c : 0;
-  if (cb && ca % 64) return 0;                      // the second tensor must start on an atom boundary
   // partial 16x4 pixel tiles are fine: the TMA zero-fills x and dz outside the image, so they add nothing
   CUtensorMap mA, mB, mG;
   if (!act_map64(&mA, x, 1)) return 0;
@@ -590,11 +595,13 @@ static int pick_bn(int unit, int ntotal) {
   return 0;
 }
 
-size_t umma_pack_bytes(int taps, int cin, int cout) { return (size_t)taps * cin * cout * 2; }
+static int pad16(int c) { return (c + 15) / 16 * 16; }
+size_t umma_pack_bytes(int taps, int cin, int cout) { return (size_t)taps * pad16(cin) * pad16(cout) * 2; }
 
 static int pack(cudaStream_t s, const float* w, void* out, int mode, int taps, int cin, int cout) {
-  const long long total = (long long)taps * cin * cout;
-  pack_weights_kernel<<<grid_for(total, 256 * 4, 4), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(out), mode, taps, cin, cout);
+  const int kp = pad16(cin);
+  const long long total = (long long)taps * kp * cout;
+  pack_weights_kernel<<<grid_for(total, 256 * 4, 4), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(out), mode, taps, cin, cout, kp);
   DNNCA_LAUNCH_CHECK("pack_weights");
   return DNNCA_OK;
 }
@@ -603,14 +610,19 @@ static bool bf16_view16(const dnnca_tensor_t* t) {
   return t && t->dtype == DNNCA_BF16 && t->c % 16 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0 &&
          (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
 }
+// operand that is only READ through the TMA: any channel count (missing channels are zero-filled out of bounds)
+static bool bf16_view_in(const dnnca_tensor_t* t) {
+  return t && t->dtype == DNNCA_BF16 && t->coff % 8 == 0 && t->cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
+}
 
 // returns 1 handled / 0 not covered / <0 error
 int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w, const float* bias,
                         const dnnca_tensor_t* y, int k, int act, float alpha, void* ws, size_t ws_bytes) {
-  if (!ws || !bf16_view16(x) || (x2 && !bf16_view16(x2)) || !bf16_view16(y)) return 0;
+  if (!ws || !bf16_view16(y)) return 0;
+  if (x2 ? (!bf16_view16(x) || !bf16_view16(x2)) : !bf16_view_in(x)) return 0;
   const int ca = x->c, cb = x2 ? x2->c : 0, cin = ca + cb, cout = y->c, taps = k * k;
   if (ws_bytes < umma_pack_bytes(taps, cin, cout)) return 0;
-  const int kc = cb ? gcd_kc(pick_kc(ca), pick_kc(cb)) : pick_kc(ca);
+  const int kc = cb ? gcd_kc(pick_kc(ca), pick_kc(cb)) : pick_kc(pad16(ca));
   const int bn = pick_bn(cout, cout);
   if (!kc || !bn) return 0;
   int r = pack(s, w, ws, 0, taps, cin, cout);
@@ -619,9 +631,9 @@ int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_ten
   if (!act_map(&mA, x, kc, 1)) return 0;
   mB = mA;
   if (x2 && !act_map(&mB, x2, kc, 1)) return 0;
-  if (!weight_map(&mW, ws, cin, cout, taps, kc, bn)) return 0;
+  if (!weight_map(&mW, ws, pad16(cin), cout, taps, kc, bn)) return 0;
   UArgs a{};
-  a.taps = taps; a.ktap = k; a.sx = 1; a.offbase = -(k / 2); a.c_a = ca; a.c_b = cb; a.H = x->h; a.W = x->w;
+  a.taps = taps; a.ktap = k; a.sx = 1; a.offbase = -(k / 2); a.c_a = cb ? ca : pad16(ca); a.c_b = cb; a.H = x->h; a.W = x->w;
   a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + 7) / 8; a.epi = EPI_FPROP; a.act = act; a.alpha = alpha; a.bias = bias;
   a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
   a.mask = nullptr; a.n_total = cout; a.cout_t = cout;

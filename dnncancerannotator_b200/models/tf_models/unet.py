@@ -90,11 +90,15 @@ class MulmoUNet(Layer):
     def emit(self, plan, x):
         fb = self.encoder_output_shape_list[0][-1]
         n = len(self.ref_shapes)
-        bott = plan.new_buf(x.h >> n, x.w >> n, fb * self.channel_len, 'bottleneck')     # tf.concat, unet.py:187
+        x0 = x[0] if isinstance(x, list) else x
+        bott = plan.new_buf(x0.h >> n, x0.w >> n, fb * self.channel_len, 'bottleneck')   # tf.concat, unet.py:187
         res_ref = None
         for m, enc in enumerate(self.encoders):
-            xin = R.TRef(x.buf, x.coff + m, 1)                                            # inputs[..., m:m+1]
-            xin.needs_grad = False
+            if isinstance(x, list):
+                xin = x[m]
+            else:
+                xin = R.TRef(x.buf, x.coff + m, 1)                                        # inputs[..., m:m+1]
+                xin.needs_grad = False
             res_list, _ = enc.emit(plan, xin, out_dst=R.TRef(bott, m * fb, fb))
             if m == self.reference_index:
                 res_ref = res_list
@@ -137,10 +141,25 @@ class UNetAnnotator(Model):
     def _emit(self, plan):
         x = plan.input
         if plan.dtype != x.buf.dtype:                                 # fp32 input -> bf16 activations
-            xb = R.TRef(plan.new_buf(x.h, x.w, x.c, 'input_cast'))
-            xb.needs_grad = False
-            plan.add(R.ConvertOp(plan, x, xb))
-            x = xb
+            wide = self.configs['n_filters_first'] % 16 == 0          # first conv runs on the tensor cores
+            if wide and isinstance(self.unet, MulmoUNet):
+                # one 16-byte-pixel buffer per modality (unet.py:182-185 slices inputs[..., m:m+1]): the TMA reads
+                # channel 0 and zero-fills the rest of the K=16 MMA step
+                xs = []
+                for m in range(x.c):
+                    xm = R.TRef(plan.new_buf(x.h, x.w, 8, f'input_cast{m}', zero=True), 0, 1)
+                    xm.needs_grad = False
+                    src = R.TRef(x.buf, m, 1)
+                    src.needs_grad = False
+                    plan.add(R.ConvertOp(plan, src, xm))
+                    xs.append(xm)
+                x = xs
+            else:
+                cpad = (x.c + 7) // 8 * 8 if wide else x.c            # 16-byte aligned pixels for the TMA
+                xb = R.TRef(plan.new_buf(x.h, x.w, cpad, 'input_cast', zero=True), 0, x.c)
+                xb.needs_grad = False
+                plan.add(R.ConvertOp(plan, x, xb))
+                x = xb
         plan.features = self.unet.emit(plan, x)
         plan.head = ('head/kernel', 'head/bias')
 

@@ -144,9 +144,10 @@ class ParamStore:
 # buffers and views
 # ----------------------------------------------------------------------------
 class Buf:
-    def __init__(self, plan, n, h, w, c, name, dtype=None, external=None):
+    def __init__(self, plan, n, h, w, c, name, dtype=None, external=None, zero=False):
         self.plan, self.n, self.h, self.w, self.c, self.name = plan, n, h, w, c, name
         self.dtype = dtype or plan.dtype
+        self.zero = zero
         self.data = external
         self.grad = None
         self.want_grad = False
@@ -155,7 +156,8 @@ class Buf:
     def allocate(self, training):
         dev = self.plan.device
         if self.data is None:
-            self.data = torch.empty(self.n, self.h, self.w, self.c, dtype=self.dtype, device=dev)
+            alloc = torch.zeros if self.zero else torch.empty
+            self.data = alloc(self.n, self.h, self.w, self.c, dtype=self.dtype, device=dev)
         if training and self.want_grad and self.grad is None:
             self.grad = torch.empty(self.n, self.h, self.w, self.c, dtype=self.dtype, device=dev)
 
@@ -210,7 +212,9 @@ def conv_workspace(plan, taps, inputs, y):
     """bf16 weight-repack workspace of the tcgen05 kernels (dnnca_conv_workspace_bytes), or None when the layer
     cannot take the tensor-core path (fp32 mode, channel counts that are not multiples of 16)."""
     ins = [t for t in inputs if t is not None]
-    if plan.dtype != torch.bfloat16 or any(t.c % 16 for t in ins) or y.c % 16:
+    if plan.dtype != torch.bfloat16 or y.c % 16 or any(t.buf.c % 8 or t.coff % 8 for t in ins):
+        return None                       # (the library re-checks; narrow inputs only need 16-byte aligned pixels)
+    if len(ins) > 1 and any(t.c % 16 for t in ins):
         return None
     nbytes = N.lib().dnnca_conv_workspace_bytes(taps, sum(t.c for t in ins), y.c)
     return torch.empty(nbytes, dtype=torch.uint8, device=plan.device)
@@ -417,8 +421,8 @@ class Plan:
         self.allocated_training = None
         self.graphs = {}
 
-    def new_buf(self, h, w, c, name, n=None):
-        return Buf(self, n or self.batch, h, w, c, name)
+    def new_buf(self, h, w, c, name, n=None, zero=False):
+        return Buf(self, n or self.batch, h, w, c, name, zero=zero)
 
     def add(self, op):
         self.ops.append(op)
