@@ -239,8 +239,7 @@ def test_conv_umma(N, variant, shape):
     lib.dnnca_debug_family_count(2, 1)
     lib.dnnca_debug_family_count(0, 1)
     _conv_case(N, 'bf16', variant, shape)
-    ca, cb = shape[3], shape[4]
-    wgrad_tc = (cb == 0 or ca % 64 == 0)        # a second input must start on a 64-channel atom boundary
+    wgrad_tc = True
     # 3 fprop + 2 dgrad (+ wgrad when the image tiles evenly) ran on the tensor cores, nothing fell back
     assert lib.dnnca_debug_family_count(2, 0) == 5 + (1 if wgrad_tc else 0)
     assert lib.dnnca_debug_family_count(0, 0) == (0 if wgrad_tc else 1)
