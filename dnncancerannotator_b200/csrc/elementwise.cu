@@ -263,6 +263,153 @@ __global__ void __launch_bounds__(256) u8_to_unit_kernel(const uint8_t* __restri
     stf(dst + i, (float)src[i] / 255.0f);
 }
 
+
+// ---------------------------------------------------------------------------
+// 128-bit vectorised bf16 variants (C % 8 == 0, 16-byte aligned slices): thread = (pixel lane, group of 8 channels).
+// One uint4 load/store moves 8 channels; per-channel parameters of the group stay in registers.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&p);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ const uint4* vptr(const View& v, long long p, int g) {
+  return reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(v.data) + p * v.cstride + v.coff + 8 * g);
+}
+__device__ __forceinline__ uint4* vptr_w(const View& v, long long p, int g) {
+  return reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(v.data) + p * v.cstride + v.coff + 8 * g);
+}
+
+// MODE 0: channel stats (x)            -> acc[0..C) += sum x, acc[C..2C) += sum x^2
+// MODE 1: BN backward reduce (x, dy)   -> acc[0..C) += sum dy, acc[C..2C) += sum dy*xhat
+template <int MODE>
+__global__ void __launch_bounds__(256) reduce_vec8_kernel(View x, View dy, const float* __restrict__ mi,
+                                                         double* __restrict__ acc, int GL, int PL, long long P) {
+  __shared__ double sm[256];
+  const int gl = threadIdx.x & (GL - 1), pl = threadIdx.x / GL;
+  const int ng = x.c / 8;
+  for (int g = gl; g < ((ng + GL - 1) / GL) * GL; g += GL) {
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+    double d0[8], d1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d0[j] = d1[j] = 0.0;
+    if (g < ng) {
+      float mean[8], inv[8];
+      if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { mean[j] = mi[8 * g + j]; inv[j] = mi[x.c + 8 * g + j]; }
+      }
+      int cnt = 0;
+      for (long long p = (long long)blockIdx.x * PL + pl; p < P; p += (long long)gridDim.x * PL) {
+        float xv[8];
+        unpack8(*vptr(x, p, g), xv);
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s0[j] += xv[j]; s1[j] = fmaf(xv[j], xv[j], s1[j]); }
+        } else {
+          float gv[8];
+          unpack8(*vptr(dy, p, g), gv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s0[j] += gv[j]; s1[j] = fmaf(gv[j], (xv[j] - mean[j]) * inv[j], s1[j]); }
+        }
+        if (++cnt == 64) {            // flush the fp32 partials into fp64 every 64 pixels
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; s0[j] = s1[j] = 0.f; }
+          cnt = 0;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double r0 = block_reduce_pl(d0[j], sm, GL, PL);
+      const double r1 = block_reduce_pl(d1[j], sm, GL, PL);
+      if (pl == 0 && g < ng) {
+        atomicAdd(acc + 8 * g + j, r0);
+        atomicAdd(acc + x.c + 8 * g + j, r1);
+      }
+    }
+  }
+}
+
+// MODE 0: y = x*scale + shift (BN apply);  MODE 1: BN backward apply (dx = k*(dy - a - xhat*b) * act'(x))
+template <int MODE>
+__global__ void __launch_bounds__(256) map_vec8_kernel(View x, View dy, const float* __restrict__ p0,
+                                                      const float* __restrict__ gamma, const double* __restrict__ sums,
+                                                      View out, int act, float alpha, float* __restrict__ dgamma,
+                                                      float* __restrict__ dbeta, int GL, int PL, long long P) {
+  const int gl = threadIdx.x & (GL - 1), pl = threadIdx.x / GL;
+  const int ng = x.c / 8;
+  const double invM = 1.0 / (double)P;
+  for (int g = gl; g < ng; g += GL) {
+    float c0[8], c1[8], c2[8], c3[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = 8 * g + j;
+      if (MODE == 0) {
+        c0[j] = p0[c];               // scale
+        c1[j] = p0[x.c + c];         // shift
+      } else {
+        c0[j] = p0[c];               // mean
+        c1[j] = p0[x.c + c];         // invstd
+        c2[j] = (float)(sums[c] * invM);
+        c3[j] = (float)(sums[x.c + c] * invM);
+        if (blockIdx.x == 0 && pl == 0) {
+          if (dgamma) dgamma[c] += (float)sums[x.c + c];
+          if (dbeta) dbeta[c] += (float)sums[c];
+        }
+      }
+    }
+    float kk[8];
+    if (MODE == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kk[j] = (gamma ? gamma[8 * g + j] : 1.f) * c1[j];
+    }
+    for (long long p = (long long)blockIdx.x * PL + pl; p < P; p += (long long)gridDim.x * PL) {
+      float xv[8], o[8];
+      unpack8(*vptr(x, p, g), xv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(xv[j], c0[j], c1[j]);
+      } else {
+        float gv[8];
+        unpack8(*vptr(dy, p, g), gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - c0[j]) * c1[j];
+          o[j] = kk[j] * (gv[j] - c2[j] - xh * c3[j]) * act_grad(xv[j], act, alpha);
+        }
+      }
+      *vptr_w(out, p, g) = pack8(o);
+    }
+  }
+}
+
+inline bool vec8_ok(const dnnca_tensor_t* t) {
+  return t->dtype == DNNCA_BF16 && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
+}
+inline ChanLayout group_layout(int c) {
+  int gl = 1;
+  while (gl < c / 8 && gl < 256) gl <<= 1;
+  return ChanLayout{gl, 256 / gl};
+}
+
 }  // namespace dnnca
 
 using namespace dnnca;
@@ -270,8 +417,14 @@ using namespace dnnca;
 // ============================ C ABI =========================================
 extern "C" int dnnca_channel_stats(void* stream, const dnnca_tensor_t* x, double* stats) {
   DNNCA_CHECK_ARG(view_ok(x) && stats, "channel_stats: bad arguments");
-  ChanLayout L = chan_layout(x->c);
   long long P = (long long)x->n * x->h * x->w;
+  if (vec8_ok(x)) {
+    ChanLayout G = group_layout(x->c);
+    reduce_vec8_kernel<0><<<grid_for(P, G.pl * 8), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(x), nullptr, stats, G.cl, G.pl, P);
+    DNNCA_LAUNCH_CHECK("channel_stats");
+    return DNNCA_OK;
+  }
+  ChanLayout L = chan_layout(x->c);
   int grid = grid_for(P, L.pl * 8);
   DNNCA_DISPATCH_DTYPE(x->dtype, channel_stats_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(mk(x), stats, L.cl, L.pl, P);)
   DNNCA_LAUNCH_CHECK("channel_stats");
@@ -303,8 +456,15 @@ extern "C" int dnnca_bn_apply(void* stream, const dnnca_tensor_t* x, const float
                               const dnnca_tensor_t* y) {
   DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && same_shape(x, y) && scale_shift, "bn_apply: bad arguments");
   DNNCA_CHECK_ARG(x->dtype == y->dtype, "bn_apply: dtype mismatch");
-  ChanLayout L = chan_layout(x->c);
   long long P = (long long)x->n * x->h * x->w;
+  if (vec8_ok(x) && vec8_ok(y)) {
+    ChanLayout G = group_layout(x->c);
+    map_vec8_kernel<0><<<grid_for(P, G.pl * 4), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(x), scale_shift, nullptr, nullptr, mk(y),
+                                                                                 0, 0.f, nullptr, nullptr, G.cl, G.pl, P);
+    DNNCA_LAUNCH_CHECK("bn_apply");
+    return DNNCA_OK;
+  }
+  ChanLayout L = chan_layout(x->c);
   int grid = grid_for(P, L.pl * 4);
   DNNCA_DISPATCH_DTYPE(x->dtype, (bn_apply_kernel<T, T><<<grid, 256, 0, (cudaStream_t)stream>>>(mk(x), scale_shift, mk(y), L.cl, L.pl, P));)
   DNNCA_LAUNCH_CHECK("bn_apply");
@@ -333,8 +493,14 @@ extern "C" int dnnca_bn_bwd_reduce(void* stream, const dnnca_tensor_t* x, const 
                                    const float* mean_invstd, double* sums) {
   DNNCA_CHECK_ARG(view_ok(x) && view_ok(dy) && same_shape(x, dy) && mean_invstd && sums, "bn_bwd_reduce: bad arguments");
   DNNCA_CHECK_ARG(x->dtype == dy->dtype, "bn_bwd_reduce: dtype mismatch");
-  ChanLayout L = chan_layout(x->c);
   long long P = (long long)x->n * x->h * x->w;
+  if (vec8_ok(x) && vec8_ok(dy)) {
+    ChanLayout G = group_layout(x->c);
+    reduce_vec8_kernel<1><<<grid_for(P, G.pl * 8), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(dy), mean_invstd, sums, G.cl, G.pl, P);
+    DNNCA_LAUNCH_CHECK("bn_bwd_reduce");
+    return DNNCA_OK;
+  }
+  ChanLayout L = chan_layout(x->c);
   int grid = grid_for(P, L.pl * 8);
   DNNCA_DISPATCH_DTYPE(x->dtype, bn_bwd_reduce_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(mk(x), mk(dy), mean_invstd, sums, L.cl, L.pl, P);)
   DNNCA_LAUNCH_CHECK("bn_bwd_reduce");
@@ -347,8 +513,15 @@ extern "C" int dnnca_bn_bwd_apply(void* stream, const dnnca_tensor_t* x, const d
   DNNCA_CHECK_ARG(view_ok(x) && view_ok(dy) && view_ok(dx) && same_shape(x, dy) && same_shape(x, dx) && mean_invstd && sums,
                   "bn_bwd_apply: bad arguments");
   DNNCA_CHECK_ARG(x->dtype == dy->dtype && x->dtype == dx->dtype, "bn_bwd_apply: dtype mismatch");
-  ChanLayout L = chan_layout(x->c);
   long long P = (long long)x->n * x->h * x->w;
+  if (vec8_ok(x) && vec8_ok(dy) && vec8_ok(dx)) {
+    ChanLayout G = group_layout(x->c);
+    map_vec8_kernel<1><<<grid_for(P, G.pl * 4), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(dy), mean_invstd, gamma, sums, mk(dx), act,
+                                                                                 alpha, dgamma, dbeta, G.cl, G.pl, P);
+    DNNCA_LAUNCH_CHECK("bn_bwd_apply");
+    return DNNCA_OK;
+  }
+  ChanLayout L = chan_layout(x->c);
   int grid = grid_for(P, L.pl * 4);
   DNNCA_DISPATCH_DTYPE(x->dtype, bn_bwd_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
       mk(x), mk(dy), mean_invstd, gamma, sums, mk(dx), act, alpha, dgamma, dbeta, L.cl, L.pl, P);)
