@@ -266,7 +266,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = int(lib.dnnca_debug_launch_count(1))
     roofline, breakdown = None, None
-    if not args.no_profile and rank == 0:
+    if not args.no_profile:      # every rank runs the pass (it contains the gradient all-reduce); rank 0 reports
         peaks = {}
         pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         if os.path.exists(pk):
