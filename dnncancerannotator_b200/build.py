@@ -35,8 +35,8 @@ UNITS = [
 for dt in (0, 1):
     for kind in (0, 1, 2):
         UNITS.append(('conv_small.cu', f'conv_small_d{dt}k{kind}', [f'-DSMALL_DT={dt}', f'-DSMALL_KIND={kind}']))
-if os.path.exists(os.path.join(CSRC, 'conv_umma.cu')):
-    UNITS.append(('conv_umma.cu', 'conv_umma', []))
+UNITS.append(('conv_umma.cu', 'conv_umma', []))
+UNITS.append(('conv_umma2.cu', 'conv_umma2', []))
 
 
 def nvcc():

@@ -17,75 +17,11 @@
 //     the finished accumulator to the epilogue.
 // wgrad (both operands pixel-major = MN-major) is wgrad_umma_kernel below.
 // Reference call sites: layers.Conv2D components.py:47-50,123-126; Convolution2DTranspose :118-120.
-#include "common.cuh"
-#include "tma.cuh"
+#include <stdlib.h>
+
+#include "umma_common.cuh"
 
 namespace dnnca {
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread t gets row (lane) t, v[j] = column j
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major swizzled operand: rows of SWB bytes, 8-row groups SBO = 8*SWB apart (mma_sm100_desc.hpp SmemDescriptor)
-template <int SWB>
-__device__ __forceinline__ uint64_t kmajor_desc(uint32_t saddr) {
-  constexpr uint64_t layout = SWB == 128 ? 2 : (SWB == 64 ? 4 : 6);   // SWIZZLE_128B / 64B / 32B
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)((8 * SWB) >> 4) << 32;                   // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
-  d |= layout << 61;                                       // layout type, bits [61,64)
-  return d;
-}
-
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);                       // F32 accum, BF16 A/B
-}
 
 // ---------------------------------------------------------------- weight packing
 // Conv2D  w[k,k,Cin,Cout] (HWIO) -> fprop pack  [tap][Cout][Cin]           (MODE 0)
@@ -126,25 +62,6 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------- the kernel
-enum { EPI_FPROP = 0, EPI_DGRAD = 1, EPI_TCONV = 2 };
-
-struct UArgs {
-  int taps, ktap;            // filter taps; ktap = sqrt(taps)
-  int sx, offbase;           // A coordinate = pixel*sx + (tap offset) + offbase   (conv: sx 1, offbase -pad)
-  int c_a, c_b;              // channels of input A / B (K extents)
-  int H, W;                  // pixel grid of the A tile space (= output grid except for ConvT fprop)
-  int tiles_x, tiles_y;
-  int epi, act;
-  float alpha;
-  const float* bias;
-  // outputs: channel-slice views (bf16).  ya: columns [0, split); yb: columns [split, N)
-  __nv_bfloat16* ya; long long ya_cs; int split;
-  __nv_bfloat16* yb; long long yb_cs;
-  const __nv_bfloat16* mask; long long mask_cs;   // dgrad: post-activation output of the layer that produced dx
-  int n_total;               // total GEMM N
-  int cout_t;                // ConvT fprop: channels per tap
-};
-
 template <int BN, int KC>
 struct UGeom {
   static constexpr int SWB = KC * 2;
@@ -255,55 +172,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
       tmem_ld_wait();
       const int ncol = n0 + c0;               // first GEMM column of this chunk
       if (!inside || ncol >= a.n_total) continue;
-      __nv_bfloat16* dst;
-      int ch;                                  // channel inside the destination view
-      long long pix;
-      if (a.epi == EPI_TCONV) {
-        const int tap = ncol / a.cout_t;
-        ch = ncol - tap * a.cout_t;
-        pix = ((long long)n * (2 * a.H) + 2 * gy + (tap >> 1)) * (2 * a.W) + 2 * gx + (tap & 1);
-        dst = a.ya + pix * a.ya_cs + ch;
-      } else {
-        pix = ((long long)n * a.H + gy) * a.W + gx;
-        if (ncol < a.split) { ch = ncol; dst = a.ya + pix * a.ya_cs + ch; }
-        else { ch = ncol - a.split; dst = a.yb + pix * a.yb_cs + ch; }
-      }
-      float f[CH];
-#pragma unroll
-      for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
-      if (a.epi == EPI_DGRAD) {
-        if (a.mask && ncol < a.split) {
-          const uint4* mp = reinterpret_cast<const uint4*>(a.mask + pix * a.mask_cs + ch);
-#pragma unroll
-          for (int q = 0; q < CH / 8; ++q) {
-            const uint4 m = mp[q];
-            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              f[q * 8 + 2 * j] *= act_grad(__uint_as_float(mw[j] << 16), a.act, a.alpha);
-              f[q * 8 + 2 * j + 1] *= act_grad(__uint_as_float(mw[j] & 0xffff0000u), a.act, a.alpha);
-            }
-          }
-        }
-      } else {
-        const int bch = a.epi == EPI_TCONV ? ch : ncol;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j] + (a.bias ? __ldg(a.bias + bch + j) : 0.f), a.act, a.alpha);
-      }
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-      for (int q = 0; q < CH / 8; ++q) {
-        uint4 o;
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(f[q * 8 + 0], f[q * 8 + 1]);
-        __nv_bfloat162 p1 = __floats2bfloat162_rn(f[q * 8 + 2], f[q * 8 + 3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(f[q * 8 + 4], f[q * 8 + 5]);
-        __nv_bfloat162 p3 = __floats2bfloat162_rn(f[q * 8 + 6], f[q * 8 + 7]);
-        o.x = *reinterpret_cast<uint32_t*>(&p0);
-        o.y = *reinterpret_cast<uint32_t*>(&p1);
-        o.z = *reinterpret_cast<uint32_t*>(&p2);
-        o.w = *reinterpret_cast<uint32_t*>(&p3);
-        d4[q] = o;
-      }
+      epilogue_chunk<CH>(a, v, n, gy, gx, ncol);
     }
   }
   tc_fence_before();
@@ -615,6 +484,14 @@ static bool bf16_view_in(const dnnca_tensor_t* t) {
   return t && t->dtype == DNNCA_BF16 && t->coff % 8 == 0 && t->cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
 }
 
+int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tensor_t* xb, const void* wpack, int ktot, int ntot,
+                     UArgs a);
+static bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("DNNCA_NO_HALO") ? 0 : 1;     // A/B switch for profiling the first-generation kernel
+  return v == 1;
+}
+
 // returns 1 handled / 0 not covered / <0 error
 int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w, const float* bias,
                         const dnnca_tensor_t* y, int k, int act, float alpha, void* ws, size_t ws_bytes) {
@@ -636,7 +513,11 @@ int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_ten
   a.taps = taps; a.ktap = k; a.sx = 1; a.offbase = -(k / 2); a.c_a = cb ? ca : pad16(ca); a.c_b = cb; a.H = x->h; a.W = x->w;
   a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + 7) / 8; a.epi = EPI_FPROP; a.act = act; a.alpha = alpha; a.bias = bias;
   a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
-  a.mask = nullptr; a.n_total = cout; a.cout_t = cout;
+  a.mask = nullptr; a.n_total = cout; a.cout_t = cout; a.nimg = x->n;
+  if (k == 3 && kc == 64 && halo_enabled()) {
+    r = try_conv3x3_halo(s, x, x2, ws, cin, cout, a);
+    if (r != 0) return r;
+  }
   if (kc == 64) return dispatch_bn<64>(s, mA, mB, mW, a, x->n, bn);
   if (kc == 32) return dispatch_bn<32>(s, mA, mB, mW, a, x->n, bn);
   return dispatch_bn<16>(s, mA, mB, mW, a, x->n, bn);
@@ -662,7 +543,11 @@ int try_conv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dz, const float* w
   a.ya = reinterpret_cast<__nv_bfloat16*>(dx->data) + dx->coff; a.ya_cs = dx->cstride; a.split = ca;
   a.yb = dx2 ? reinterpret_cast<__nv_bfloat16*>(dx2->data) + dx2->coff : a.ya; a.yb_cs = dx2 ? dx2->cstride : a.ya_cs;
   a.mask = mask ? reinterpret_cast<const __nv_bfloat16*>(mask->data) + mask->coff : nullptr; a.mask_cs = mask ? mask->cstride : 0;
-  a.n_total = cin; a.cout_t = cin;
+  a.n_total = cin; a.cout_t = cin; a.nimg = dx->n;
+  if (k == 3 && kc == 64 && halo_enabled()) {
+    r = try_conv3x3_halo(s, dz, nullptr, ws, cout, cin, a);
+    if (r != 0) return r;
+  }
   if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, dx->n, bn);
   if (kc == 32) return dispatch_bn<32>(s, mA, mA, mW, a, dx->n, bn);
   return dispatch_bn<16>(s, mA, mA, mW, a, dx->n, bn);

@@ -1,0 +1,275 @@
+// tcgen05 implicit-GEMM 3x3 convolution, second generation: persistent CTAs, ONE halo tile per channel chunk
+// instead of nine shifted tiles, weights resident in shared memory when they fit, double-buffered TMEM so the
+// epilogue of tile i overlaps the MMAs of tile i+1.  Serves Conv2D fprop and dgrad for inputs whose channel
+// counts are multiples of 64 (configs/unet_big.yaml: every layer but the first).
+//
+// Why: the first-generation kernel (conv_umma.cu) re-loads the activation tile for each of the 9 taps and the
+// weight tile for every pixel tile.  At 64-channel layers that is 216 KB of L2->SMEM traffic per 1152 tensor-pipe
+// cycles (187 B/clk/SM against ~45 B/clk/SM of L2 bandwidth): ncu shows 4-20 % tensor-pipe activity there
+// (profiles/r01_ncu_full_umma_unet_big_b8.csv).
+//
+// Geometry: M tile = 16 rows x 8 pixels.  The halo box {64 ch, 16 px, 18 rows} lands as pixel rows of 128 bytes
+// (SWIZZLE_128B), 16 pixels per image row, so the A operand of tap (dy,dx) is the SAME buffer read through a
+// descriptor whose start address is shifted by (dy*16 + dx) rows: the 8 pixels of a tile row form one 8-row core
+// group, consecutive tile rows are SBO = 16*128 = 2048 bytes apart (a multiple of the 1024-byte swizzle period,
+// so one `base_offset` = dx describes every group).  Only pixels x0-1..x0+8 of the 16 are used.
+#include "umma_common.cuh"
+
+namespace dnnca {
+
+constexpr int A_SLOT = 18 * 16 * 128;      // halo tile of one 64-channel chunk (36 KB)
+
+template <int BN>
+struct HGeom {
+  static constexpr int B_TAP = BN * 128;                   // one tap of one 64-channel chunk
+  static constexpr int A_SLOTS = 2;
+  static constexpr int CTRL = 1024;
+  // resident: all 9 * (Cin/64) weight blocks stay in shared memory for the CTA's lifetime
+  static constexpr int smem_resident(int kchunks) { return CTRL + A_SLOTS * A_SLOT + 9 * kchunks * B_TAP + 1024; }
+  static constexpr int B_STAGES = BN > 128 ? 3 : 4;
+  static constexpr int SMEM_STREAM = CTRL + A_SLOTS * A_SLOT + B_STAGES * B_TAP + 1024;
+};
+
+// K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups and a base offset (rows the start
+// address is displaced inside the 1024-byte swizzle period)
+__device__ __forceinline__ uint64_t kmajor128_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_off & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN, bool RESIDENT>
+__global__ void __launch_bounds__(192) conv_umma_halo_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                            const __grid_constant__ CUtensorMap mapB,
+                                                            const __grid_constant__ CUtensorMap mapW, UArgs a) {
+  using G = HGeom<BN>;
+  constexpr int B_STAGES = RESIDENT ? 1 : G::B_STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(smem);      // [2]
+  uint64_t* emptyA = fullA + 2;                              // [2]
+  uint64_t* fullB = emptyA + 2;                              // [B_STAGES] (resident: [1], completes once)
+  uint64_t* emptyB = fullB + 8;                              // [B_STAGES]
+  uint64_t* tfull = emptyB + 8;                              // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;                              // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  unsigned char* aring = smem + G::CTRL;
+  unsigned char* bring = aring + G::A_SLOTS * A_SLOT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kca = a.c_a / 64, kcb = a.c_b / 64, kchunks = kca + kcb;
+  const int n0 = blockIdx.y * BN;
+  const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, 1); mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+    for (int s = 0; s < B_STAGES; ++s) { mbar_init(fullB + s, 1); mbar_init(emptyB + s, 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&mapA);
+      tma_prefetch_desc(&mapW);
+      if (RESIDENT) {                       // every weight block once: [tap][kc] blocks of BN x 64
+        mbar_expect_tx(fullB, (uint32_t)(9 * kchunks * G::B_TAP));
+        for (int kc = 0; kc < kchunks; ++kc)
+          for (int tap = 0; tap < 9; ++tap)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(smem_u32(bring + (kc * 9 + tap) * G::B_TAP)), "l"(reinterpret_cast<uint64_t>(&mapW)), "r"(smem_u32(fullB)),
+                "r"(kc * 64), "r"(n0), "r"(tap)
+                : "memory");
+      }
+      int ai = 0, bi = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int b = t;
+        const int tix = b % a.tiles_x; b /= a.tiles_x;
+        const int tiy = b % a.tiles_y;
+        const int n = b / a.tiles_y;
+        const int x0 = tix * 8, y0 = tiy * 16;
+        for (int kc = 0; kc < kchunks; ++kc, ++ai) {
+          const int s = ai & 1;
+          if (ai >= 2) mbar_wait(emptyA + s, ((ai >> 1) - 1) & 1);
+          mbar_expect_tx(fullA + s, A_SLOT);
+          const bool second = kc >= kca;
+          tma_load_4d(aring + s * A_SLOT, second ? &mapB : &mapA, fullA + s, (second ? kc - kca : kc) * 64, x0 - 1, y0 - 1, n);
+          if (!RESIDENT) {
+            for (int tap = 0; tap < 9; ++tap, ++bi) {
+              const int sb = bi % B_STAGES;
+              if (bi >= B_STAGES) mbar_wait(emptyB + sb, ((bi / B_STAGES) - 1) & 1);
+              mbar_expect_tx(fullB + sb, G::B_TAP);
+              asm volatile(
+                  "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                  ::"r"(smem_u32(bring + sb * G::B_TAP)), "l"(reinterpret_cast<uint64_t>(&mapW)), "r"(smem_u32(fullB + sb)),
+                  "r"(kc * 64), "r"(n0), "r"(tap)
+                  : "memory");
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      if (RESIDENT) { mbar_wait(fullB, 0); }
+      int ai = 0, bi = 0, ti = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+        const int buf = ti & 1;
+        if (ti >= 2) mbar_wait(tempty + buf, ((ti >> 1) - 1) & 1);    // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t dtm = tmem_base + (uint32_t)(buf * BN);
+        for (int kc = 0; kc < kchunks; ++kc, ++ai) {
+          const int s = ai & 1;
+          mbar_wait(fullA + s, (ai >> 1) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(aring + s * A_SLOT);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t sb;
+            if (RESIDENT) {
+              sb = smem_u32(bring + (kc * 9 + tap) * G::B_TAP);
+            } else {
+              const int st = bi % B_STAGES;
+              mbar_wait(fullB + st, (bi / B_STAGES) & 1);
+              tc_fence_after();
+              sb = smem_u32(bring + st * G::B_TAP);
+            }
+            const int dy = tap / 3, dx = tap % 3;
+            const uint32_t astart = sa + (uint32_t)((dy * 16 + dx) * 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = kmajor128_desc(astart + k * 32, 2048, (uint32_t)dx);
+              const uint64_t db = kmajor128_desc(sb + k * 32, 1024, 0);
+              umma_bf16(dtm, da, db, idesc, (kc | tap | k) ? 1u : 0u);
+            }
+            if (!RESIDENT) { umma_commit(emptyB + (bi % B_STAGES)); ++bi; }
+          }
+          umma_commit(emptyA + s);          // halo slot free once these MMAs retire
+        }
+        umma_commit(tfull + buf);           // accumulator of this tile complete
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lanes 32*(warp%4).. =====
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;           // row of the 16x8 pixel tile
+    const int ty = r >> 3, tx = r & 7;
+    int ti = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+      int b = t;
+      const int tix = b % a.tiles_x; b /= a.tiles_x;
+      const int tiy = b % a.tiles_y;
+      const int n = b / a.tiles_y;
+      const int gy = tiy * 16 + ty, gx = tix * 8 + tx;
+      const bool inside = gy < a.H && gx < a.W;
+      const int buf = ti & 1;
+      mbar_wait(tfull + buf, (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+        tmem_ld_wait();
+        const int ncol = n0 + c0;
+        if (inside && ncol < a.n_total) epilogue_chunk<32>(a, v, n, gy, gx, ncol);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ---------------------------------------------------------------- host side
+static bool halo_map(CUtensorMap* m, const dnnca_tensor_t* t) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  char* base = reinterpret_cast<char*>(t->data) + (size_t)t->coff * 2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (t->cstride * 2) % 16) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
+  cuuint64_t strides[3] = {(cuuint64_t)t->cstride * 2, (cuuint64_t)t->w * t->cstride * 2, (cuuint64_t)t->h * t->w * t->cstride * 2};
+  cuuint32_t box[4] = {64, 16, 18, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool weight_map64(CUtensorMap* m, const void* wp, int ktot, int ntot, int bn) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)ntot, 9};
+  cuuint64_t strides[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)ktot * ntot * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, bool RESIDENT>
+static int launch_halo(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mW, const UArgs& a,
+                       int kchunks) {
+  using G = HGeom<BN>;
+  const int smem = RESIDENT ? G::smem_resident(kchunks) : G::SMEM_STREAM;
+  auto kern = conv_umma_halo_kernel<BN, RESIDENT>;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_umma_halo: cudaFuncSetAttribute");
+    smem_set = smem;
+  }
+  const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
+  const int nt = (a.n_total + BN - 1) / BN;
+  int per = sm_count() / nt;                 // persistent CTAs per N tile (1 CTA per SM: smem + 2*BN TMEM columns)
+  if (per < 1) per = 1;
+  if (per > ntiles) per = ntiles;
+  dim3 grid((unsigned)per, (unsigned)nt);
+  kern<<<grid, 192, smem, s>>>(mA, mB, mW, a);
+  DNNCA_LAUNCH_CHECK("conv_umma_halo");
+  note_family(2);
+  return 1;
+}
+
+// Conv2D 3x3 fprop (pack mode 0 already in `wpack`: [tap][N][K]) or dgrad (pack mode 1); returns 1 / 0 / <0
+int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tensor_t* xb, const void* wpack, int ktot, int ntot,
+                     UArgs a) {
+  if (xa->c % 64 || (xb && xb->c % 64) || ntot % 64) return 0;
+  const int bn = ntot % 256 == 0 ? 256 : (ntot % 128 == 0 ? 128 : 64);
+  if (a.split % bn) return 0;               // an N tile must not straddle the two dgrad destinations
+  CUtensorMap mA, mB, mW;
+  if (!halo_map(&mA, xa)) return 0;
+  mB = mA;
+  if (xb && !halo_map(&mB, xb)) return 0;
+  if (!weight_map64(&mW, wpack, ktot, ntot, bn)) return 0;
+  a.tiles_x = (a.W + 7) / 8;
+  a.tiles_y = (a.H + 15) / 16;
+  const int kchunks = ktot / 64;
+  const size_t limit = 220 * 1024;
+  if (bn == 64) {
+    if ((size_t)HGeom<64>::smem_resident(kchunks) <= limit) return launch_halo<64, true>(s, mA, mB, mW, a, kchunks);
+    return launch_halo<64, false>(s, mA, mB, mW, a, kchunks);
+  }
+  if (bn == 128) {
+    if ((size_t)HGeom<128>::smem_resident(kchunks) <= limit) return launch_halo<128, true>(s, mA, mB, mW, a, kchunks);
+    return launch_halo<128, false>(s, mA, mB, mW, a, kchunks);
+  }
+  return launch_halo<256, false>(s, mA, mB, mW, a, kchunks);
+}
+
+}  // namespace dnnca

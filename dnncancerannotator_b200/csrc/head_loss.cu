@@ -167,6 +167,98 @@ __global__ void __launch_bounds__(256) head_bce_kernel(View f, const float* __re
   }
 }
 
+
+// 128-bit vectorised bf16 variant for F % 8 == 0 (unet_big F=64, mulmo F=16): LPP = F/8 lanes share a pixel, each lane
+// owns 8 channels (one uint4 of f, one of df); the logit is a shuffle-reduction over the LPP lanes.
+template <int LPP>
+__global__ void __launch_bounds__(256) head_bce_vec_kernel(View f, const float* __restrict__ w,
+                                                          const float* __restrict__ b, const float* __restrict__ label,
+                                                          const dnnca_label_stats_t* __restrict__ ls,
+                                                          dnnca_loss_config_t cfg, float* __restrict__ logits,
+                                                          float* __restrict__ probs, float* __restrict__ per_sample,
+                                                          View df, int has_df, int act, float alpha,
+                                                          float* __restrict__ dw, float* __restrict__ db) {
+  constexpr int F = LPP * 8;
+  constexpr int PPB = 256 / LPP;                    // pixels per block iteration
+  __shared__ float red[F + 2];
+  for (int i = threadIdx.x; i < F + 2; i += 256) red[i] = 0.f;
+  __syncthreads();
+  const long long HW = (long long)f.h * f.w;
+  const long long total = HW * f.n;
+  float weight;
+  if (cfg.has_weight) {
+    weight = cfg.weight;
+  } else {
+    const float r = (float)(ls->sum / (double)total);
+    weight = r > 0.f ? 1.f / r : 1.f;
+  }
+  weight = cfg.weight_mul * weight + cfg.weight_add;
+  const float bias = b ? b[0] : 0.f;
+  const int sub = threadIdx.x % LPP, pslot = threadIdx.x / LPP;
+  float wr[8], dwacc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { wr[j] = w[sub * 8 + j]; dwacc[j] = 0.f; }
+  float dbacc = 0.f, lossacc = 0.f;
+  const long long base = (long long)blockIdx.y * HW;
+  for (long long q = (long long)blockIdx.x * PPB + pslot; q < HW; q += (long long)gridDim.x * PPB) {
+    const long long p = base + q;
+    const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(f.data) + p * f.cstride + f.coff + sub * 8);
+    const uint32_t wd[4] = {raw.x, raw.y, raw.z, raw.w};
+    float fv[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { fv[2 * j] = __uint_as_float(wd[j] << 16); fv[2 * j + 1] = __uint_as_float(wd[j] & 0xffff0000u); }
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z = fmaf(fv[j], wr[j], z);
+#pragma unroll
+    for (int o = 1; o < LPP; o <<= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    z += bias;
+    const float y = label[p];
+    const float mask = y * (weight - 1.f) + 1.f;
+    const float pr = 1.f / (1.f + expf(-z));
+    const float dz = mask * (pr - y) * cfg.grad_scale;
+    if (sub == 0) {
+      lossacc += (fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)))) * mask;
+      dbacc += dz;
+      if (logits) logits[p] = z;
+      if (probs) probs[p] = pr;
+    }
+    float o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dwacc[j] = fmaf(dz, fv[j], dwacc[j]);
+      o8[j] = dz * wr[j] * act_grad(fv[j], act, alpha);
+    }
+    if (has_df) {
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(o8[2 * j], o8[2 * j + 1]);
+        ow[j] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(df.data) + p * df.cstride + df.coff + sub * 8) =
+          make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+  // lanes with the same channel group: reduce over the warp first (stride LPP), then one smem atomic per warp
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = dwacc[j];
+#pragma unroll
+    for (int o = LPP; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) < LPP) atomicAdd(red + sub * 8 + j, v);
+  }
+  lossacc = warp_sum(lossacc);
+  dbacc = warp_sum(dbacc);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(red + F, dbacc); atomicAdd(red + F + 1, lossacc); }
+  __syncthreads();
+  for (int c = threadIdx.x; c < F + 2; c += 256) {
+    if (c < F) { if (dw) atomicAdd(dw + c, red[c]); }
+    else if (c == F) { if (db) atomicAdd(db, red[c]); }
+    else atomicAdd(per_sample + blockIdx.y, red[c] / (float)HW);
+  }
+}
+
 }  // namespace dnnca
 
 using namespace dnnca;
@@ -225,6 +317,22 @@ extern "C" int dnnca_head_bce_fwd_bwd(void* stream, const dnnca_tensor_t* f, con
   dim3 grid(gx, f->n);
   View vdf = df ? mk(df) : mk(f);
   cudaStream_t s = (cudaStream_t)stream;
+  auto al = [](const dnnca_tensor_t* t) {
+    return t->dtype == DNNCA_BF16 && t->coff % 8 == 0 && t->cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
+  };
+  if ((f->c == 16 || f->c == 32 || f->c == 64) && al(f) && (!df || al(df))) {
+    const int lpp = f->c / 8;
+    int gv = (int)((HW + (256 / lpp) * 8 - 1) / ((256 / lpp) * 8));
+    if (gv > cap) gv = cap;
+    if (gv < 1) gv = 1;
+    dim3 g2(gv, f->n);
+#define LAUNCH_VEC(L) head_bce_vec_kernel<L><<<g2, 256, 0, s>>>(mk(f), w, b, label, lstats, *cfg, logits, probs, per_sample, vdf, \
+                                                                df != nullptr, act, alpha, dw, db)
+    if (lpp == 2) LAUNCH_VEC(2); else if (lpp == 4) LAUNCH_VEC(4); else LAUNCH_VEC(8);
+#undef LAUNCH_VEC
+    DNNCA_LAUNCH_CHECK("head_bce_fwd_bwd");
+    return DNNCA_OK;
+  }
 #define LAUNCH_HEAD(FM)                                                                                          \
   DNNCA_DISPATCH_DTYPE(f->dtype, (head_bce_kernel<T, FM><<<grid, 256, 0, s>>>(mk(f), w, b, label, lstats, *cfg, logits, \
                                                                                probs, per_sample, vdf, df != nullptr, \

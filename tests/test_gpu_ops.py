@@ -387,7 +387,7 @@ def test_head_bce_fused(N, mode, F, healthy, weight):
     wt = rng.normal(size=F).astype(np.float32)
     b = np.array([0.1], np.float32)
     y = (rng.uniform(size=(n, h, w)) < (0.0 if healthy else 0.05)).astype(np.float32)
-    fb, fo, _ = embed(f, dt, 1, 0)
+    fb, fo, _ = embed(f, dt, 8 if F % 8 == 0 else 1, 0)      # 16-byte aligned slices take the vectorised bf16 kernel
     fv = view(N, fb, fo, F)
     ls = torch.zeros(16, dtype=torch.uint8, device='cuda')
     yd = dev(y)
@@ -488,3 +488,49 @@ def test_bad_arguments_fail_loudly(N):
     yv2 = N.tensor_view(torch.zeros(1, 5, 4, 3, device='cuda'))
     with pytest.raises(N.DnncaError):
         N.call('dnnca_conv2d_fprop', None, C.byref(xv), None, N.ptr(x), None, C.byref(yv2), 3, 0, 0.0, None, None, 0)
+
+
+@pytest.mark.parametrize('shape', [(4, 128, 128, 64, 0, 64), (2, 96, 72, 64, 64, 128), (3, 64, 64, 128, 0, 256),
+                                   (2, 40, 56, 256, 0, 64)])
+def test_conv_umma_persistent_many_tiles(N, shape):
+    """More pixel tiles than persistent CTAs: exercises the halo-tile ring, the resident / streamed weight modes and
+    the double-buffered TMEM hand-off of the second-generation tcgen05 kernel over several tiles per CTA
+    (fprop with two inputs, dgrad with two outputs and mask), against torch autograd."""
+    n, h, w, ca, cb, cout = shape
+    cin = ca + cb
+    dt = torch.bfloat16
+    rng = np.random.default_rng(sum(shape))
+    x = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), dt)
+    wt = (rng.normal(size=(3, 3, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32)
+    b = rng.normal(size=cout).astype(np.float32)
+    dz = q(rng.normal(size=(n, h, w, cout)).astype(np.float32), dt)
+    lib = N.lib()
+    ws = torch.zeros(int(lib.dnnca_conv_workspace_bytes(9, cin, cout)), dtype=torch.uint8, device='cuda')
+    wd, bd = dev(wt), dev(b)
+    xa = dev(x[..., :ca], dt)
+    xb = dev(x[..., ca:], dt) if cb else None
+    y = torch.zeros(n, h, w, cout, dtype=dt, device='cuda')
+    xav, yv = N.tensor_view(xa), N.tensor_view(y)
+    xbv = N.tensor_view(xb) if cb else None
+    lib.dnnca_debug_family_count(2, 1)
+    N.call('dnnca_conv2d_fprop', None, C.byref(xav), C.byref(xbv) if cb else None, N.ptr(wd), N.ptr(bd), C.byref(yv), 3,
+           N.ACT_RELU, 0.0, None, N.ptr(ws), ws.numel())
+    sync()
+    xt = torch.from_numpy(x).requires_grad_()
+    ref = torch.relu(ops.conv2d(xt, torch.from_numpy(wt), torch.from_numpy(b)))
+    close(y.float().cpu().numpy(), ref.detach().numpy(), 'bf16')
+    # dgrad: two outputs, relu mask on the first
+    dzd = dev(dz, dt)
+    dxa = torch.zeros(n, h, w, ca, dtype=dt, device='cuda')
+    dxb = torch.zeros(n, h, w, max(cb, 1), dtype=dt, device='cuda')
+    dzv, dxav, dxbv = N.tensor_view(dzd), N.tensor_view(dxa), N.tensor_view(dxb)
+    N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(wd), C.byref(dxav), C.byref(dxbv) if cb else None, 3,
+           C.byref(xav), N.ACT_RELU, 0.0, N.ptr(ws), ws.numel())
+    sync()
+    lin = ops.conv2d(xt, torch.from_numpy(wt), None)
+    (g,) = torch.autograd.grad(lin, xt, torch.from_numpy(dz))
+    g = g.numpy()
+    close(dxa.float().cpu().numpy(), g[..., :ca] * (x[..., :ca] > 0), 'bf16', scale=np.abs(g).max())
+    if cb:
+        close(dxb.float().cpu().numpy(), g[..., ca:], 'bf16', scale=np.abs(g).max())
+    assert lib.dnnca_debug_family_count(2, 0) == 2
