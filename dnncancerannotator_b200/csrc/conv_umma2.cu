@@ -11,8 +11,9 @@
 // Geometry: M tile = 16 rows x 8 pixels.  The halo box {64 ch, 16 px, 18 rows} lands as pixel rows of 128 bytes
 // (SWIZZLE_128B), 16 pixels per image row, so the A operand of tap (dy,dx) is the SAME buffer read through a
 // descriptor whose start address is shifted by (dy*16 + dx) rows: the 8 pixels of a tile row form one 8-row core
-// group, consecutive tile rows are SBO = 16*128 = 2048 bytes apart (a multiple of the 1024-byte swizzle period,
-// so one `base_offset` = dx describes every group).  Only pixels x0-1..x0+8 of the 16 are used.
+// group, consecutive tile rows are SBO = 16*128 = 2048 bytes apart.  Only pixels x0-1..x0+8 of the 16 are used.
+#include <stdlib.h>
+
 #include "umma_common.cuh"
 
 namespace dnnca {
@@ -151,7 +152,10 @@ __global__ void __launch_bounds__(192) conv_umma_halo_kernel(const __grid_consta
             const uint32_t astart = sa + (uint32_t)((dy * 16 + dx) * 128);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t da = kmajor128_desc(astart + k * 32, 2048, (uint32_t)dx);
+              // base_offset stays 0: measured on B200, the 128B swizzle XOR is taken from the absolute shared-memory
+              // address bits (the same bits the TMA used when writing), so a start address displaced by whole
+              // 128-byte rows needs no correction (base_offset = dx produced wrong results).
+              const uint64_t da = kmajor128_desc(astart + k * 32, 2048, 0);
               const uint64_t db = kmajor128_desc(sb + k * 32, 1024, 0);
               umma_bf16(dtm, da, db, idesc, (kc | tap | k) ? 1u : 0u);
             }
@@ -259,6 +263,7 @@ int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tenso
   if (!weight_map64(&mW, wpack, ktot, ntot, bn)) return 0;
   a.tiles_x = (a.W + 7) / 8;
   a.tiles_y = (a.H + 15) / 16;
+  a.dbg = getenv("DNNCA_HALO_DBG") ? atoi(getenv("DNNCA_HALO_DBG")) : 0;
   const int kchunks = ktot / 64;
   const size_t limit = 220 * 1024;
   if (bn == 64) {

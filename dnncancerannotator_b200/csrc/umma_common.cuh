@@ -89,6 +89,7 @@ struct UArgs {
   int n_total;               // total GEMM N
   int cout_t;                // ConvT fprop: channels per tap
   int nimg;                  // images (persistent kernels)
+  int dbg;                   // experiment switch (descriptor variants)
 };
 
 // epilogue of one 32-(or 16-)column chunk of one accumulator row: bias+act (fprop / ConvT) or act'(mask) (dgrad),
