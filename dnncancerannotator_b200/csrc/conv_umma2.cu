@@ -24,7 +24,7 @@ template <int BN>
 struct HGeom {
   static constexpr int B_TAP = BN * 128;                   // one tap of one 64-channel chunk
   static constexpr int A_SLOTS = 2;
-  static constexpr int CTRL = 1024;
+  static constexpr int CTRL = 2048;                        // barriers + TMEM slot + bias slice (BN floats at +256)
   // resident: all 9 * (Cin/64) weight blocks stay in shared memory for the CTA's lifetime
   static constexpr int smem_resident(int kchunks) { return CTRL + A_SLOTS * A_SLOT + 9 * kchunks * B_TAP + 1024; }
   static constexpr int B_STAGES = BN > 128 ? 3 : 4;
@@ -45,7 +45,7 @@ __device__ __forceinline__ uint64_t kmajor128_desc(uint32_t saddr, uint32_t sbo_
 }
 
 template <int BN, bool RESIDENT>
-__global__ void __launch_bounds__(192) conv_umma_halo_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_constant__ CUtensorMap mapA,
                                                             const __grid_constant__ CUtensorMap mapB,
                                                             const __grid_constant__ CUtensorMap mapW, UArgs a) {
   using G = HGeom<BN>;
@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(192) conv_umma_halo_kernel(const __grid_consta
   uint64_t* tfull = emptyB + 8;                              // [2] accumulator ready
   uint64_t* tempty = tfull + 2;                              // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + 256);      // [BN] bias slice of this CTA's N tile (fprop)
   unsigned char* aring = smem + G::CTRL;
   unsigned char* bring = aring + G::A_SLOTS * A_SLOT;
 
@@ -68,11 +69,13 @@ __global__ void __launch_bounds__(192) conv_umma_halo_kernel(const __grid_consta
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, 1); mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, 1); mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(fullB + s, 1); mbar_init(emptyB + s, 1); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  for (int i = threadIdx.x; i < BN; i += blockDim.x)
+    sbias[i] = (a.bias && a.epi != EPI_DGRAD && n0 + i < a.n_total) ? a.bias[n0 + i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -136,30 +139,30 @@ __global__ void __launch_bounds__(192) conv_umma_halo_kernel(const __grid_consta
           const int s = ai & 1;
           mbar_wait(fullA + s, (ai >> 1) & 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(aring + s * A_SLOT);
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            uint32_t sb;
-            if (RESIDENT) {
-              sb = smem_u32(bring + (kc * 9 + tap) * G::B_TAP);
-            } else {
+          // descriptors differ only in the 14-bit start-address field: build one per operand and add immediates
+          // (the MMA-issuing thread is a serial instruction stream; at N = 64 an MMA retires every ~32 cycles)
+          const uint64_t a_base = kmajor128_desc(smem_u32(aring + s * A_SLOT), 2048, 0);
+          if (RESIDENT) {
+            const uint64_t b_base = kmajor128_desc(smem_u32(bring + kc * 9 * G::B_TAP), 1024, 0);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t da0 = a_base + (uint64_t)(((tap / 3) * 16 + (tap % 3)) * 8);      // (dy*16+dx) rows of 128 B, >>4
+              const uint64_t db0 = b_base + (uint64_t)(tap * (G::B_TAP >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(dtm, da0 + 2 * k, db0 + 2 * k, idesc, (kc | tap | k) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap, ++bi) {
               const int st = bi % B_STAGES;
               mbar_wait(fullB + st, (bi / B_STAGES) & 1);
               tc_fence_after();
-              sb = smem_u32(bring + st * G::B_TAP);
-            }
-            const int dy = tap / 3, dx = tap % 3;
-            const uint32_t astart = sa + (uint32_t)((dy * 16 + dx) * 128);
+              const uint64_t db0 = kmajor128_desc(smem_u32(bring + st * G::B_TAP), 1024, 0);
+              const uint64_t da0 = a_base + (uint64_t)(((tap / 3) * 16 + (tap % 3)) * 8);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // base_offset stays 0: measured on B200, the 128B swizzle XOR is taken from the absolute shared-memory
-              // address bits (the same bits the TMA used when writing), so a start address displaced by whole
-              // 128-byte rows needs no correction (base_offset = dx produced wrong results).
-              const uint64_t da = kmajor128_desc(astart + k * 32, 2048, 0);
-              const uint64_t db = kmajor128_desc(sb + k * 32, 1024, 0);
-              umma_bf16(dtm, da, db, idesc, (kc | tap | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) umma_bf16(dtm, da0 + 2 * k, db0 + 2 * k, idesc, (kc | tap | k) ? 1u : 0u);
+              umma_commit(emptyB + st);
             }
-            if (!RESIDENT) { umma_commit(emptyB + (bi % B_STAGES)); ++bi; }
           }
           umma_commit(emptyA + s);          // halo slot free once these MMAs retire
         }
@@ -167,10 +170,13 @@ __global__ void __launch_bounds__(192) conv_umma_halo_kernel(const __grid_consta
       }
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lanes 32*(warp%4).. =====
+    // ===== epilogue: warps 2..9.  A warp may only touch TMEM lanes 32*(warp%4)..+31, so two warps share each lane
+    // quarter and split the columns; the mask row (dgrad) is prefetched before the accumulator is ready =====
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;       // 0: columns [0, BN/2), 1: [BN/2, BN)
     const int r = lg * 32 + lane;           // row of the 16x8 pixel tile
     const int ty = r >> 3, tx = r & 7;
+    constexpr int NCHUNK = BN / 64;         // 32-column chunks per warp
     int ti = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
       int b = t;
@@ -180,15 +186,26 @@ __global__ void __launch_bounds__(192) conv_umma_halo_kernel(const __grid_consta
       const int gy = tiy * 16 + ty, gx = tix * 8 + tx;
       const bool inside = gy < a.H && gx < a.W;
       const int buf = ti & 1;
+      ChunkAddr ca[NCHUNK];
+      uint4 m[NCHUNK][4];
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int col = half * (BN / 2) + c * 32;
+        ca[c] = chunk_addr(a, n, inside ? gy : 0, inside ? gx : 0, n0 + col);
+        if (ca[c].msk && inside) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m[c][q] = reinterpret_cast<const uint4*>(ca[c].msk)[q];
+        }
+      }
       mbar_wait(tfull + buf, (ti >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int col = half * (BN / 2) + c * 32;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN + col), v);
         tmem_ld_wait();
-        const int ncol = n0 + c0;
-        if (inside && ncol < a.n_total) epilogue_chunk<32>(a, v, n, gy, gx, ncol);
+        if (inside && n0 + col < a.n_total) epilogue_chunk32(a, v, ca[c], m[c], sbias + col);
       }
       tc_fence_before();
       __syncwarp();
@@ -244,7 +261,7 @@ static int launch_halo(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap&
   if (per < 1) per = 1;
   if (per > ntiles) per = ntiles;
   dim3 grid((unsigned)per, (unsigned)nt);
-  kern<<<grid, 192, smem, s>>>(mA, mB, mW, a);
+  kern<<<grid, 320, smem, s>>>(mA, mB, mW, a);
   DNNCA_LAUNCH_CHECK("conv_umma_halo");
   note_family(2);
   return 1;

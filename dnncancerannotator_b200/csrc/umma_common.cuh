@@ -94,6 +94,71 @@ struct UArgs {
 
 // epilogue of one 32-(or 16-)column chunk of one accumulator row: bias+act (fprop / ConvT) or act'(mask) (dgrad),
 // bf16 conversion, 16-byte stores into the (possibly channel-sliced) NHWC destination
+// destination / mask addressing of one accumulator-row chunk
+struct ChunkAddr {
+  __nv_bfloat16* dst;
+  const __nv_bfloat16* msk;   // nullptr when no mask applies to this chunk
+  int bch;                    // bias channel
+};
+__device__ __forceinline__ ChunkAddr chunk_addr(const UArgs& a, int n, int gy, int gx, int ncol) {
+  ChunkAddr r;
+  long long pix;
+  int ch;
+  if (a.epi == EPI_TCONV) {
+    const int tap = ncol / a.cout_t;
+    ch = ncol - tap * a.cout_t;
+    pix = ((long long)n * (2 * a.H) + 2 * gy + (tap >> 1)) * (2 * a.W) + 2 * gx + (tap & 1);
+    r.dst = a.ya + pix * a.ya_cs + ch;
+    r.bch = ch;
+  } else {
+    pix = ((long long)n * a.H + gy) * a.W + gx;
+    if (ncol < a.split) { ch = ncol; r.dst = a.ya + pix * a.ya_cs + ch; }
+    else { ch = ncol - a.split; r.dst = a.yb + pix * a.yb_cs + ch; }
+    r.bch = ncol;
+  }
+  r.msk = (a.epi == EPI_DGRAD && a.mask && ncol < a.split) ? a.mask + pix * a.mask_cs + ch : nullptr;
+  return r;
+}
+
+// persistent-kernel epilogue of a 32-column chunk: `m` holds the mask row prefetched before the accumulator was ready,
+// `sbias` is the CTA's bias slice in shared memory
+__device__ __forceinline__ void epilogue_chunk32(const UArgs& a, const uint32_t (&v)[32], const ChunkAddr& ca, const uint4 (&m)[4],
+                                                 const float* sbias) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (a.epi == EPI_DGRAD) {
+    if (ca.msk) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t mw[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[q * 8 + 2 * j] *= act_grad(__uint_as_float(mw[j] << 16), a.act, a.alpha);
+          f[q * 8 + 2 * j + 1] *= act_grad(__uint_as_float(mw[j] & 0xffff0000u), a.act, a.alpha);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j] + sbias[j], a.act, a.alpha);
+  }
+  uint4* d4 = reinterpret_cast<uint4*>(ca.dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 o;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[q * 8 + 0], f[q * 8 + 1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(f[q * 8 + 2], f[q * 8 + 3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[q * 8 + 4], f[q * 8 + 5]);
+    __nv_bfloat162 p3 = __floats2bfloat162_rn(f[q * 8 + 6], f[q * 8 + 7]);
+    o.x = *reinterpret_cast<uint32_t*>(&p0);
+    o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2);
+    o.w = *reinterpret_cast<uint32_t*>(&p3);
+    d4[q] = o;
+  }
+}
+
 template <int CH>
 __device__ __forceinline__ void epilogue_chunk(const UArgs& a, const uint32_t (&v)[32], int n, int gy, int gx, int ncol) {
   __nv_bfloat16* dst;
