@@ -98,8 +98,10 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': r['steps'], 'warmup': max(args.warmup, 1), 'ms_per_step': r['ms_per_step'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'configs/{args.config}.yaml train step, batch {args.cpu_batch} of '
-                               f'{args.size}x{args.size}x{args.channels} slices, host CPU'},
+        'config': {'workload': f'configs/{args.config}.yaml UNetAnnotator training step, per-GPU batch {args.batch} of '
+                               f'{args.size}x{args.size}x{args.channels} slices ({args.dtype} activations, fp32 accumulate/master weights)',
+                   'global_batch': args.batch * args.gpus, 'parallelism': f'dp{args.gpus}',
+                   'sample': f'each timed step = batch {args.cpu_batch} of the same slices on the host CPU (fp32)'},
         'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
                          'sample': r['sample'] + '; torch-CPU restatement of the reference (TensorFlow unavailable)'},
         'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},

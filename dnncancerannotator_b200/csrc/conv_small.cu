@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const __grid_constan
       mbar_expect_tx(bar, ROWS * Raw<T, CBS, TW, 1>::NCH * 16);
       tma_load_4d(raw, &mapB, bar, 0, Raw<T, CBS, TW, 1>::chunk_start(x0), y0 - 1, n);
     }
-#pragma unroll (COTP <= 4 ? 3 : (COTP <= 8 ? 2 : 1))
+#pragma unroll 1
     for (int ci = 0; ci < cs; ++ci) {
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) {
@@ -250,9 +250,7 @@ struct WGeom {
   static constexpr int COB = COUT % 3 == 0 ? 3 : (COUT % 4 == 0 ? 4 : COUT);
   static constexpr int NCB = COUT / COB;
   static constexpr int TPS = CIN * NCB;                                    // threads per pixel-group slot
-  static constexpr int G_ = 256 / TPS;
-  // largest power of two <= G_: the 64/128 pixel groups of a tile then split evenly over the slots
-  static constexpr int G = G_ >= 128 ? 128 : (G_ >= 64 ? 64 : (G_ >= 32 ? 32 : (G_ >= 16 ? 16 : (G_ >= 8 ? 8 : (G_ >= 4 ? 4 : (G_ >= 2 ? 2 : 1))))));
+  static constexpr int G = 256 / TPS;      // (a power-of-two slot count was measured slower: fewer active threads)
   static constexpr int NCHA = Raw<T, CA, TW, 1>::NCH, NCHB = Raw<T, CB, TW, 1>::NCH, NCHG = Raw<T, COUT, TW, 0>::NCH;
   static constexpr int RAWA = ru(ROWS * NCHA * 16, 128), RAWB = ru(ROWS * NCHB * 16, 128), RAWG = ru(TYN * NCHG * 16, 128);
   static constexpr int XS = ru(CIN * ROWS * PITCH * 4, 128), GS = ru(COUT * TYN * TW * 4, 128);

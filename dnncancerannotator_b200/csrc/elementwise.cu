@@ -420,7 +420,8 @@ extern "C" int dnnca_channel_stats(void* stream, const dnnca_tensor_t* x, double
   long long P = (long long)x->n * x->h * x->w;
   if (vec8_ok(x)) {
     ChanLayout G = group_layout(x->c);
-    reduce_vec8_kernel<0><<<grid_for(P, G.pl * 8), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(x), nullptr, stats, G.cl, G.pl, P);
+    // >= 64 pixels per thread: every block ends with 2*C fp64 atomics, so small tensors get few blocks
+    reduce_vec8_kernel<0><<<grid_for(P, G.pl * 64), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(x), nullptr, stats, G.cl, G.pl, P);
     DNNCA_LAUNCH_CHECK("channel_stats");
     return DNNCA_OK;
   }
@@ -496,7 +497,7 @@ extern "C" int dnnca_bn_bwd_reduce(void* stream, const dnnca_tensor_t* x, const 
   long long P = (long long)x->n * x->h * x->w;
   if (vec8_ok(x) && vec8_ok(dy)) {
     ChanLayout G = group_layout(x->c);
-    reduce_vec8_kernel<1><<<grid_for(P, G.pl * 8), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(dy), mean_invstd, sums, G.cl, G.pl, P);
+    reduce_vec8_kernel<1><<<grid_for(P, G.pl * 64), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(dy), mean_invstd, sums, G.cl, G.pl, P);
     DNNCA_LAUNCH_CHECK("bn_bwd_reduce");
     return DNNCA_OK;
   }
