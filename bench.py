@@ -267,7 +267,7 @@ def run_ours(args):
     m._train_on_static(plan)
     torch.cuda.synchronize()
     launches_per_step = int(lib.dnnca_debug_launch_count(1))
-    roofline, breakdown = None, None
+    roofline, breakdown, categories = None, None, None
     if not args.no_profile:      # every rank runs the pass (it contains the gradient all-reduce); rank 0 reports
         peaks = {}
         pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -283,6 +283,21 @@ def run_ours(args):
         breakdown = [{'kernel': k, 'share': round(d['ms'] / tot, 4), 'ms': round(d['ms'] / 3, 4),
                       'gbs': round(d['bytes'] / d['ms'] / 1e6, 1) if d['ms'] else None,
                       'tflops': round(d['flops'] / d['ms'] / 1e9, 2) if d['ms'] else None} for k, d in rows[:12]]
+        cats = {}
+        for kname, v in agg.items():
+            base = kname.split('[')[0]
+            cat = ('conv_' + base.split('_')[-1] if base.startswith('conv2d') else
+                   'convT' if base.startswith('convtranspose') else
+                   'batchnorm' if base.startswith('bn_') or base == 'channel_stats' else
+                   'pool' if base.startswith('maxpool') else
+                   'head_loss' if base.startswith('head') or base.startswith('label') else base)
+            c = cats.setdefault(cat, [0.0, 0.0, 0.0])
+            c[0] += v['ms'] / 3
+            c[1] += v['flops'] / 3
+            c[2] += v['bytes'] / 3
+        categories = {k2: {'ms': round(v[0], 3), 'share': round(v[0] * 3 / tot, 4),
+                           'tflops': round(v[1] / v[0] / 1e9, 1) if v[1] else None,
+                           'gbs': round(v[2] / v[0] / 1e6, 1)} for k2, v in sorted(cats.items(), key=lambda kv: -kv[1][0])}
         k, d = rows[0]
         tens_peak = float(peaks.get('bf16_tflops_sustained', 1400.0))      # kernels timed inside a long step
         conv_ms = sum(v['ms'] for v in agg.values() if v['flops'])
@@ -329,7 +344,7 @@ def run_ours(args):
                    'l2': 'working set per step (>1 GB of activations) exceeds the 126 MB L2; no flush needed',
                    'cuda_graph': True},
         'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
-        'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'breakdown': breakdown,
+        'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'breakdown': breakdown, 'categories': categories,
         'loss_first': loss0, 'loss_last': final_loss, 'wall_s_timed_region': wall,
     }
     print(json.dumps(line), flush=True)

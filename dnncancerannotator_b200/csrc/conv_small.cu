@@ -55,7 +55,11 @@ struct FGeom {
   static constexpr int WS_BYTES = ru(CIN * 9 * COTP * 8, 128);
   static constexpr int OSA_BYTES = ru(TYN * TW * OA * (int)sizeof(T), 128);
   static constexpr int OSB_BYTES = ru(TYN * TW * OB * (int)sizeof(T), 128);
-  static constexpr int XS_BYTES = cmax(ru(CK * ROWS * PITCH * 4, 128), OSA_BYTES + OSB_BYTES);
+  static constexpr int PLANES = CK * ROWS * PITCH;        // floats
+  // a second, one-pixel-shifted copy of the planes (aligned odd pixel pairs without register moves) where shared
+  // memory is cheap: the 1/3/4-channel layers at full resolution, whose few FFMA2 per window amortise moves worst
+  static constexpr bool SHIFT = false;     // measured: the extra STS/LDS cost more than the moves they save here
+  static constexpr int XS_BYTES = cmax(ru((SHIFT ? 2 : 1) * PLANES * 4, 128), OSA_BYTES + OSB_BYTES);
   static constexpr int OFF_RAW = 128, OFF_WS = OFF_RAW + RAW_BYTES, OFF_XS = OFF_WS + WS_BYTES;
   static constexpr int SMEM = OFF_XS + XS_BYTES;
   static constexpr int EPC = 16 / (int)sizeof(T);
@@ -128,8 +132,8 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const __grid_constan
     const int cs = s == 0 ? CA : CB;
     const int cbase = s == 0 ? 0 : CA;
     mbar_wait(bar, s);
-    if (s == 0) deinterleave<T, CA, TW, 1>(raw, xs, ROWS, PITCH);
-    else        deinterleave<T, CBS, TW, 1>(raw, xs, ROWS, PITCH);
+    if (s == 0) deinterleave<T, CA, TW, 1>(raw, xs, ROWS, PITCH, G::SHIFT ? G::PLANES : 0);
+    else        deinterleave<T, CBS, TW, 1>(raw, xs, ROWS, PITCH, G::SHIFT ? G::PLANES : 0);
     __syncthreads();                                   // planes ready, raw buffer free, weights visible
     if (CB && s == 0 && threadIdx.x == 0) {            // second input streams in behind the first one's math
       mbar_expect_tx(bar, ROWS * Raw<T, CBS, TW, 1>::NCH * 16);
@@ -140,10 +144,16 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const __grid_constan
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) {
         const float* xr = xs + (ci * ROWS + ty + dy) * PITCH + tx * PX;
-        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(xr);
-        const u64 p45 = *reinterpret_cast<const u64*>(xr + 4);
+        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(xr);                 // (c0,c1) (c2,c3)
+        const u64 p45 = *reinterpret_cast<const u64*>(xr + 4);                         // (c4,c5)
         const u64 p01 = q.x, p23 = q.y;
-        const u64 p12 = pack2(hi32(p01), lo32(p23)), p34 = pack2(hi32(p23), lo32(p45));
+        u64 p12, p34;
+        if (G::SHIFT) {
+          const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(xr + G::PLANES);  // shifted copy: (c1,c2) (c3,c4)
+          p12 = q1.x; p34 = q1.y;
+        } else {
+          p12 = pack2(hi32(p01), lo32(p23)); p34 = pack2(hi32(p23), lo32(p45));
+        }
         const float* wrow = ws2 + ((cbase + ci) * 9 + dy * 3) * COTP * 2;
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
@@ -253,10 +263,14 @@ struct WGeom {
   static constexpr int G = 256 / TPS;      // (a power-of-two slot count was measured slower: fewer active threads)
   static constexpr int NCHA = Raw<T, CA, TW, 1>::NCH, NCHB = Raw<T, CB, TW, 1>::NCH, NCHG = Raw<T, COUT, TW, 0>::NCH;
   static constexpr int RAWA = ru(ROWS * NCHA * 16, 128), RAWB = ru(ROWS * NCHB * 16, 128), RAWG = ru(TYN * NCHG * 16, 128);
-  static constexpr int XS = ru(CIN * ROWS * PITCH * 4, 128), GS = ru(COUT * TYN * TW * 4, 128);
+  static constexpr int PLANES = CIN * ROWS * PITCH;       // floats
+  static constexpr bool SHIFT = CIN <= 6;                 // + one-pixel-shifted copy of the planes (see FGeom)
+  static constexpr int NS = (RAWA + RAWB + RAWG) <= 16 * 1024 ? 3 : 2;   // TMA stages (raw tiles in flight)
+  static constexpr int XS = ru((SHIFT ? 2 : 1) * PLANES * 4, 128), GS = ru(COUT * TYN * TW * 4, 128);
   static constexpr int RED = ru((9 * CIN * COUT + COUT) * 4, 128);
-  static constexpr int OFF_RA = 128, OFF_RB = OFF_RA + RAWA, OFF_RG = OFF_RB + RAWB, OFF_XS = OFF_RG + RAWG,
-                       OFF_GS = OFF_XS + XS, OFF_RED = OFF_GS + GS, SMEM = OFF_RED + RED;
+  static constexpr int RAWS = RAWA + RAWB + RAWG;         // one stage of raw tiles
+  static constexpr int OFF_RA = 128, OFF_XS = OFF_RA + NS * RAWS, OFF_GS = OFF_XS + XS, OFF_RED = OFF_GS + GS,
+                       SMEM = OFF_RED + RED;
   static constexpr bool FITS = COUT % COB == 0 && TPS <= 256 && NCHA <= 256 && NCHB <= 256 && NCHG <= 256 && SMEM <= 200 * 1024;
 };
 
@@ -272,13 +286,12 @@ __global__ void __launch_bounds__(256, 2) conv3x3_small_wgrad_kernel(const __gri
   constexpr int NGRP = TYN * TXN;
   constexpr int CBS = CB ? CB : 1;
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  T* rawA = reinterpret_cast<T*>(smem + G::OFF_RA);
-  T* rawB = reinterpret_cast<T*>(smem + G::OFF_RB);
-  T* rawG = reinterpret_cast<T*>(smem + G::OFF_RG);
-  float* xs = reinterpret_cast<float*>(smem + G::OFF_XS);   // [CIN][ROWS][PITCH]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);        // [NS]
+  unsigned char* rawbase = smem + G::OFF_RA;
+  float* xs = reinterpret_cast<float*>(smem + G::OFF_XS);   // [CIN][ROWS][PITCH] + shifted copy
   float* gs = reinterpret_cast<float*>(smem + G::OFF_GS);   // [COUT][TYN][TW]
   float* red = reinterpret_cast<float*>(smem + G::OFF_RED);
+  constexpr int NS = G::NS;
 
   const int slot = threadIdx.x / G::TPS;
   const int rem = threadIdx.x % G::TPS;
@@ -296,34 +309,40 @@ __global__ void __launch_bounds__(256, 2) conv3x3_small_wgrad_kernel(const __gri
   for (int e = threadIdx.x; e < 9 * CIN * COUT + COUT; e += 256) red[e] = 0.f;
 
   constexpr uint32_t TX_BYTES = ROWS * G::NCHA * 16 + ROWS * G::NCHB * 16 + TYN * G::NCHG * 16;
-  auto issue = [&](int tile) {
+  auto issue = [&](int tile, int st) {
     int b = tile;
     const int tix = b % tiles_x; b /= tiles_x;
     const int tiy = b % tiles_y;
     const int n = b / tiles_y;
     const int x0 = tix * TW, y0 = tiy * TYN;
-    mbar_expect_tx(bar, TX_BYTES);
-    tma_load_4d(rawA, &mapA, bar, 0, Raw<T, CA, TW, 1>::chunk_start(x0), y0 - 1, n);
-    if (CB) tma_load_4d(rawB, &mapB, bar, 0, Raw<T, CBS, TW, 1>::chunk_start(x0), y0 - 1, n);
-    tma_load_4d(rawG, &mapG, bar, 0, Raw<T, COUT, TW, 0>::chunk_start(x0), y0, n);
+    unsigned char* rb = rawbase + st * G::RAWS;
+    mbar_expect_tx(bar + st, TX_BYTES);
+    tma_load_4d(rb, &mapA, bar + st, 0, Raw<T, CA, TW, 1>::chunk_start(x0), y0 - 1, n);
+    if (CB) tma_load_4d(rb + G::RAWA, &mapB, bar + st, 0, Raw<T, CBS, TW, 1>::chunk_start(x0), y0 - 1, n);
+    tma_load_4d(rb + G::RAWA + G::RAWB, &mapG, bar + st, 0, Raw<T, COUT, TW, 0>::chunk_start(x0), y0, n);
   };
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+    for (int i = 0; i < NS; ++i) mbar_init(bar + i, 1);
     fence_mbar_init();
-    issue(blockIdx.x);
+    for (int i = 0; i < NS - 1; ++i)                        // NS-1 tiles in flight before the first wait
+      if (blockIdx.x + i * (int)gridDim.x < ntiles) issue(blockIdx.x + i * gridDim.x, i);
   }
   __syncthreads();
 
-  uint32_t phase = 0;
+  int it = 0;
 #pragma unroll 1
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    deinterleave<T, CA, TW, 1>(rawA, xs, ROWS, PITCH);
-    if (CB) deinterleave<T, CBS, TW, 1>(rawB, xs + CA * ROWS * PITCH, ROWS, PITCH);
-    deinterleave<T, COUT, TW, 0>(rawG, gs, TYN, TW);
-    __syncthreads();                                       // planes ready, raw buffers free
-    if (threadIdx.x == 0 && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);   // overlaps the math below
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int st = it % NS;
+    mbar_wait(bar + st, (it / NS) & 1);
+    const unsigned char* rb = rawbase + st * G::RAWS;
+    deinterleave<T, CA, TW, 1>(reinterpret_cast<const T*>(rb), xs, ROWS, PITCH, G::SHIFT ? G::PLANES : 0);
+    if (CB) deinterleave<T, CBS, TW, 1>(reinterpret_cast<const T*>(rb + G::RAWA), xs + CA * ROWS * PITCH, ROWS, PITCH, G::SHIFT ? G::PLANES : 0);
+    deinterleave<T, COUT, TW, 0>(reinterpret_cast<const T*>(rb + G::RAWA + G::RAWB), gs, TYN, TW);
+    __syncthreads();                                       // planes ready, this raw stage free
+    {
+      const int nt = tile + (NS - 1) * (int)gridDim.x;     // refill the stage consumed in the previous iteration
+      if (threadIdx.x == 0 && nt < ntiles) issue(nt, (it + NS - 1) % NS);
+    }
     if (active) {
 #pragma unroll 1
       for (int g = slot; g < NGRP; g += G::G) {
@@ -333,12 +352,17 @@ __global__ void __launch_bounds__(256, 2) conv3x3_small_wgrad_kernel(const __gri
         for (int dy = 0; dy < 3; ++dy) {
           const float* xr = xs + (ci * ROWS + ty + dy) * PITCH + tx * PX;
           const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(xr);
-          const u64 p45 = *reinterpret_cast<const u64*>(xr + 4);
           pr[dy][0] = q.x;
           pr[dy][2] = q.y;
-          pr[dy][4] = p45;
-          pr[dy][1] = pack2(hi32(q.x), lo32(q.y));
-          pr[dy][3] = pack2(hi32(q.y), lo32(p45));
+          pr[dy][4] = *reinterpret_cast<const u64*>(xr + 4);
+          if (G::SHIFT) {
+            const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(xr + G::PLANES);
+            pr[dy][1] = q1.x;
+            pr[dy][3] = q1.y;
+          } else {
+            pr[dy][1] = pack2(hi32(q.x), lo32(q.y));
+            pr[dy][3] = pack2(hi32(q.y), lo32(pr[dy][4]));
+          }
         }
 #pragma unroll
         for (int c = 0; c < COB; ++c) {

@@ -34,8 +34,12 @@ struct Raw {
 };
 
 // raw tile [rows][NCH*EPC] (T, interleaved) -> planes dst[ci][rows][pitch] (fp32); one thread per pixel
+// `shift` != 0: a second copy of every plane displaced by one pixel (dst1[.. col] = dst[.. col+1]) is written `shift`
+// floats behind the first, so that the odd pixel pairs (c1,c2),(c3,c4) of a 3-tap window are naturally aligned
+// 64-bit shared-memory loads instead of register moves (IMAD.MOV would compete with FFMA2 for the FMA pipe).
 template <typename T, int C, int TW, int HALO>
-__device__ __forceinline__ void deinterleave(const T* __restrict__ raw, float* __restrict__ dst, int rows, int pitch) {
+__device__ __forceinline__ void deinterleave(const T* __restrict__ raw, float* __restrict__ dst, int rows, int pitch,
+                                             int shift = 0) {
   using G = Raw<T, C, TW, HALO>;
   constexpr int COLS = TW + 2 * HALO;
   constexpr int RP = G::NCH * G::EPC;
@@ -44,17 +48,24 @@ __device__ __forceinline__ void deinterleave(const T* __restrict__ raw, float* _
     const int row = e / COLS, col = e - row * COLS;
     const T* src = raw + row * RP + G::OFF + col * C;
     float* d = dst + row * pitch + col;
+    float v[C];
     if (WORDS) {                                     // bf16 pairs: one 32-bit LDS per two channels
       const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
 #pragma unroll
       for (int j = 0; j < C / 2; ++j) {
         const uint32_t wd = s32[j];
-        d[(2 * j) * rows * pitch] = __uint_as_float(wd << 16);
-        d[(2 * j + 1) * rows * pitch] = __uint_as_float(wd & 0xffff0000u);
+        v[2 * j] = __uint_as_float(wd << 16);
+        v[2 * j + 1] = __uint_as_float(wd & 0xffff0000u);
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < C; ++j) d[j * rows * pitch] = ldf(src + j);
+      for (int j = 0; j < C; ++j) v[j] = ldf(src + j);
+    }
+#pragma unroll
+    for (int j = 0; j < C; ++j) d[j * rows * pitch] = v[j];
+    if (shift && col > 0) {
+#pragma unroll
+      for (int j = 0; j < C; ++j) d[shift - 1 + j * rows * pitch] = v[j];
     }
   }
 }
