@@ -87,6 +87,10 @@ int try_tconv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const float*, cons
 int try_tconv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float, void*, size_t);
 int try_conv_wgrad_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*, int);
 int try_tconv_wgrad_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
+// tcgen05 row-Toeplitz family for few-channel 3x3 convs (conv_row_umma.cu)
+int try_conv_fprop_row(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float);
+int try_conv_dgrad_row(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
+int try_conv_wgrad_row(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
 // return 1 when the shape was handled, 0 when not covered, <0 on error
 int try_conv_fprop_small_f32(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
 int try_conv_fprop_small_bf16(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
@@ -150,6 +154,11 @@ extern "C" int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const d
   if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_fprop: kernel size %d (only 1 and 3 are used by the reference models)", ksize);
   cudaStream_t s = (cudaStream_t)stream;
   int r = 0;
+  if (!g_force_generic && ksize == 3 && x->dtype == DNNCA_BF16) {
+    r = try_conv_fprop_row(s, x, x2, w, bias, y, act, alpha);
+    if (r < 0) return r;
+    if (r == 1) return stats ? dnnca_channel_stats(stream, y, stats) : DNNCA_OK;
+  }
   if (!g_force_generic && ksize == 3) {
     r = x->dtype == DNNCA_F32 ? try_conv_fprop_small_f32(s, x, x2, w, bias, y, act, alpha, stats)
                               : try_conv_fprop_small_bf16(s, x, x2, w, bias, y, act, alpha, stats);
@@ -177,6 +186,11 @@ extern "C" int dnnca_conv2d_dgrad(void* stream, const dnnca_tensor_t* dz, const 
   DNNCA_CHECK_ARG(act_ok(act), "conv2d_dgrad: unknown activation %d", act);
   if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_dgrad: kernel size %d", ksize);
   cudaStream_t s = (cudaStream_t)stream;
+  if (!g_force_generic && ksize == 3 && dx->dtype == DNNCA_BF16) {
+    int r = try_conv_dgrad_row(s, dz, w, dx, dx2, mask, act, alpha);
+    if (r < 0) return r;
+    if (r == 1) return DNNCA_OK;
+  }
   if (!g_force_generic && ksize == 3) {
     int r = dx->dtype == DNNCA_F32 ? try_conv_dgrad_small_f32(s, dz, w, dx, dx2, mask, act, alpha)
                                    : try_conv_dgrad_small_bf16(s, dz, w, dx, dx2, mask, act, alpha);
@@ -198,6 +212,11 @@ extern "C" int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const d
   DNNCA_CHECK_ARG(second_ok(x, x2), "conv2d_wgrad: x2 must share n,h,w and dtype with x");
   if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_wgrad: kernel size %d", ksize);
   cudaStream_t s = (cudaStream_t)stream;
+  if (!g_force_generic && !g_no_umma && ksize == 3 && x->dtype == DNNCA_BF16) {
+    int r = try_conv_wgrad_row(s, x, x2, dz, dw, db);
+    if (r < 0) return r;
+    if (r == 1) return DNNCA_OK;
+  }
   if (!g_force_generic && ksize == 3) {
     int r = x->dtype == DNNCA_F32 ? try_conv_wgrad_small_f32(s, x, x2, dz, dw, db)
                                   : try_conv_wgrad_small_bf16(s, x, x2, dz, dw, db);

@@ -92,6 +92,7 @@ def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
     sliced: every tensor is a channel slice of a wider buffer; generic: shape-generic kernels forced."""
     lib = N.lib()
     lib.dnnca_debug_family_count(1, 1)
+    lib.dnnca_debug_family_count(2, 1)
     _conv_case(N, mode, variant, shape)
     n, h, w, ca, cb, cout, k = shape
     small = {(3, 0, 3), (3, 0, 6), (6, 0, 6), (12, 12, 12), (12, 0, 12), (1, 0, 16), (5, 0, 3), (3, 3, 3), (6, 6, 6),
@@ -100,7 +101,8 @@ def test_conv_fprop_dgrad_wgrad(N, mode, variant, shape):
         es = 4 if mode == 'fp32' else 2
         assert all((w * c * es) % 16 == 0 for c in (ca, cb, cout) if c)
         # 3 fprop + wgrad + 2 dgrad, except first-layer style shapes whose dgrad is not instantiated
-        assert lib.dnnca_debug_family_count(1, 0) >= 4, 'the TMA/FFMA2 small-channel kernels did not take this shape'
+        taken = lib.dnnca_debug_family_count(1, 0) + lib.dnnca_debug_family_count(2, 0)
+        assert taken >= 4, 'neither the row-Toeplitz tcgen05 kernels nor the TMA/FFMA2 small-channel kernels took this shape'
 
 
 def _conv_case(N, mode, variant, shape):
@@ -534,3 +536,71 @@ def test_conv_umma_persistent_many_tiles(N, shape):
     if cb:
         close(dxb.float().cpu().numpy(), g[..., ca:], 'bf16', scale=np.abs(g).max())
     assert lib.dnnca_debug_family_count(2, 0) == 2
+
+
+# ---- row-Toeplitz tcgen05 kernels (conv_row_umma.cu): every conv shape of configs/unet.yaml, several tiles per CTA ------
+ROW_SHAPES = [  # (n, h, w, c_x, c_x2, cout)
+    (2, 256, 256, 3, 0, 3), (2, 128, 128, 3, 0, 6), (3, 128, 128, 6, 0, 6), (3, 64, 64, 6, 0, 12), (5, 64, 64, 12, 0, 12),
+    (3, 64, 64, 12, 12, 12), (2, 128, 128, 6, 6, 6), (2, 256, 256, 3, 3, 3), (40, 32, 64, 3, 0, 3), (2, 48, 32, 6, 0, 6),
+    (1, 16, 16, 4, 4, 4), (2, 32, 32, 5, 0, 3), (150, 128, 32, 3, 0, 3),
+]
+
+
+@pytest.mark.parametrize('shape', ROW_SHAPES)
+def test_conv_row_umma(N, shape):
+    """bf16 few-channel 3x3 convs on the tensor cores: fprop (+bias+ReLU), masked and unmasked dgrad with two
+    destinations, wgrad + bias gradient, against torch fp64 autograd on the same bf16-rounded inputs."""
+    n, h, w, ca, cb, cout = shape
+    cin = ca + cb
+    lib = N.lib()
+    rng = np.random.default_rng(abs(hash(shape)) % 2 ** 31)
+    bf = torch.bfloat16
+    x = q(rng.normal(size=(n, h, w, cin)).astype(np.float32), bf)
+    wt = (rng.normal(size=(3, 3, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32)
+    b = rng.normal(size=cout).astype(np.float32)
+    dz = q(rng.normal(size=(n, h, w, cout)).astype(np.float32), bf)
+    mask = q(rng.normal(size=(n, h, w, ca)).astype(np.float32), bf)
+    wd, bd = dev(wt), dev(b)
+    xa = dev(x[..., :ca], bf)
+    xav = view(N, xa, 0, ca)
+    xbp = None
+    if cb:
+        xb = dev(x[..., ca:], bf)
+        xbv = view(N, xb, 0, cb)
+        xbp = C.byref(xbv)
+    y = torch.full((n, h, w, cout), 5.0, dtype=bf, device='cuda')
+    yv = view(N, y, 0, cout)
+    for fam in (0, 1, 2):
+        lib.dnnca_debug_family_count(fam, 1)
+    N.call('dnnca_conv2d_fprop', None, C.byref(xav), xbp, N.ptr(wd), N.ptr(bd), C.byref(yv), 3, N.ACT_RELU, 0.0, None, None, 0)
+    dzd, md = dev(dz, bf), dev(mask, bf)
+    dzv, mv = view(N, dzd, 0, cout), view(N, md, 0, ca)
+    dx = torch.full((n, h, w, ca), 3.0, dtype=bf, device='cuda')
+    dx2 = torch.full((n, h, w, max(cb, 1)), 3.0, dtype=bf, device='cuda')
+    dxv, dx2v = view(N, dx, 0, ca), view(N, dx2, 0, max(cb, 1))
+    dx2p = C.byref(dx2v) if cb else None
+    N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(wd), C.byref(dxv), dx2p, 3, C.byref(mv), N.ACT_RELU, 0.0, None, 0)
+    dw = torch.zeros(3, 3, cin, cout, dtype=torch.float32, device='cuda')
+    db = torch.zeros(cout, dtype=torch.float32, device='cuda')
+    N.call('dnnca_conv2d_wgrad', None, C.byref(xav), xbp, C.byref(dzv), N.ptr(dw), N.ptr(db), 3)
+    sync()
+    assert lib.dnnca_debug_family_count(2, 0) == 3, 'the row-Toeplitz tcgen05 kernels did not take this shape'
+    # reference: torch fp64 autograd (NCHW) on the same rounded inputs
+    xt = torch.from_numpy(x).double().permute(0, 3, 1, 2).requires_grad_(True)
+    wtt = torch.from_numpy(wt).double().permute(3, 2, 0, 1).requires_grad_(True)
+    bt = torch.from_numpy(b).double().requires_grad_(True)
+    pre = torch.nn.functional.conv2d(xt, wtt, bt, padding=1)
+    pre.backward(torch.from_numpy(dz).double().permute(0, 3, 1, 2))
+    ref_y = torch.relu(pre).detach().permute(0, 2, 3, 1).numpy()
+    rdx = xt.grad.permute(0, 2, 3, 1).numpy()
+    rdw = wtt.grad.permute(2, 3, 1, 0).numpy()
+    rdb = bt.grad.numpy()
+    close(y.float().cpu().numpy(), ref_y, 'bf16')
+    close(dx.float().cpu().numpy(), rdx[..., :ca] * (mask > 0), 'bf16', scale=np.abs(rdx).max())
+    if cb:
+        close(dx2.float().cpu().numpy(), rdx[..., ca:], 'bf16', scale=np.abs(rdx).max())
+    close(dw.cpu().numpy(), rdw, 'fp32', scale=np.abs(rdw).max() * 50)
+    close(db.cpu().numpy(), rdb, 'fp32', scale=np.abs(rdb).max() * 50)
+    N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(wd), C.byref(dxv), dx2p, 3, None, N.ACT_NONE, 0.0, None, 0)
+    sync()
+    close(dx.float().cpu().numpy(), rdx[..., :ca], 'bf16', scale=np.abs(rdx).max())
