@@ -282,7 +282,7 @@ def run_ours(args):
         rows = sorted(agg.items(), key=lambda kv: -kv[1]['ms'])
         breakdown = [{'kernel': k, 'share': round(d['ms'] / tot, 4), 'ms': round(d['ms'] / 3, 4),
                       'gbs': round(d['bytes'] / d['ms'] / 1e6, 1) if d['ms'] else None,
-                      'tflops': round(d['flops'] / d['ms'] / 1e9, 2) if d['ms'] else None} for k, d in rows[:12]]
+                      'tflops': round(d['flops'] / d['ms'] / 1e9, 2) if d['ms'] else None} for k, d in rows[:40]]
         cats = {}
         for kname, v in agg.items():
             base = kname.split('[')[0]

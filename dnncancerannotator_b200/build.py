@@ -38,6 +38,7 @@ for dt in (0, 1):
 UNITS.append(('conv_umma.cu', 'conv_umma', []))
 UNITS.append(('conv_umma2.cu', 'conv_umma2', []))
 UNITS.append(('conv_row_umma.cu', 'conv_row_umma', []))
+UNITS.append(('pool_vec.cu', 'pool_vec', []))
 
 
 def nvcc():

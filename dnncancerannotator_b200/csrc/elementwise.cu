@@ -415,6 +415,13 @@ inline ChanLayout group_layout(int c) {
 using namespace dnnca;
 
 // ============================ C ABI =========================================
+namespace dnnca {
+int try_maxpool_fwd_vec(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, uint8_t*, double*);
+int try_maxpool_bwd_vec(cudaStream_t, const dnnca_tensor_t*, const uint8_t*, const dnnca_tensor_t*, const dnnca_tensor_t*,
+                        const dnnca_tensor_t*, int, float);
+int try_convert_vec(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*);
+}  // namespace dnnca
+
 extern "C" int dnnca_channel_stats(void* stream, const dnnca_tensor_t* x, double* stats) {
   DNNCA_CHECK_ARG(view_ok(x) && stats, "channel_stats: bad arguments");
   long long P = (long long)x->n * x->h * x->w;
@@ -474,6 +481,10 @@ extern "C" int dnnca_bn_apply(void* stream, const dnnca_tensor_t* x, const float
 
 extern "C" int dnnca_convert(void* stream, const dnnca_tensor_t* src, const dnnca_tensor_t* dst) {
   DNNCA_CHECK_ARG(view_ok(src) && view_ok(dst) && same_shape(src, dst), "convert: bad arguments");
+  {
+    const int r = try_convert_vec((cudaStream_t)stream, src, dst);
+    if (r != 0) return r < 0 ? r : DNNCA_OK;
+  }
   ChanLayout L = chan_layout(src->c);
   long long P = (long long)src->n * src->h * src->w;
   int grid = grid_for(P, L.pl * 4);
@@ -536,6 +547,10 @@ extern "C" int dnnca_maxpool2x2_fwd(void* stream, const dnnca_tensor_t* x, const
   DNNCA_CHECK_ARG(x->h % 2 == 0 && x->w % 2 == 0 && y->h == x->h / 2 && y->w == x->w / 2 && y->n == x->n && y->c == x->c,
                   "maxpool_fwd: y must be [n,h/2,w/2,c] of an even-sized x");
   DNNCA_CHECK_ARG(x->dtype == y->dtype, "maxpool_fwd: dtype mismatch");
+  {
+    const int r = try_maxpool_fwd_vec((cudaStream_t)stream, x, y, idx, stats);
+    if (r != 0) return r < 0 ? r : DNNCA_OK;
+  }
   ChanLayout L = chan_layout(x->c);
   long long PO = (long long)y->n * y->h * y->w;
   int grid = grid_for(PO, L.pl * 4);
@@ -552,6 +567,10 @@ extern "C" int dnnca_maxpool2x2_bwd(void* stream, const dnnca_tensor_t* dy, cons
   DNNCA_CHECK_ARG(!dskip || (view_ok(dskip) && same_shape(dskip, dx) && dskip->dtype == dx->dtype), "maxpool_bwd: bad dskip");
   DNNCA_CHECK_ARG(!mask || (view_ok(mask) && same_shape(mask, dx) && mask->dtype == dx->dtype), "maxpool_bwd: bad mask");
   DNNCA_CHECK_ARG(dy->dtype == dx->dtype, "maxpool_bwd: dtype mismatch");
+  {
+    const int r = try_maxpool_bwd_vec((cudaStream_t)stream, dy, idx, dskip, dx, mask, act, alpha);
+    if (r != 0) return r < 0 ? r : DNNCA_OK;
+  }
   ChanLayout L = chan_layout(dy->c);
   long long PO = (long long)dy->n * dy->h * dy->w;
   int grid = grid_for(PO, L.pl * 2);

@@ -604,3 +604,45 @@ def test_conv_row_umma(N, shape):
     N.call('dnnca_conv2d_dgrad', None, C.byref(dzv), N.ptr(wd), C.byref(dxv), dx2p, 3, None, N.ACT_NONE, 0.0, None, 0)
     sync()
     close(dx.float().cpu().numpy(), rdx[..., :ca], 'bf16', scale=np.abs(rdx).max())
+
+
+@pytest.mark.parametrize('c,h,w', [(3, 12, 32), (6, 8, 16), (12, 20, 8), (3, 256, 256)])
+def test_maxpool_vec_dense_bit_exact(N, c, h, w):
+    """dense bf16 tensors with 3/6/12 channels take the 128-bit vectorised kernels (pool_vec.cu); results must be
+    bit-identical to the oracle (first maximum wins, skip gradient added, ReLU mask from the pooled layer's input)."""
+    bf = torch.bfloat16
+    rng = np.random.default_rng(c * 1000 + h)
+    n = 2
+    x = q(np.maximum(rng.normal(size=(n, h, w, c)), 0).astype(np.float32), bf)
+    xd = dev(x, bf)
+    y = torch.zeros(n, h // 2, w // 2, c, dtype=bf, device='cuda')
+    idx = torch.zeros(n, h // 2, w // 2, c, dtype=torch.uint8, device='cuda')
+    xv, yv = view(N, xd, 0, c), view(N, y, 0, c)
+    N.call('dnnca_maxpool2x2_fwd', None, C.byref(xv), C.byref(yv), N.ptr(idx), None)
+    sync()
+    ty, tidx = ops.maxpool(torch.from_numpy(x), 2, return_indices=True)
+    np.testing.assert_array_equal(y.float().cpu().numpy(), ty.numpy())
+    np.testing.assert_array_equal(idx.cpu().numpy(), tidx.numpy())
+    dy = q(rng.normal(size=ty.shape).astype(np.float32), bf)
+    dskip = q(rng.normal(size=x.shape).astype(np.float32), bf)
+    dyd, dxd = dev(dy, bf), dev(dskip, bf)
+    dyv, dxv = view(N, dyd, 0, c), view(N, dxd, 0, c)
+    N.call('dnnca_maxpool2x2_bwd', None, C.byref(dyv), N.ptr(idx), C.byref(dxv), C.byref(dxv), C.byref(xv), N.ACT_RELU, 0.0)
+    sync()
+    scat = np.zeros_like(x)
+    ti = tidx.numpy()
+    for a in range(2):
+        for b in range(2):
+            scat[:, a::2, b::2, :] = np.where(ti == 2 * a + b, dy, 0.0)
+    ref = q(((scat + dskip) * (x > 0)).astype(np.float32), bf)
+    np.testing.assert_array_equal(dxd.float().cpu().numpy(), ref)
+    N.call('dnnca_maxpool2x2_bwd', None, C.byref(dyv), N.ptr(idx), None, C.byref(dxv), None, N.ACT_NONE, 0.0)
+    sync()
+    np.testing.assert_array_equal(dxd.float().cpu().numpy(), scat)
+    # flat fp32 -> bf16 conversion (input staging)
+    src = dev(rng.normal(size=(n, h, w, c)).astype(np.float32))
+    dst = torch.zeros(n, h, w, c, dtype=bf, device='cuda')
+    sv, dv = view(N, src, 0, c), view(N, dst, 0, c)
+    N.call('dnnca_convert', None, C.byref(sv), C.byref(dv))
+    sync()
+    assert torch.equal(dst, src.to(bf))
