@@ -91,6 +91,9 @@ int try_tconv_wgrad_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor
 int try_conv_fprop_row(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float);
 int try_conv_dgrad_row(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
 int try_conv_wgrad_row(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
+int try_tconv_fprop_row(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*);
+int try_tconv_dgrad_row(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
+int try_tconv_wgrad_row(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
 // return 1 when the shape was handled, 0 when not covered, <0 on error
 int try_conv_fprop_small_f32(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
 int try_conv_fprop_small_bf16(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float, double*);
@@ -237,7 +240,8 @@ extern "C" int dnnca_convtranspose2x2_fprop(void* stream, const dnnca_tensor_t* 
   DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && k, "convtranspose2x2_fprop: bad tensor arguments");
   DNNCA_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && x->dtype == y->dtype,
                   "convtranspose2x2_fprop: y must be [n,2h,2w,cout] with x's dtype");
-  int r = g_force_generic ? 0 : try_tconv_fprop_small((cudaStream_t)stream, x, k, bias, y);
+  int r = (g_force_generic || x->dtype != DNNCA_BF16) ? 0 : try_tconv_fprop_row((cudaStream_t)stream, x, k, bias, y);
+  if (r == 0 && !g_force_generic) r = try_tconv_fprop_small((cudaStream_t)stream, x, k, bias, y);
   if (r == 0 && !g_force_generic) r = try_tconv_fprop_umma((cudaStream_t)stream, x, k, bias, y, workspace, workspace_bytes);
   if (r < 0) return r;
   if (r == 0) r = launch_tconv_fprop_generic((cudaStream_t)stream, x, k, bias, y);
@@ -256,7 +260,8 @@ extern "C" int dnnca_convtranspose2x2_dgrad(void* stream, const dnnca_tensor_t* 
   DNNCA_CHECK_ARG(!mask || (view_ok(mask) && same_shape(mask, dx) && mask->dtype == dx->dtype), "convtranspose2x2_dgrad: bad mask");
   DNNCA_CHECK_ARG(act_ok(act), "convtranspose2x2_dgrad: unknown activation %d", act);
   if (!g_force_generic) {
-    int r = try_tconv_dgrad_small((cudaStream_t)stream, dy, k, dx, mask, act, alpha);
+    int r = dx->dtype == DNNCA_BF16 ? try_tconv_dgrad_row((cudaStream_t)stream, dy, k, dx, mask, act, alpha) : 0;
+    if (r == 0) r = try_tconv_dgrad_small((cudaStream_t)stream, dy, k, dx, mask, act, alpha);
     if (r == 0) r = try_tconv_dgrad_umma((cudaStream_t)stream, dy, k, dx, mask, act, alpha, workspace, workspace_bytes);
     if (r < 0) return r;
     if (r == 1) return DNNCA_OK;
@@ -270,7 +275,8 @@ extern "C" int dnnca_convtranspose2x2_wgrad(void* stream, const dnnca_tensor_t* 
   DNNCA_CHECK_ARG(dy->n == x->n && dy->h == 2 * x->h && dy->w == 2 * x->w && x->dtype == dy->dtype,
                   "convtranspose2x2_wgrad: dy must be [n,2h,2w,cout]");
   if (!g_force_generic) {
-    int r = try_tconv_wgrad_small((cudaStream_t)stream, x, dy, dk, db);
+    int r = (x->dtype == DNNCA_BF16 && !g_no_umma) ? try_tconv_wgrad_row((cudaStream_t)stream, x, dy, dk, db) : 0;
+    if (r == 0) r = try_tconv_wgrad_small((cudaStream_t)stream, x, dy, dk, db);
     if (r == 0 && !g_no_umma) r = try_tconv_wgrad_umma((cudaStream_t)stream, x, dy, dk, db);
     if (r < 0) return r;
     if (r == 1) return DNNCA_OK;

@@ -91,7 +91,7 @@ struct RowUnit {
 // wgrad: one accumulator = one MMA per K step; its M = 128 rows are two 64-element blocks (or one two-atom window)
 enum { WB_NONE = 0, WB_WINDOW = 1, WB_ONES = 2, WB_WINDOW128 = 3 };
 struct RowAcc {
-  unsigned char kind[2], op[2], tap[2], m64, pad;
+  unsigned char kind[2], op[2], tap[2], m64, zi;     // zi: which dZ tap buffer (ConvT wgrad: rows 2i+zi)
   int first, second;             // byte offsets from the stage start; -1 = the all-ones block (second unused when m64)
 };
 
@@ -103,6 +103,14 @@ struct RowArgs {
   int oa, ob;                     // channels of destination a / b
   int Hs, tiles_x, tiles_y, nimg; // rows per tile (<= 128), strips per row, row tiles per image
   int abuf, nstage;               // bytes of one window-atom buffer; ring depth
+  // Conv2DTranspose k=s=2 variants (kernel [2][2][Cout][Cin], components.py:118-120):
+  //   tconv 1 = fprop: window = P input pixels (no halo, one tap); columns = (a, 2P output pixels, co), output rows 2i+a
+  //   tconv 2 = dgrad: taps a = rows 2i+a of dy (loaded as separate buffers through a 4-D map), window = 2P dy pixels
+  //   tconv 3 = wgrad: x window against the dy rows 2i+a
+  int tconv, pad, ltaps, ntaps;   // pad = halo rows above/below a tile; ltaps = separately loaded tap buffers
+  int win_step[2];                // window start element = strip * win_step - halo
+  int tap_stride;                 // bytes between the A operands of consecutive taps inside a stage
+  int box_w, box_h;               // output TMA box (elements of destination a, rows)
   int dgrad, act, has_mask;
   float alpha;
   const float* w;                 // [3][3][cin_tot][cout] fp32 (HWIO)
@@ -113,7 +121,7 @@ struct RowArgs {
   RowUnit unit[ROW_MAX_UNITS];
   unsigned short mma_a[ROW_MAX_MMA], mma_b[ROW_MAX_MMA];
   // wgrad only
-  int zatoms, zbuf, nacc;
+  int zatoms, zbuf, nacc, ztaps, nwt;   // nwt = weight-gradient elements (9*cin*cout or 4*cin*cout)
   RowAcc acc[ROW_MAX_ACC];
   float* dw;
   float* db;
@@ -121,7 +129,9 @@ struct RowArgs {
                                   // 4 no MMA issue, 8 no epilogue arithmetic, 16 print CTA 0's per-role clock trace
 };
 
-__host__ __device__ inline int row_stage_bytes(const RowArgs& a) { return (a.atoms[0] + (a.nops > 1 ? a.atoms[1] : 0)) * a.abuf; }
+__host__ __device__ inline int row_stage_bytes(const RowArgs& a) {
+  return a.ltaps * (a.atoms[0] + (a.nops > 1 ? a.atoms[1] : 0)) * a.abuf;
+}
 __host__ __device__ inline int row_out_bytes(const RowArgs& a) { return a.Hs * a.N * 2; }
 __host__ __device__ inline int row_mask_bytes(const RowArgs& a) { return a.has_mask ? a.Hs * a.nsplit * 2 : 0; }
 constexpr int ROW_CTRL = 256 + ROW_MAX_MMA * 8 + 1024 + 1024;      // barriers, MMA table, bias slice, debug trace + lut
@@ -241,6 +251,40 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
     }
   }
   __syncthreads();
+  auto put_band = [&](int op, int tap, int n, int k, float v) {
+    const int atom = k >> 6, kin = k & 63;
+    const int e = ulut[(op * 3 + tap) * 2 + atom];
+    const int ch = (e >> 8) * 2 + (kin >> 3);
+    unsigned char* blk = bbase + (e & 0xff) * bblk + (kin & 7) * 2;
+    if (a.parts > 1) {                                      // bf16 hi | lo parts
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const int n2 = n + a.N;
+      *reinterpret_cast<__nv_bfloat16*>(blk + n * 128 + ((ch ^ (n & 7)) << 4)) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(blk + n2 * 128 + ((ch ^ (n2 & 7)) << 4)) = __float2bfloat16_rn(v - __bfloat162float(hi));
+    } else {                                                // single bf16 band
+      *reinterpret_cast<__nv_bfloat16*>(blk + n * 128 + ((ch ^ (n & 7)) << 4)) = __float2bfloat16_rn(v);
+    }
+  };
+  if (a.tconv == 1) {
+    // ConvT fprop: column n = (a, pp = 2p+b, co); non-zeros k = p*Cin + ci with K[a][b][co][ci]
+    const int cin = a.C[0], nh = a.N >> 1;
+    for (int idx = threadIdx.x; idx < a.N * cin; idx += blockDim.x) {
+      const int n = idx / cin, ci = idx - n * cin;
+      const int ar = n / nh, rem = n - ar * nh;
+      const int pp = rem / a.cout, co = rem - pp * a.cout;
+      put_band(0, 0, n, (pp >> 1) * cin + ci, __ldg(a.w + (((ar * 2 + (pp & 1)) * a.cout + co) * cin + ci)));
+    }
+  } else if (a.tconv == 2) {
+    // ConvT dgrad: tap = a; column n = (p, ci); non-zeros k = (2p+b)*Cout + co with K[a][b][co][ci]
+    const int cz = a.C[0], c2 = 2 * cz, per = a.N * c2, cin = a.oa;
+    for (int idx = threadIdx.x; idx < 2 * per; idx += blockDim.x) {
+      const int ar = idx / per, r = idx - ar * per;
+      const int n = r / c2, j = r - n * c2;
+      const int b = j / cz, co = j - b * cz;
+      const int p = n / cin, ci = n - p * cin;
+      put_band(0, ar, n, (2 * p + b) * cz + co, __ldg(a.w + (((ar * 2 + b) * cz + co) * cin + ci)));
+    }
+  } else {
   for (int op = 0; op < a.nops; ++op) {
     const int C = a.C[op], c3 = 3 * C, per = a.N * c3;
     for (int idx = threadIdx.x; idx < 3 * per; idx += blockDim.x) {
@@ -259,20 +303,9 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
         else { const int m = n - a.nsplit; p = m / a.ob; ci = a.oa + m - p * a.ob; }
         v = __ldg(a.w + (((2 - tap) * 3 + (2 - dxi)) * a.cin_tot + ci) * a.cout + c);
       }
-      const int k = a.halo[op] + (p + dxi - 1) * C + c;       // window element of pixel p + dx
-      const int atom = k >> 6, kin = k & 63;
-      const int e = ulut[(op * 3 + tap) * 2 + atom];
-      const int ch = (e >> 8) * 2 + (kin >> 3);
-      unsigned char* blk = bbase + (e & 0xff) * bblk + (kin & 7) * 2;
-      if (a.parts > 1) {                                      // bf16 hi | lo parts
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const int n2 = n + a.N;
-        *reinterpret_cast<__nv_bfloat16*>(blk + n * 128 + ((ch ^ (n & 7)) << 4)) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(blk + n2 * 128 + ((ch ^ (n2 & 7)) << 4)) = __float2bfloat16_rn(v - __bfloat162float(hi));
-      } else {                                                // single bf16 band
-        *reinterpret_cast<__nv_bfloat16*>(blk + n * 128 + ((ch ^ (n & 7)) << 4)) = __float2bfloat16_rn(v);
-      }
+      put_band(op, tap, n, a.halo[op] + (p + dxi - 1) * C + c, v);   // window element of pixel p + dx
     }
+  }
   }
   fence_proxy_async();
   tc_fence_before();
@@ -285,7 +318,7 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
     if (lane == 0) {
       tma_prefetch_desc(&mapA);
       const int natoms = a.atoms[0] + (a.nops > 1 ? a.atoms[1] : 0);
-      const uint32_t abytes = (uint32_t)(natoms * (a.Hs + 2) * 128);
+      const uint32_t abytes = (uint32_t)(a.ltaps * natoms * (a.Hs + 2 * a.pad) * 128);
       const uint32_t mbytes = (uint32_t)(a.Hs * a.nsplit * 2);
       int it = 0, s = 0;
       uint32_t ph = 1;                                       // parity of the "previous" phase: passes on a fresh barrier
@@ -293,7 +326,7 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
       const int step_x = gridDim.x % a.tiles_x, step_r = gridDim.x / a.tiles_x;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int tiy = rest % a.tiles_y, n = rest / a.tiles_y;
-        const int x0 = tix * a.P, y0 = tiy * a.Hs;
+        const int y0 = tiy * a.Hs;
         mbar_wait(emptyA + s, ph);
         ROW_TRACE(0, it);
         if ((a.dbg & 2) && it >= a.nstage) {
@@ -301,15 +334,21 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
         } else {
           mbar_expect_tx(fullA + s, abytes);
           unsigned char* dst = aring + s * stage_bytes;
-          for (int op = 0; op < a.nops; ++op)
-            for (int at = 0; at < a.atoms[op]; ++at, dst += a.abuf)
-              tma_load_3d(dst, op ? &mapB : &mapA, fullA + s, x0 * a.C[op] - a.halo[op] + at * 64, y0 - 1, n);
+          if (a.tconv == 2) {                                  // dy rows 2i+tap through the {row, parity, i, n} map
+            for (int tap = 0; tap < 2; ++tap)
+              for (int at = 0; at < a.atoms[0]; ++at, dst += a.abuf)
+                tma_load_4d(dst, &mapA, fullA + s, tix * a.win_step[0] + at * 64, tap, y0, n);
+          } else {
+            for (int op = 0; op < a.nops; ++op)
+              for (int at = 0; at < a.atoms[op]; ++at, dst += a.abuf)
+                tma_load_3d(dst, op ? &mapB : &mapA, fullA + s, tix * a.win_step[op] - a.halo[op] + at * 64, y0 - a.pad, n);
+          }
         }
         if (HAS_MASK) {
           const int mb = it & 1;
           if (it >= 2) mbar_wait(mempty + mb, ((it >> 1) - 1) & 1);
           mbar_expect_tx(mfull + mb, mbytes);
-          tma_load_3d(mbase + mb * row_mask_bytes(a), &mapM, mfull + mb, x0 * a.oa, y0, n);
+          tma_load_3d(mbase + mb * row_mask_bytes(a), &mapM, mfull + mb, tix * a.box_w, y0, n);
         }
         if (++s == a.nstage) { s = 0; ph ^= 1u; }
         tix += step_x; rest += step_r;
@@ -380,7 +419,6 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
       const int tix = b % a.tiles_x; b /= a.tiles_x;
       const int tiy = b % a.tiles_y;
       const int n = b / a.tiles_y;
-      const int x0 = tix * a.P, y0 = tiy * a.Hs;
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
       if (issuer) tma_store_wait_read0();                    // the store that last read this staging buffer is done
       group_bar_sync(g);
@@ -428,8 +466,8 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
       if (issuer) ROW_TRACE(4, it);
       if (threadIdx.x == 64) ROW_ETRACE(4, it >> 1);
       if (issuer && !(a.dbg & 1)) {
-        tma_store_3d(&mapOA, outb, x0 * a.oa, y0, n);
-        if (a.ob) tma_store_3d(&mapOB, outb + a.Hs * a.nsplit * 2, x0 * a.ob, y0, n);
+        tma_store_3d(&mapOA, outb, tix * a.box_w, tiy * a.box_h, n);
+        if (a.ob) tma_store_3d(&mapOB, outb + a.Hs * a.nsplit * 2, tix * a.P * a.ob, tiy * a.box_h, n);
         tma_store_commit();
       }
     }
@@ -456,8 +494,8 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
 // costs 2 MMAs instead of 4.  Two-atom windows take M = 128 per tap plus an M = 64 all-ones MMA.  The 3-wide band of D is
 // folded into dw[3][3][cin][cout] once at the end.
 // ---------------------------------------------------------------------------------------------------------------
-__host__ __device__ inline int roww_stage_bytes(const RowArgs& a) { return row_stage_bytes(a) + a.zatoms * a.zbuf; }
-__host__ __device__ inline int roww_nw(const RowArgs& a) { return 9 * a.cin_tot * a.cout + a.cout; }
+__host__ __device__ inline int roww_stage_bytes(const RowArgs& a) { return row_stage_bytes(a) + a.ztaps * a.zatoms * a.zbuf; }
+__host__ __device__ inline int roww_nw(const RowArgs& a) { return a.nwt + a.cout; }
 constexpr int ROWW_CTRL = 512 + 1024 + 8 * ROW_MAX_ACC * 8;       // barriers, trace, per-stage descriptor table
 __host__ __device__ inline int roww_smem_bytes(const RowArgs& a) {
   return a.nstage * roww_stage_bytes(a) + a.abuf + ((roww_nw(a) * 4 + 127) & ~127) + ROWW_CTRL + 1024;
@@ -481,6 +519,7 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
   uint32_t* trace = reinterpret_cast<uint32_t*>(ctrl + 512);    // [3][48] clock stamps (dbg & 16)
   uint2* wtab = reinterpret_cast<uint2*>(ctrl + 512 + 1024);    // [stage][acc] {A descriptor low word at K step 0, idesc}
+  uint32_t* zoff = reinterpret_cast<uint32_t*>(ctrl + 512 + 960);   // [acc] dZ tap-buffer offset, 16-byte units
   const bool tracing = (a.dbg & 16) && blockIdx.x == 0;
 #define ROW_TRACE(role, i) do { if (tracing && (i) < 48) trace[(role) * 48 + (i)] = (uint32_t)clock(); } while (0)
 
@@ -504,6 +543,7 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
     const uint32_t first = ac.first < 0 ? ones_addr : stage + (uint32_t)ac.first;
     const uint32_t second = ac.m64 ? first + 1024 : (ac.second < 0 ? ones_addr : stage + (uint32_t)ac.second);
     wtab[s * ROW_MAX_ACC + j] = make_uint2(desc_lo(first, second - first), make_idesc(ac.m64 ? 64 : 128, a.N, 1, 1));
+    if (s == 0) zoff[j] = (uint32_t)(ac.zi * a.zatoms * a.zbuf) >> 4;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -516,22 +556,27 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
       tma_prefetch_desc(&mapA);
       tma_prefetch_desc(&mapZ);
       const int natoms = a.atoms[0] + (a.nops > 1 ? a.atoms[1] : 0);
-      const uint32_t bytes = (uint32_t)(natoms * (a.Hs + 2) * 128 + a.zatoms * a.Hs * 128);
+      const uint32_t bytes = (uint32_t)(natoms * (a.Hs + 2 * a.pad) * 128 + a.ztaps * a.zatoms * a.Hs * 128);
       int it = 0, s = 0;
       uint32_t ph = 1;
       int tix = blockIdx.x % a.tiles_x, rest = blockIdx.x / a.tiles_x;
       const int step_x = gridDim.x % a.tiles_x, step_r = gridDim.x / a.tiles_x;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int tiy = rest % a.tiles_y, n = rest / a.tiles_y;
-        const int x0 = tix * a.P, y0 = tiy * a.Hs;
+        const int y0 = tiy * a.Hs;
         mbar_wait(empty + s, ph);
         ROW_TRACE(0, it);
         mbar_expect_tx(full + s, bytes);
         unsigned char* dst = ring + s * stage_bytes;
         for (int op = 0; op < a.nops; ++op)
           for (int at = 0; at < a.atoms[op]; ++at, dst += a.abuf)
-            tma_load_3d(dst, op ? &mapB : &mapA, full + s, x0 * a.C[op] - a.halo[op] + at * 64, y0 - 1, n);
-        for (int z = 0; z < a.zatoms; ++z, dst += a.zbuf) tma_load_3d(dst, &mapZ, full + s, x0 * a.cout + z * 64, y0, n);
+            tma_load_3d(dst, op ? &mapB : &mapA, full + s, tix * a.win_step[op] - a.halo[op] + at * 64, y0 - a.pad, n);
+        if (a.tconv) {                                        // dy rows 2i+tap
+          for (int tap = 0; tap < 2; ++tap)
+            for (int z = 0; z < a.zatoms; ++z, dst += a.zbuf) tma_load_4d(dst, &mapZ, full + s, tix * a.N + z * 64, tap, y0, n);
+        } else {
+          for (int z = 0; z < a.zatoms; ++z, dst += a.zbuf) tma_load_3d(dst, &mapZ, full + s, tix * a.N + z * 64, y0, n);
+        }
         if (++s == a.nstage) { s = 0; ph ^= 1u; }
         tix += step_x; rest += step_r;
         if (tix >= a.tiles_x) { tix -= a.tiles_x; ++rest; }
@@ -555,10 +600,11 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
         uint32_t dcol = tmem_base;
         for (int j = 0; j < nacc; ++j, dcol += a.N) {
           const uint2 e = wtab[s * ROW_MAX_ACC + j];
-          umma_lo_if(dcol, e.x, z_lo0, e.y, accf, leader);
+          const uint32_t z_lo = z_lo0 + zoff[j];
+          umma_lo_if(dcol, e.x, z_lo, e.y, accf, leader);
 #pragma unroll 8
           for (int ks = 1; ks < ksteps; ++ks)                // 16 rows = 2048 bytes = 128 descriptor units
-            umma_lo_if(dcol, e.x + ks * 128, z_lo0 + ks * 128, e.y, 1u, leader);
+            umma_lo_if(dcol, e.x + ks * 128, z_lo + ks * 128, e.y, 1u, leader);
         }
         if (committer) umma_commit(empty + s);
         __syncwarp();
@@ -573,7 +619,7 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
     mbar_wait(accum, 0);
     tc_fence_after();
     const int k = lg * 32 + lane;
-    float* sdb = sW + 9 * a.cin_tot * a.cout;
+    float* sdb = sW + a.nwt;
     uint32_t col = 0;
     for (int j = 0; j < a.nacc; ++j) {
       const RowAcc ac = a.acc[j];
@@ -584,8 +630,9 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
       const bool in_block = full128 || !ac.m64 || k < 64;
       const int C = a.C[op];
       const int rel = krow - a.halo[op] + C;
-      const bool valid = in_block && (kind == WB_WINDOW || kind == WB_WINDOW128) && rel >= 0 && rel < (a.P + 2) * C;
-      const int q = valid ? rel / C - 1 : 0;
+      const bool valid = in_block && (kind == WB_WINDOW || kind == WB_WINDOW128) && rel >= 0 &&
+                         rel < (a.tconv ? (a.P + 1) * C : (a.P + 2) * C);
+      const int q = valid ? rel / C - 1 : 0;                  // window pixel (conv: -1..P; ConvT: 0..P-1, halo = 0)
       const int cin = a.coff[op] + rel - (q + 1) * C;
       const bool db_row = in_block && kind == WB_ONES && krow == 0;
       int p = 0, co = 0;
@@ -595,9 +642,14 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int dx = q - p;
-          if (valid && dx >= -1 && dx <= 1)
-            atomicAdd(sW + ((tap * 3 + dx + 1) * a.cin_tot + cin) * a.cout + co, __uint_as_float(v[e]));
+          if (a.tconv) {                                      // column = (pp = 2p+b, co): dk[tap][b][co][ci]
+            if (valid && (p >> 1) == q)
+              atomicAdd(sW + ((tap * 2 + (p & 1)) * a.cout + co) * a.cin_tot + cin, __uint_as_float(v[e]));
+          } else {
+            const int dx = q - p;
+            if (valid && dx >= -1 && dx <= 1)
+              atomicAdd(sW + ((tap * 3 + dx + 1) * a.cin_tot + cin) * a.cout + co, __uint_as_float(v[e]));
+          }
           if (db_row) atomicAdd(sdb + co, __uint_as_float(v[e]));
           if (++co == a.cout) { co = 0; ++p; }
         }
@@ -606,7 +658,7 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  const int nw = 9 * a.cin_tot * a.cout;
+  const int nw = a.nwt;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) atomicAdd(a.dw + i, sW[i]);
   if (a.db)
     for (int i = threadIdx.x; i < a.cout; i += blockDim.x) atomicAdd(a.db + i, sW[nw + i]);
@@ -665,10 +717,13 @@ static int row_dbg() {
 // window geometry of one input operand for P pixels per strip; false when it does not fit two 64-element atoms
 static bool row_operand(RowArgs& a, int op, int C, int P) {
   if ((P * C) % 8) return false;
-  const int halo = (C + 7) / 8 * 8;
-  const int need = halo + P * C + C;
+  // conv: P pixels + one halo pixel each side, start aligned down to 16 bytes; ConvT: P (fprop, wgrad) or 2P (dgrad)
+  // pixels, no halo
+  const int halo = a.tconv ? 0 : (C + 7) / 8 * 8;
+  const int need = a.tconv ? (a.tconv == 2 ? 2 * P * C : P * C) : halo + P * C + C;
   if (need > 128) return false;
   a.C[op] = C; a.halo[op] = halo; a.ksteps[op] = (need + 15) / 16; a.atoms[op] = (a.ksteps[op] + 3) / 4;
+  a.win_step[op] = a.tconv == 2 ? 2 * P * C : P * C;
   return true;
 }
 
@@ -681,7 +736,8 @@ static bool row_common_geometry(RowArgs& a, const dnnca_tensor_t* x) {
   if (!a.Hs) return false;
   a.tiles_x = W / a.P; a.tiles_y = H / a.Hs; a.nimg = x->n;
   if ((long long)a.tiles_x * a.tiles_y * a.nimg > 0x7fffffffLL) return false;
-  a.abuf = ((a.Hs + 2) * 128 + 1023) & ~1023;
+  a.pad = a.tconv ? 0 : 1;
+  a.abuf = ((a.Hs + 2 * a.pad) * 128 + 1023) & ~1023;
   return true;
 }
 
@@ -692,8 +748,11 @@ static bool row_plan_mmas(RowArgs& a) {
   int nblocks = 0, nunits = 0, nmma = 0;
   int narrow_block = -1, narrow_used = 4;
   int a_off = 0;                                        // operand offset inside the stage, 16-byte units
+  a.ntaps = a.tconv == 1 ? 1 : (a.tconv == 2 ? 2 : 3);
+  a.ltaps = a.tconv == 2 ? 2 : 1;
+  a.tap_stride = a.tconv == 2 ? a.atoms[0] * a.abuf : 128;     // conv: the next image row of the same buffer
   for (int op = 0; op < a.nops; ++op) {
-    for (int tap = 0; tap < 3; ++tap)
+    for (int tap = 0; tap < a.ntaps; ++tap)
       for (int at = 0; at < a.atoms[op]; ++at) {
         const int nk = a.ksteps[op] - 4 * at < 4 ? a.ksteps[op] - 4 * at : 4;
         if (nunits >= ROW_MAX_UNITS) return false;
@@ -708,14 +767,14 @@ static bool row_plan_mmas(RowArgs& a) {
         }
         for (int kk = 0; kk < nk; ++kk) {
           if (nmma >= ROW_MAX_MMA) return false;
-          const int ao = a_off + (at * a.abuf + tap * 128 + kk * 32) / 16;
+          const int ao = a_off + (at * a.abuf + tap * a.tap_stride + kk * 32) / 16;
           const int bo = u.block * bblk16 + (u.kk0 + kk) * 2;
           if (ao > 0xFFFF || bo > 0xFFFF) return false;
           a.mma_a[nmma] = (unsigned short)ao; a.mma_b[nmma] = (unsigned short)bo;
           ++nmma;
         }
       }
-    a_off += a.atoms[op] * a.abuf / 16;
+    a_off += a.ltaps * a.atoms[op] * a.abuf / 16;
   }
   a.nblocks = nblocks; a.nunits = nunits; a.nmma = nmma;
   return true;
@@ -743,8 +802,22 @@ static int launch_row_epi(cudaStream_t s, const CUtensorMap& mA, const CUtensorM
   return 1;
 }
 
-// fprop: inputs ina [, inb] -> outa ; dgrad: input ina = dz -> outa = dx [, outb = dx2]
-static int launch_row(cudaStream_t s, bool dgrad, const dnnca_tensor_t* ina, const dnnca_tensor_t* inb, const float* w,
+// 4-D view of a [n, 2h, 2w, c] tensor as {row elements, row parity, h, n}: box {64, 1, rows, 1} = rows 2i+parity
+static bool row_map_parity(CUtensorMap* m, const dnnca_tensor_t* t, int box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc || box_rows > 256 || (t->h & 1)) return false;
+  const cuuint64_t rowe = (cuuint64_t)t->w * t->c;
+  cuuint64_t dims[4] = {rowe, 2, (cuuint64_t)t->h / 2, (cuuint64_t)t->n};
+  cuuint64_t strides[3] = {rowe * 2, rowe * 4, rowe * 2 * t->h};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// conv fprop: inputs ina [, inb] -> outa ; conv dgrad: ina = dz -> outa = dx [, outb = dx2]
+// tconv 1 (ConvT fprop): ina = x [n,h,w,cin] -> outa = y [n,2h,2w,cout] ; tconv 2 (ConvT dgrad): ina = dy -> outa = dx
+static int launch_row(cudaStream_t s, bool dgrad, int tconv, const dnnca_tensor_t* ina, const dnnca_tensor_t* inb, const float* w,
                       const float* bias, const dnnca_tensor_t* outa, const dnnca_tensor_t* outb, const dnnca_tensor_t* mask,
                       int act, float alpha) {
   if (!row_enabled()) return 0;
@@ -757,12 +830,14 @@ static int launch_row(cudaStream_t s, bool dgrad, const dnnca_tensor_t* ina, con
   RowArgs a;
   memset(&a, 0, sizeof(a));
   a.nops = inb ? 2 : 1;
+  a.tconv = tconv;
   a.dgrad = dgrad ? 1 : 0; a.act = act; a.alpha = alpha; a.has_mask = mask ? 1 : 0;
   a.w = w; a.bias = bias; a.oa = oa; a.ob = ob;
   a.dbg = row_dbg();
   a.parts = row_parts();
   if (dgrad) { a.cin_tot = oa + ob; a.cout = ca; }
   else { a.cin_tot = ca + cb; a.cout = oa; a.coff[0] = 0; a.coff[1] = ca; }
+  const dnnca_tensor_t* grid_t = tconv == 2 ? outa : ina;        // tensor whose rows are the GEMM M
   // strip width P: cheapest tensor time per pixel (MMAs per tile x their N) among the widths whose plan fits
   bool found = false;
   RowArgs best;
@@ -770,10 +845,13 @@ static int launch_row(cudaStream_t s, bool dgrad, const dnnca_tensor_t* ina, con
   for (int P = 16; P >= 2; P >>= 1) {
     a.P = P;
     if (!row_operand(a, 0, ca, P) || (inb && !row_operand(a, 1, cb, P))) continue;
-    if ((P * oa) % 8 || (ob && (P * ob) % 8)) continue;
-    a.N = P * (oa + ob); a.nsplit = P * oa; a.NP = a.parts * a.N;
+    if (tconv == 1) { a.N = 4 * P * oa; a.nsplit = a.N; a.box_w = 2 * P * oa; }
+    else { a.N = P * (oa + ob); a.nsplit = P * oa; a.box_w = P * oa; }
+    if (a.nsplit % 8 || (a.N - a.nsplit) % 8 || a.box_w % 8) continue;
+    a.NP = a.parts * a.N;
     if (a.N % 16 || a.NP > 256 || a.N < 16) continue;
-    if (!row_common_geometry(a, ina)) continue;
+    if (!row_common_geometry(a, grid_t)) continue;
+    a.box_h = tconv == 1 ? 2 * a.Hs : a.Hs;
     if (!row_plan_mmas(a)) continue;
     bool fits = false;
     for (a.nstage = 4; a.nstage >= 2; --a.nstage)
@@ -785,14 +863,16 @@ static int launch_row(cudaStream_t s, bool dgrad, const dnnca_tensor_t* ina, con
   if (found) a = best;
   if (!found) return 0;
   CUtensorMap mA, mB, mOA, mOB, mM;
-  if (!row_map(&mA, ina, 64, a.Hs + 2, true)) return 0;
+  if (tconv == 2) {
+    if (!row_map_parity(&mA, ina, a.Hs)) return 0;
+  } else if (!row_map(&mA, ina, 64, a.Hs + 2 * a.pad, true)) return 0;
   mB = mA;
-  if (inb && !row_map(&mB, inb, 64, a.Hs + 2, true)) return 0;
-  if (!row_map(&mOA, outa, a.P * oa, a.Hs, false)) return 0;
+  if (inb && !row_map(&mB, inb, 64, a.Hs + 2 * a.pad, true)) return 0;
+  if (!row_map(&mOA, outa, a.box_w, a.box_h, false)) return 0;
   mOB = mOA;
   if (outb && !row_map(&mOB, outb, a.P * ob, a.Hs, false)) return 0;
   mM = mOA;
-  if (mask && !row_map(&mM, mask, a.P * oa, a.Hs, false)) return 0;
+  if (mask && !row_map(&mM, mask, a.box_w, a.Hs, false)) return 0;
   if (!dgrad) {
     if (act == DNNCA_ACT_RELU) return launch_row_epi<REPI_RELU>(s, mA, mB, mOA, mOB, mM, a);
     if (act == DNNCA_ACT_LEAKY) return launch_row_epi<REPI_LEAKY>(s, mA, mB, mOA, mOB, mM, a);
@@ -805,17 +885,36 @@ static int launch_row(cudaStream_t s, bool dgrad, const dnnca_tensor_t* ina, con
 
 int try_conv_fprop_row(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w, const float* bias,
                        const dnnca_tensor_t* y, int act, float alpha) {
-  return launch_row(s, false, x, x2, w, bias, y, nullptr, nullptr, act, alpha);
+  return launch_row(s, false, 0, x, x2, w, bias, y, nullptr, nullptr, act, alpha);
 }
 
 int try_conv_dgrad_row(cudaStream_t s, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
                        const dnnca_tensor_t* dx2, const dnnca_tensor_t* mask, int act, float alpha) {
-  return launch_row(s, true, dz, nullptr, w, nullptr, dx, dx2, mask, act, alpha);
+  return launch_row(s, true, 0, dz, nullptr, w, nullptr, dx, dx2, mask, act, alpha);
+}
+
+// Conv2DTranspose k=s=2 (components.py:118-120): y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci] k[a,b,co,ci] + bias[co]
+int try_tconv_fprop_row(cudaStream_t s, const dnnca_tensor_t* x, const float* k, const float* bias, const dnnca_tensor_t* y) {
+  return launch_row(s, false, 1, x, nullptr, k, bias, y, nullptr, nullptr, DNNCA_ACT_NONE, 0.f);
+}
+int try_tconv_dgrad_row(cudaStream_t s, const dnnca_tensor_t* dy, const float* k, const dnnca_tensor_t* dx,
+                        const dnnca_tensor_t* mask, int act, float alpha) {
+  return launch_row(s, true, 2, dy, nullptr, k, nullptr, dx, nullptr, mask, act, alpha);
 }
 
 // accumulators of one K step: pair the 64-element blocks (taps of one-atom windows, then the all-ones block)
 static bool roww_plan(RowArgs& a) {
   int n = 0;
+  if (a.tconv) {                 // (x window | ones) against the dy rows 2i and 2i+1
+    if (a.atoms[0] > 1) return false;
+    for (int ar = 0; ar < 2; ++ar) {
+      RowAcc& c = a.acc[n++];
+      memset(&c, 0, sizeof(c));
+      c.kind[0] = WB_WINDOW; c.tap[0] = (unsigned char)ar; c.kind[1] = WB_ONES; c.first = 0; c.second = -1; c.zi = (unsigned char)ar;
+    }
+    a.nacc = n;
+    return n * a.N <= 512;
+  }
   auto window_off = [&](int op, int tap) { return (op ? a.atoms[0] * a.abuf : 0) + tap * 128; };
   if (a.atoms[0] > 1) {
     for (int op = 0; op < a.nops; ++op)
@@ -851,8 +950,8 @@ static bool roww_plan(RowArgs& a) {
   return n <= ROW_MAX_ACC && n * a.N <= 512;
 }
 
-int try_conv_wgrad_row(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* dz, float* dw,
-                       float* db) {
+static int launch_row_wgrad(cudaStream_t s, int tconv, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* dz,
+                            float* dw, float* db) {
   if (!row_enabled()) return 0;
   if (!row_dense_bf16(x) || (x2 && !row_dense_bf16(x2)) || !row_dense_bf16(dz)) return 0;
   const int ca = x->c, cb = x2 ? x2->c : 0, co = dz->c;
@@ -860,7 +959,11 @@ int try_conv_wgrad_row(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tens
   RowArgs a;
   memset(&a, 0, sizeof(a));
   a.nops = x2 ? 2 : 1;
+  a.tconv = tconv ? 3 : 0;
   a.cin_tot = ca + cb; a.cout = co; a.coff[0] = 0; a.coff[1] = ca; a.dw = dw; a.db = db;
+  a.nwt = (tconv ? 4 : 9) * a.cin_tot * co;
+  a.ztaps = tconv ? 2 : 1;
+  a.ltaps = 1;
   a.dbg = row_dbg();
   bool found = false;
   RowArgs best;
@@ -869,7 +972,7 @@ int try_conv_wgrad_row(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tens
     a.P = P;
     if (!row_operand(a, 0, ca, P) || (x2 && !row_operand(a, 1, cb, P))) continue;
     if (x2 && a.atoms[0] != a.atoms[1]) continue;
-    a.N = P * co;
+    a.N = (tconv ? 2 : 1) * P * co;
     if (a.N % 16 || a.N > 256 || a.N < 16) continue;
     if (!row_common_geometry(a, x)) continue;
     if (!roww_plan(a)) continue;
@@ -884,10 +987,12 @@ int try_conv_wgrad_row(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tens
   if (found) a = best;
   if (!found) return 0;
   CUtensorMap mA, mB, mZ;
-  if (!row_map(&mA, x, 64, a.Hs + 2, true)) return 0;
+  if (!row_map(&mA, x, 64, a.Hs + 2 * a.pad, true)) return 0;
   mB = mA;
-  if (x2 && !row_map(&mB, x2, 64, a.Hs + 2, true)) return 0;
-  if (!row_map(&mZ, dz, 64, a.Hs, true)) return 0;
+  if (x2 && !row_map(&mB, x2, 64, a.Hs + 2 * a.pad, true)) return 0;
+  if (tconv) {
+    if (!row_map_parity(&mZ, dz, a.Hs)) return 0;
+  } else if (!row_map(&mZ, dz, 64, a.Hs, true)) return 0;
   const int smem = roww_smem_bytes(a);
   static int smem_set = 0;
   if (smem > smem_set) {
@@ -900,6 +1005,15 @@ int try_conv_wgrad_row(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tens
   DNNCA_LAUNCH_CHECK("conv_row_wgrad");
   note_family(2);
   return 1;
+}
+
+int try_conv_wgrad_row(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* dz, float* dw,
+                       float* db) {
+  return launch_row_wgrad(s, 0, x, x2, dz, dw, db);
+}
+// dk[a][b][co][ci] += sum x[n,i,j,ci] dy[n,2i+a,2j+b,co] ; db[co] += sum dy
+int try_tconv_wgrad_row(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* dy, float* dk, float* db) {
+  return launch_row_wgrad(s, 1, x, nullptr, dy, dk, db);
 }
 
 }  // namespace dnnca

@@ -646,3 +646,15 @@ def test_maxpool_vec_dense_bit_exact(N, c, h, w):
     N.call('dnnca_convert', None, C.byref(sv), C.byref(dv))
     sync()
     assert torch.equal(dst, src.to(bf))
+
+
+@pytest.mark.parametrize('shape', [(3, 32, 32, 12, 12), (2, 64, 64, 12, 6), (2, 128, 128, 6, 3), (150, 16, 32, 6, 3),
+                                   (2, 48, 16, 12, 6), (1, 64, 64, 3, 3)])
+def test_tconv_row_umma(N, shape):
+    """Conv2DTranspose k=s=2 with few channels (configs/unet.yaml decoder) on the row-Toeplitz tcgen05 kernels:
+    fprop + bias, masked and unmasked dgrad, wgrad + bias gradient."""
+    lib = N.lib()
+    for fam in (0, 1, 2):
+        lib.dnnca_debug_family_count(fam, 1)
+    _tconv_dense(N, 'bf16', shape, np.random.default_rng(sum(shape)))
+    assert lib.dnnca_debug_family_count(2, 0) == 4, 'the row-Toeplitz tcgen05 kernels did not take this ConvT shape'
