@@ -527,6 +527,7 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
   uint32_t tcols = 32;
   while (tcols < (uint32_t)(a.nacc * a.N)) tcols <<= 1;
+  const uint32_t t_entry = (uint32_t)clock();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -550,6 +551,8 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_setup = (uint32_t)clock();
+  uint32_t t_acc = 0, t_ext = 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -614,59 +617,87 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
       if (committer) umma_commit(accum);
     }
   } else {
-    // ===== band extraction: warps 2..5, TMEM lane quarter = warp % 4; accumulator row = lane index =====
+    // ===== band extraction: warps 2..5, TMEM lane quarter = warp % 4; accumulator row = lane index.  Each accumulator
+    // is dumped to shared memory (the operand ring is idle once the last MMA has retired) with a padded row stride,
+    // then every gradient element is summed by ONE thread: no atomics, no divergent selects =====
     const int lg = warp & 3;
+    const int et = threadIdx.x - 64;                          // 0..127
     mbar_wait(accum, 0);
     tc_fence_after();
+    t_acc = (uint32_t)clock();
     const int k = lg * 32 + lane;
+    float* dump = reinterpret_cast<float*>(ring);
+    const int ld = a.N + 1;
     float* sdb = sW + a.nwt;
     uint32_t col = 0;
     for (int j = 0; j < a.nacc; ++j) {
       const RowAcc ac = a.acc[j];
-      const bool full128 = ac.kind[0] == WB_WINDOW128;
-      const int h = (full128 || ac.m64) ? 0 : (k >> 6);       // which 64-row block this lane reads
-      const int kind = ac.kind[h], op = ac.op[h], tap = ac.tap[h];
-      const int krow = full128 ? k : (k & 63);
-      const bool in_block = full128 || !ac.m64 || k < 64;
-      const int C = a.C[op];
-      const int rel = krow - a.halo[op] + C;
-      const bool valid = in_block && (kind == WB_WINDOW || kind == WB_WINDOW128) && rel >= 0 &&
-                         rel < (a.tconv ? (a.P + 1) * C : (a.P + 2) * C);
-      const int q = valid ? rel / C - 1 : 0;                  // window pixel (conv: -1..P; ConvT: 0..P-1, halo = 0)
-      const int cin = a.coff[op] + rel - (q + 1) * C;
-      const bool db_row = in_block && kind == WB_ONES && krow == 0;
-      int p = 0, co = 0;
       for (int c0 = 0; c0 < a.N; c0 += 8, col += 8) {
         uint32_t v[8];
         tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + col, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if (a.tconv) {                                      // column = (pp = 2p+b, co): dk[tap][b][co][ci]
-            if (valid && (p >> 1) == q)
-              atomicAdd(sW + ((tap * 2 + (p & 1)) * a.cout + co) * a.cin_tot + cin, __uint_as_float(v[e]));
-          } else {
-            const int dx = q - p;
-            if (valid && dx >= -1 && dx <= 1)
-              atomicAdd(sW + ((tap * 3 + dx + 1) * a.cin_tot + cin) * a.cout + co, __uint_as_float(v[e]));
+        for (int e = 0; e < 8; ++e) dump[k * ld + c0 + e] = __uint_as_float(v[e]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const bool full128 = ac.kind[0] == WB_WINDOW128;
+      const int nhalf = (full128 || ac.m64) ? 1 : 2;
+      for (int h = 0; h < nhalf; ++h) {
+        const int kind = ac.kind[h], op = ac.op[h], tap = ac.tap[h];
+        const float* blk = dump + (h * 64) * ld;               // rows of this 64-element block (or the whole window)
+        if (kind == WB_ONES) {
+          for (int co = et; co < a.cout; co += 128) {
+            float sum = 0.f;
+            for (int n = co; n < a.N; n += a.cout) sum += blk[n];
+            sdb[co] += sum;
           }
-          if (db_row) atomicAdd(sdb + co, __uint_as_float(v[e]));
-          if (++co == a.cout) { co = 0; ++p; }
+        } else if (a.tconv) {                                   // dk[tap][b][co][ci] = sum_p D[(p,ci)][(2p+b,co)]
+          const int C = a.C[op], nout = 2 * a.cout * C;
+          for (int o = et; o < nout; o += 128) {
+            const int ci = o % C, r = o / C;
+            const int co = r % a.cout, b = r / a.cout;
+            float sum = 0.f;
+            for (int p = 0; p < a.P; ++p) sum += blk[(p * C + ci) * ld + (2 * p + b) * a.cout + co];
+            sW[((tap * 2 + b) * a.cout + co) * a.cin_tot + ci] = sum;
+          }
+        } else {                                                // dw[tap][dx][ci][co] = sum_p D[(p+dx,ci)][(p,co)]
+          const int C = a.C[op], nout = 3 * C * a.cout;
+          for (int o = et; o < nout; o += 128) {
+            const int co = o % a.cout, r = o / a.cout;
+            const int ci = r % C, dxi = r / C;
+            const float* src = blk + (a.halo[op] + (dxi - 1) * C + ci) * ld + co;
+            float sum = 0.f;
+            for (int p = 0; p < a.P; ++p) sum += src[p * (C * ld + a.cout)];
+            sW[((tap * 3 + dxi) * a.cin_tot + a.coff[op] + ci) * a.cout + co] = sum;
+          }
         }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
   }
+  t_ext = (uint32_t)clock();
   tc_fence_before();
   __syncthreads();
+  // flush: CTAs start at different offsets so that they do not all hit the same L2 lines at the same time
   const int nw = a.nwt;
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) atomicAdd(a.dw + i, sW[i]);
+  const int rot = (int)(((long long)blockIdx.x * nw) / gridDim.x);
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+    int e = i + rot;
+    if (e >= nw) e -= nw;
+    atomicAdd(a.dw + e, sW[e]);
+  }
   if (a.db)
     for (int i = threadIdx.x; i < a.cout; i += blockDim.x) atomicAdd(a.db + i, sW[nw + i]);
   if (warp == 1) tmem_dealloc(tmem_base, tcols);
-  if (tracing && threadIdx.x == 0) {
+  if (tracing && threadIdx.x == 64) {
+    __threadfence();
+    const uint32_t t_end = (uint32_t)clock();
     const uint32_t t0 = trace[0];
-    for (int i = 0; i < 24; ++i)
+    for (int i = 0; i < 4; ++i)
       printf("tile %2d  tma %7u  mma_start %7u  mma_done %7u\n", i, trace[i] - t0, trace[48 + i] - t0, trace[96 + i] - t0);
+    const int last = min(47, (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x);
+    printf("entry %d setup %d first_tma 0 last_mma_issue(%d) %u accum_done %u extracted %u end %u\n", (int)(t_entry - t0),
+           (int)(t_setup - t0), last, trace[96 + last] - t0, t_acc - t0, t_ext - t0, t_end - t0);
   }
 #undef ROW_TRACE
 }
@@ -980,7 +1011,7 @@ static int launch_row_wgrad(cudaStream_t s, int tconv, const dnnca_tensor_t* x, 
     bool fits = false;
     for (a.nstage = 6; a.nstage >= 2; --a.nstage)
       if (roww_smem_bytes(a) <= ROW_SMEM_LIMIT) { fits = true; break; }
-    if (!fits) continue;
+    if (!fits || (a.N + 1) * 512 > a.nstage * roww_stage_bytes(a)) continue;     // the ring also hosts the accumulator dump
     const double cost = (a.nacc * (a.Hs / 16) * row_mma_cycles(a.N) + 200.0) / P;
     if (!found || cost < best_cost) { best = a; best_cost = cost; found = true; }
   }
