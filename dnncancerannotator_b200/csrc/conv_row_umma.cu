@@ -52,8 +52,16 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(p));
   return p != 0;
 }
-// named barrier of one epilogue group (128 threads); ids 1 and 2
-__device__ __forceinline__ void group_bar_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+// named barrier of one epilogue group (256 threads); ids 1 and 2
+__device__ __forceinline__ void group_bar_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // SWIZZLE_128B shared-memory descriptor split into its two 32-bit words.  The high word (SBO = 1024 bytes between
@@ -136,7 +144,7 @@ __host__ __device__ inline int row_out_bytes(const RowArgs& a) { return a.Hs * a
 __host__ __device__ inline int row_mask_bytes(const RowArgs& a) { return a.has_mask ? a.Hs * a.nsplit * 2 : 0; }
 constexpr int ROW_CTRL = 256 + ROW_MAX_MMA * 8 + 1024 + 1024;      // barriers, MMA table, bias slice, debug trace + lut
 __host__ __device__ inline int row_smem_bytes(const RowArgs& a) {
-  return a.nstage * row_stage_bytes(a) + a.nblocks * a.NP * 128 + 2 * row_out_bytes(a) + 2 * row_mask_bytes(a) + ROW_CTRL + 1024;
+  return a.nstage * row_stage_bytes(a) + a.nblocks * a.NP * 128 + 4 * row_out_bytes(a) + 2 * row_mask_bytes(a) + ROW_CTRL + 1024;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -152,13 +160,14 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
 
 enum { REPI_NONE = 0, REPI_RELU = 1, REPI_LEAKY = 2, REPI_DGRAD = 3, REPI_DGRAD_RELU = 4, REPI_DGRAD_LEAKY = 5 };
 
-// one 8-column chunk of one accumulator row -> 8 bf16 (16 bytes)
+// one 8-column chunk of one accumulator row -> 8 bf16 (16 bytes); sb / mrow are shared-space addresses (mrow 0 = no mask)
 template <int EPI>
-__device__ __forceinline__ uint4 row_epilogue8(float* f, const float* sb, const unsigned char* mrow, float alpha) {
+__device__ __forceinline__ uint4 row_epilogue8(float* f, uint32_t sb, uint32_t mrow, float alpha) {
   uint4 o;
   if (EPI <= REPI_LEAKY) {
-    const float4 b0 = *reinterpret_cast<const float4*>(sb), b1 = *reinterpret_cast<const float4*>(sb + 4);
-    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    const uint4 b0 = lds128(sb), b1 = lds128(sb + 16);
+    f[0] += __uint_as_float(b0.x); f[1] += __uint_as_float(b0.y); f[2] += __uint_as_float(b0.z); f[3] += __uint_as_float(b0.w);
+    f[4] += __uint_as_float(b1.x); f[5] += __uint_as_float(b1.y); f[6] += __uint_as_float(b1.z); f[7] += __uint_as_float(b1.w);
     if (EPI == REPI_LEAKY) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : alpha * f[e];
@@ -171,7 +180,7 @@ __device__ __forceinline__ uint4 row_epilogue8(float* f, const float* sb, const 
     }
   } else {
     if (EPI != REPI_DGRAD && mrow) {
-      const uint4 m = *reinterpret_cast<const uint4*>(mrow);
+      const uint4 m = lds128(mrow);
       const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -191,7 +200,7 @@ __device__ __forceinline__ uint4 row_epilogue8(float* f, const float* sb, const 
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                            const __grid_constant__ CUtensorMap mapB,
                                                            const __grid_constant__ CUtensorMap mapOA,
                                                            const __grid_constant__ CUtensorMap mapOB,
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
   unsigned char* aring = smem;                                   // first: UMMA over-reads of short tiles stay inside
   unsigned char* bbase = aring + a.nstage * stage_bytes;
   unsigned char* obase = bbase + a.nblocks * bblk;
-  unsigned char* mbase = obase + 2 * row_out_bytes(a);
+  unsigned char* mbase = obase + 4 * row_out_bytes(a);
   unsigned char* ctrl = mbase + 2 * row_mask_bytes(a);
   uint64_t* fullA = reinterpret_cast<uint64_t*>(ctrl);          // [8]
   uint64_t* emptyA = fullA + 8;                                  // [8]
@@ -212,7 +221,8 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
   uint64_t* tempty = tfull + 2;                                  // [2]
   uint64_t* mfull = tempty + 2;                                  // [2]
   uint64_t* mempty = mfull + 2;                                  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mempty + 2);
+  uint64_t* bready = mempty + 2;                                 // [1] band blocks built (17 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bready + 1);
   uint2* mma_tab = reinterpret_cast<uint2*>(ctrl + 256);         // [nmma] {A offset from the stage, B descriptor low word}
   float* sbias = reinterpret_cast<float*>(ctrl + 256 + ROW_MAX_MMA * 8);
   constexpr bool HAS_MASK = EPI == REPI_DGRAD_RELU || EPI == REPI_DGRAD_LEAKY;
@@ -227,10 +237,12 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
   uint32_t tcols = 32;
   while (tcols < (uint32_t)(2 * a.NP)) tcols <<= 1;
+  const uint32_t t_entry = (uint32_t)clock();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.nstage; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); mbar_init(mfull + s, 1); mbar_init(mempty + s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); mbar_init(mfull + s, 1); mbar_init(mempty + s, 8); }
+    mbar_init(bready, 17);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tcols);
@@ -250,7 +262,20 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
       ulut[(un.op * 3 + un.tap) * 2 + un.atom] = (unsigned short)(un.block | (un.kk0 << 8));
     }
   }
+  // the fp32 weights, staged once in the (still idle) output staging area: the scatter below then reads shared memory
+  // instead of issuing one dependent global load per band element
+  float* wsm = reinterpret_cast<float*>(obase);
+  {
+    const int nwt = (a.tconv ? 4 : 9) * a.cin_tot * a.cout;
+    for (int i = threadIdx.x; i < nwt; i += blockDim.x) wsm[i] = __ldg(a.w + i);
+  }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_setup = (uint32_t)clock();
+  // the TMA producer (warp 0) starts streaming tiles now; warps 1..17 expand the bands and meet at named barrier 3
+  if (warp != 0) {
   auto put_band = [&](int op, int tap, int n, int k, float v) {
     const int atom = k >> 6, kin = k & 63;
     const int e = ulut[(op * 3 + tap) * 2 + atom];
@@ -265,53 +290,57 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
       *reinterpret_cast<__nv_bfloat16*>(blk + n * 128 + ((ch ^ (n & 7)) << 4)) = __float2bfloat16_rn(v);
     }
   };
+  // one (operand, tap, column) per thread-iteration; its non-zeros are walked with running indices (no divisions
+  // in the inner loops: they dominated the prologue of the 12-channel layers)
+  const int bt = threadIdx.x - 32, nbt = blockDim.x - 32;
   if (a.tconv == 1) {
     // ConvT fprop: column n = (a, pp = 2p+b, co); non-zeros k = p*Cin + ci with K[a][b][co][ci]
     const int cin = a.C[0], nh = a.N >> 1;
-    for (int idx = threadIdx.x; idx < a.N * cin; idx += blockDim.x) {
-      const int n = idx / cin, ci = idx - n * cin;
+    for (int n = bt; n < a.N; n += nbt) {
       const int ar = n / nh, rem = n - ar * nh;
       const int pp = rem / a.cout, co = rem - pp * a.cout;
-      put_band(0, 0, n, (pp >> 1) * cin + ci, __ldg(a.w + (((ar * 2 + (pp & 1)) * a.cout + co) * cin + ci)));
+      const float* wrow = wsm + ((ar * 2 + (pp & 1)) * a.cout + co) * cin;
+      for (int ci = 0; ci < cin; ++ci) put_band(0, 0, n, (pp >> 1) * cin + ci, wrow[ci]);
     }
   } else if (a.tconv == 2) {
     // ConvT dgrad: tap = a; column n = (p, ci); non-zeros k = (2p+b)*Cout + co with K[a][b][co][ci]
-    const int cz = a.C[0], c2 = 2 * cz, per = a.N * c2, cin = a.oa;
-    for (int idx = threadIdx.x; idx < 2 * per; idx += blockDim.x) {
-      const int ar = idx / per, r = idx - ar * per;
-      const int n = r / c2, j = r - n * c2;
-      const int b = j / cz, co = j - b * cz;
+    const int cz = a.C[0], cin = a.oa;
+    for (int pi = bt; pi < 2 * a.N; pi += nbt) {
+      const int ar = pi / a.N, n = pi - ar * a.N;
       const int p = n / cin, ci = n - p * cin;
-      put_band(0, ar, n, (2 * p + b) * cz + co, __ldg(a.w + (((ar * 2 + b) * cz + co) * cin + ci)));
+      for (int b = 0; b < 2; ++b)
+        for (int co = 0; co < cz; ++co)
+          put_band(0, ar, n, (2 * p + b) * cz + co, wsm[((ar * 2 + b) * cz + co) * cin + ci]);
     }
   } else {
-  for (int op = 0; op < a.nops; ++op) {
-    const int C = a.C[op], c3 = 3 * C, per = a.N * c3;
-    for (int idx = threadIdx.x; idx < 3 * per; idx += blockDim.x) {
-      const int tap = idx / per, r = idx - tap * per;
-      const int n = r / c3, j = r - n * c3;
-      const int dxi = j / C, c = j - dxi * C;                 // dx = dxi - 1, window channel c
-      int p;
-      float v;
-      if (!a.dgrad) {
-        p = n / a.cout;
-        const int co = n - p * a.cout;
-        v = __ldg(a.w + ((tap * 3 + dxi) * a.cin_tot + a.coff[op] + c) * a.cout + co);
-      } else {                                                // column = (p, ci) of dx / dx2; window channel = forward co
-        int ci;
-        if (n < a.nsplit) { p = n / a.oa; ci = n - p * a.oa; }
-        else { const int m = n - a.nsplit; p = m / a.ob; ci = a.oa + m - p * a.ob; }
-        v = __ldg(a.w + (((2 - tap) * 3 + (2 - dxi)) * a.cin_tot + ci) * a.cout + c);
+    for (int op = 0; op < a.nops; ++op) {
+      const int C = a.C[op];
+      for (int pi = bt; pi < 3 * a.N; pi += nbt) {
+        const int tap = pi / a.N, n = pi - tap * a.N;
+        int p, widx, wstep_c, wstep_dx;                       // weight index = widx + dxi*wstep_dx + c*wstep_c
+        if (!a.dgrad) {
+          p = n / a.cout;
+          const int co = n - p * a.cout;
+          widx = (tap * 3 * a.cin_tot + a.coff[op]) * a.cout + co;
+          wstep_dx = a.cin_tot * a.cout; wstep_c = a.cout;
+        } else {                                              // column = (p, ci) of dx / dx2; window channel = forward co
+          int ci;
+          if (n < a.nsplit) { p = n / a.oa; ci = n - p * a.oa; }
+          else { const int m = n - a.nsplit; p = m / a.ob; ci = a.oa + m - p * a.ob; }
+          widx = (((2 - tap) * 3 + 2) * a.cin_tot + ci) * a.cout;
+          wstep_dx = -a.cin_tot * a.cout; wstep_c = 1;
+        }
+        int k = a.halo[op] + (p - 1) * C;                     // window element of pixel p + dx, channel 0
+        for (int dxi = 0; dxi < 3; ++dxi, widx += wstep_dx)
+          for (int c = 0; c < C; ++c, ++k) put_band(op, tap, n, k, wsm[widx + c * wstep_c]);
       }
-      put_band(op, tap, n, a.halo[op] + (p + dxi - 1) * C + c, v);   // window element of pixel p + dx
     }
   }
-  }
   fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bready);
+  asm volatile("bar.sync 3, 544;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -346,6 +375,7 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
         }
         if (HAS_MASK) {
           const int mb = it & 1;
+          if (it == 0) mbar_wait(bready, 0);
           if (it >= 2) mbar_wait(mempty + mb, ((it >> 1) - 1) & 1);
           mbar_expect_tx(mfull + mb, mbytes);
           tma_load_3d(mbase + mb * row_mask_bytes(a), &mapM, mfull + mb, tix * a.box_w, y0, n);
@@ -357,7 +387,9 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the per-tile MMA list is a table; only the stage / accumulator bases change.  The whole warp
-    // runs the loop (so addresses stay in uniform registers); one elected lane issues =====
+    // runs the loop (so addresses stay in uniform registers); one elected lane issues.  (Tried and rejected on the
+    // B200: two issuing warps on alternate tiles fall into lock-step with the two epilogue groups, and taking the next
+    // tile's barrier waits before the last MMAs delays this tile's accumulator -- both were slower.) =====
     {
       const uint32_t leader = (elect_one() && !(a.dbg & 4)) ? 1u : 0u;
       const bool committer = elect_one();
@@ -394,33 +426,39 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
       }
     }
   } else {
-    // ===== epilogue: two groups of 4 warps take alternate tiles (group g <-> accumulator / staging buffer g), so the
-    // TMEM-read -> smem -> TMA-store latency chain of one tile overlaps the next tile's.  A warp owns TMEM lanes
-    // 32*(warp%4).. = image rows; a thread handles all N columns of its row =====
-    const int g = (warp - 2) >> 2;
+    // ===== epilogue: two groups of 8 warps take alternate tiles (group g <-> accumulator buffer g), so the TMEM-read
+    // -> smem -> TMA-store latency chain of one tile overlaps the next tile's; each group double-buffers its staging
+    // tile so a store may still be reading while the next tile is written.  A warp owns TMEM lanes 32*(warp%4).. =
+    // image rows; the two warps of a lane quarter split the columns =====
+    const int ew = warp - 2;                        // warps 2..17
+    const int g = ew >> 3;
     const int lg = warp & 3;
+    const int half = (ew & 7) >> 2;
     const int row = lg * 32 + lane;
     const bool warp_live = lg * 32 < a.Hs;
     const bool live = row < a.Hs;
-    const bool issuer = threadIdx.x == 64 + g * 128;
-    const int nchunk = a.N >> 3;                    // 8-column chunks
+    const bool issuer = threadIdx.x == 64 + g * 256;
+    const int nchunk = a.N >> 4;                    // 8-column chunks per warp
+    const int c_first = half * nchunk;
     const int csplit = a.nsplit >> 3;               // chunks [0, csplit) belong to destination a
     const int nb = a.N - a.nsplit;
     const int offA = row * a.nsplit * 2;                              // + chunk*16
     const int offB = a.Hs * a.nsplit * 2 + row * nb * 2 - a.nsplit * 2;   // + chunk*16
     const float alpha = a.alpha;
-    unsigned char* outb = obase + g * row_out_bytes(a);
-    const unsigned char* msk = mbase + g * row_mask_bytes(a) + offA;
-    const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * a.NP);
+    const uint32_t out_s = smem_u32(obase) + (uint32_t)(2 * g * row_out_bytes(a));
+    const uint32_t msk_s = smem_u32(mbase) + (uint32_t)(g * row_mask_bytes(a) + offA);
+    const uint32_t bias_s = smem_u32(sbias);
+    const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * a.NP + c_first * 8);
     const bool two = a.parts > 1;
-    int it = g;
-    for (int t = blockIdx.x + g * gridDim.x; t < ntiles; t += 2 * gridDim.x, it += 2) {
+    int it = g, git = 0;
+    for (int t = blockIdx.x + g * gridDim.x; t < ntiles; t += 2 * gridDim.x, it += 2, ++git) {
       int b = t;
       const int tix = b % a.tiles_x; b /= a.tiles_x;
       const int tiy = b % a.tiles_y;
       const int n = b / a.tiles_y;
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
-      if (issuer) tma_store_wait_read0();                    // the store that last read this staging buffer is done
+      const uint32_t outb = out_s + (uint32_t)((git & 1) * row_out_bytes(a));
+      if (issuer) tma_store_wait_read1();                    // the store that last read THIS staging buffer is done
       group_bar_sync(g);
       if (threadIdx.x == 64) ROW_ETRACE(0, it >> 1);
       if (HAS_MASK) mbar_wait(mfull + g, par);
@@ -442,13 +480,13 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             if (j < cnt) {
-              const int c = c0 + j;
+              const int c = c_first + c0 + j;
               const bool to_a = c < csplit;
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]) + (two ? __uint_as_float(u[8 * j + e]) : 0.f);
-              const uint4 o = row_epilogue8<EPI>(f, sbias + c * 8, (HAS_MASK && to_a && live) ? msk + c * 16 : nullptr, alpha);
-              if (live) *reinterpret_cast<uint4*>(outb + (to_a ? offA : offB) + c * 16) = o;
+              const uint4 o = row_epilogue8<EPI>(f, bias_s + c * 32, (HAS_MASK && to_a && live) ? msk_s + c * 16 : 0u, alpha);
+              if (live) sts128(outb + (uint32_t)((to_a ? offA : offB) + c * 16), o);
             }
           }
         }
@@ -466,8 +504,15 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
       if (issuer) ROW_TRACE(4, it);
       if (threadIdx.x == 64) ROW_ETRACE(4, it >> 1);
       if (issuer && !(a.dbg & 1)) {
-        tma_store_3d(&mapOA, outb, tix * a.box_w, tiy * a.box_h, n);
-        if (a.ob) tma_store_3d(&mapOB, outb + a.Hs * a.nsplit * 2, tix * a.P * a.ob, tiy * a.box_h, n);
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(&mapOA)),
+                     "r"(outb), "r"(tix * a.box_w), "r"(tiy * a.box_h), "r"(n)
+                     : "memory");
+        if (a.ob)
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&mapOB)),
+                       "r"(outb + (uint32_t)(a.Hs * a.nsplit * 2)), "r"(tix * a.P * a.ob), "r"(tiy * a.box_h), "r"(n)
+                       : "memory");
         tma_store_commit();
       }
     }
@@ -478,9 +523,14 @@ __global__ void __launch_bounds__(320) conv_row_umma_kernel(const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, tcols);
   if (tracing && threadIdx.x == 0) {
     const uint32_t t0 = trace[0];
+    const uint32_t t_end = (uint32_t)clock();
+    const int last = min(47, (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x);
     for (int i = 0; i < 24; ++i)
       printf("tile %2d  tma %7u  mma_start %7u  mma_done %7u  epi_start %7u  epi_done %7u\n", i, trace[i] - t0, trace[48 + i] - t0,
              trace[96 + i] - t0, trace[144 + i] - t0, trace[192 + i] - t0);
+    if (!etrace)
+      printf("entry %d setup %d first_tma 0 last tile(%d): mma_done %u epi_done %u end %u\n", (int)(t_entry - t0), (int)(t_setup - t0),
+             last, trace[96 + last] - t0, trace[192 + last] - t0, t_end - t0);
   }
 #undef ROW_TRACE
 #undef ROW_ETRACE
@@ -827,7 +877,7 @@ static int launch_row_epi(cudaStream_t s, const CUtensorMap& mA, const CUtensorM
     smem_set = smem;
   }
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
-  conv_row_umma_kernel<EPI><<<persistent_grid(ntiles), 320, smem, s>>>(mA, mB, mOA, mOB, mM, a);
+  conv_row_umma_kernel<EPI><<<persistent_grid(ntiles), 576, smem, s>>>(mA, mB, mOA, mOB, mM, a);
   DNNCA_LAUNCH_CHECK("conv_row_umma");
   note_family(2);
   return 1;
@@ -888,6 +938,7 @@ static int launch_row(cudaStream_t s, bool dgrad, int tconv, const dnnca_tensor_
     for (a.nstage = 4; a.nstage >= 2; --a.nstage)
       if (row_smem_bytes(a) <= ROW_SMEM_LIMIT) { fits = true; break; }
     if (!fits) continue;
+    if ((tconv ? 4 : 9) * a.cin_tot * a.cout * 4 > 4 * row_out_bytes(a) + 2 * row_mask_bytes(a)) continue;   // weight staging
     const double cost = (a.nmma * row_mma_cycles(a.NP) + 300.0) / P;
     if (!found || cost < best_cost) { best = a; best_cost = cost; found = true; }
   }
