@@ -775,7 +775,7 @@ static bool row_map(CUtensorMap* m, const dnnca_tensor_t* t, int box_e, int box_
 }
 
 static const int ROW_SMEM_LIMIT = 226 * 1024;
-static const int ROW_MAX_C = 12;
+static const int ROW_MAX_C = 16;
 
 static bool row_enabled() {
   static int on = -1;

@@ -143,11 +143,11 @@ class UNetAnnotator(Model):
         if plan.dtype != x.buf.dtype:                                 # fp32 input -> bf16 activations
             wide = self.configs['n_filters_first'] % 16 == 0          # first conv runs on the tensor cores
             if wide and isinstance(self.unet, MulmoUNet):
-                # one 16-byte-pixel buffer per modality (unet.py:182-185 slices inputs[..., m:m+1]): the TMA reads
-                # channel 0 and zero-fills the rest of the K=16 MMA step
+                # one dense single-channel buffer per modality (unet.py:182-185 slices inputs[..., m:m+1]): the
+                # 1 -> F first convs then run on the row-Toeplitz tcgen05 kernels (conv_row_umma.cu)
                 xs = []
                 for m in range(x.c):
-                    xm = R.TRef(plan.new_buf(x.h, x.w, 8, f'input_cast{m}', zero=True), 0, 1)
+                    xm = R.TRef(plan.new_buf(x.h, x.w, 1, f'input_cast{m}', zero=True), 0, 1)
                     xm.needs_grad = False
                     src = R.TRef(x.buf, m, 1)
                     src.needs_grad = False
