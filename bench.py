@@ -311,6 +311,13 @@ def run_ours(args):
             ach = d['bytes'] / d['ms'] / 1e6
             roofline = {'bound': 'hbm', 'kernel': k, 'achieved': round(ach, 1), 'peak': hbm_peak, 'unit': 'GB/s',
                         'frac': round(ach / hbm_peak, 4), 'traffic': None}
+        tr_path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')        # committed ncu --set full capture, per launch
+        if os.path.exists(tr_path):
+            tr = json.load(open(tr_path)).get(k)
+            if tr:
+                roofline['traffic'] = tr['dram_read_bytes'] + tr['dram_write_bytes']
+                roofline['traffic_source'] = 'profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)'
+                roofline['algorithmic_bytes_per_launch'] = tr['algorithmic_bytes']
         roofline.update({'share_of_step': round(d['ms'] / tot, 4), 'peak_source': src,
                          'step_algorithmic_gbs': round(sum(v['bytes'] for v in agg.values()) / tot / 1e6, 1),
                          'conv_kernels': {'share_of_step': round(conv_ms / tot, 4),
