@@ -161,10 +161,10 @@ def test_unet_big_and_mulmo_lowering_structure():
     m = getattr(tf_models, cfg['model'])(**cfg['model_options'])
     plan = cpu_plan(m, 1, 32, 3, training=False)
     assert m.count_params() == 1719089 and m.count_params(True) == 1713329
-    # bf16: one 16-byte-pixel input buffer per modality so the 1->16 first convs run on the tensor cores
+    # bf16: one dense single-channel input buffer per modality so the 1->16 first convs run on the tensor cores
     assert op_counts(plan) == {'ConvertOp': 3, 'ConvOp': 32, 'BNOp': 48, 'PoolOp': 12, 'TConvOp': 4}
     first = [op for op in plan.ops if isinstance(op, R.ConvOp)][0]
-    assert first.x.c == 1 and first.x.buf.c == 8                 # inputs[..., m:m+1], 16-byte aligned pixels
+    assert first.x.c == 1 and first.x.buf.c == 1                 # inputs[..., m:m+1] as a dense tensor (row-Toeplitz kernels)
     bott = [b for b in plan.bufs if b.name == 'bottleneck'][0]
     assert (bott.h, bott.w, bott.c) == (2, 2, 384)               # concat of the three 128-channel encoders
 
