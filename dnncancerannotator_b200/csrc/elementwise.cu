@@ -250,12 +250,27 @@ __global__ void __launch_bounds__(256) u8_to_unit_kernel(const uint8_t* __restri
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
-    uint4 v = s4[i];
+    uint4 v = __ldg(s4 + i);
     uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float f[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      float f = (float)((w[k >> 2] >> ((k & 3) * 8)) & 0xffu) / 255.0f;
-      stf(dst + i * 16 + k, f);
+    for (int k = 0; k < 16; ++k) f[k] = (float)((w[k >> 2] >> ((k & 3) * 8)) & 0xffu) / 255.0f;
+    if (sizeof(TO) == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {          // 4 x 16-byte stores
+      float4* d4 = reinterpret_cast<float4*>(dst + i * 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d4[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+    } else if (sizeof(TO) == 2 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {   // 2 x 16-byte stores
+      uint4* d4 = reinterpret_cast<uint4*>(dst + i * 16);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * k], f[8 * k + 1]), p1 = __floats2bfloat162_rn(f[8 * k + 2], f[8 * k + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * k + 4], f[8 * k + 5]), p3 = __floats2bfloat162_rn(f[8 * k + 6], f[8 * k + 7]);
+        d4[k] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                           *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) stf(dst + i * 16 + k, f[k]);
     }
   }
   for (long long i = nvec * 16 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;

@@ -168,6 +168,119 @@ __global__ void __launch_bounds__(256) head_bce_kernel(View f, const float* __re
 }
 
 
+// 8 pixels per thread for DENSE bf16 features with few channels (configs/unet.yaml: F = 3): F 16-byte loads of f, two
+// float4 of labels; df / probs / logits leave as 16-byte stores.  Same per-pixel arithmetic as head_bce_kernel.
+template <int F>
+__global__ void __launch_bounds__(256) head_bce_pix8_kernel(const __nv_bfloat16* __restrict__ f, const float* __restrict__ w,
+                                                           const float* __restrict__ b, const float* __restrict__ label,
+                                                           const dnnca_label_stats_t* __restrict__ ls, dnnca_loss_config_t cfg,
+                                                           float* __restrict__ logits, float* __restrict__ probs,
+                                                           float* __restrict__ per_sample, __nv_bfloat16* __restrict__ df,
+                                                           int act, float alpha, float* __restrict__ dw, float* __restrict__ db,
+                                                           long long HW, long long total) {
+  float weight;
+  if (cfg.has_weight) {
+    weight = cfg.weight;
+  } else {
+    const float r = (float)(ls->sum / (double)total);  // losses.py:95
+    weight = r > 0.f ? 1.f / r : 1.f;                  // losses.py:27
+  }
+  weight = cfg.weight_mul * weight + cfg.weight_add;    // losses.py:29
+  const float bias = b ? b[0] : 0.f;
+  float wr[F], dwacc[F];
+#pragma unroll
+  for (int c = 0; c < F; ++c) { wr[c] = w[c]; dwacc[c] = 0.f; }
+  float dbacc = 0.f, lossacc = 0.f;
+  const long long base = (long long)blockIdx.y * HW;
+  const long long ngroups = HW / 8;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (long long)gridDim.x * blockDim.x) {
+    const long long p0 = base + g * 8;
+    float fv[8 * F];
+    {
+      const uint4* q = reinterpret_cast<const uint4*>(f + p0 * F);
+#pragma unroll
+      for (int i = 0; i < F; ++i) {
+        const uint4 v = __ldg(q + i);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          fv[i * 8 + 2 * j] = __uint_as_float(u[j] << 16);
+          fv[i * 8 + 2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u);
+        }
+      }
+    }
+    float yv[8];
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(label + p0)), c = __ldg(reinterpret_cast<const float4*>(label + p0) + 1);
+      yv[0] = a.x; yv[1] = a.y; yv[2] = a.z; yv[3] = a.w; yv[4] = c.x; yv[5] = c.y; yv[6] = c.z; yv[7] = c.w;
+    }
+    float zv[8], pv[8], dfv[8 * F];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float z = bias;
+#pragma unroll
+      for (int c = 0; c < F; ++c) z = fmaf(fv[k * F + c], wr[c], z);
+      const float y = yv[k];
+      const float mask = y * (weight - 1.f) + 1.f;                          // losses.py:31
+      const float bce = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));    // from_logits BCE
+      lossacc += bce * mask;
+      const float pr = 1.f / (1.f + expf(-z));
+      zv[k] = z; pv[k] = pr;
+      const float dz = mask * (pr - y) * cfg.grad_scale;
+      dbacc += dz;
+#pragma unroll
+      for (int c = 0; c < F; ++c) {
+        dwacc[c] = fmaf(dz, fv[k * F + c], dwacc[c]);
+        dfv[k * F + c] = dz * wr[c] * act_grad(fv[k * F + c], act, alpha);
+      }
+    }
+    if (logits) {
+      float4* q = reinterpret_cast<float4*>(logits + p0);
+      q[0] = make_float4(zv[0], zv[1], zv[2], zv[3]); q[1] = make_float4(zv[4], zv[5], zv[6], zv[7]);
+    }
+    if (probs) {
+      float4* q = reinterpret_cast<float4*>(probs + p0);
+      q[0] = make_float4(pv[0], pv[1], pv[2], pv[3]); q[1] = make_float4(pv[4], pv[5], pv[6], pv[7]);
+    }
+    if (df) {
+      uint4* q = reinterpret_cast<uint4*>(df + p0 * F);
+#pragma unroll
+      for (int i = 0; i < F; ++i) {
+        __nv_bfloat162 a0 = __floats2bfloat162_rn(dfv[i * 8], dfv[i * 8 + 1]), a1 = __floats2bfloat162_rn(dfv[i * 8 + 2], dfv[i * 8 + 3]);
+        __nv_bfloat162 a2 = __floats2bfloat162_rn(dfv[i * 8 + 4], dfv[i * 8 + 5]), a3 = __floats2bfloat162_rn(dfv[i * 8 + 6], dfv[i * 8 + 7]);
+        q[i] = make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1), *reinterpret_cast<uint32_t*>(&a2),
+                          *reinterpret_cast<uint32_t*>(&a3));
+      }
+    }
+  }
+  __shared__ float sm[8][F + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  lossacc = warp_sum(lossacc);
+  dbacc = warp_sum(dbacc);
+#pragma unroll
+  for (int c = 0; c < F; ++c) dwacc[c] = warp_sum(dwacc[c]);
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < F; ++c) sm[warp][c] = dwacc[c];
+    sm[warp][F] = dbacc;
+    sm[warp][F + 1] = lossacc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < F + 2; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sm[i][c];
+    if (c < F) {
+      if (dw) atomicAdd(dw + c, s);
+    } else if (c == F) {
+      if (db) atomicAdd(db, s);
+    } else {
+      atomicAdd(per_sample + blockIdx.y, s / (float)HW);                 // losses.py:36
+    }
+  }
+}
+
+
 // 128-bit vectorised bf16 variant for F % 8 == 0 (unet_big F=64, mulmo F=16): LPP = F/8 lanes share a pixel, each lane
 // owns 8 channels (one uint4 of f, one of df); the logit is a shuffle-reduction over the LPP lanes.
 template <int LPP>
@@ -320,6 +433,27 @@ extern "C" int dnnca_head_bce_fwd_bwd(void* stream, const dnnca_tensor_t* f, con
   auto al = [](const dnnca_tensor_t* t) {
     return t->dtype == DNNCA_BF16 && t->coff % 8 == 0 && t->cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
   };
+  {   // few dense bf16 features: 8 pixels per thread, 16-byte accesses
+    auto dense = [](const dnnca_tensor_t* t) {
+      return t->dtype == DNNCA_BF16 && t->coff == 0 && t->cstride == t->c && (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
+    };
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if ((f->c == 3 || f->c == 4 || f->c == 6) && HW % 8 == 0 && dense(f) && (!df || dense(df)) && al16(label) &&
+        (!logits || al16(logits)) && (!probs || al16(probs))) {
+      int gp = (int)((HW / 8 + 255) / 256);
+      if (gp > cap) gp = cap;
+      if (gp < 1) gp = 1;
+      dim3 g3(gp, f->n);
+      const __nv_bfloat16* fp = reinterpret_cast<const __nv_bfloat16*>(f->data);
+      __nv_bfloat16* dfp = df ? reinterpret_cast<__nv_bfloat16*>(df->data) : nullptr;
+#define LAUNCH_P8(FF) head_bce_pix8_kernel<FF><<<g3, 256, 0, s>>>(fp, w, b, label, lstats, *cfg, logits, probs, per_sample, dfp, act, \
+                                                                  alpha, dw, db, HW, HW * f->n)
+      if (f->c == 3) LAUNCH_P8(3); else if (f->c == 4) LAUNCH_P8(4); else LAUNCH_P8(6);
+#undef LAUNCH_P8
+      DNNCA_LAUNCH_CHECK("head_bce_fwd_bwd");
+      return DNNCA_OK;
+    }
+  }
   if ((f->c == 16 || f->c == 32 || f->c == 64) && al(f) && (!df || al(df))) {
     const int lpp = f->c / 8;
     int gv = (int)((HW + (256 / lpp) * 8 - 1) / ((256 / lpp) * 8));

@@ -382,6 +382,16 @@ def test_batchnorm_train_fwd_bwd_and_inference(N, mode, c, scale):
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
 @pytest.mark.parametrize('F,healthy,weight', [(3, False, None), (16, False, None), (64, True, None), (3, False, 5.0)])
 def test_head_bce_fused(N, mode, F, healthy, weight):
+    _head_case(N, mode, F, healthy, weight, 8 if F % 8 == 0 else 1)
+
+
+@pytest.mark.parametrize('F,healthy,weight', [(3, False, None), (3, True, None), (4, False, 2.0), (6, False, None)])
+def test_head_bce_pix8_dense(N, F, healthy, weight):
+    """dense bf16 features with few channels (configs/unet.yaml: F = 3) take the 8-pixels-per-thread kernel"""
+    _head_case(N, 'bf16', F, healthy, weight, 0)
+
+
+def _head_case(N, mode, F, healthy, weight, pad):
     dt = DT[mode]
     rng = np.random.default_rng(F)
     n, h, w = 3, 16, 24
@@ -389,7 +399,7 @@ def test_head_bce_fused(N, mode, F, healthy, weight):
     wt = rng.normal(size=F).astype(np.float32)
     b = np.array([0.1], np.float32)
     y = (rng.uniform(size=(n, h, w)) < (0.0 if healthy else 0.05)).astype(np.float32)
-    fb, fo, _ = embed(f, dt, 8 if F % 8 == 0 else 1, 0)      # 16-byte aligned slices take the vectorised bf16 kernel
+    fb, fo, _ = embed(f, dt, pad, 0)      # 16-byte aligned slices take the vectorised bf16 kernel
     fv = view(N, fb, fo, F)
     ls = torch.zeros(16, dtype=torch.uint8, device='cuda')
     yd = dev(y)
