@@ -81,7 +81,7 @@ int try_tconv_dgrad_small(cudaStream_t, const dnnca_tensor_t*, const float*, con
 int try_tconv_wgrad_small(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
 // tcgen05 implicit-GEMM family (conv_umma.cu)
 size_t umma_pack_bytes(int taps, int cin, int cout);
-int try_conv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, int, float, void*, size_t);
+int try_conv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, int, float, void*, size_t, double*);
 int try_conv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, const dnnca_tensor_t*, int, float, void*, size_t);
 int try_tconv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, void*, size_t);
 int try_tconv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float, void*, size_t);
@@ -169,8 +169,9 @@ extern "C" int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const d
     if (r == 1) return DNNCA_OK;
   }
   if (!g_force_generic) {
-    r = try_conv_fprop_umma(s, x, x2, w, bias, y, ksize, act, alpha, workspace, workspace_bytes);
+    r = try_conv_fprop_umma(s, x, x2, w, bias, y, ksize, act, alpha, workspace, workspace_bytes, stats);
     if (r < 0) return r;
+    if (r == 2) return DNNCA_OK;                    // statistics taken in the conv epilogue
     if (r == 1) return stats ? dnnca_channel_stats(stream, y, stats) : DNNCA_OK;
   }
   r = launch_conv_fprop_generic(s, x, x2, w, bias, y, ksize, act, alpha);

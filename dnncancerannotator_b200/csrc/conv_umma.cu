@@ -493,8 +493,9 @@ static bool halo_enabled() {
 }
 
 // returns 1 handled / 0 not covered / <0 error
+// returns 2 when the kernel also accumulated the BatchNorm statistics into `stats` (else the caller runs channel_stats)
 int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w, const float* bias,
-                        const dnnca_tensor_t* y, int k, int act, float alpha, void* ws, size_t ws_bytes) {
+                        const dnnca_tensor_t* y, int k, int act, float alpha, void* ws, size_t ws_bytes, double* stats) {
   if (!ws || !bf16_view16(y)) return 0;
   if (x2 ? (!bf16_view16(x) || !bf16_view16(x2)) : !bf16_view_in(x)) return 0;
   const int ca = x->c, cb = x2 ? x2->c : 0, cin = ca + cb, cout = y->c, taps = k * k;
@@ -515,8 +516,10 @@ int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_ten
   a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
   a.mask = nullptr; a.n_total = cout; a.cout_t = cout; a.nimg = x->n;
   if (k == 3 && kc == 64 && halo_enabled()) {
+    a.stats = stats;
     r = try_conv3x3_halo(s, x, x2, ws, cin, cout, a);
-    if (r != 0) return r;
+    if (r != 0) return (r == 1 && stats) ? 2 : r;
+    a.stats = nullptr;
   }
   if (kc == 64) return dispatch_bn<64>(s, mA, mB, mW, a, x->n, bn);
   if (kc == 32) return dispatch_bn<32>(s, mA, mB, mW, a, x->n, bn);

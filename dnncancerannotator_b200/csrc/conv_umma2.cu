@@ -24,7 +24,7 @@ template <int BN>
 struct HGeom {
   static constexpr int B_TAP = BN * 128;                   // one tap of one 64-channel chunk
   static constexpr int A_SLOTS = 2;
-  static constexpr int CTRL = 2048;                        // barriers + TMEM slot + bias slice (BN floats at +256)
+  static constexpr int CTRL = 6144;                        // barriers + TMEM slot + bias slice (BN floats at +256) + BN-statistics accumulators (2*BN doubles at +2048)
   // resident: all 9 * (Cin/64) weight blocks stay in shared memory for the CTA's lifetime
   static constexpr int smem_resident(int kchunks) { return CTRL + A_SLOTS * A_SLOT + 9 * kchunks * B_TAP + 1024; }
   static constexpr int B_STAGES = BN > 128 ? 3 : 4;
@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
   uint64_t* tempty = tfull + 2;                              // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* sbias = reinterpret_cast<float*>(smem + 256);      // [BN] bias slice of this CTA's N tile (fprop)
+  double* sstat = reinterpret_cast<double*>(smem + 2048);   // [2*BN] per-channel sum | sum of squares (fprop + stats)
+  const bool do_stats = a.stats != nullptr && a.epi == EPI_FPROP;
   unsigned char* aring = smem + G::CTRL;
   unsigned char* bring = aring + G::A_SLOTS * A_SLOT;
 
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   for (int i = threadIdx.x; i < BN; i += blockDim.x)
     sbias[i] = (a.bias && a.epi != EPI_DGRAD && n0 + i < a.n_total) ? a.bias[n0 + i] : 0.f;
+  for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sstat[i] = 0.0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -177,6 +180,14 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
     const int r = lg * 32 + lane;           // row of the 16x8 pixel tile
     const int ty = r >> 3, tx = r & 7;
     constexpr int NCHUNK = BN / 64;         // 32-column chunks per warp
+    // BN statistics: for BN = 64 every thread keeps per-column partial sums of ITS tile row in registers over all of
+    // the CTA's tiles and the warp reduction runs once at the end; wider tiles reduce per tile (register budget)
+    constexpr bool REG_STATS = BN <= 64;
+    float acc1[REG_STATS ? NCHUNK : 1][32], acc2[REG_STATS ? NCHUNK : 1][32];
+#pragma unroll
+    for (int c = 0; c < (REG_STATS ? NCHUNK : 1); ++c)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { acc1[c][j] = 0.f; acc2[c][j] = 0.f; }
     int ti = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
       int b = t;
@@ -205,16 +216,61 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN + col), v);
         tmem_ld_wait();
-        if (inside && n0 + col < a.n_total) epilogue_chunk32(a, v, ca[c], m[c], sbias + col);
+        if (!do_stats) {
+          if (inside && n0 + col < a.n_total) epilogue_chunk32(a, v, ca[c], m[c], sbias + col);
+        } else {
+          // BatchNormalization statistics of the stored tensor (components.py:57-58,130-132) in the epilogue: rows of
+          // the tile are lanes, so a column sum is a 31-shuffle warp reduction; one shared fp64 atomic per lane
+          float r1[32], r2[32];
+          epilogue_chunk32<true>(a, v, ca[c], m[c], sbias + col, r1, inside && n0 + col < a.n_total);
+          if (REG_STATS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float r = inside ? r1[j] : 0.f;
+              acc1[REG_STATS ? c : 0][j] += r;
+              acc2[REG_STATS ? c : 0][j] = fmaf(r, r, acc2[REG_STATS ? c : 0][j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              r1[j] = inside ? r1[j] : 0.f;
+              r2[j] = r1[j] * r1[j];
+            }
+            warp_colsum32(r1, lane);
+            warp_colsum32(r2, lane);
+            if (n0 + col + lane < a.n_total) {
+              atomicAdd(sstat + col + lane, (double)r1[0]);
+              atomicAdd(sstat + BN + col + lane, (double)r2[0]);
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + buf);
     }
+    if (REG_STATS && do_stats) {
+#pragma unroll
+      for (int c = 0; c < (REG_STATS ? NCHUNK : 1); ++c) {
+        const int col = half * (BN / 2) + c * 32;
+        warp_colsum32(acc1[c], lane);
+        warp_colsum32(acc2[c], lane);
+        if (n0 + col + lane < a.n_total) {
+          atomicAdd(sstat + col + lane, (double)acc1[c][0]);
+          atomicAdd(sstat + BN + col + lane, (double)acc2[c][0]);
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+  if (do_stats)
+    for (int i = threadIdx.x; i < BN; i += blockDim.x)
+      if (n0 + i < a.n_total) {
+        atomicAdd(a.stats + n0 + i, sstat[i]);
+        atomicAdd(a.stats + a.n_total + n0 + i, sstat[BN + i]);
+      }
 }
 
 // ---------------------------------------------------------------- host side

@@ -90,6 +90,7 @@ struct UArgs {
   int cout_t;                // ConvT fprop: channels per tap
   int nimg;                  // images (persistent kernels)
   int dbg;                   // experiment switch (descriptor variants)
+  double* stats;             // fprop (persistent halo kernel): per-channel sum | sum of squares of the STORED output, or NULL
 };
 
 // epilogue of one 32-(or 16-)column chunk of one accumulator row: bias+act (fprop / ConvT) or act'(mask) (dgrad),
@@ -122,8 +123,23 @@ __device__ __forceinline__ ChunkAddr chunk_addr(const UArgs& a, int n, int gy, i
 
 // persistent-kernel epilogue of a 32-column chunk: `m` holds the mask row prefetched before the accumulator was ready,
 // `sbias` is the CTA's bias slice in shared memory
+// after the call v[0] = sum over the 32 lanes of column `lane` (31 shuffles: lanes trade halves of the column set)
+__device__ __forceinline__ void warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h];
+      const float keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+}
+
+template <bool STATS = false>
 __device__ __forceinline__ void epilogue_chunk32(const UArgs& a, const uint32_t (&v)[32], const ChunkAddr& ca, const uint4 (&m)[4],
-                                                 const float* sbias) {
+                                                 const float* sbias, float* rounded = nullptr, bool store = true) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -155,7 +171,15 @@ __device__ __forceinline__ void epilogue_chunk32(const UArgs& a, const uint32_t 
     o.y = *reinterpret_cast<uint32_t*>(&p1);
     o.z = *reinterpret_cast<uint32_t*>(&p2);
     o.w = *reinterpret_cast<uint32_t*>(&p3);
-    d4[q] = o;
+    if (store) d4[q] = o;
+    if (STATS) {                              // the values as they read back from the bf16 tensor
+      const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rounded[q * 8 + 2 * j] = __uint_as_float(ow[j] << 16);
+        rounded[q * 8 + 2 * j + 1] = __uint_as_float(ow[j] & 0xffff0000u);
+      }
+    }
   }
 }
 
