@@ -37,6 +37,7 @@ for dt in (0, 1):
         UNITS.append(('conv_small.cu', f'conv_small_d{dt}k{kind}', [f'-DSMALL_DT={dt}', f'-DSMALL_KIND={kind}']))
 UNITS.append(('conv_umma.cu', 'conv_umma', []))
 UNITS.append(('conv_umma2.cu', 'conv_umma2', []))
+UNITS.append(('conv_umma3.cu', 'conv_umma3', []))
 UNITS.append(('conv_row_umma.cu', 'conv_row_umma', []))
 UNITS.append(('pool_vec.cu', 'pool_vec', []))
 

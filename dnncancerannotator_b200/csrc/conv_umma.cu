@@ -356,11 +356,28 @@ static int launch_wgrad_umma(cudaStream_t s, const CUtensorMap& mA, const CUtens
 }
 
 int launch_channel_sum(cudaStream_t s, const dnnca_tensor_t* g, float* out);
+int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g, float* dw);
+static bool wgrad_halo_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("DNNCA_DISABLE_WGRAD_HALO") ? 0 : 1;
+  return on == 1;
+}
 
 static int wgrad_umma_common(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g,
                              float* dw, float* db, int k, int tconv) {
   if (!bf16_view_in(x) || (x2 && !bf16_view_in(x2)) || !bf16_view_in(g)) return 0;
   const int ca = x->c, cb = x2 ? x2->c : 0;
+  if (!tconv && k == 3 && wgrad_halo_enabled()) {     // halo-tile kernel (conv_umma3.cu) for channel counts % 64 == 0
+    int r = try_conv3x3_wgrad_halo(s, x, x2, g, dw);
+    if (r < 0) return r;
+    if (r == 1) {
+      if (db) {
+        int e = launch_channel_sum(s, g, db);
+        if (e != DNNCA_OK) return e;
+      }
+      return 1;
+    }
+  }
   // partial 16x4 pixel tiles are fine: the TMA zero-fills x and dz outside the image, so they add nothing
   CUtensorMap mA, mB, mG;
   if (!act_map64(&mA, x, 1)) return 0;
