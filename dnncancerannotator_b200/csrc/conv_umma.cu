@@ -532,9 +532,9 @@ int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_ten
   a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + 7) / 8; a.epi = EPI_FPROP; a.act = act; a.alpha = alpha; a.bias = bias;
   a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
   a.mask = nullptr; a.n_total = cout; a.cout_t = cout; a.nimg = x->n;
-  if (k == 3 && kc == 64 && halo_enabled()) {
+  if (k == 3 && (kc == 64 || (!x2 && ca < 64)) && halo_enabled()) {
     a.stats = stats;
-    r = try_conv3x3_halo(s, x, x2, ws, cin, cout, a);
+    r = try_conv3x3_halo(s, x, x2, ws, kc == 64 ? cin : pad16(cin), cout, a);
     if (r != 0) return (r == 1 && stats) ? 2 : r;
     a.stats = nullptr;
   }

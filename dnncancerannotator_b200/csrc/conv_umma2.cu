@@ -326,7 +326,10 @@ static int launch_halo(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap&
 // Conv2D 3x3 fprop (pack mode 0 already in `wpack`: [tap][N][K]) or dgrad (pack mode 1); returns 1 / 0 / <0
 int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tensor_t* xb, const void* wpack, int ktot, int ntot,
                      UArgs a) {
-  if (xa->c % 64 || (xb && xb->c % 64) || ntot % 64) return 0;
+  // a single input with fewer than 64 channels (first layers) is one K chunk whose missing channels are zero-filled by
+  // the TMA (activations and packed weights alike)
+  const bool narrow = !xb && xa->c < 64;
+  if ((!narrow && (xa->c % 64 || (xb && xb->c % 64))) || ntot % 64) return 0;
   const int bn = ntot % 256 == 0 ? 256 : (ntot % 128 == 0 ? 128 : 64);
   if (a.split % bn) return 0;               // an N tile must not straddle the two dgrad destinations
   CUtensorMap mA, mB, mW;
@@ -337,7 +340,8 @@ int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tenso
   a.tiles_x = (a.W + 7) / 8;
   a.tiles_y = (a.H + 15) / 16;
   a.dbg = getenv("DNNCA_HALO_DBG") ? atoi(getenv("DNNCA_HALO_DBG")) : 0;
-  const int kchunks = ktot / 64;
+  const int kchunks = narrow ? 1 : ktot / 64;
+  if (narrow) a.c_a = 64;
   const size_t limit = 220 * 1024;
   if (bn == 64) {
     if ((size_t)HGeom<64>::smem_resident(kchunks) <= limit) return launch_halo<64, true>(s, mA, mB, mW, a, kchunks);

@@ -261,7 +261,10 @@ static int launch_wgrad_halo(cudaStream_t s, const CUtensorMap& mA, const CUtens
 // Conv2D 3x3 wgrad for bf16 views whose channel counts are multiples of 64; returns 1 / 0 (not covered) / <0
 int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g, float* dw) {
   const int ca = x->c, cb = x2 ? x2->c : 0, cout = g->c;
-  if (ca % 64 || cb % 64 || cout % 64) return 0;
+  // a single input with fewer than 64 channels (first layers: 1/3/5 modalities in 16-byte pixels) is one PAIRED M tile
+  // whose missing channels the TMA zero-fills
+  const bool narrow = !x2 && ca < 64;
+  if ((!narrow && (ca % 64 || cb % 64)) || cout % 64) return 0;
   // PAIRED (64-channel M tiles, all nine taps per CTA) measured faster up to 128 input channels per tensor; above
   // that the FULL variant (128-channel M tiles, one filter row per CTA) wins (tools/wgrad_microbench.py)
   static int paired_max = -1;
@@ -271,7 +274,7 @@ int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_
   a.c_a = ca; a.c_b = cb; a.cout = cout; a.dw = dw;
   a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + WH_R - 1) / WH_R; a.nimg = x->n;
   const int mch = paired ? 64 : 128;
-  a.mt_a = ca / mch;
+  a.mt_a = narrow ? 1 : ca / mch;
   const int mt = a.mt_a + cb / mch;
   CUtensorMap mA, mB, mG;
   if (!wh_map(&mA, x, WH_PW, paired ? WH_R + 2 : WH_R)) return 0;
