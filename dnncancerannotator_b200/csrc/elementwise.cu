@@ -312,7 +312,8 @@ __device__ __forceinline__ uint4* vptr_w(const View& v, long long p, int g) {
 template <int MODE>
 __global__ void __launch_bounds__(256) reduce_vec8_kernel(View x, View dy, const float* __restrict__ mi,
                                                          double* __restrict__ acc, int GL, int PL, long long P) {
-  __shared__ double sm[256];
+  // per-thread partials of 8 channels x 2 quantities meet in shared memory ONCE per channel group (two barriers)
+  __shared__ double sm[256 * 16];
   const int gl = threadIdx.x & (GL - 1), pl = threadIdx.x / GL;
   const int ng = x.c / 8;
   for (int g = gl; g < ((ng + GL - 1) / GL) * GL; g += GL) {
@@ -329,7 +330,37 @@ __global__ void __launch_bounds__(256) reduce_vec8_kernel(View x, View dy, const
         for (int j = 0; j < 8; ++j) { mean[j] = mi[8 * g + j]; inv[j] = mi[x.c + 8 * g + j]; }
       }
       int cnt = 0;
-      for (long long p = (long long)blockIdx.x * PL + pl; p < P; p += (long long)gridDim.x * PL) {
+      const long long stride = (long long)gridDim.x * PL;
+      long long p = (long long)blockIdx.x * PL + pl;
+      // four pixels per iteration: all loads are issued before the first use (memory-level parallelism)
+      for (; p + 3 * stride < P; p += 4 * stride) {
+        uint4 xr[4], gr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          xr[u] = __ldg(vptr(x, p + u * stride, g));
+          if (MODE == 1) gr[u] = __ldg(vptr(dy, p + u * stride, g));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float xv[8];
+          unpack8(xr[u], xv);
+          if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s0[j] += xv[j]; s1[j] = fmaf(xv[j], xv[j], s1[j]); }
+          } else {
+            float gv[8];
+            unpack8(gr[u], gv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s0[j] += gv[j]; s1[j] = fmaf(gv[j], (xv[j] - mean[j]) * inv[j], s1[j]); }
+          }
+        }
+        if ((cnt += 4) >= 64) {       // flush the fp32 partials into fp64 every 64 pixels
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; s0[j] = s1[j] = 0.f; }
+          cnt = 0;
+        }
+      }
+      for (; p < P; p += stride) {
         float xv[8];
         unpack8(*vptr(x, p, g), xv);
         if (MODE == 0) {
@@ -341,24 +372,23 @@ __global__ void __launch_bounds__(256) reduce_vec8_kernel(View x, View dy, const
 #pragma unroll
           for (int j = 0; j < 8; ++j) { s0[j] += gv[j]; s1[j] = fmaf(gv[j], (xv[j] - mean[j]) * inv[j], s1[j]); }
         }
-        if (++cnt == 64) {            // flush the fp32 partials into fp64 every 64 pixels
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; s0[j] = s1[j] = 0.f; }
-          cnt = 0;
-        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; }
     }
+    // sm[(pl*GL + gl)*16 + q]: thread (pl = 0.., gl) then sums its group's 16 quantities over the PL pixel lanes
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double r0 = block_reduce_pl(d0[j], sm, GL, PL);
-      const double r1 = block_reduce_pl(d1[j], sm, GL, PL);
-      if (pl == 0 && g < ng) {
-        atomicAdd(acc + 8 * g + j, r0);
-        atomicAdd(acc + x.c + 8 * g + j, r1);
-      }
+    for (int j = 0; j < 8; ++j) { sm[threadIdx.x * 16 + j] = d0[j]; sm[threadIdx.x * 16 + 8 + j] = d1[j]; }
+    __syncthreads();
+    // 16*GL sums of PL terms, spread over the 256 threads
+    for (int o = threadIdx.x; o < 16 * GL; o += 256) {
+      const int q = o & 15, gg = o >> 4;
+      double r = 0.0;
+      for (int l = 0; l < PL; ++l) r += sm[(l * GL + gg) * 16 + q];
+      const int gch = g - gl + gg;               // channel group of lane gg in this pass
+      if (gch < ng) atomicAdd(acc + (q < 8 ? 0 : x.c) + 8 * gch + (q & 7), r);
     }
+    __syncthreads();
   }
 }
 

@@ -160,6 +160,137 @@ __global__ void __launch_bounds__(256) f32_to_bf16_vec_kernel(const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// C % 8 == 0 (configs/unet_big.yaml, mulmo_unet.yaml): thread = (pooled pixel lane, group of 8 channels), one 16-byte
+// access per tensor and window position; channel-slice views allowed.  The forward kernel can also accumulate the
+// BatchNormalization statistics of its output (components.py:59) like reduce_vec8_kernel does.
+// ---------------------------------------------------------------------------------------------------------------
+struct PV { const __nv_bfloat16* p; long long cs; };     // base pointer (already at the slice's first channel), pixel stride
+__device__ __forceinline__ void unpack8f(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { f[2 * j] = bf_lo(w[j]); f[2 * j + 1] = bf_hi(w[j]); }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) maxpool_fwd_vec8_kernel(PV x, __nv_bfloat16* y, long long ycs, uint8_t* __restrict__ idx,
+                                                              double* __restrict__ stats, int C, int Ho, int Wo, long long PO,
+                                                              int GL, int PL) {
+  __shared__ double sm[STATS ? 256 * 16 : 1];
+  const int gl = threadIdx.x & (GL - 1), pl = threadIdx.x / GL;
+  const int ng = C / 8;
+  const long long W = 2LL * Wo;
+  for (int g = gl; g < ((ng + GL - 1) / GL) * GL; g += GL) {
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+    double d0[8], d1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d0[j] = d1[j] = 0.0;
+    if (g < ng) {
+      int cnt = 0;
+      for (long long p = (long long)blockIdx.x * PL + pl; p < PO; p += (long long)gridDim.x * PL) {
+        const int ox = (int)(p % Wo);
+        const long long t = p / Wo;
+        const int oy = (int)(t % Ho);
+        const long long n = t / Ho;
+        const long long q00 = (n * 2 * Ho + 2 * oy) * W + 2 * ox;
+        uint4 r[4];
+        r[0] = __ldg(reinterpret_cast<const uint4*>(x.p + q00 * x.cs + 8 * g));
+        r[1] = __ldg(reinterpret_cast<const uint4*>(x.p + (q00 + 1) * x.cs + 8 * g));
+        r[2] = __ldg(reinterpret_cast<const uint4*>(x.p + (q00 + W) * x.cs + 8 * g));
+        r[3] = __ldg(reinterpret_cast<const uint4*>(x.p + (q00 + W + 1) * x.cs + 8 * g));
+        float best[8], v[8];
+        uint32_t bi[2] = {0u, 0u};
+        unpack8f(r[0], best);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          unpack8f(r[k], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (v[j] > best[j]) { best[j] = v[j]; bi[j >> 2] = (bi[j >> 2] & ~(0xffu << ((j & 3) * 8))) | ((uint32_t)k << ((j & 3) * 8)); }
+        }
+        *reinterpret_cast<uint4*>(y + p * ycs + 8 * g) =
+            make_uint4(pack2(best[0], best[1]), pack2(best[2], best[3]), pack2(best[4], best[5]), pack2(best[6], best[7]));
+        if (idx) *reinterpret_cast<uint2*>(idx + p * C + 8 * g) = make_uint2(bi[0], bi[1]);
+        if (STATS) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s0[j] += best[j]; s1[j] = fmaf(best[j], best[j], s1[j]); }
+          if (++cnt == 64) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; s0[j] = s1[j] = 0.f; }
+            cnt = 0;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; }
+    }
+    if (STATS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sm[threadIdx.x * 16 + j] = d0[j]; sm[threadIdx.x * 16 + 8 + j] = d1[j]; }
+      __syncthreads();
+      for (int o = threadIdx.x; o < 16 * GL; o += 256) {
+        const int q = o & 15, gg = o >> 4;
+        double rsum = 0.0;
+        for (int l = 0; l < PL; ++l) rsum += sm[(l * GL + gg) * 16 + q];
+        const int gch = g - gl + gg;
+        if (gch < ng) atomicAdd(stats + (q < 8 ? 0 : C) + 8 * gch + (q & 7), rsum);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) maxpool_bwd_vec8_kernel(PV dy, const uint8_t* __restrict__ idx, PV dskip, int has_skip,
+                                                              __nv_bfloat16* dx, long long dxcs, PV mask, float alpha, int C, int Ho,
+                                                              int Wo, long long total) {
+  const int ng = C / 8;
+  const long long W = 2LL * Wo;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long p = t / ng;
+    const int g = (int)(t - p * ng);
+    const int ox = (int)(p % Wo);
+    const long long u = p / Wo;
+    const int oy = (int)(u % Ho);
+    const long long n = u / Ho;
+    const long long q00 = (n * 2 * Ho + 2 * oy) * W + 2 * ox;
+    float gv[8];
+    unpack8f(__ldg(reinterpret_cast<const uint4*>(dy.p + p * dy.cs + 8 * g)), gv);
+    const uint2 iv = __ldg(reinterpret_cast<const uint2*>(idx + p * C + 8 * g));
+    const uint32_t ib[2] = {iv.x, iv.y};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long q = q00 + (k >> 1) * W + (k & 1);
+      float f[8];
+      if (has_skip) unpack8f(*reinterpret_cast<const uint4*>(dskip.p + q * dskip.cs + 8 * g), f);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = ((((ib[j >> 2] >> ((j & 3) * 8)) & 0xffu) == (uint32_t)k) ? gv[j] : 0.f) + f[j];
+      if (MODE != 0) {
+        float m[8];
+        unpack8f(__ldg(reinterpret_cast<const uint4*>(mask.p + q * mask.cs + 8 * g)), m);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= (m[j] > 0.f ? 1.f : (MODE == 1 ? 0.f : alpha));
+      }
+      *reinterpret_cast<uint4*>(dx + q * dxcs + 8 * g) =
+          make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+  }
+}
+
+static bool vec8_view(const dnnca_tensor_t* t) {
+  return t->dtype == DNNCA_BF16 && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
+}
+static PV pv(const dnnca_tensor_t* t) {
+  return PV{reinterpret_cast<const __nv_bfloat16*>(t->data) + t->coff, (long long)t->cstride};
+}
+
 static bool dense_bf16(const dnnca_tensor_t* t) {
   return t->dtype == DNNCA_BF16 && t->coff == 0 && t->cstride == t->c && (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
 }
@@ -172,6 +303,21 @@ static int vec_grid(long long threads) {
 
 // returns 1 when handled, 0 when the shape is not covered
 int try_maxpool_fwd_vec(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* y, uint8_t* idx, double* stats) {
+  if (vec8_view(x) && vec8_view(y) && (!idx || (reinterpret_cast<uintptr_t>(idx) & 7) == 0)) {
+    const int C = x->c;
+    int gl = 1;
+    while (gl < C / 8 && gl < 256) gl <<= 1;
+    const int pl = 256 / gl;
+    const long long PO = (long long)y->n * y->h * y->w;
+    long long b = (PO + (long long)pl * (stats ? 32 : 4) - 1) / ((long long)pl * (stats ? 32 : 4)), cap = (long long)sm_count() * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff;
+    if (stats) maxpool_fwd_vec8_kernel<true><<<(int)b, 256, 0, s>>>(pv(x), yp, y->cstride, idx, stats, C, y->h, y->w, PO, gl, pl);
+    else maxpool_fwd_vec8_kernel<false><<<(int)b, 256, 0, s>>>(pv(x), yp, y->cstride, idx, stats, C, y->h, y->w, PO, gl, pl);
+    DNNCA_LAUNCH_CHECK("maxpool_fwd_vec8");
+    return 1;
+  }
   if (stats || !dense_bf16(x) || !dense_bf16(y)) return 0;
   const int C = x->c;
   if ((C != 3 && C != 6 && C != 12) || ((long long)y->w * C) % 24) return 0;
@@ -199,6 +345,20 @@ static void launch_pool_bwd(cudaStream_t s, int grid, int mode, const __nv_bfloa
 
 int try_maxpool_bwd_vec(cudaStream_t s, const dnnca_tensor_t* dy, const uint8_t* idx, const dnnca_tensor_t* dskip,
                         const dnnca_tensor_t* dx, const dnnca_tensor_t* mask, int act, float alpha) {
+  if (vec8_view(dy) && vec8_view(dx) && (!dskip || vec8_view(dskip)) && (!mask || vec8_view(mask)) &&
+      (reinterpret_cast<uintptr_t>(idx) & 7) == 0) {
+    const int C = dy->c;
+    const int mode8 = (!mask || act == DNNCA_ACT_NONE) ? 0 : (act == DNNCA_ACT_RELU ? 1 : 2);
+    const long long total = (long long)dy->n * dy->h * dy->w * (C / 8);
+    const int grid = vec_grid(total);
+    const PV sk = dskip ? pv(dskip) : pv(dx), mk8 = mask ? pv(mask) : pv(dx);
+    __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx->data) + dx->coff;
+    if (mode8 == 0) maxpool_bwd_vec8_kernel<0><<<grid, 256, 0, s>>>(pv(dy), idx, sk, dskip != nullptr, dxp, dx->cstride, mk8, alpha, C, dy->h, dy->w, total);
+    else if (mode8 == 1) maxpool_bwd_vec8_kernel<1><<<grid, 256, 0, s>>>(pv(dy), idx, sk, dskip != nullptr, dxp, dx->cstride, mk8, alpha, C, dy->h, dy->w, total);
+    else maxpool_bwd_vec8_kernel<2><<<grid, 256, 0, s>>>(pv(dy), idx, sk, dskip != nullptr, dxp, dx->cstride, mk8, alpha, C, dy->h, dy->w, total);
+    DNNCA_LAUNCH_CHECK("maxpool_bwd_vec8");
+    return 1;
+  }
   if (!dense_bf16(dy) || !dense_bf16(dx) || (dskip && !dense_bf16(dskip)) || (mask && !dense_bf16(mask))) return 0;
   const int C = dy->c;
   if ((C != 3 && C != 6 && C != 12) || ((long long)dy->w * C) % 24 || (reinterpret_cast<uintptr_t>(idx) & 7)) return 0;

@@ -616,7 +616,7 @@ def test_conv_row_umma(N, shape):
     close(dx.float().cpu().numpy(), rdx[..., :ca], 'bf16', scale=np.abs(rdx).max())
 
 
-@pytest.mark.parametrize('c,h,w', [(3, 12, 32), (6, 8, 16), (12, 20, 8), (3, 256, 256)])
+@pytest.mark.parametrize('c,h,w', [(3, 12, 32), (6, 8, 16), (12, 20, 8), (3, 256, 256), (64, 8, 12), (16, 12, 20), (136, 6, 10)])
 def test_maxpool_vec_dense_bit_exact(N, c, h, w):
     """dense bf16 tensors with 3/6/12 channels take the 128-bit vectorised kernels (pool_vec.cu); results must be
     bit-identical to the oracle (first maximum wins, skip gradient added, ReLU mask from the pooled layer's input)."""
@@ -628,11 +628,16 @@ def test_maxpool_vec_dense_bit_exact(N, c, h, w):
     y = torch.zeros(n, h // 2, w // 2, c, dtype=bf, device='cuda')
     idx = torch.zeros(n, h // 2, w // 2, c, dtype=torch.uint8, device='cuda')
     xv, yv = view(N, xd, 0, c), view(N, y, 0, c)
-    N.call('dnnca_maxpool2x2_fwd', None, C.byref(xv), C.byref(yv), N.ptr(idx), None)
+    stats = torch.zeros(2 * c, dtype=torch.float64, device='cuda') if c % 8 == 0 else None   # fused BN statistics (vec8 kernel)
+    N.call('dnnca_maxpool2x2_fwd', None, C.byref(xv), C.byref(yv), N.ptr(idx), N.ptr(stats))
     sync()
     ty, tidx = ops.maxpool(torch.from_numpy(x), 2, return_indices=True)
     np.testing.assert_array_equal(y.float().cpu().numpy(), ty.numpy())
     np.testing.assert_array_equal(idx.cpu().numpy(), tidx.numpy())
+    if stats is not None:
+        t64 = ty.numpy().astype(np.float64)
+        np.testing.assert_allclose(stats.cpu().numpy()[:c], t64.sum((0, 1, 2)), rtol=1e-6, atol=1e-4)
+        np.testing.assert_allclose(stats.cpu().numpy()[c:], (t64 ** 2).sum((0, 1, 2)), rtol=1e-6, atol=1e-4)
     dy = q(rng.normal(size=ty.shape).astype(np.float32), bf)
     dskip = q(rng.normal(size=x.shape).astype(np.float32), bf)
     dyd, dxd = dev(dy, bf), dev(dskip, bf)
