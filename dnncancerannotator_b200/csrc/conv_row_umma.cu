@@ -31,6 +31,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <utility>
+
 #include "umma_common.cuh"
 
 namespace dnnca {
@@ -41,6 +43,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "r"(taddr)
                : "memory");
 }
+// programmatic dependent launch: the kernel may start while its predecessor in the stream is still draining; everything
+// that reads the predecessor's output (the TMA loads of activations / gradients) sits behind pdl_wait()
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t p;
   asm volatile(
@@ -342,10 +349,12 @@ __global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constan
   asm volatile("bar.sync 3, 544;" ::: "memory");
   }
 
+  pdl_launch_dependents();                 // the next kernel may be scheduled as soon as SMs free up
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       tma_prefetch_desc(&mapA);
+      pdl_wait();                          // the producer of our inputs has completed and flushed
       const int natoms = a.atoms[0] + (a.nops > 1 ? a.atoms[1] : 0);
       const uint32_t abytes = (uint32_t)(a.ltaps * natoms * (a.Hs + 2 * a.pad) * 128);
       const uint32_t mbytes = (uint32_t)(a.Hs * a.nsplit * 2);
@@ -604,10 +613,12 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
   const uint32_t t_setup = (uint32_t)clock();
   uint32_t t_acc = 0, t_ext = 0;
 
+  pdl_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&mapA);
       tma_prefetch_desc(&mapZ);
+      pdl_wait();
       const int natoms = a.atoms[0] + (a.nops > 1 ? a.atoms[1] : 0);
       const uint32_t bytes = (uint32_t)(natoms * (a.Hs + 2 * a.pad) * 128 + a.ztaps * a.zatoms * a.Hs * 128);
       int it = 0, s = 0;
@@ -861,6 +872,21 @@ static bool row_plan_mmas(RowArgs& a) {
   return true;
 }
 
+// launch with the programmatic-stream-serialization attribute (DNNCA_NO_PDL=1: plain launch)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, int smem, cudaStream_t s, Args&&... args) {
+  static int pdl = -1;
+  if (pdl < 0) pdl = getenv("DNNCA_NO_PDL") ? 0 : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 static int persistent_grid(int ntiles) {
   int g = sm_count();
   return g < ntiles ? g : ntiles;
@@ -877,7 +903,10 @@ static int launch_row_epi(cudaStream_t s, const CUtensorMap& mA, const CUtensorM
     smem_set = smem;
   }
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
-  conv_row_umma_kernel<EPI><<<persistent_grid(ntiles), 576, smem, s>>>(mA, mB, mOA, mOB, mM, a);
+  {
+    cudaError_t e = launch_pdl(conv_row_umma_kernel<EPI>, persistent_grid(ntiles), 576, smem, s, mA, mB, mOA, mOB, mM, a);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_row_umma: launch");
+  }
   DNNCA_LAUNCH_CHECK("conv_row_umma");
   note_family(2);
   return 1;
@@ -1083,7 +1112,10 @@ static int launch_row_wgrad(cudaStream_t s, int tconv, const dnnca_tensor_t* x, 
     smem_set = smem;
   }
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
-  conv_row_wgrad_kernel<<<persistent_grid(ntiles), 192, smem, s>>>(mA, mB, mZ, a);
+  {
+    cudaError_t e = launch_pdl(conv_row_wgrad_kernel, persistent_grid(ntiles), 192, smem, s, mA, mB, mZ, a);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_row_wgrad: launch");
+  }
   DNNCA_LAUNCH_CHECK("conv_row_wgrad");
   note_family(2);
   return 1;
