@@ -207,7 +207,7 @@ __device__ __forceinline__ uint4 row_epilogue8(float* f, uint32_t sb, uint32_t m
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(608) conv_row_umma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                            const __grid_constant__ CUtensorMap mapB,
                                                            const __grid_constant__ CUtensorMap mapOA,
                                                            const __grid_constant__ CUtensorMap mapOB,
@@ -224,12 +224,13 @@ __global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constan
   unsigned char* ctrl = mbase + 2 * row_mask_bytes(a);
   uint64_t* fullA = reinterpret_cast<uint64_t*>(ctrl);          // [8]
   uint64_t* emptyA = fullA + 8;                                  // [8]
-  uint64_t* tfull = emptyA + 8;                                  // [2]
-  uint64_t* tempty = tfull + 2;                                  // [2]
-  uint64_t* mfull = tempty + 2;                                  // [2]
+  uint64_t* tfull = emptyA + 8;                                  // [4] accumulator buffers (NBUF = 4 when they fit TMEM)
+  uint64_t* tempty = tfull + 4;                                  // [4]
+  uint64_t* mfull = tempty + 4;                                  // [2]
   uint64_t* mempty = mfull + 2;                                  // [2]
-  uint64_t* bready = mempty + 2;                                 // [1] band blocks built (17 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bready + 1);
+  uint64_t* bready = mempty + 2;                                 // [1] band blocks built (18 warps)
+  uint64_t* turn = bready + 1;                                   // [2] hand-over between the two MMA-issuing warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
   uint2* mma_tab = reinterpret_cast<uint2*>(ctrl + 256);         // [nmma] {A offset from the stage, B descriptor low word}
   float* sbias = reinterpret_cast<float*>(ctrl + 256 + ROW_MAX_MMA * 8);
   constexpr bool HAS_MASK = EPI == REPI_DGRAD_RELU || EPI == REPI_DGRAD_LEAKY;
@@ -242,14 +243,17 @@ __global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
+  const int nbuf = 4 * a.NP <= 512 ? 4 : 2;          // accumulator buffers: tile it uses buffer it % nbuf
   uint32_t tcols = 32;
-  while (tcols < (uint32_t)(2 * a.NP)) tcols <<= 1;
+  while (tcols < (uint32_t)(nbuf * a.NP)) tcols <<= 1;
   const uint32_t t_entry = (uint32_t)clock();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.nstage; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); mbar_init(mfull + s, 1); mbar_init(mempty + s, 8); }
-    mbar_init(bready, 17);
+    for (int s = 0; s < 4; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(mfull + s, 1); mbar_init(mempty + s, 8); }
+    mbar_init(bready, 18);
+    mbar_init(turn, 1); mbar_init(turn + 1, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tcols);
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t t_setup = (uint32_t)clock();
-  // the TMA producer (warp 0) starts streaming tiles now; warps 1..17 expand the bands and meet at named barrier 3
+  // the TMA producer (warp 0) starts streaming tiles now; warps 1..18 expand the bands and meet at named barrier 3
   if (warp != 0) {
   auto put_band = [&](int op, int tap, int n, int k, float v) {
     const int atom = k >> 6, kin = k & 63;
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constan
   fence_proxy_async();
   __syncwarp();
   if (lane == 0) mbar_arrive(bready);
-  asm volatile("bar.sync 3, 544;" ::: "memory");
+  asm volatile("bar.sync 3, 576;" ::: "memory");
   }
 
   pdl_launch_dependents();                 // the next kernel may be scheduled as soon as SMs free up
@@ -394,24 +398,28 @@ __global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constan
         if (tix >= a.tiles_x) { tix -= a.tiles_x; ++rest; }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer: the per-tile MMA list is a table; only the stage / accumulator bases change.  The whole warp
-    // runs the loop (so addresses stay in uniform registers); one elected lane issues.  (Tried and rejected on the
-    // B200: two issuing warps on alternate tiles fall into lock-step with the two epilogue groups, and taking the next
-    // tile's barrier waits before the last MMAs delays this tile's accumulator -- both were slower.) =====
+  } else if (warp == 1 || warp == 18) {
+    // ===== MMA issuers: two warps take alternate tiles (warp <-> accumulator buffer).  A warp takes its barrier waits
+    // (accumulator drained, operands landed) while the other one is issuing, then waits for its TURN, so MMAs enter the
+    // tensor pipe in tile order without the ~480-cycle bubble a single issuer leaves between tiles.  The per-tile MMA
+    // list is a table; the whole warp runs the loop (addresses stay in uniform registers), one elected lane issues =====
     {
+      const int mw = warp == 1 ? 0 : 1;
       const uint32_t leader = (elect_one() && !(a.dbg & 4)) ? 1u : 0u;
       const bool committer = elect_one();
       const uint32_t idesc = make_idesc(128, a.NP, 0, 0);
       const uint32_t a_ring_lo = desc_lo(smem_u32(aring), 16);
       const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
       const int nmma = a.nmma;
-      int it = 0, s = 0;
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if (it >= 2) mbar_wait(tempty + buf, ((it >> 1) - 1) & 1);
+      int s = mw % a.nstage;
+      uint32_t ph = (uint32_t)(mw / a.nstage) & 1u;
+      uint32_t tph = mw ? 0u : 1u;                            // warp 0's first turn is free (fresh barrier, parity 1)
+      for (int t = blockIdx.x + mw * gridDim.x, it = mw; t < ntiles; t += 2 * gridDim.x, it += 2) {
+        const int buf = nbuf == 4 ? (it & 3) : (it & 1), use = nbuf == 4 ? (it >> 2) : (it >> 1);
+        if (use >= 1) mbar_wait(tempty + buf, (use - 1) & 1);
         mbar_wait(fullA + s, ph);
+        mbar_wait(turn + mw, tph);
+        tph ^= 1u;
         tc_fence_after();
         if (lane == 0) ROW_TRACE(1, it);
         const uint32_t dtm = tmem_base + (uint32_t)(buf * a.NP);
@@ -426,12 +434,14 @@ __global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constan
           umma_lo_if(dtm, a_lo0 + e.x, e.y, idesc, 1u, leader);
         }
         if (committer) {
+          mbar_arrive(turn + (mw ^ 1));                       // the other warp may issue the next tile
           umma_commit(emptyA + s);
           umma_commit(tfull + buf);
         }
         __syncwarp();
         if (lane == 0) ROW_TRACE(2, it);
-        if (++s == a.nstage) { s = 0; ph ^= 1u; }
+        s += 2;                                               // two tiles ahead in the ring
+        while (s >= a.nstage) { s -= a.nstage; ph ^= 1u; }
       }
     }
   } else {
@@ -457,21 +467,28 @@ __global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constan
     const uint32_t out_s = smem_u32(obase) + (uint32_t)(2 * g * row_out_bytes(a));
     const uint32_t msk_s = smem_u32(mbase) + (uint32_t)(g * row_mask_bytes(a) + offA);
     const uint32_t bias_s = smem_u32(sbias);
-    const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * a.NP + c_first * 8);
+    const uint32_t tlane = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c_first * 8);
     const bool two = a.parts > 1;
+    // tile coordinates advance incrementally (integer divisions by run-time values cost ~100 cycles each, serially)
+    const int t0 = blockIdx.x + g * gridDim.x, tstep = 2 * gridDim.x;
+    int tix = t0 % a.tiles_x, rest = t0 / a.tiles_x;
+    int tiy = rest % a.tiles_y, n = rest / a.tiles_y;
+    const int step_x = tstep % a.tiles_x, step_r = tstep / a.tiles_x;
+    const int step_y = step_r % a.tiles_y, step_n = step_r / a.tiles_y;
+    const uint32_t out_bytes = (uint32_t)row_out_bytes(a);
+    const bool nbuf4 = nbuf == 4;
     int it = g, git = 0;
-    for (int t = blockIdx.x + g * gridDim.x; t < ntiles; t += 2 * gridDim.x, it += 2, ++git) {
-      int b = t;
-      const int tix = b % a.tiles_x; b /= a.tiles_x;
-      const int tiy = b % a.tiles_y;
-      const int n = b / a.tiles_y;
-      const uint32_t par = (uint32_t)(it >> 1) & 1u;
-      const uint32_t outb = out_s + (uint32_t)((git & 1) * row_out_bytes(a));
+    for (int t = t0; t < ntiles; t += tstep, it += 2, ++git) {
+      const uint32_t par = (uint32_t)(it >> 1) & 1u;                     // mask stage of this group
+      const int buf = nbuf4 ? (it & 3) : (it & 1);
+      const uint32_t tpar = (uint32_t)(nbuf4 ? (it >> 2) : (it >> 1)) & 1u;
+      const uint32_t tbase = tlane + (uint32_t)(buf * a.NP);
+      const uint32_t outb = out_s + (uint32_t)(git & 1) * out_bytes;
       if (issuer) tma_store_wait_read1();                    // the store that last read THIS staging buffer is done
       group_bar_sync(g);
       if (threadIdx.x == 64) ROW_ETRACE(0, it >> 1);
       if (HAS_MASK) mbar_wait(mfull + g, par);
-      mbar_wait(tfull + g, par);
+      mbar_wait(tfull + buf, tpar);
       tc_fence_after();
       if (issuer) ROW_TRACE(3, it);
       if (threadIdx.x == 64) ROW_ETRACE(1, it >> 1);
@@ -505,7 +522,7 @@ __global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constan
       fence_proxy_async();                                   // staging writes -> visible to the TMA store
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(tempty + g);
+        mbar_arrive(tempty + buf);
         if (HAS_MASK) mbar_arrive(mempty + g);
       }
       if (threadIdx.x == 64) ROW_ETRACE(3, it >> 1);
@@ -524,6 +541,9 @@ __global__ void __launch_bounds__(576) conv_row_umma_kernel(const __grid_constan
                        : "memory");
         tma_store_commit();
       }
+      tix += step_x; tiy += step_y; n += step_n;
+      if (tix >= a.tiles_x) { tix -= a.tiles_x; ++tiy; }
+      if (tiy >= a.tiles_y) { tiy -= a.tiles_y; ++n; }
     }
     if (issuer) tma_store_wait_all();
   }
@@ -904,7 +924,7 @@ static int launch_row_epi(cudaStream_t s, const CUtensorMap& mA, const CUtensorM
   }
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
   {
-    cudaError_t e = launch_pdl(conv_row_umma_kernel<EPI>, persistent_grid(ntiles), 576, smem, s, mA, mB, mOA, mOB, mM, a);
+    cudaError_t e = launch_pdl(conv_row_umma_kernel<EPI>, persistent_grid(ntiles), 608, smem, s, mA, mB, mOA, mOB, mM, a);
     if (e != cudaSuccess) return cuda_fail(e, "conv_row_umma: launch");
   }
   DNNCA_LAUNCH_CHECK("conv_row_umma");
