@@ -356,7 +356,8 @@ static int launch_wgrad_umma(cudaStream_t s, const CUtensorMap& mA, const CUtens
 }
 
 int launch_channel_sum(cudaStream_t s, const dnnca_tensor_t* g, float* out);
-int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g, float* dw);
+int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g, float* dw,
+                           float* db);
 static bool wgrad_halo_enabled() {
   static int on = -1;
   if (on < 0) on = getenv("DNNCA_DISABLE_WGRAD_HALO") ? 0 : 1;
@@ -368,8 +369,9 @@ static int wgrad_umma_common(cudaStream_t s, const dnnca_tensor_t* x, const dnnc
   if (!bf16_view_in(x) || (x2 && !bf16_view_in(x2)) || !bf16_view_in(g)) return 0;
   const int ca = x->c, cb = x2 ? x2->c : 0;
   if (!tconv && k == 3 && wgrad_halo_enabled()) {     // halo-tile kernel (conv_umma3.cu) for channel counts % 64 == 0
-    int r = try_conv3x3_wgrad_halo(s, x, x2, g, dw);
+    int r = try_conv3x3_wgrad_halo(s, x, x2, g, dw, db);
     if (r < 0) return r;
+    if (r == 2) return 1;                                  // bias gradient taken inside the kernel
     if (r == 1) {
       if (db) {
         int e = launch_channel_sum(s, g, db);

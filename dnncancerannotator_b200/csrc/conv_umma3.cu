@@ -29,6 +29,7 @@ struct WHArgs {
   int tiles_x, tiles_y, nimg;
   int ksplit, mt_a;            // pixel-tile slices; M tiles that belong to x (the rest to x2)
   float* dw;
+  float* db;                   // PAIRED: bias gradient from the all-ones block paired with the ninth tap (or NULL)
 };
 
 __device__ __forceinline__ bool wh_elect() {
@@ -68,8 +69,9 @@ struct WHGeom {
   static constexpr int NXA = PAIRED ? 1 : 2, NZA = BN / 64;
   static constexpr int STAGE = NXA * XATOM + NZA * WH_ZATOM;
   static constexpr int NACC = PAIRED ? 5 : 3;
-  static constexpr int STAGES = (200 * 1024) / STAGE > 4 ? 4 : (200 * 1024) / STAGE;
-  static constexpr int SMEM = 1024 + STAGES * STAGE + 1024;
+  static constexpr int STAGES = (196 * 1024 - (PAIRED ? XATOM : 0)) / STAGE > 4 ? 4 : (196 * 1024 - (PAIRED ? XATOM : 0)) / STAGE;
+  static constexpr int ONES = PAIRED ? XATOM : 0;              // all-ones block paired with the ninth tap: sum(dz) = db
+  static constexpr int SMEM = 1024 + STAGES * STAGE + ONES + 1024;
   static constexpr int TCOLS = NACC * BN <= 256 ? 256 : 512;
 };
 
@@ -105,6 +107,11 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, G::TCOLS);
+  unsigned char* ones = ring + STAGES * G::STAGE;
+  if (PAIRED) {
+    for (int i = threadIdx.x; i < G::ONES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
             const int ta = 2 * j, tb = 2 * j + 1;
             row0 = (uint32_t)((ta / 3) * WH_PW + ta % 3);
             if (tb < 9) lbo = (uint32_t)((((tb / 3) - (ta / 3)) * WH_PW + (tb % 3) - (ta % 3)) * 128);
-            else { lbo = 1024; m64 = true; }
+            else lbo = smem_u32(ones) - (xaddr + row0 * 128);   // ninth tap | all-ones block: rows 64.. = sum(dz)
           } else {
             row0 = (uint32_t)j;                       // dx = j (the box is already shifted by dy)
             lbo = G::XATOM;
@@ -186,14 +193,12 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
       for (int j = 0; j < NACC; ++j) {
         int tap, ch;
         bool live;
+        bool db_row = false;
         if (PAIRED) {
-          const bool single = 2 * j + 1 >= 9;                  // M = 64 accumulator: row m sits in lane (m%16) + 32*(m/16)
-          if (single) {
-            tap = 8; ch = lg * 16 + lane; live = lane < 16;
-          } else {
-            const int row = lg * 32 + lane;
-            tap = 2 * j + (row >> 6); ch = row & 63; live = true;
-          }
+          const int row = lg * 32 + lane;
+          tap = 2 * j + (row >> 6); ch = row & 63; live = tap < 9;
+          db_row = tap == 9 && ch == 0 && a.db != nullptr && blockIdx.x == 0;      // first row of the all-ones half
+          if (tap > 8) tap = 8;
         } else {
           tap = dy * 3 + j; ch = lg * 32 + lane; live = true;
         }
@@ -204,6 +209,11 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(j * BN + c0), v);
           tmem_ld_wait();
+          if (db_row) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (n0 + c0 + e < a.cout) atomicAdd(a.db + n0 + c0 + e, __uint_as_float(v[e]));
+          }
           if (!live) continue;
 #pragma unroll
           for (int e = 0; e < 32; ++e)
@@ -259,7 +269,9 @@ static int launch_wgrad_halo(cudaStream_t s, const CUtensorMap& mA, const CUtens
 }
 
 // Conv2D 3x3 wgrad for bf16 views whose channel counts are multiples of 64; returns 1 / 0 (not covered) / <0
-int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g, float* dw) {
+// returns 2 when the bias gradient was accumulated into `db` as well (PAIRED variant)
+int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g, float* dw,
+                           float* db) {
   const int ca = x->c, cb = x2 ? x2->c : 0, cout = g->c;
   // a single input with fewer than 64 channels (first layers: 1/3/5 modalities in 16-byte pixels) is one PAIRED M tile
   // whose missing channels the TMA zero-fills
@@ -281,7 +293,11 @@ int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_
   mB = mA;
   if (x2 && !wh_map(&mB, x2, WH_PW, paired ? WH_R + 2 : WH_R)) return 0;
   if (!wh_map(&mG, g, 16, WH_R)) return 0;
-  if (paired) return launch_wgrad_halo<64, true>(s, mA, mB, mG, a, mt, cout / 64);
+  if (paired) {
+    a.db = db;
+    const int r = launch_wgrad_halo<64, true>(s, mA, mB, mG, a, mt, cout / 64);
+    return (r == 1 && db) ? 2 : r;
+  }
   if (cout % 128 == 0) return launch_wgrad_halo<128, false>(s, mA, mB, mG, a, mt, cout / 128);
   return launch_wgrad_halo<64, false>(s, mA, mB, mG, a, mt, cout / 64);
 }
