@@ -273,21 +273,21 @@ static int launch_wgrad_halo(cudaStream_t s, const CUtensorMap& mA, const CUtens
 int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g, float* dw,
                            float* db) {
   const int ca = x->c, cb = x2 ? x2->c : 0, cout = g->c;
-  // a single input with fewer than 64 channels (first layers: 1/3/5 modalities in 16-byte pixels) is one PAIRED M tile
-  // whose missing channels the TMA zero-fills
-  const bool narrow = !x2 && ca < 64;
-  if ((!narrow && (ca % 64 || cb % 64)) || cout % 64) return 0;
+  // tensors with fewer than 64 channels (first layers: 1/3/5 modalities in 16-byte pixels; the 16/32-channel layers of
+  // mulmo_unet.yaml) are ONE PAIRED M tile each whose missing channels the TMA zero-fills; likewise the last N tile
+  const bool narrow_a = ca < 64, narrow_b = x2 && cb < 64;
+  if ((!narrow_a && ca % 64) || (x2 && !narrow_b && cb % 64) || cout % 16) return 0;
   // PAIRED (64-channel M tiles, all nine taps per CTA) measured faster up to 128 input channels per tensor; above
   // that the FULL variant (128-channel M tiles, one filter row per CTA) wins (tools/wgrad_microbench.py)
   static int paired_max = -1;
   if (paired_max < 0) paired_max = getenv("DNNCA_WGRAD_PAIRED_MAX") ? atoi(getenv("DNNCA_WGRAD_PAIRED_MAX")) : 128;
-  const bool paired = (ca % 128 != 0) || (cb % 128 != 0) || (ca <= paired_max && cb <= paired_max);
+  const bool paired = (ca % 128 != 0) || (cb % 128 != 0) || (ca <= paired_max && cb <= paired_max) || cout % 64 != 0;
   WHArgs a{};
   a.c_a = ca; a.c_b = cb; a.cout = cout; a.dw = dw;
   a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + WH_R - 1) / WH_R; a.nimg = x->n;
   const int mch = paired ? 64 : 128;
-  a.mt_a = narrow ? 1 : ca / mch;
-  const int mt = a.mt_a + cb / mch;
+  a.mt_a = (ca + mch - 1) / mch;
+  const int mt = a.mt_a + (cb + mch - 1) / mch;
   CUtensorMap mA, mB, mG;
   if (!wh_map(&mA, x, WH_PW, paired ? WH_R + 2 : WH_R)) return 0;
   mB = mA;
@@ -295,7 +295,7 @@ int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_
   if (!wh_map(&mG, g, 16, WH_R)) return 0;
   if (paired) {
     a.db = db;
-    const int r = launch_wgrad_halo<64, true>(s, mA, mB, mG, a, mt, cout / 64);
+    const int r = launch_wgrad_halo<64, true>(s, mA, mB, mG, a, mt, (cout + 63) / 64);
     return (r == 1 && db) ? 2 : r;
   }
   if (cout % 128 == 0) return launch_wgrad_halo<128, false>(s, mA, mB, mG, a, mt, cout / 128);
