@@ -62,6 +62,13 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------- the kernel
+// short K loops (<= 8 iterations: ConvT fprop, 1x1 convs) run with a 2-deep ring so that 3-4 CTAs fit an SM and overlap
+// each other's load / MMA / epilogue phases (the one-tile-per-CTA kernel has no intra-CTA overlap of those)
+__host__ __device__ inline int umma_ring_depth(int kiters, int max_stages) {
+  const int want = kiters <= 8 ? (kiters < 2 ? kiters : 2) : max_stages;
+  return want < max_stages ? want : max_stages;
+}
+
 template <int BN, int KC>
 struct UGeom {
   static constexpr int SWB = KC * 2;
@@ -98,6 +105,9 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
 
   const int kca = a.c_a / KC, kcb = a.c_b / KC;
   const int kiters = a.taps * (kca + kcb);
+  // ring depth = min(STAGES, K iterations): short-K launches (ConvT fprop, 1x1) then need little shared memory and
+  // several CTAs share an SM, overlapping each other's load / MMA / epilogue phases
+  const int nst = umma_ring_depth(kiters, STAGES);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -116,8 +126,8 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
       tma_prefetch_desc(&mapA);
       tma_prefetch_desc(&mapW);
       for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        if (it >= STAGES) mbar_wait(empty + s, ((it / STAGES) - 1) & 1);
+        const int s = it % nst;
+        if (it >= nst) mbar_wait(empty + s, ((it / nst) - 1) & 1);
         // iteration order: input (A then B) -> tap -> channel chunk
         int r = it;
         const bool second = r >= a.taps * kca;
@@ -142,8 +152,8 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(128, BN < 16 ? 16 : BN, 0, 0);
       for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        mbar_wait(full + s, (it / STAGES) & 1);
+        const int s = it % nst;
+        mbar_wait(full + s, (it / nst) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + s * G::STAGE), sb = sa + G::A_BYTES;
         const uint64_t da = kmajor_desc<SWB>(sa), db = kmajor_desc<SWB>(sb);
@@ -454,7 +464,9 @@ static int launch_umma(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap&
     done = true;
   }
   dim3 grid((unsigned)((long long)a.tiles_x * a.tiles_y * nimg), (unsigned)((a.n_total + BN - 1) / BN));
-  kern<<<grid, 192, G::SMEM, s>>>(mA, mB, mW, a);
+  const int kiters = a.taps * (a.c_a / KC + a.c_b / KC);
+  const int nst = umma_ring_depth(kiters, G::STAGES);
+  kern<<<grid, 192, 1024 + nst * G::STAGE + 1024, s>>>(mA, mB, mW, a);
   DNNCA_LAUNCH_CHECK("conv_umma");
   note_family(2);
   return 1;
