@@ -30,6 +30,7 @@ UNITS = [
     ('conv_generic.cu', 'conv_generic', []),
     ('head_loss.cu', 'head_loss', []),
     ('optim.cu', 'optim', []),
+    ('metrics.cu', 'metrics', []),
     ('tconv_small.cu', 'tconv_small', []),
 ]
 for dt in (0, 1):

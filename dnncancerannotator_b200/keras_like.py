@@ -62,6 +62,7 @@ class Model:
         self.loss = None
         self.optimizer = None
         self.metrics = []
+        self._metric_set = None
         self.stop_training = False
         self.use_cuda_graph = os.environ.get('DNNCA_NO_GRAPH', '0') != '1'
         self.trainable_model = True     # MultiResUnet (inference-only in this build) sets False
@@ -104,8 +105,21 @@ class Model:
             optimizer = {}
         self.optimizer = dict(learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7)
         self.optimizer.update(optimizer or {})
-        self.metrics = list(metrics or [])
+        self.metrics = list(metrics or [])      # keras-style specs (metrics.yaml:1-23) or utils.metrics.Metric instances
+        self._metric_set = None                 # utils.metrics.MetricSet, created on first use (needs the device)
         self._hyper_dirty = True
+
+    def metric_set(self):
+        """The compiled pixel-threshold metrics (engine.py:273) as device counters, or None."""
+        if self._metric_set is None and getattr(self, 'metrics', None):
+            from .utils.metrics import MetricSet
+            self._metric_set = MetricSet(self.metrics, self.device)
+        return self._metric_set if self._metric_set else None
+
+    def reset_metrics(self):
+        ms = self.metric_set()
+        if ms:
+            ms.reset_state()
 
     def count_params(self, trainable=None):
         return self.params.count(trainable)
@@ -325,7 +339,11 @@ class Model:
         self._load_batch(plan, x, y)
         if self.loss.label_smoothing:
             plan.y_in.copy_(self.loss.prepare_labels(plan.y_in))
-        return self._train_on_static(plan)
+        loss = self._train_on_static(plan)
+        ms = self.metric_set()
+        if ms:                                   # keras updates the compiled metrics inside every train step
+            ms.update_state(plan.y_in, plan.probs)
+        return loss
 
     def _train_on_static(self, plan):
         """The hot path once the batch sits in ``plan.x_in`` / ``plan.y_in``."""
@@ -384,6 +402,7 @@ class Model:
         self.prefetch(*nxt)
         for epoch in range(initial_epoch, epochs):
             lr = lr_schedule(epoch, self.optimizer['learning_rate']) if lr_schedule else None
+            self.reset_metrics()
             losses = []
             n = steps_per_epoch or 1
             for _ in range(n):
@@ -392,6 +411,8 @@ class Model:
                 nxt = next_batch()
                 self.prefetch(*nxt)          # H2D of the next batch overlaps the step just launched
             logs = {'loss': float(torch.stack(losses).mean())}
+            if self.metric_set():
+                logs.update(self.metric_set().result())
             if validation_data is not None and validation_freq and (epoch + 1) % validation_freq == 0:
                 logs.update({'val_' + k: v for k, v in self.evaluate(validation_data, return_dict=True).items()})
             hist.record(epoch, logs)
@@ -410,6 +431,9 @@ class Model:
         if self.loss is None:
             self.compile()
         tot, cnt = 0.0, 0
+        ms = self.metric_set()
+        if ms:
+            ms.reset_state()
         for xb, yb in x:
             xb, yb = _to_device_f32(xb, self.device), _to_device_f32(yb, self.device)
             plan = self._plan(*xb.shape[:3])
@@ -424,7 +448,11 @@ class Model:
                 plan.head_loss(cfg, with_grads=False)
             self._run(plan, 'eval', seq)
             self.last_logits = plan.logits
+            if ms:
+                ms.update_state(plan.y_in, plan.probs)
             tot += float(plan.per_sample.sum())
             cnt += plan.batch
         out = {'loss': tot / max(cnt, 1)}
+        if ms:
+            out.update(ms.result())
         return out if return_dict else out['loss']

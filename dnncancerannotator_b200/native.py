@@ -72,6 +72,7 @@ _PROTOS = {
     'dnnca_head_fwd': [_vp, _TP, _vp, _vp, _vp, _vp],
     'dnnca_head_bce_fwd_bwd': [_vp, _TP, _vp, _vp, _vp, _vp, C.POINTER(LossConfig), _vp, _vp, _vp, _TP, _i, _f,
                                _vp, _vp],
+    'dnnca_threshold_hist': [_vp, _vp, _vp, _i64, _vp, _i, _vp],
     'dnnca_add_relu_affine': [_vp, _TP, _vp, _TP, _vp, _vp, _TP],
     'dnnca_u8_to_unit': [_vp, _vp, _i64, _vp, _i],
     'dnnca_convert': [_vp, _TP, _TP],

@@ -214,6 +214,19 @@ DNNCA_API int dnnca_head_bce_fwd_bwd(void* stream, const dnnca_tensor_t* f, cons
                            float alpha, float* dw, float* db);
 
 /* ---------------------------------------------------------------------------
+ * Pixel-threshold confusion counters
+ *   replaces the update_state of tf.keras.metrics.Precision / Recall / AUC and of the reference's FBetaScore
+ *   (annotator/utils/metrics.py:37-77) for the metrics of configs/additionals/metrics.yaml:1-23, which
+ *   engine.py:273 attaches to the model: every one of them is a function of
+ *       TP_k = #(y != 0 and p > t_k),  FP_k = #(y == 0 and p > t_k),  P = #(y != 0),  N = #(y == 0).
+ *   `thresholds` (device, fp32, ASCENDING, nthr <= 1023).  hist: uint64 [2*(nthr+1)], ACCUMULATED (the caller zeroes
+ *   it at reset_state): hist[b] += #(y != 0 and b(p) == b), hist[nthr+1+b] += #(y == 0 and b(p) == b) with
+ *   b(p) = #{k : t_k < p};  hence TP_k = sum_{b > k} hist[b], FP_k likewise, P = sum_b hist[b].
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_threshold_hist(void* stream, const float* probs, const float* labels, int64_t count,
+                                   const float* thresholds, int nthr, uint64_t* hist);
+
+/* ---------------------------------------------------------------------------
  * MultiResUnet elementwise tail (inference): y = s2*relu(a*sa+ta + b*sb+tb)+t2
  *   replaces BatchNormalization -> add -> Activation('relu') -> BatchNormalization
  *   at multiresunet.py:120-124 and add -> relu -> BN at :148-150, :160-162.
