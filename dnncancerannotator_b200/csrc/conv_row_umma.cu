@@ -324,27 +324,29 @@ __global__ void __launch_bounds__(608) conv_row_umma_kernel(const __grid_constan
           put_band(0, ar, n, (2 * p + b) * cz + co, wsm[((ar * 2 + b) * cz + co) * cin + ci]);
     }
   } else {
-    for (int op = 0; op < a.nops; ++op) {
+    // work item = (operand, tap, column, dx): C band elements each, so even the 12-channel layers keep every thread busy
+    const int per_op = 9 * a.N;
+    for (int wi = bt; wi < a.nops * per_op; wi += nbt) {
+      const int op = wi >= per_op ? 1 : 0;
+      const int r = wi - op * per_op;
+      const int tap = r / (3 * a.N), r2 = r - tap * 3 * a.N;
+      const int n = r2 / 3, dxi = r2 - n * 3;
       const int C = a.C[op];
-      for (int pi = bt; pi < 3 * a.N; pi += nbt) {
-        const int tap = pi / a.N, n = pi - tap * a.N;
-        int p, widx, wstep_c, wstep_dx;                       // weight index = widx + dxi*wstep_dx + c*wstep_c
-        if (!a.dgrad) {
-          p = n / a.cout;
-          const int co = n - p * a.cout;
-          widx = (tap * 3 * a.cin_tot + a.coff[op]) * a.cout + co;
-          wstep_dx = a.cin_tot * a.cout; wstep_c = a.cout;
-        } else {                                              // column = (p, ci) of dx / dx2; window channel = forward co
-          int ci;
-          if (n < a.nsplit) { p = n / a.oa; ci = n - p * a.oa; }
-          else { const int m = n - a.nsplit; p = m / a.ob; ci = a.oa + m - p * a.ob; }
-          widx = (((2 - tap) * 3 + 2) * a.cin_tot + ci) * a.cout;
-          wstep_dx = -a.cin_tot * a.cout; wstep_c = 1;
-        }
-        int k = a.halo[op] + (p - 1) * C;                     // window element of pixel p + dx, channel 0
-        for (int dxi = 0; dxi < 3; ++dxi, widx += wstep_dx)
-          for (int c = 0; c < C; ++c, ++k) put_band(op, tap, n, k, wsm[widx + c * wstep_c]);
+      int p, widx, wstep_c;                                 // weight index = widx + c*wstep_c
+      if (!a.dgrad) {
+        p = n / a.cout;
+        const int co = n - p * a.cout;
+        widx = ((tap * 3 + dxi) * a.cin_tot + a.coff[op]) * a.cout + co;
+        wstep_c = a.cout;
+      } else {                                              // column = (p, ci) of dx / dx2; window channel = forward co
+        int ci;
+        if (n < a.nsplit) { p = n / a.oa; ci = n - p * a.oa; }
+        else { const int m = n - a.nsplit; p = m / a.ob; ci = a.oa + m - p * a.ob; }
+        widx = (((2 - tap) * 3 + (2 - dxi)) * a.cin_tot + ci) * a.cout;
+        wstep_c = 1;
       }
+      int k = a.halo[op] + (p + dxi - 1) * C;               // window element of pixel p + dx, channel 0
+      for (int c = 0; c < C; ++c, ++k) put_band(op, tap, n, k, wsm[widx + c * wstep_c]);
     }
   }
   fence_proxy_async();
