@@ -207,6 +207,7 @@ class Model:
         x = _to_device_f32(x, self.device)
         plan = self._plan(*x.shape[:3])
         plan.allocate(False)
+        plan.prestaged = False
         plan.x_in.copy_(x, non_blocking=True)
 
         def seq():
@@ -265,6 +266,7 @@ class Model:
         x, y = _to_device_f32(x, self.device), _to_device_f32(y, self.device)
         plan = self._plan(*x.shape[:3])
         plan.allocate(True)
+        plan.prestaged = False
         plan.x_in.copy_(x, non_blocking=True)
         plan.y_in.copy_(self.loss.prepare_labels(y), non_blocking=True)
         cfg = self._loss_cfg(plan)
@@ -317,9 +319,17 @@ class Model:
             xs = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))
             ys = y if torch.is_tensor(y) else torch.from_numpy(np.ascontiguousarray(y))
             xs, ys = xs.to(self.device, non_blocking=True), ys.to(self.device, non_blocking=True)
+        # uint8 slices of a bf16 plan go straight into the cast input buffer (one pass: /255 and rounding, data.py:206);
+        # the graph variant keyed '..._u8' then skips the fp32 -> bf16 convert
+        cast = getattr(plan, 'input_cast', None)
+        plan.prestaged = bool(xs.dtype == torch.uint8 and cast is not None and cast.buf.data is not None and
+                              cast.buf.data.dtype == torch.bfloat16)
         for src, dst in ((xs, plan.x_in), (ys, plan.y_in)):
             if src.dtype == torch.uint8:                                   # data.py:206: float32(uint8) / 255 on device
-                N.call('dnnca_u8_to_unit', N.stream_ptr(), N.ptr(src), src.numel(), N.ptr(dst), N.F32)
+                if dst is plan.x_in and plan.prestaged:
+                    N.call('dnnca_u8_to_unit', N.stream_ptr(), N.ptr(src), src.numel(), N.ptr(cast.buf.data), N.BF16)
+                else:
+                    N.call('dnnca_u8_to_unit', N.stream_ptr(), N.ptr(src), src.numel(), N.ptr(dst), N.F32)
             else:
                 dst.copy_(src, non_blocking=True)
         if st is not None:
@@ -357,14 +367,14 @@ class Model:
                 plan.head_loss(cfg)
                 plan.backward()
                 self._adam()
-            self._run(plan, 'train', seq)
+            self._run(plan, 'train_u8' if getattr(plan, 'prestaged', False) else 'train', seq)
         else:
             def seq_a():
                 plan.zero_step_state()
                 plan.forward(True)
                 plan.head_loss(cfg)
                 plan.backward()
-            self._run(plan, 'train_fb', seq_a)
+            self._run(plan, 'train_fb_u8' if getattr(plan, 'prestaged', False) else 'train_fb', seq_a)
             self._dp.all_reduce(self.params.grads[:max(self.params.n_trainable, 1)])
             self._run(plan, 'train_adam', self._adam)
         self.last_logits = plan.logits
@@ -438,6 +448,7 @@ class Model:
             xb, yb = _to_device_f32(xb, self.device), _to_device_f32(yb, self.device)
             plan = self._plan(*xb.shape[:3])
             plan.allocate(False)
+            plan.prestaged = False
             plan.x_in.copy_(xb, non_blocking=True)
             plan.y_in.copy_(self.loss.prepare_labels(yb), non_blocking=True)
             cfg = self._loss_cfg(plan)

@@ -372,9 +372,13 @@ class ConvertOp(Op):
     """fp32 network input -> activation dtype (the tail of data.py:193-206 on the device)."""
 
     def __init__(self, plan, x, y):
-        self.x, self.y = x, y
+        self.plan, self.x, self.y = plan, x, y
+        if y.coff == 0 and y.c == y.buf.c and x.coff == 0 and x.c == x.buf.c and x.c == y.c:
+            plan.input_cast = y          # dense cast target: uint8 batches can be staged straight into it (Model._load_batch)
 
     def fwd(self, train):
+        if getattr(self.plan, 'prestaged', False):
+            return                       # the batch was written in the activation dtype by dnnca_u8_to_unit
         N.call('dnnca_convert', N.stream_ptr(), self.x.ct(), self.y.ct())
 
 

@@ -340,3 +340,24 @@ def test_wide_configs_fp32_mode_exact(cfgname, C, size, B):
     assert abs(per.mean() - r['data_loss']) <= 1e-4 * abs(r['data_loss']), REPORT[tag]
     assert rel_l2(allg, allr) <= 5e-3, REPORT[tag]
     check_masks(logits, r['logits'].numpy(), exact=True)
+
+
+def test_uint8_host_contract_matches_float32_inputs():
+    """data.py:193-206: the raw uint8 slices (image channels and label) divided by 255 ON THE DEVICE -- staged straight
+    into the bf16 input buffer -- must give the same step as float32 [0,1] inputs prepared on the host."""
+    from dnncancerannotator_b200.synthetic import make_slices
+    x8, y8 = make_slices(4, 64, 64, 3, seed=11, as_uint8=True)
+    xf, yf = (x8.astype(np.float32) / np.float32(255.0)), (y8.astype(np.float32) / np.float32(255.0))
+    losses, weights = [], []
+    for xin, yin in ((x8, y8), (xf, yf)):
+        m = product_model('UNetAnnotator', dict(n_filters_first=3, n_downsample=3, rate=2, kernel_size=3, conv_stride=1,
+                                                padding='same'), 'bf16')
+        m.build((None, 64, 64, 3))
+        m.compile()
+        ls = [float(m.train_step(xin, yin)) for _ in range(4)]       # eager warm-ups, graph capture, replay
+        losses.append(ls)
+        weights.append(m.get_weights())
+    assert losses[0][0] == losses[1][0], (losses[0], losses[1])          # same forward pass, bit for bit
+    np.testing.assert_allclose(losses[0], losses[1], rtol=1e-6)          # later steps: fp32 atomics reorder the gradient sums
+    for k in weights[0]:
+        np.testing.assert_allclose(weights[0][k], weights[1][k], rtol=0, atol=2e-6)
