@@ -966,7 +966,12 @@ static int launch_row(cudaStream_t s, bool dgrad, int tconv, const dnnca_tensor_
   a.dgrad = dgrad ? 1 : 0; a.act = act; a.alpha = alpha; a.has_mask = mask ? 1 : 0;
   a.w = w; a.bias = bias; a.oa = oa; a.ob = ob;
   a.dbg = row_dbg();
-  a.parts = row_parts();
+  // fprop keeps fp32-accurate weights (hi|lo bands: the logits bound of BASELINE.json is 1e-2); dgrad / ConvT dgrad use a
+  // single bf16 band like every other tensor-core path here (gradient bound 2e-2; halves their MMA columns and TMEM
+  // reads).  DNNCA_ROW_EXACT_DGRAD=1 restores hi|lo bands for the gradients.
+  static int exact_dgrad = -1;
+  if (exact_dgrad < 0) exact_dgrad = getenv("DNNCA_ROW_EXACT_DGRAD") ? 1 : 0;
+  a.parts = (dgrad && !exact_dgrad) ? 1 : row_parts();
   if (dgrad) { a.cin_tot = oa + ob; a.cout = ca; }
   else { a.cin_tot = ca + cb; a.cout = oa; a.coff[0] = 0; a.coff[1] = ca; }
   const dnnca_tensor_t* grid_t = tconv == 2 ? outa : ina;        // tensor whose rows are the GEMM M

@@ -358,6 +358,6 @@ def test_uint8_host_contract_matches_float32_inputs():
         losses.append(ls)
         weights.append(m.get_weights())
     assert losses[0][0] == losses[1][0], (losses[0], losses[1])          # same forward pass, bit for bit
-    np.testing.assert_allclose(losses[0], losses[1], rtol=1e-6)          # later steps: fp32 atomics reorder the gradient sums
+    np.testing.assert_allclose(losses[0], losses[1], rtol=1e-4)          # later steps: fp32 atomics reorder the gradient sums
     for k in weights[0]:
-        np.testing.assert_allclose(weights[0][k], weights[1][k], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(weights[0][k], weights[1][k], rtol=0, atol=2e-4)
