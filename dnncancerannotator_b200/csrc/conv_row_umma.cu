@@ -15,15 +15,15 @@
 // through descriptors whose start address is shifted by one 128-byte row (the swizzle is address-based, see
 // conv_umma2.cu).  The TMA's out-of-bounds zero fill is the 'same' padding in both directions.  Only 3 of every P+2
 // window pixels carry non-zero weights, so ~15-25 % of the MMA flops are useful -- which still leaves every layer of
-// unet.yaml far from tensor-bound; what paces a tile is the shared-memory read of the A operand (128 rows x 32 bytes per
-// K=16 step, ~60 cycles per MMA measured), so N is made as wide as possible per MMA.
+// unet.yaml far from the tensor roofline; a tile is paced by the MMA time of these small-N shapes (~8 + 1.1*N cycles per
+// K=16 step measured) and by the TMEM read of the epilogue (64 B/clk/SM), both close to the tile's HBM time.
 //
-// Weight precision: by default the bands are expanded twice, as hi = bf16(w) and lo = bf16(w - hi) (the activations are
-// exact bf16 already), side by side along N (columns [0,N) and [N,2N) of the same MMA; the epilogue adds them), so the
-// result equals the FP32-pipe kernels' up to accumulation order.  That doubles the tensor and TMEM-read time (measured:
-// tcgen05 time is ~8 + 1.1*N cycles per K=16 step with these layouts, TMEM reads 64 B/clk/SM);
-// DNNCA_ROW_BF16_WEIGHTS=1 issues a single bf16 band (weights rounded to bf16, like conv_umma*.cu).  A mixed bf16 x fp16
-// MMA (fp16 bands) is not an option: kind::f16 with different A and B formats is an illegal instruction on sm_100a.
+// Weight precision: fprop expands every band twice, as hi = bf16(w) and lo = bf16(w - hi) (the activations are exact
+// bf16 already), side by side along N (columns [0,N) and [N,2N) of the same MMA; the epilogue adds them), so the result
+// equals the FP32-pipe kernels' up to accumulation order; that doubles the tensor and TMEM-read time.  dgrad uses a single
+// bf16 band (DNNCA_ROW_EXACT_DGRAD=1: hi|lo as well); DNNCA_ROW_BF16_WEIGHTS=1 issues a single band everywhere (weights
+// rounded to bf16, like conv_umma*.cu).  A mixed bf16 x fp16 MMA (fp16 bands) is not an option: kind::f16 with different
+// A and B formats is an illegal instruction on sm_100a.
 //
 // Kernels: conv_row_umma_kernel (fprop and dgrad: dgrad is the same GEMM over dz with rot180/transposed bands and an
 // act'(mask) epilogue) and conv_row_wgrad_kernel (M = window elements, N = P x Cout, K = image rows; both operands
