@@ -368,6 +368,7 @@ static int launch_wgrad_umma(cudaStream_t s, const CUtensorMap& mA, const CUtens
 int launch_channel_sum(cudaStream_t s, const dnnca_tensor_t* g, float* out);
 int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* g, float* dw,
                            float* db);
+int try_tconv_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* dy, float* dk);
 static bool wgrad_halo_enabled() {
   static int on = -1;
   if (on < 0) on = getenv("DNNCA_DISABLE_WGRAD_HALO") ? 0 : 1;
@@ -382,6 +383,17 @@ static int wgrad_umma_common(cudaStream_t s, const dnnca_tensor_t* x, const dnnc
     int r = try_conv3x3_wgrad_halo(s, x, x2, g, dw, db);
     if (r < 0) return r;
     if (r == 2) return 1;                                  // bias gradient taken inside the kernel
+    if (r == 1) {
+      if (db) {
+        int e = launch_channel_sum(s, g, db);
+        if (e != DNNCA_OK) return e;
+      }
+      return 1;
+    }
+  }
+  if (tconv && wgrad_halo_enabled()) {                  // ConvT on the halo-tile kernel: Cin % 128 == 0, Cout % 64 == 0
+    int r = try_tconv_wgrad_halo(s, x, g, dw);
+    if (r < 0) return r;
     if (r == 1) {
       if (db) {
         int e = launch_channel_sum(s, g, db);
@@ -517,6 +529,8 @@ static bool bf16_view_in(const dnnca_tensor_t* t) {
 
 int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tensor_t* xb, const void* wpack, int ktot, int ntot,
                      UArgs a);
+int try_tconv_fprop_halo(cudaStream_t s, const dnnca_tensor_t* x, const void* wpack, int cin, int cout, UArgs a);
+int try_tconv_dgrad_halo(cudaStream_t s, const dnnca_tensor_t* dy, const void* wpack, int cin, int cout, UArgs a);
 static bool halo_enabled() {
   static int v = -1;
   if (v < 0) v = getenv("DNNCA_NO_HALO") ? 0 : 1;     // A/B switch for profiling the first-generation kernel
@@ -605,6 +619,10 @@ int try_tconv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const float* k
   a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + 7) / 8; a.epi = EPI_TCONV; a.act = DNNCA_ACT_NONE; a.alpha = 0.f; a.bias = bias;
   a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = 4 * cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
   a.mask = nullptr; a.n_total = 4 * cout; a.cout_t = cout;
+  if (kc == 64 && halo_enabled()) {
+    r = try_tconv_fprop_halo(s, x, ws, cin, cout, a);
+    if (r != 0) return r;
+  }
   if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, x->n, bn);
   if (kc == 32) return dispatch_bn<32>(s, mA, mA, mW, a, x->n, bn);
   return dispatch_bn<16>(s, mA, mA, mW, a, x->n, bn);
@@ -628,7 +646,11 @@ int try_tconv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dy, const float* 
   a.tiles_x = (dx->w + 15) / 16; a.tiles_y = (dx->h + 7) / 8; a.epi = EPI_DGRAD; a.act = act; a.alpha = alpha; a.bias = nullptr;
   a.ya = reinterpret_cast<__nv_bfloat16*>(dx->data) + dx->coff; a.ya_cs = dx->cstride; a.split = cin; a.yb = a.ya; a.yb_cs = a.ya_cs;
   a.mask = mask ? reinterpret_cast<const __nv_bfloat16*>(mask->data) + mask->coff : nullptr; a.mask_cs = mask ? mask->cstride : 0;
-  a.n_total = cin; a.cout_t = cin;
+  a.n_total = cin; a.cout_t = cin; a.nimg = dx->n;
+  if (kc == 64 && halo_enabled()) {
+    r = try_tconv_dgrad_halo(s, dy, ws, cin, cout, a);
+    if (r != 0) return r;
+  }
   if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, dx->n, bn);
   if (kc == 32) return dispatch_bn<32>(s, mA, mA, mW, a, dx->n, bn);
   return dispatch_bn<16>(s, mA, mA, mW, a, dx->n, bn);

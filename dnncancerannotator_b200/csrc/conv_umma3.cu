@@ -13,6 +13,9 @@
 //   PAIRED (64-channel M tiles):  M = 128 = TWO TAPS of the same 64 channels -- the second 64-row block of the MMA is the
 //          same atom LBO bytes further ((dy'-dy)*18 + dx'-dx pixel rows) -- so a CTA keeps all nine taps as 4 paired
 //          accumulators + 1 single and x is loaded once per pixel tile.
+//   TCONV  (ConvT 2x2/s2, Cin multiple of 128): M = 128 input channels of the x tile itself (no halo); the four filter
+//          taps are four accumulators whose N operand is dy read through a stride-2 map at (2y + ty, 2x + tx): every
+//          byte of x and dy enters shared memory once per (M tile, N tile) pair.
 // dz box {64 ch, 16 px, 8 rows} is the N operand (MN-major, LBO = next 64 output channels).  Partial sums leave with
 // red.global.add like the first-generation kernel; the bias gradient stays a separate channel-sum pass.
 #include <stdlib.h>
@@ -62,24 +65,30 @@ __device__ __forceinline__ void wh_umma(uint32_t d_tmem, uint32_t a_lo, uint32_t
       : "memory");
 }
 
-template <int BN, bool PAIRED>
+enum { WH_FULL = 0, WH_PAIRED = 1, WH_TCONV = 2 };
+
+template <int BN, int MODE>
 struct WHGeom {
-  static constexpr int XROWS = (PAIRED ? WH_R + 2 : WH_R) * WH_PW;
+  static constexpr bool PAIRED = MODE == WH_PAIRED, TCONV = MODE == WH_TCONV;
+  static constexpr int PW = TCONV ? 16 : WH_PW;                // pixel rows of 128 bytes per image row of the x box
+  static constexpr int XROWS = (PAIRED ? WH_R + 2 : WH_R) * PW;
   static constexpr int XATOM = (XROWS * 128 + 1023) & ~1023;
   static constexpr int NXA = PAIRED ? 1 : 2, NZA = BN / 64;
-  static constexpr int STAGE = NXA * XATOM + NZA * WH_ZATOM;
-  static constexpr int NACC = PAIRED ? 5 : 3;
+  static constexpr int ZTAPS = TCONV ? 4 : 1;                  // dz tiles per stage (ConvT: one per filter tap)
+  static constexpr int STAGE = NXA * XATOM + ZTAPS * NZA * WH_ZATOM;
+  static constexpr int NACC = PAIRED ? 5 : (TCONV ? 4 : 3);
   static constexpr int STAGES = (196 * 1024 - (PAIRED ? XATOM : 0)) / STAGE > 4 ? 4 : (196 * 1024 - (PAIRED ? XATOM : 0)) / STAGE;
   static constexpr int ONES = PAIRED ? XATOM : 0;              // all-ones block paired with the ninth tap: sum(dz) = db
   static constexpr int SMEM = 1024 + STAGES * STAGE + ONES + 1024;
   static constexpr int TCOLS = NACC * BN <= 256 ? 256 : 512;
 };
 
-template <int BN, bool PAIRED>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapA,
                                                         const __grid_constant__ CUtensorMap mapB,
                                                         const __grid_constant__ CUtensorMap mapG, const WHArgs a) {
-  using G = WHGeom<BN, PAIRED>;
+  using G = WHGeom<BN, MODE>;
+  constexpr bool PAIRED = MODE == WH_PAIRED, TCONV = MODE == WH_TCONV;
   constexpr int STAGES = G::STAGES, NACC = G::NACC;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,8 +103,8 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
   constexpr int MCH = PAIRED ? 64 : 128;                                 // input channels per M tile
   const int m0 = (second ? (int)blockIdx.x - a.mt_a : (int)blockIdx.x) * MCH;
   const int n0 = blockIdx.y * BN;
-  const int dy = PAIRED ? 0 : (int)blockIdx.z / a.ksplit;                // FULL: this CTA's filter row (0..2)
-  const int ks = PAIRED ? (int)blockIdx.z : (int)blockIdx.z % a.ksplit;
+  const int dy = MODE != WH_FULL ? 0 : (int)blockIdx.z / a.ksplit;       // FULL: this CTA's filter row (0..2)
+  const int ks = MODE != WH_FULL ? (int)blockIdx.z : (int)blockIdx.z % a.ksplit;
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
   const int per = (ntiles + a.ksplit - 1) / a.ksplit;
   const int t_beg = ks * per, t_end = min(ntiles, t_beg + per);
@@ -132,13 +141,24 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
           const int x0 = tix * 16, y0 = tiy * WH_R;
           mbar_wait(empty + s, ph);
           unsigned char* st = ring + s * G::STAGE;
-          mbar_expect_tx(full + s, (uint32_t)(G::NXA * G::XROWS * 128 + G::NZA * WH_ZATOM));
+          mbar_expect_tx(full + s, (uint32_t)(G::NXA * G::XROWS * 128 + G::ZTAPS * G::NZA * WH_ZATOM));
           // x: pixels x0-1..x0+16; rows y0-1..y0+8 (PAIRED: all taps) or y0+dy-1..+7 (FULL: this CTA's filter row)
+          if (TCONV) {
 #pragma unroll
-          for (int h = 0; h < G::NXA; ++h)
-            tma_load_4d(st + h * G::XATOM, second ? &mapB : &mapA, full + s, m0 + 64 * h, x0 - 1, y0 - 1 + dy, n);
+            for (int h = 0; h < G::NXA; ++h) tma_load_4d(st + h * G::XATOM, &mapA, full + s, m0 + 64 * h, x0, y0, n);
 #pragma unroll
-          for (int h = 0; h < G::NZA; ++h) tma_load_4d(st + G::NXA * G::XATOM + h * WH_ZATOM, &mapG, full + s, n0 + 64 * h, x0, y0, n);
+            for (int tap = 0; tap < 4; ++tap)
+#pragma unroll
+              for (int h = 0; h < G::NZA; ++h)
+                tma_load_4d(st + G::NXA * G::XATOM + (tap * G::NZA + h) * WH_ZATOM, &mapG, full + s, n0 + 64 * h, 2 * x0 + (tap & 1),
+                            2 * y0 + (tap >> 1), n);
+          } else {
+#pragma unroll
+            for (int h = 0; h < G::NXA; ++h)
+              tma_load_4d(st + h * G::XATOM, second ? &mapB : &mapA, full + s, m0 + 64 * h, x0 - 1, y0 - 1 + dy, n);
+#pragma unroll
+            for (int h = 0; h < G::NZA; ++h) tma_load_4d(st + G::NXA * G::XATOM + h * WH_ZATOM, &mapG, full + s, n0 + 64 * h, x0, y0, n);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -166,15 +186,16 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
             if (tb < 9) lbo = (uint32_t)((((tb / 3) - (ta / 3)) * WH_PW + (tb % 3) - (ta % 3)) * 128);
             else lbo = smem_u32(ones) - (xaddr + row0 * 128);   // ninth tap | all-ones block: rows 64.. = sum(dz)
           } else {
-            row0 = (uint32_t)j;                       // dx = j (the box is already shifted by dy)
+            row0 = TCONV ? 0u : (uint32_t)j;          // FULL: dx = j (the box is already shifted by dy)
             lbo = G::XATOM;
           }
           const uint32_t x_lo0 = wh_desc_lo(xaddr + row0 * 128, lbo);
           const uint32_t idesc = m64 ? idesc64 : idesc128;
           const uint32_t dcol = tmem_base + (uint32_t)(j * BN);
+          const uint32_t z_lo = TCONV ? z_lo0 + (uint32_t)(j * G::NZA * (WH_ZATOM >> 4)) : z_lo0;     // ConvT: tap j's dy tile
 #pragma unroll
           for (int r = 0; r < WH_R; ++r)               // one tile row = 16 pixels = one K step
-            wh_umma(dcol, x_lo0 + (uint32_t)(r * WH_PW * 8), z_lo0 + (uint32_t)(r * 128), idesc, r ? 1u : accf, leader);
+            wh_umma(dcol, x_lo0 + (uint32_t)(r * G::PW * 8), z_lo + (uint32_t)(r * 128), idesc, r ? 1u : accf, leader);
         }
         if (committer) umma_commit(empty + s);
         __syncwarp();
@@ -200,10 +221,12 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
           db_row = tap == 9 && ch == 0 && a.db != nullptr && blockIdx.x == 0;      // first row of the all-ones half
           if (tap > 8) tap = 8;
         } else {
-          tap = dy * 3 + j; ch = lg * 32 + lane; live = true;
+          tap = TCONV ? j : dy * 3 + j; ch = lg * 32 + lane; live = true;
         }
         live = live && (m0 + ch) < ctens;
-        float* dst_row = a.dw + ((size_t)tap * cin + coff + m0 + ch) * a.cout + n0;
+        // conv: dw[tap][ci][co] (a thread's row is contiguous); ConvT: dk[tap][co][ci] (the warp's lanes are contiguous)
+        float* dst_row = TCONV ? a.dw + ((size_t)tap * a.cout + n0) * cin + m0 + ch : a.dw + ((size_t)tap * cin + coff + m0 + ch) * a.cout + n0;
+        const size_t estep = TCONV ? (size_t)cin : 1;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
@@ -217,7 +240,7 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
           if (!live) continue;
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (n0 + c0 + e < a.cout) atomicAdd(dst_row + c0 + e, __uint_as_float(v[e]));
+            if (n0 + c0 + e < a.cout) atomicAdd(dst_row + (size_t)(c0 + e) * estep, __uint_as_float(v[e]));
         }
       }
     }
@@ -228,24 +251,25 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
 }
 
 // 4-D {C, W, H, N} view; box {64 channels, px, rows, 1}, SWIZZLE_128B; channels / pixels outside read as zero
-static bool wh_map(CUtensorMap* m, const dnnca_tensor_t* t, int px, int rows) {
+static bool wh_map(CUtensorMap* m, const dnnca_tensor_t* t, int px, int rows, int estride = 1) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   char* base = reinterpret_cast<char*>(t->data) + (size_t)t->coff * 2;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (t->cstride * 2) % 16) return false;
   cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
   cuuint64_t strides[3] = {(cuuint64_t)t->cstride * 2, (cuuint64_t)t->w * t->cstride * 2, (cuuint64_t)t->h * t->w * t->cstride * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)px, (cuuint32_t)rows, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  // with a traversal stride the box extent is given in tensor elements (pixels * stride)
+  cuuint32_t box[4] = {64, (cuuint32_t)(px * estride), (cuuint32_t)(rows * estride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, bool PAIRED>
+template <int BN, int MODE>
 static int launch_wgrad_halo(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mG, WHArgs a, int mt,
                              int nt) {
-  using G = WHGeom<BN, PAIRED>;
-  auto kern = wgrad_halo_kernel<BN, PAIRED>;
+  using G = WHGeom<BN, MODE>;
+  auto kern = wgrad_halo_kernel<BN, MODE>;
   static bool done = false;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
@@ -253,7 +277,7 @@ static int launch_wgrad_halo(cudaStream_t s, const CUtensorMap& mA, const CUtens
     done = true;
   }
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
-  const int groups = PAIRED ? 1 : 3;
+  const int groups = MODE == WH_FULL ? 3 : 1;
   // pixel slices so that the grid is ONE resident wave (1 CTA per SM: TMEM and smem): every extra slice costs a full
   // red.global.add flush of the accumulators (measured: 2 waves = 1.4x slower at 64 channels)
   long long want = (long long)sm_count() / ((long long)mt * nt * groups);
@@ -295,11 +319,25 @@ int try_conv3x3_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_
   if (!wh_map(&mG, g, 16, WH_R)) return 0;
   if (paired) {
     a.db = db;
-    const int r = launch_wgrad_halo<64, true>(s, mA, mB, mG, a, mt, (cout + 63) / 64);
+    const int r = launch_wgrad_halo<64, WH_PAIRED>(s, mA, mB, mG, a, mt, (cout + 63) / 64);
     return (r == 1 && db) ? 2 : r;
   }
-  if (cout % 128 == 0) return launch_wgrad_halo<128, false>(s, mA, mB, mG, a, mt, cout / 128);
-  return launch_wgrad_halo<64, false>(s, mA, mB, mG, a, mt, cout / 64);
+  if (cout % 128 == 0) return launch_wgrad_halo<128, WH_FULL>(s, mA, mB, mG, a, mt, cout / 128);
+  return launch_wgrad_halo<64, WH_FULL>(s, mA, mB, mG, a, mt, cout / 64);
+}
+
+// ConvT 2x2/s2 wgrad dk[tap][co][ci] for bf16 views with Cin % 128 == 0 and Cout % 64 == 0; returns 1 / 0 / <0
+int try_tconv_wgrad_halo(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* dy, float* dk) {
+  const int cin = x->c, cout = dy->c;
+  if (cin % 128 || cout % 64) return 0;
+  WHArgs a{};
+  a.c_a = cin; a.c_b = 0; a.cout = cout; a.dw = dk;
+  a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + WH_R - 1) / WH_R; a.nimg = x->n;
+  a.mt_a = cin / 128;
+  CUtensorMap mA, mG;
+  if (!wh_map(&mA, x, 16, WH_R)) return 0;
+  if (!wh_map(&mG, dy, 16, WH_R, 2)) return 0;
+  return launch_wgrad_halo<64, WH_TCONV>(s, mA, mA, mG, a, a.mt_a, cout / 64);
 }
 
 }  // namespace dnnca

@@ -26,6 +26,38 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// Warp-uniform issue: the WHOLE warp runs the issue loop and one elected lane (`leader`) executes the MMA, so the
+// descriptors stay in uniform registers (an `if (lane == 0)` body keeps them in vector registers and pays an R2UR
+// round trip per MMA: ~100 cycles of issue per MMA measured, which exposes N <= 128 MMAs).  Descriptors are passed as
+// 32-bit halves: `*_lo` = start address >> 4 | LBO field, `*_hi` = SBO field | version | swizzle mode.
+__device__ __forceinline__ bool umma_elect() {
+  uint32_t p;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(p));
+  return p != 0;
+}
+__host__ __device__ constexpr uint32_t kmajor128_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t kmajor128_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16_uniform(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t acc, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -101,11 +133,14 @@ struct ChunkAddr {
   const __nv_bfloat16* msk;   // nullptr when no mask applies to this chunk
   int bch;                    // bias channel
 };
+// EPI >= 0: the epilogue kind is a compile-time constant (persistent kernels); -1: read a.epi
+template <int EPI = -1>
 __device__ __forceinline__ ChunkAddr chunk_addr(const UArgs& a, int n, int gy, int gx, int ncol) {
   ChunkAddr r;
   long long pix;
   int ch;
-  if (a.epi == EPI_TCONV) {
+  const int epi = EPI >= 0 ? EPI : a.epi;
+  if (epi == EPI_TCONV) {
     const int tap = ncol / a.cout_t;
     ch = ncol - tap * a.cout_t;
     pix = ((long long)n * (2 * a.H) + 2 * gy + (tap >> 1)) * (2 * a.W) + 2 * gx + (tap & 1);
@@ -117,9 +152,32 @@ __device__ __forceinline__ ChunkAddr chunk_addr(const UArgs& a, int n, int gy, i
     else { ch = ncol - a.split; r.dst = a.yb + pix * a.yb_cs + ch; }
     r.bch = ncol;
   }
-  r.msk = (a.epi == EPI_DGRAD && a.mask && ncol < a.split) ? a.mask + pix * a.mask_cs + ch : nullptr;
+  r.msk = (epi == EPI_DGRAD && a.mask && ncol < a.split) ? a.mask + pix * a.mask_cs + ch : nullptr;
   return r;
 }
+
+__device__ __forceinline__ float act_slope(int act, float alpha) {
+  return act == DNNCA_ACT_RELU ? 0.f : (act == DNNCA_ACT_LEAKY ? alpha : 1.f);
+}
+__device__ __forceinline__ float act_slope_apply(float v, float slope) { return fmaf(slope, fminf(v, 0.f), fmaxf(v, 0.f)); }
+
+// tile index -> (tile column, tile row, image) of a persistent CTA walking tiles blockIdx.x, +gridDim.x, ...: the two
+// divisions run once, every step is adds and compares (a division by a run-time value costs ~100 cycles)
+struct TileWalk {
+  int tix, tiy, n;
+  int sx, sy, sn, tiles_x, tiles_y;
+  __device__ __forceinline__ TileWalk(int first, int step, int tx_, int ty_) : tiles_x(tx_), tiles_y(ty_) {
+    tix = first % tx_; int r = first / tx_; tiy = r % ty_; n = r / ty_;
+    sx = step % tx_; r = step / tx_; sy = r % ty_; sn = r / ty_;
+  }
+  __device__ __forceinline__ void next() {
+    tix += sx;
+    if (tix >= tiles_x) { tix -= tiles_x; ++tiy; }
+    tiy += sy;
+    if (tiy >= tiles_y) { tiy -= tiles_y; ++n; }
+    n += sn;
+  }
+};
 
 // persistent-kernel epilogue of a 32-column chunk: `m` holds the mask row prefetched before the accumulator was ready,
 // `sbias` is the CTA's bias slice in shared memory
@@ -137,27 +195,39 @@ __device__ __forceinline__ void warp_colsum32(float (&v)[32], int lane) {
   }
 }
 
-template <bool STATS = false>
-__device__ __forceinline__ void epilogue_chunk32(const UArgs& a, const uint32_t (&v)[32], const ChunkAddr& ca, const uint4 (&m)[4],
-                                                 const float* sbias, float* rounded = nullptr, bool store = true) {
+// STATS: on return v[] holds the values as they read back from the bf16 tensor (fp32 bit patterns)
+template <bool STATS = false, int EPI = -1>
+__device__ __forceinline__ void epilogue_chunk32(const UArgs& a, uint32_t (&v)[32], const ChunkAddr& ca, const uint4 (&m)[4],
+                                                 const float* sbias, bool store = true) {
+  const int epi = EPI >= 0 ? EPI : a.epi;
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-  if (a.epi == EPI_DGRAD) {
+  // branch-free activation: act(v) = max(v,0) + slope*min(v,0), act'(y) = y > 0 ? 1 : slope with slope = 0 (ReLU),
+  // alpha (LeakyReLU), 1 (none) -- a per-element switch on a.act compiles to two uniform branches per element
+  const float slope = act_slope(a.act, a.alpha);
+  if (epi == EPI_DGRAD) {
     if (ca.msk) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t mw[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f[q * 8 + 2 * j] *= act_grad(__uint_as_float(mw[j] << 16), a.act, a.alpha);
-          f[q * 8 + 2 * j + 1] *= act_grad(__uint_as_float(mw[j] & 0xffff0000u), a.act, a.alpha);
+          f[q * 8 + 2 * j] *= __uint_as_float(mw[j] << 16) > 0.f ? 1.f : slope;
+          f[q * 8 + 2 * j + 1] *= __uint_as_float(mw[j] & 0xffff0000u) > 0.f ? 1.f : slope;
         }
       }
     }
   } else {
+    const float4* sb4 = reinterpret_cast<const float4*>(sbias);      // 128-byte aligned: chunks start at multiples of 32
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j] + sbias[j], a.act, a.alpha);
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = sb4[j];
+      f[4 * j + 0] = act_slope_apply(f[4 * j + 0] + b4.x, slope);
+      f[4 * j + 1] = act_slope_apply(f[4 * j + 1] + b4.y, slope);
+      f[4 * j + 2] = act_slope_apply(f[4 * j + 2] + b4.z, slope);
+      f[4 * j + 3] = act_slope_apply(f[4 * j + 3] + b4.w, slope);
+    }
   }
   uint4* d4 = reinterpret_cast<uint4*>(ca.dst);
 #pragma unroll
@@ -176,8 +246,8 @@ __device__ __forceinline__ void epilogue_chunk32(const UArgs& a, const uint32_t 
       const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        rounded[q * 8 + 2 * j] = __uint_as_float(ow[j] << 16);
-        rounded[q * 8 + 2 * j + 1] = __uint_as_float(ow[j] & 0xffff0000u);
+        v[q * 8 + 2 * j] = ow[j] << 16;
+        v[q * 8 + 2 * j + 1] = ow[j] & 0xffff0000u;
       }
     }
   }
@@ -201,6 +271,7 @@ __device__ __forceinline__ void epilogue_chunk(const UArgs& a, const uint32_t (&
   float f[CH];
 #pragma unroll
   for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+  const float slope = act_slope(a.act, a.alpha);
   if (a.epi == EPI_DGRAD) {
     if (a.mask && ncol < a.split) {
       const uint4* mp = reinterpret_cast<const uint4*>(a.mask + pix * a.mask_cs + ch);
@@ -210,15 +281,20 @@ __device__ __forceinline__ void epilogue_chunk(const UArgs& a, const uint32_t (&
         const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f[q * 8 + 2 * j] *= act_grad(__uint_as_float(mw[j] << 16), a.act, a.alpha);
-          f[q * 8 + 2 * j + 1] *= act_grad(__uint_as_float(mw[j] & 0xffff0000u), a.act, a.alpha);
+          f[q * 8 + 2 * j] *= __uint_as_float(mw[j] << 16) > 0.f ? 1.f : slope;
+          f[q * 8 + 2 * j + 1] *= __uint_as_float(mw[j] & 0xffff0000u) > 0.f ? 1.f : slope;
         }
       }
     }
   } else {
     const int bch = a.epi == EPI_TCONV ? ch : ncol;
+    if (a.bias) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j] + (a.bias ? __ldg(a.bias + bch + j) : 0.f), a.act, a.alpha);
+      for (int j = 0; j < CH; ++j) f[j] = act_slope_apply(f[j] + __ldg(a.bias + bch + j), slope);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) f[j] = act_slope_apply(f[j], slope);
+    }
   }
   uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll

@@ -187,7 +187,8 @@ def _conv_case(N, mode, variant, shape):
 @pytest.mark.parametrize('variant', ['dense', 'sliced'])
 @pytest.mark.parametrize('shape', [(2, 8, 8, 12, 12), (1, 6, 16, 24, 8), (2, 5, 7, 6, 3), (1, 4, 4, 40, 70),
                                    (1, 20, 72, 12, 6), (2, 12, 40, 6, 3), (1, 36, 32, 8, 8),
-                                   (1, 8, 16, 64, 32), (2, 16, 16, 128, 64), (1, 8, 32, 32, 16), (1, 8, 16, 384, 128)])
+                                   (1, 8, 16, 64, 32), (2, 16, 16, 128, 64), (1, 8, 32, 32, 16), (1, 8, 16, 384, 128),
+                                   (1, 24, 20, 64, 64), (1, 16, 16, 512, 256), (2, 40, 24, 256, 64), (3, 12, 36, 128, 192)])
 def test_tconv(N, mode, variant, shape):
     n, h, w, cin, cout = shape
     dt = DT[mode]
