@@ -8,10 +8,12 @@
 // cycles (187 B/clk/SM against ~45 B/clk/SM of L2 bandwidth): ncu shows 4-20 % tensor-pipe activity there
 // (profiles/r01_ncu_full_umma_unet_big_b8.csv).
 //
-// Geometry: M tile = 16 rows x 8 pixels.  The halo box {64 ch, 16 px, 18 rows} lands as pixel rows of 128 bytes
-// (SWIZZLE_128B), 16 pixels per image row, so the A operand of tap (dy,dx) is the SAME buffer read through a
-// descriptor whose start address is shifted by (dy*16 + dx) rows: the 8 pixels of a tile row form one 8-row core
-// group, consecutive tile rows are SBO = 16*128 = 2048 bytes apart.  Only pixels x0-1..x0+8 of the 16 are used.
+// Geometry: M tile = 16 rows x 8 pixels.  The halo box {64 ch, 10 px, 18 rows} lands as pixel rows of 128 bytes
+// (SWIZZLE_128B), 10 pixels per image row, so the A operand of tap (dy,dx) is the SAME buffer read through a
+// descriptor whose start address is shifted by (dy*10 + dx) rows: the 8 pixels of a tile row form one 8-row core
+// group, consecutive tile rows are SBO = 10*128 = 1280 bytes apart (the 128-byte swizzle is a function of the
+// shared-memory address, for the TMA write and the MMA read alike, so neither the group start nor the group stride
+// needs to be a multiple of the 1024-byte swizzle period).
 #include <stdlib.h>
 
 #include "umma_common.cuh"
@@ -35,10 +37,12 @@ namespace dnnca {
 // With so little K per tile the activation ring is four slots deep so that loads run two or more tiles ahead.
 template <int BN, int TAPS = 9>
 struct HGeom {
-  static constexpr int A_SLOT = TAPS == 9 ? 18 * 16 * 128 : 16 * 8 * 128;   // tile of one 64-channel chunk (36 / 16 KB)
-  static constexpr int A_SBO = TAPS == 9 ? 2048 : 1024;    // bytes between consecutive tile rows (8-pixel core groups)
+  static constexpr int HPX = TAPS == 9 ? 10 : 8;           // pixels per image row of the activation box
+  static constexpr int A_BYTES = (TAPS == 9 ? 18 : 16) * HPX * 128;         // bytes one box load delivers (22.5 / 16 KB)
+  static constexpr int A_SLOT = (A_BYTES + 1023) & ~1023;  // ring slot (1024-byte aligned for the swizzle period)
+  static constexpr int A_SBO = HPX * 128;                  // bytes between consecutive tile rows (8-pixel core groups)
   static constexpr int B_TAP = BN * 128;                   // one tap of one 64-channel chunk
-  static constexpr int A_SLOTS = TAPS == 9 ? 2 : 4;
+  static constexpr int A_SLOTS = TAPS == 9 ? 3 : 4;
   static constexpr int CTRL = 6144;                        // barriers + TMEM slot + bias slice (BN floats at +256) + BN-statistics accumulators (2*BN doubles at +2048)
   // resident: all TAPS * (Cin/64) weight blocks stay in shared memory for the CTA's lifetime
   static constexpr int smem_resident(int kchunks) { return CTRL + A_SLOTS * A_SLOT + TAPS * kchunks * B_TAP + 1024; }
@@ -81,7 +85,9 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
   unsigned char* aring = smem + G::CTRL;
   unsigned char* bring = aring + G::A_SLOTS * A_SLOT;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tid;                                  // volatile: the compiler otherwise re-reads SR_TID.X inside the tile loops
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+  const int warp = tid >> 5, lane = tid & 31;
   const int kca = a.c_a / 64, kcb = a.c_b / 64, kchunks = TAPS == 9 ? kca + kcb : a.taps * kca;
   const int n0 = blockIdx.y * BN;
   const int ntiles = a.tiles_x * a.tiles_y * a.nimg;
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
           const long long tq = HALO_CLOCK();
           if (ai >= A_SLOTS) mbar_wait(emptyA + s, ((ai / A_SLOTS) - 1) & 1);
           tw += HALO_CLOCK() - tq;
-          mbar_expect_tx(fullA + s, A_SLOT);
+          mbar_expect_tx(fullA + s, G::A_BYTES);
           if (TAPS == 9) {
             const bool second = kc >= kca;
             tma_load_4d(aring + s * A_SLOT, second ? &mapB : &mapA, fullA + s, (second ? kc - kca : kc) * 64, x0 - 1, y0 - 1, n);
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
             const uint32_t b_base = bring_lo + (uint32_t)(kc * TAPS * (G::B_TAP >> 4));
 #pragma unroll
             for (int tap = 0; tap < TAPS; ++tap) {
-              const uint32_t da0 = a_base + (uint32_t)(TAPS == 9 ? ((tap / 3) * 16 + (tap % 3)) * 8 : 0);      // (dy*16+dx) rows of 128 B, >>4
+              const uint32_t da0 = a_base + (uint32_t)(TAPS == 9 ? ((tap / 3) * G::HPX + (tap % 3)) * 8 : 0);      // (dy*HPX+dx) rows of 128 B, >>4
               const uint32_t db0 = b_base + (uint32_t)(tap * (G::B_TAP >> 4));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
               mbar_wait(fullB + st, (bi / B_STAGES) & 1);
               tc_fence_after();
               const uint32_t db0 = bring_lo + (uint32_t)(st * (G::B_TAP >> 4));
-              const uint32_t da0 = a_base + (uint32_t)(TAPS == 9 ? ((tap / 3) * 16 + (tap % 3)) * 8 : 0);
+              const uint32_t da0 = a_base + (uint32_t)(TAPS == 9 ? ((tap / 3) * G::HPX + (tap % 3)) * 8 : 0);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16_uniform(dtm, da0 + 2 * k, a_hi, db0 + 2 * k, b_hi, idesc, (kc | tap | k) ? 1u : 0u, leader);
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------- host side
-static bool halo_map(CUtensorMap* m, const dnnca_tensor_t* t, int box_w = 16, int box_h = 18, int estride = 1) {
+static bool halo_map(CUtensorMap* m, const dnnca_tensor_t* t, int box_w = 10, int box_h = 18, int estride = 1) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   char* base = reinterpret_cast<char*>(t->data) + (size_t)t->coff * 2;
