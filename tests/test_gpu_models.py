@@ -359,5 +359,9 @@ def test_uint8_host_contract_matches_float32_inputs():
         weights.append(m.get_weights())
     assert losses[0][0] == losses[1][0], (losses[0], losses[1])          # same forward pass, bit for bit
     np.testing.assert_allclose(losses[0], losses[1], rtol=1e-4)          # later steps: fp32 atomics reorder the gradient sums
+    # Adam normalises each gradient by its own running magnitude, so a weight whose gradient is ~0 can move by up to
+    # lr = 1e-3 per step in either run: at most one step's worth anywhere, and 2e-4 for all but a handful of weights
     for k in weights[0]:
-        np.testing.assert_allclose(weights[0][k], weights[1][k], rtol=0, atol=2e-4)
+        d = np.abs(weights[0][k] - weights[1][k])
+        assert d.max() <= 1e-3, (k, d.max())
+        assert (d > 2e-4).mean() <= 0.01, (k, (d > 2e-4).mean())
