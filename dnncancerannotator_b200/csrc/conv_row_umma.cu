@@ -75,6 +75,24 @@ __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.
 // 8-row groups, descriptor version, layout type) is the same for every operand of these kernels; the low word holds
 // the start address (>>4) and the leading byte offset (>>4; MN-major: bytes between 64-element blocks; K-major: unused).
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+// loads / stores of a row tile: {row elements, rows, image} maps, or {row elements, image in group, rows, image group}
+// when ipt > 1 images are interleaved row by row in one tile (see row_common_geometry)
+__device__ __forceinline__ void row_tma_load(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int n, int ipt) {
+  if (ipt > 1) tma_load_4d(dst, map, bar, x, 0, y, n);
+  else tma_load_3d(dst, map, bar, x, y, n);
+}
+__device__ __forceinline__ void row_tma_store(const CUtensorMap* map, uint32_t src, int x, int y, int n, int ipt) {
+  if (ipt > 1)
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(x), "r"(0), "r"(y), "r"(n)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(x), "r"(y), "r"(n)
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
   return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
 }
@@ -116,13 +134,16 @@ struct RowArgs {
   int P, N, nsplit;               // pixels per strip; GEMM N = P*(oa+ob); columns [0,nsplit) go to destination a
   int parts, NP;                  // hi/lo weight parts; MMA N = parts * N
   int oa, ob;                     // channels of destination a / b
-  int Hs, tiles_x, tiles_y, nimg; // rows per tile (<= 128), strips per row, row tiles per image
+  int Hs, tiles_x, tiles_y, nimg; // rows per tile (<= 128), strips per row, row tiles per image, image groups
+  int ipt_max;                    // host search: 1 = do not interleave images
+  int ipt, hrows;                 // images interleaved in one tile (tile row v = image row v / ipt of image v % ipt); Hs / ipt
   int abuf, nstage;               // bytes of one window-atom buffer; ring depth
   // Conv2DTranspose k=s=2 variants (kernel [2][2][Cout][Cin], components.py:118-120):
   //   tconv 1 = fprop: window = P input pixels (no halo, one tap); columns = (a, 2P output pixels, co), output rows 2i+a
   //   tconv 2 = dgrad: taps a = rows 2i+a of dy (loaded as separate buffers through a 4-D map), window = 2P dy pixels
   //   tconv 3 = wgrad: x window against the dy rows 2i+a
-  int tconv, pad, ltaps, ntaps;   // pad = halo rows above/below a tile; ltaps = separately loaded tap buffers
+  int tconv, pad, ltaps, ntaps;   // pad = halo TILE rows above/below a tile (padr image rows x ipt); ltaps = separately loaded tap buffers
+  int padr;
   int win_step[2];                // window start element = strip * win_step - halo
   int tap_stride;                 // bytes between the A operands of consecutive taps inside a stage
   int box_w, box_h;               // output TMA box (elements of destination a, rows)
@@ -370,7 +391,7 @@ __global__ void __launch_bounds__(608) conv_row_umma_kernel(const __grid_constan
       const int step_x = gridDim.x % a.tiles_x, step_r = gridDim.x / a.tiles_x;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int tiy = rest % a.tiles_y, n = rest / a.tiles_y;
-        const int y0 = tiy * a.Hs;
+        const int y0 = tiy * a.hrows;
         mbar_wait(emptyA + s, ph);
         ROW_TRACE(0, it);
         if ((a.dbg & 2) && it >= a.nstage) {
@@ -385,7 +406,7 @@ __global__ void __launch_bounds__(608) conv_row_umma_kernel(const __grid_constan
           } else {
             for (int op = 0; op < a.nops; ++op)
               for (int at = 0; at < a.atoms[op]; ++at, dst += a.abuf)
-                tma_load_3d(dst, op ? &mapB : &mapA, fullA + s, tix * a.win_step[op] - a.halo[op] + at * 64, y0 - a.pad, n);
+                row_tma_load(dst, op ? &mapB : &mapA, fullA + s, tix * a.win_step[op] - a.halo[op] + at * 64, y0 - a.padr, n, a.ipt);
           }
         }
         if (HAS_MASK) {
@@ -393,7 +414,7 @@ __global__ void __launch_bounds__(608) conv_row_umma_kernel(const __grid_constan
           if (it == 0) mbar_wait(bready, 0);
           if (it >= 2) mbar_wait(mempty + mb, ((it >> 1) - 1) & 1);
           mbar_expect_tx(mfull + mb, mbytes);
-          tma_load_3d(mbase + mb * row_mask_bytes(a), &mapM, mfull + mb, tix * a.box_w, y0, n);
+          row_tma_load(mbase + mb * row_mask_bytes(a), &mapM, mfull + mb, tix * a.box_w, y0, n, a.ipt);
         }
         if (++s == a.nstage) { s = 0; ph ^= 1u; }
         tix += step_x; rest += step_r;
@@ -532,15 +553,8 @@ __global__ void __launch_bounds__(608) conv_row_umma_kernel(const __grid_constan
       if (issuer) ROW_TRACE(4, it);
       if (threadIdx.x == 64) ROW_ETRACE(4, it >> 1);
       if (issuer && !(a.dbg & 1)) {
-        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                         reinterpret_cast<uint64_t>(&mapOA)),
-                     "r"(outb), "r"(tix * a.box_w), "r"(tiy * a.box_h), "r"(n)
-                     : "memory");
-        if (a.ob)
-          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(&mapOB)),
-                       "r"(outb + (uint32_t)(a.Hs * a.nsplit * 2)), "r"(tix * a.P * a.ob), "r"(tiy * a.box_h), "r"(n)
-                       : "memory");
+        row_tma_store(&mapOA, outb, tix * a.box_w, tiy * a.box_h, n, a.ipt);
+        if (a.ob) row_tma_store(&mapOB, outb + (uint32_t)(a.Hs * a.nsplit * 2), tix * a.P * a.ob, tiy * a.box_h, n, a.ipt);
         tma_store_commit();
       }
       tix += step_x; tiy += step_y; n += step_n;
@@ -649,19 +663,19 @@ __global__ void __launch_bounds__(192) conv_row_wgrad_kernel(const __grid_consta
       const int step_x = gridDim.x % a.tiles_x, step_r = gridDim.x / a.tiles_x;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int tiy = rest % a.tiles_y, n = rest / a.tiles_y;
-        const int y0 = tiy * a.Hs;
+        const int y0 = tiy * a.hrows;
         mbar_wait(empty + s, ph);
         ROW_TRACE(0, it);
         mbar_expect_tx(full + s, bytes);
         unsigned char* dst = ring + s * stage_bytes;
         for (int op = 0; op < a.nops; ++op)
           for (int at = 0; at < a.atoms[op]; ++at, dst += a.abuf)
-            tma_load_3d(dst, op ? &mapB : &mapA, full + s, tix * a.win_step[op] - a.halo[op] + at * 64, y0 - a.pad, n);
+            row_tma_load(dst, op ? &mapB : &mapA, full + s, tix * a.win_step[op] - a.halo[op] + at * 64, y0 - a.padr, n, a.ipt);
         if (a.tconv) {                                        // dy rows 2i+tap
           for (int tap = 0; tap < 2; ++tap)
             for (int z = 0; z < a.zatoms; ++z, dst += a.zbuf) tma_load_4d(dst, &mapZ, full + s, tix * a.N + z * 64, tap, y0, n);
         } else {
-          for (int z = 0; z < a.zatoms; ++z, dst += a.zbuf) tma_load_3d(dst, &mapZ, full + s, tix * a.N + z * 64, y0, n);
+          for (int z = 0; z < a.zatoms; ++z, dst += a.zbuf) row_tma_load(dst, &mapZ, full + s, tix * a.N + z * 64, y0, n, a.ipt);
         }
         if (++s == a.nstage) { s = 0; ph ^= 1u; }
         tix += step_x; rest += step_r;
@@ -793,11 +807,22 @@ static bool row_dense_bf16(const dnnca_tensor_t* t) {
          (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
 }
 
-// tensor viewed as {W*C, H, N}; box {box_e, box_rows, 1}
-static bool row_map(CUtensorMap* m, const dnnca_tensor_t* t, int box_e, int box_rows, bool swz) {
+// tensor viewed as {W*C, H, N}; box {box_e, box_rows, 1}.  ipt > 1: {W*C, ipt, H, N/ipt} with box {box_e, ipt, box_rows, 1},
+// which lands (and leaves) as rows ordered (image row, image in group): the images of a group interleaved row by row
+static bool row_map(CUtensorMap* m, const dnnca_tensor_t* t, int box_e, int box_rows, bool swz, int ipt = 1) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc || box_e > 256 || box_rows > 256 || (box_e * 2) % 16) return false;
   const cuuint64_t rowe = (cuuint64_t)t->w * t->c;
+  if (ipt > 1) {
+    if (t->n % ipt) return false;
+    cuuint64_t dims[4] = {rowe, (cuuint64_t)ipt, (cuuint64_t)t->h, (cuuint64_t)(t->n / ipt)};
+    cuuint64_t strides[3] = {rowe * 2 * t->h, rowe * 2, rowe * 2 * t->h * ipt};
+    cuuint32_t box[4] = {(cuuint32_t)box_e, (cuuint32_t)ipt, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
   cuuint64_t dims[3] = {rowe, (cuuint64_t)t->h, (cuuint64_t)t->n};
   cuuint64_t strides[2] = {rowe * 2, rowe * 2 * t->h};
   cuuint32_t box[3] = {(cuuint32_t)box_e, (cuuint32_t)box_rows, 1};
@@ -844,13 +869,23 @@ static bool row_operand(RowArgs& a, int op, int C, int P) {
 static bool row_common_geometry(RowArgs& a, const dnnca_tensor_t* x) {
   const int H = x->h, W = x->w;
   if (W % a.P) return false;
-  a.Hs = 0;
+  a.hrows = 0;
   for (int d = 128; d >= 16; d -= 16)        // tallest row tile that divides the image
-    if (H % d == 0) { a.Hs = d; break; }
-  if (!a.Hs) return false;
-  a.tiles_x = W / a.P; a.tiles_y = H / a.Hs; a.nimg = x->n;
+    if (H % d == 0) { a.hrows = d; break; }
+  if (!a.hrows) return false;
+  // images of 64 rows or fewer would leave half (or more) of the 128 MMA rows empty at the same tensor time: interleave
+  // ipt images row by row in one tile (tile row v = row v / ipt of image v % ipt), each with its own zero halo rows, so
+  // the dy taps stay a plain shift by ipt tile rows.  Conv only (the ConvT maps already spend the fourth dimension).
+  a.ipt = 1;
+  static int no_ipt = -1;
+  if (no_ipt < 0) no_ipt = getenv("DNNCA_ROW_NO_INTERLEAVE") ? 1 : 0;
+  if (!a.tconv && !no_ipt)
+    while (a.ipt < a.ipt_max && 2 * a.ipt * a.hrows <= 128 && x->n % (2 * a.ipt) == 0) a.ipt *= 2;
+  a.Hs = a.hrows * a.ipt;
+  a.tiles_x = W / a.P; a.tiles_y = H / a.hrows; a.nimg = x->n / a.ipt;
   if ((long long)a.tiles_x * a.tiles_y * a.nimg > 0x7fffffffLL) return false;
-  a.pad = a.tconv ? 0 : 1;
+  a.padr = a.tconv ? 0 : 1;                  // halo image rows above / below
+  a.pad = a.padr * a.ipt;                    // the same in tile rows
   a.abuf = ((a.Hs + 2 * a.pad) * 128 + 1023) & ~1023;
   return true;
 }
@@ -864,7 +899,7 @@ static bool row_plan_mmas(RowArgs& a) {
   int a_off = 0;                                        // operand offset inside the stage, 16-byte units
   a.ntaps = a.tconv == 1 ? 1 : (a.tconv == 2 ? 2 : 3);
   a.ltaps = a.tconv == 2 ? 2 : 1;
-  a.tap_stride = a.tconv == 2 ? a.atoms[0] * a.abuf : 128;     // conv: the next image row of the same buffer
+  a.tap_stride = a.tconv == 2 ? a.atoms[0] * a.abuf : 128 * a.ipt;     // conv: the next image row of the same buffer
   for (int op = 0; op < a.nops; ++op) {
     for (int tap = 0; tap < a.ntaps; ++tap)
       for (int at = 0; at < a.atoms[op]; ++at) {
@@ -979,7 +1014,10 @@ static int launch_row(cudaStream_t s, bool dgrad, int tconv, const dnnca_tensor_
   bool found = false;
   RowArgs best;
   double best_cost = 0.0;
+  // every strip width, with short images interleaved up to 8 per tile and without: cheapest tensor time per pixel
+  for (int pass = 0; pass < 2; ++pass)
   for (int P = 16; P >= 2; P >>= 1) {
+    a.ipt_max = pass ? 1 : 8;
     a.P = P;
     if (!row_operand(a, 0, ca, P) || (inb && !row_operand(a, 1, cb, P))) continue;
     if (tconv == 1) { a.N = 4 * P * oa; a.nsplit = a.N; a.box_w = 2 * P * oa; }
@@ -988,14 +1026,14 @@ static int launch_row(cudaStream_t s, bool dgrad, int tconv, const dnnca_tensor_
     a.NP = a.parts * a.N;
     if (a.N % 16 || a.NP > 256 || a.N < 16) continue;
     if (!row_common_geometry(a, grid_t)) continue;
-    a.box_h = tconv == 1 ? 2 * a.Hs : a.Hs;
+    a.box_h = tconv == 1 ? 2 * a.Hs : a.hrows;
     if (!row_plan_mmas(a)) continue;
     bool fits = false;
     for (a.nstage = 4; a.nstage >= 2; --a.nstage)
       if (row_smem_bytes(a) <= ROW_SMEM_LIMIT) { fits = true; break; }
     if (!fits) continue;
     if ((tconv ? 4 : 9) * a.cin_tot * a.cout * 4 > 4 * row_out_bytes(a) + 2 * row_mask_bytes(a)) continue;   // weight staging
-    const double cost = (a.nmma * row_mma_cycles(a.NP) + 300.0) / P;
+    const double cost = (a.nmma * row_mma_cycles(a.NP) + 300.0) / ((double)P * a.Hs);
     if (!found || cost < best_cost) { best = a; best_cost = cost; found = true; }
   }
   if (found) a = best;
@@ -1003,14 +1041,14 @@ static int launch_row(cudaStream_t s, bool dgrad, int tconv, const dnnca_tensor_
   CUtensorMap mA, mB, mOA, mOB, mM;
   if (tconv == 2) {
     if (!row_map_parity(&mA, ina, a.Hs)) return 0;
-  } else if (!row_map(&mA, ina, 64, a.Hs + 2 * a.pad, true)) return 0;
+  } else if (!row_map(&mA, ina, 64, a.hrows + 2 * a.padr, true, a.ipt)) return 0;
   mB = mA;
-  if (inb && !row_map(&mB, inb, 64, a.Hs + 2 * a.pad, true)) return 0;
-  if (!row_map(&mOA, outa, a.box_w, a.box_h, false)) return 0;
+  if (inb && !row_map(&mB, inb, 64, a.hrows + 2 * a.padr, true, a.ipt)) return 0;
+  if (!row_map(&mOA, outa, a.box_w, a.box_h, false, a.ipt)) return 0;
   mOB = mOA;
-  if (outb && !row_map(&mOB, outb, a.P * ob, a.Hs, false)) return 0;
+  if (outb && !row_map(&mOB, outb, a.P * ob, a.hrows, false, a.ipt)) return 0;
   mM = mOA;
-  if (mask && !row_map(&mM, mask, a.box_w, a.Hs, false)) return 0;
+  if (mask && !row_map(&mM, mask, a.box_w, a.hrows, false, a.ipt)) return 0;
   if (!dgrad) {
     if (act == DNNCA_ACT_RELU) return launch_row_epi<REPI_RELU>(s, mA, mB, mOA, mOB, mM, a);
     if (act == DNNCA_ACT_LEAKY) return launch_row_epi<REPI_LEAKY>(s, mA, mB, mOA, mOB, mM, a);
@@ -1053,7 +1091,7 @@ static bool roww_plan(RowArgs& a) {
     a.nacc = n;
     return n * a.N <= 512;
   }
-  auto window_off = [&](int op, int tap) { return (op ? a.atoms[0] * a.abuf : 0) + tap * 128; };
+  auto window_off = [&](int op, int tap) { return (op ? a.atoms[0] * a.abuf : 0) + tap * 128 * a.ipt; };
   if (a.atoms[0] > 1) {
     for (int op = 0; op < a.nops; ++op)
       for (int tap = 0; tap < 3; ++tap) {
@@ -1106,7 +1144,9 @@ static int launch_row_wgrad(cudaStream_t s, int tconv, const dnnca_tensor_t* x, 
   bool found = false;
   RowArgs best;
   double best_cost = 0.0;
+  for (int pass = 0; pass < 2; ++pass)
   for (int P = 16; P >= 2; P >>= 1) {
+    a.ipt_max = pass ? 1 : 8;
     a.P = P;
     if (!row_operand(a, 0, ca, P) || (x2 && !row_operand(a, 1, cb, P))) continue;
     if (x2 && a.atoms[0] != a.atoms[1]) continue;
@@ -1119,18 +1159,18 @@ static int launch_row_wgrad(cudaStream_t s, int tconv, const dnnca_tensor_t* x, 
     for (a.nstage = 6; a.nstage >= 2; --a.nstage)
       if (roww_smem_bytes(a) <= ROW_SMEM_LIMIT) { fits = true; break; }
     if (!fits || (a.N + 1) * 512 > a.nstage * roww_stage_bytes(a)) continue;     // the ring also hosts the accumulator dump
-    const double cost = (a.nacc * (a.Hs / 16) * row_mma_cycles(a.N) + 200.0) / P;
+    const double cost = (a.nacc * (a.Hs / 16) * row_mma_cycles(a.N) + 200.0) / ((double)P * a.Hs);
     if (!found || cost < best_cost) { best = a; best_cost = cost; found = true; }
   }
   if (found) a = best;
   if (!found) return 0;
   CUtensorMap mA, mB, mZ;
-  if (!row_map(&mA, x, 64, a.Hs + 2 * a.pad, true)) return 0;
+  if (!row_map(&mA, x, 64, a.hrows + 2 * a.padr, true, a.ipt)) return 0;
   mB = mA;
-  if (x2 && !row_map(&mB, x2, 64, a.Hs + 2 * a.pad, true)) return 0;
+  if (x2 && !row_map(&mB, x2, 64, a.hrows + 2 * a.padr, true, a.ipt)) return 0;
   if (tconv) {
     if (!row_map_parity(&mZ, dz, a.Hs)) return 0;
-  } else if (!row_map(&mZ, dz, 64, a.Hs, true)) return 0;
+  } else if (!row_map(&mZ, dz, 64, a.hrows, true, a.ipt)) return 0;
   const int smem = roww_smem_bytes(a);
   static int smem_set = 0;
   if (smem > smem_set) {

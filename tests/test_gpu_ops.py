@@ -554,6 +554,8 @@ ROW_SHAPES = [  # (n, h, w, c_x, c_x2, cout)
     (2, 256, 256, 3, 0, 3), (2, 128, 128, 3, 0, 6), (3, 128, 128, 6, 0, 6), (3, 64, 64, 6, 0, 12), (5, 64, 64, 12, 0, 12),
     (3, 64, 64, 12, 12, 12), (2, 128, 128, 6, 6, 6), (2, 256, 256, 3, 3, 3), (40, 32, 64, 3, 0, 3), (2, 48, 32, 6, 0, 6),
     (1, 16, 16, 4, 4, 4), (2, 32, 32, 5, 0, 3), (150, 128, 32, 3, 0, 3),
+    # images of <= 64 rows are interleaved row by row, 2 / 4 / 8 per 128-row tile (even batch)
+    (4, 64, 64, 12, 12, 12), (6, 64, 64, 6, 0, 12), (8, 16, 32, 6, 0, 6), (12, 32, 64, 12, 0, 6), (2, 64, 128, 3, 3, 3),
 ]
 
 
