@@ -170,7 +170,10 @@ def run_ours(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+    numa_cpus = None
     if world > 1:
+        from dnncancerannotator_b200.parallel import bind_host_to_gpu
+        numa_cpus = bind_host_to_gpu(local)       # before any pinned buffer exists: staging memory on the GPU's NUMA node
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
 
@@ -348,7 +351,8 @@ def run_ours(args):
                                f'{S}x{S}x{Cc} slices ({args.dtype} activations, fp32 accumulate/master weights)',
                    'global_batch': B * world, 'parallelism': f'dp{world}',
                    'l2': 'working set per step (>1 GB of activations) exceeds the 126 MB L2; no flush needed',
-                   'cuda_graph': True},
+                   'cuda_graph': True,
+                   'host_numa_cpus': (f'{len(numa_cpus)} CPUs local to the GPU' if numa_cpus else None)},
         'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
         'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'breakdown': breakdown, 'categories': categories,
         'loss_first': loss0, 'loss_last': final_loss, 'wall_s_timed_region': wall,

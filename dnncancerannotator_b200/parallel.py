@@ -14,6 +14,31 @@ import torch
 import torch.distributed as dist
 
 
+def bind_host_to_gpu(device_index=None):
+    """Pin this process to the CPUs NVML reports as local to its GPU, so the pinned staging buffers it allocates afterwards
+    (first touch) and the threads that fill them sit on the GPU's NUMA node: with one rank per GPU every rank otherwise
+    allocates from the socket the launcher happened to start on and all host->device copies cross one memory controller.
+    Returns the CPU list it bound to, or None when NVML / the affinity call is unavailable (nothing changes then)."""
+    import os
+    try:
+        import pynvml
+        idx = torch.cuda.current_device() if device_index is None else device_index
+        props = torch.cuda.get_device_properties(idx)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + str(props.uuid)).encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(local & allowed)
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:       # no NVML, no uuid, restricted cpuset: keep the inherited affinity
+        return None
+
+
 def bucket_ranges(numel, bucket_elems):
     """[(start, stop)] covering [0, numel) in reverse order (last layers' gradients are ready
     first during the backward pass)."""
