@@ -22,8 +22,10 @@
 // long-scoreboard instructions: they cost the epilogue ~10 % when compiled in)
 #ifdef DNNCA_HALO_TRACE
 #define HALO_CLOCK() clock64()
+#define HALO_PRINT(...) printf(__VA_ARGS__)
 #else
 #define HALO_CLOCK() 0ll
+#define HALO_PRINT(...) ((void)0)
 #endif
 
 namespace dnnca {
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
           if (++kcc == kca) { kcc = 0; ++ktap; }
         }
       }
-      if ((a.dbg & 16) && blockIdx.x == 0 && blockIdx.y == 0) printf("producer: total %lld wait emptyA %lld loads %d\n", HALO_CLOCK() - t00, tw, ai);
+      if ((a.dbg & 16) && blockIdx.x == 0 && blockIdx.y == 0) HALO_PRINT("producer: total %lld wait emptyA %lld loads %d\n", HALO_CLOCK() - t00, tw, ai);
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (descriptors in uniform registers) =====
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
         __syncwarp();
       }
       if ((a.dbg & 16) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
-        printf("mma: total %lld wait fullA %lld wait tempty %lld tiles %d\n", HALO_CLOCK() - t00, twa, twt, ti);
+        HALO_PRINT("mma: total %lld wait fullA %lld wait tempty %lld tiles %d\n", HALO_CLOCK() - t00, twa, twt, ti);
     }
   } else {
     // ===== epilogue: warps 2..9.  A warp may only touch TMEM lanes 32*(warp%4)..+31, so two warps share each lane
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
       if (lane == 0) mbar_arrive(tempty + buf);
     }
     if ((a.dbg & 16) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 2 || warp == 9))
-      printf("epi warp %d: total %lld wait tfull %lld\n", warp, HALO_CLOCK() - t00, twf);
+      HALO_PRINT("epi warp %d: total %lld wait tfull %lld\n", warp, HALO_CLOCK() - t00, twf);
     if (REG_STATS && do_stats) {
 #pragma unroll
       for (int c = 0; c < (REG_STATS ? NCHUNK : 1); ++c) {

@@ -206,3 +206,12 @@ def test_weights_roundtrip_and_checkpoint_naming(tmp_path):
         m2.set_weights({'nope': np.zeros(1)})
     with pytest.raises(ValueError):
         m2.set_weights({'head/bias': np.zeros(2)})
+
+
+def test_bind_host_to_gpu_is_a_noop_without_nvml_or_gpu():
+    """parallel.bind_host_to_gpu must never raise or change the affinity when there is no GPU / NVML to ask."""
+    import os
+    from dnncancerannotator_b200.parallel import bind_host_to_gpu
+    before = os.sched_getaffinity(0)
+    assert bind_host_to_gpu(0) is None
+    assert os.sched_getaffinity(0) == before
