@@ -425,7 +425,36 @@ __global__ void __launch_bounds__(256) map_vec8_kernel(View x, View dy, const fl
 #pragma unroll
       for (int j = 0; j < 8; ++j) kk[j] = (gamma ? gamma[8 * g + j] : 1.f) * c1[j];
     }
-    for (long long p = (long long)blockIdx.x * PL + pl; p < P; p += (long long)gridDim.x * PL) {
+    const long long stride = (long long)gridDim.x * PL;
+    long long p = (long long)blockIdx.x * PL + pl;
+    // four pixels per iteration: all loads are issued before the first use (memory-level parallelism)
+    for (; p + 3 * stride < P; p += 4 * stride) {
+      uint4 xr[4], gr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xr[u] = __ldg(vptr(x, p + u * stride, g));
+        if (MODE == 1) gr[u] = __ldg(vptr(dy, p + u * stride, g));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float xv[8], o[8];
+        unpack8(xr[u], xv);
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(xv[j], c0[j], c1[j]);
+        } else {
+          float gv[8];
+          unpack8(gr[u], gv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = (xv[j] - c0[j]) * c1[j];
+            o[j] = kk[j] * (gv[j] - c2[j] - xh * c3[j]) * act_grad(xv[j], act, alpha);
+          }
+        }
+        __stcs(vptr_w(out, p + u * stride, g), pack8(o));      // streaming: the result is not re-read by this kernel
+      }
+    }
+    for (; p < P; p += stride) {
       float xv[8], o[8];
       unpack8(*vptr(x, p, g), xv);
       if (MODE == 0) {

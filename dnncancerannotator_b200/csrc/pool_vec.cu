@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(256) maxpool_fwd_vec8_kernel(PV x, __nv_bfloat
           for (int j = 0; j < 8; ++j)
             if (v[j] > best[j]) { best[j] = v[j]; bi[j >> 2] = (bi[j >> 2] & ~(0xffu << ((j & 3) * 8))) | ((uint32_t)k << ((j & 3) * 8)); }
         }
-        *reinterpret_cast<uint4*>(y + p * ycs + 8 * g) =
-            make_uint4(pack2(best[0], best[1]), pack2(best[2], best[3]), pack2(best[4], best[5]), pack2(best[6], best[7]));
+        __stcs(reinterpret_cast<uint4*>(y + p * ycs + 8 * g),
+               make_uint4(pack2(best[0], best[1]), pack2(best[2], best[3]), pack2(best[4], best[5]), pack2(best[6], best[7])));
         if (idx) *reinterpret_cast<uint2*>(idx + p * C + 8 * g) = make_uint2(bi[0], bi[1]);
         if (STATS) {
 #pragma unroll
@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(256) maxpool_bwd_vec8_kernel(PV dy, const uint
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] *= (m[j] > 0.f ? 1.f : (MODE == 1 ? 0.f : alpha));
       }
-      *reinterpret_cast<uint4*>(dx + q * dxcs + 8 * g) =
-          make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+      __stcs(reinterpret_cast<uint4*>(dx + q * dxcs + 8 * g),
+             make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7])));
     }
   }
 }

@@ -241,7 +241,8 @@ __device__ __forceinline__ void epilogue_chunk32(const UArgs& a, uint32_t (&v)[3
     o.y = *reinterpret_cast<uint32_t*>(&p1);
     o.z = *reinterpret_cast<uint32_t*>(&p2);
     o.w = *reinterpret_cast<uint32_t*>(&p3);
-    if (store) d4[q] = o;
+    if (store) d4[q] = o;                     // (a streaming st.global.cs here measured 3 % slower: the consumer kernel
+                                              // that follows finds part of this output in L2)
     if (STATS) {                              // the values as they read back from the bf16 tensor
       const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
