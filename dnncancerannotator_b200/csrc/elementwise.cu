@@ -474,6 +474,19 @@ __global__ void __launch_bounds__(256) map_vec8_kernel(View x, View dy, const fl
   }
 }
 
+// grid of a grid-stride kernel: enough blocks for the work, at most ONE resident wave (a block count that is not a multiple
+// of the resident slots leaves a partial last wave: the 118-register BN backward reduction held 2 blocks per SM and ran
+// 1024 blocks = 3.46 waves)
+template <typename K>
+inline int resident_grid(K kern, long long work_items, int per_block) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)sm_count() * per_sm;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
 inline bool vec8_ok(const dnnca_tensor_t* t) {
   return t->dtype == DNNCA_BF16 && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0 &&
          (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
@@ -502,7 +515,9 @@ extern "C" int dnnca_channel_stats(void* stream, const dnnca_tensor_t* x, double
   if (vec8_ok(x)) {
     ChanLayout G = group_layout(x->c);
     // >= 64 pixels per thread: every block ends with 2*C fp64 atomics, so small tensors get few blocks
-    reduce_vec8_kernel<0><<<grid_for(P, G.pl * 64), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(x), nullptr, stats, G.cl, G.pl, P);
+    static const int occ0 = resident_grid(reduce_vec8_kernel<0>, 1LL << 40, 1);      // resident blocks on this device
+    const int g0 = grid_for(P, G.pl * 64);
+    reduce_vec8_kernel<0><<<g0 < occ0 ? g0 : occ0, 256, 0, (cudaStream_t)stream>>>(mk(x), mk(x), nullptr, stats, G.cl, G.pl, P);
     DNNCA_LAUNCH_CHECK("channel_stats");
     return DNNCA_OK;
   }
@@ -582,7 +597,9 @@ extern "C" int dnnca_bn_bwd_reduce(void* stream, const dnnca_tensor_t* x, const 
   long long P = (long long)x->n * x->h * x->w;
   if (vec8_ok(x) && vec8_ok(dy)) {
     ChanLayout G = group_layout(x->c);
-    reduce_vec8_kernel<1><<<grid_for(P, G.pl * 64), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(dy), mean_invstd, sums, G.cl, G.pl, P);
+    static const int occ1 = resident_grid(reduce_vec8_kernel<1>, 1LL << 40, 1);
+    const int g1 = grid_for(P, G.pl * 64);
+    reduce_vec8_kernel<1><<<g1 < occ1 ? g1 : occ1, 256, 0, (cudaStream_t)stream>>>(mk(x), mk(dy), mean_invstd, sums, G.cl, G.pl, P);
     DNNCA_LAUNCH_CHECK("bn_bwd_reduce");
     return DNNCA_OK;
   }
