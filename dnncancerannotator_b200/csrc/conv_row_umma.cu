@@ -135,6 +135,8 @@ struct RowArgs {
   int parts, NP;                  // hi/lo weight parts; MMA N = parts * N
   int oa, ob;                     // channels of destination a / b
   int Hs, tiles_x, tiles_y, nimg; // rows per tile (<= 128), strips per row, row tiles per image, image groups
+  int obufs;                      // output staging buffers per epilogue group: 2 (a TMA store may still read one while the
+                                  // next tile is written) or 1 when shared memory is short (wide N: 1->16 first layers)
   int ipt_max;                    // host search: 1 = do not interleave images
   int ipt, hrows;                 // images interleaved in one tile (tile row v = image row v / ipt of image v % ipt); Hs / ipt
   int abuf, nstage;               // bytes of one window-atom buffer; ring depth
@@ -172,7 +174,7 @@ __host__ __device__ inline int row_out_bytes(const RowArgs& a) { return a.Hs * a
 __host__ __device__ inline int row_mask_bytes(const RowArgs& a) { return a.has_mask ? a.Hs * a.nsplit * 2 : 0; }
 constexpr int ROW_CTRL = 256 + ROW_MAX_MMA * 8 + 1024 + 1024;      // barriers, MMA table, bias slice, debug trace + lut
 __host__ __device__ inline int row_smem_bytes(const RowArgs& a) {
-  return a.nstage * row_stage_bytes(a) + a.nblocks * a.NP * 128 + 4 * row_out_bytes(a) + 2 * row_mask_bytes(a) + ROW_CTRL + 1024;
+  return a.nstage * row_stage_bytes(a) + a.nblocks * a.NP * 128 + 2 * a.obufs * row_out_bytes(a) + 2 * row_mask_bytes(a) + ROW_CTRL + 1024;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(608) conv_row_umma_kernel(const __grid_constan
   unsigned char* aring = smem;                                   // first: UMMA over-reads of short tiles stay inside
   unsigned char* bbase = aring + a.nstage * stage_bytes;
   unsigned char* obase = bbase + a.nblocks * bblk;
-  unsigned char* mbase = obase + 4 * row_out_bytes(a);
+  unsigned char* mbase = obase + 2 * a.obufs * row_out_bytes(a);
   unsigned char* ctrl = mbase + 2 * row_mask_bytes(a);
   uint64_t* fullA = reinterpret_cast<uint64_t*>(ctrl);          // [8]
   uint64_t* emptyA = fullA + 8;                                  // [8]
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(608) conv_row_umma_kernel(const __grid_constan
     const int offA = row * a.nsplit * 2;                              // + chunk*16
     const int offB = a.Hs * a.nsplit * 2 + row * nb * 2 - a.nsplit * 2;   // + chunk*16
     const float alpha = a.alpha;
-    const uint32_t out_s = smem_u32(obase) + (uint32_t)(2 * g * row_out_bytes(a));
+    const uint32_t out_s = smem_u32(obase) + (uint32_t)(a.obufs * g * row_out_bytes(a));
     const uint32_t msk_s = smem_u32(mbase) + (uint32_t)(g * row_mask_bytes(a) + offA);
     const uint32_t bias_s = smem_u32(sbias);
     const uint32_t tlane = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c_first * 8);
@@ -506,8 +508,11 @@ __global__ void __launch_bounds__(608) conv_row_umma_kernel(const __grid_constan
       const int buf = nbuf4 ? (it & 3) : (it & 1);
       const uint32_t tpar = (uint32_t)(nbuf4 ? (it >> 2) : (it >> 1)) & 1u;
       const uint32_t tbase = tlane + (uint32_t)(buf * a.NP);
-      const uint32_t outb = out_s + (uint32_t)(git & 1) * out_bytes;
-      if (issuer) tma_store_wait_read1();                    // the store that last read THIS staging buffer is done
+      const uint32_t outb = out_s + (a.obufs > 1 ? (uint32_t)(git & 1) * out_bytes : 0u);
+      if (issuer) {                                          // the store that last read THIS staging buffer is done
+        if (a.obufs > 1) tma_store_wait_read1();
+        else tma_store_wait_read0();
+      }
       group_bar_sync(g);
       if (threadIdx.x == 64) ROW_ETRACE(0, it >> 1);
       if (HAS_MASK) mbar_wait(mfull + g, par);
@@ -1029,10 +1034,12 @@ static int launch_row(cudaStream_t s, bool dgrad, int tconv, const dnnca_tensor_
     a.box_h = tconv == 1 ? 2 * a.Hs : a.hrows;
     if (!row_plan_mmas(a)) continue;
     bool fits = false;
-    for (a.nstage = 4; a.nstage >= 2; --a.nstage)
-      if (row_smem_bytes(a) <= ROW_SMEM_LIMIT) { fits = true; break; }
+    for (a.obufs = 2; a.obufs >= 1 && !fits; --a.obufs)
+      for (a.nstage = 4; a.nstage >= 2; --a.nstage)
+        if (row_smem_bytes(a) <= ROW_SMEM_LIMIT) { fits = true; break; }
     if (!fits) continue;
-    if ((tconv ? 4 : 9) * a.cin_tot * a.cout * 4 > 4 * row_out_bytes(a) + 2 * row_mask_bytes(a)) continue;   // weight staging
+    ++a.obufs;                                              // the loop's decrement after the fitting pass
+    if ((tconv ? 4 : 9) * a.cin_tot * a.cout * 4 > 2 * a.obufs * row_out_bytes(a) + 2 * row_mask_bytes(a)) continue;   // weight staging
     const double cost = (a.nmma * row_mma_cycles(a.NP) + 300.0) / ((double)P * a.Hs);
     if (!found || cost < best_cost) { best = a; best_cost = cost; found = true; }
   }
