@@ -592,7 +592,7 @@ int try_conv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dz, const float* w
   a.yb = dx2 ? reinterpret_cast<__nv_bfloat16*>(dx2->data) + dx2->coff : a.ya; a.yb_cs = dx2 ? dx2->cstride : a.ya_cs;
   a.mask = mask ? reinterpret_cast<const __nv_bfloat16*>(mask->data) + mask->coff : nullptr; a.mask_cs = mask ? mask->cstride : 0;
   a.n_total = cin; a.cout_t = cin; a.nimg = dx->n;
-  if (k == 3 && kc == 64 && halo_enabled()) {
+  if (k == 3 && (kc == 64 || cout < 64) && halo_enabled()) {     // cout < 64: one K chunk, missing channels zero-filled
     r = try_conv3x3_halo(s, dz, nullptr, ws, cout, cin, a);
     if (r != 0) return r;
   }

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
       for (int c = 0; c < NCHUNK; ++c) {
         const int col = half * (BN / 2) + c * 32;
         ca[c] = chunk_addr<EPI>(a, n, inside ? gy : 0, inside ? gx : 0, n0 + col);
-        if (EPI == EPI_DGRAD && ca[c].msk && inside) {
+        if (EPI == EPI_DGRAD && ca[c].msk && inside && n0 + col < a.n_total) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) m[EPI == EPI_DGRAD ? c : 0][q] = reinterpret_cast<const uint4*>(ca[c].msk)[q];
         }
@@ -396,7 +396,9 @@ int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tenso
   // a single input with fewer than 64 channels (first layers) is one K chunk whose missing channels are zero-filled by
   // the TMA (activations and packed weights alike)
   const bool narrow = !xb && xa->c < 64;
-  if ((!narrow && (xa->c % 64 || (xb && xb->c % 64))) || ntot % 64) return 0;
+  // N (output channels) in multiples of 32: the last N tile may be half empty (the weight TMA zero-fills the missing rows,
+  // the epilogue skips 32-column chunks at or beyond n_total)
+  if ((!narrow && (xa->c % 64 || (xb && xb->c % 64))) || ntot % 32) return 0;
   const int bn = ntot % 256 == 0 ? 256 : (ntot % 128 == 0 ? 128 : 64);
   if (a.split % 32) return 0;               // the epilogue routes 32-column chunks to the two dgrad destinations
   CUtensorMap mA, mB, mW;

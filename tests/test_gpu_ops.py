@@ -231,6 +231,8 @@ UMMA_SHAPES = [  # (n, h, w, c_x, c_x2, cout, k): channel counts the tcgen05 imp
     (1, 16, 32, 64, 0, 64, 3), (2, 8, 16, 16, 0, 32, 3), (1, 16, 16, 64, 64, 64, 3), (1, 8, 16, 128, 0, 256, 3),
     (1, 24, 48, 32, 32, 32, 3), (2, 16, 16, 16, 16, 16, 3), (1, 8, 32, 256, 0, 128, 3), (1, 12, 20, 64, 0, 48, 3),
     (1, 16, 16, 64, 0, 64, 1), (1, 8, 16, 512, 512, 512, 3),
+    # 32-channel layers (mulmo_unet.yaml) on the persistent halo kernel: half-empty N tile / zero-filled K chunk
+    (2, 32, 32, 32, 0, 32, 3), (1, 16, 24, 16, 0, 32, 3), (1, 16, 16, 32, 0, 64, 3), (1, 16, 16, 64, 0, 32, 3), (1, 16, 16, 64, 0, 96, 3),
 ]
 
 
