@@ -376,15 +376,31 @@ __global__ void __launch_bounds__(256) reduce_vec8_kernel(View x, View dy, const
 #pragma unroll
       for (int j = 0; j < 8; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; }
     }
-    // sm[(pl*GL + gl)*16 + q]: thread (pl = 0.., gl) then sums its group's 16 quantities over the PL pixel lanes
+    // lanes of a warp that share a channel group (GL < 32: lane = pixel lane * GL + gl) meet through shuffles first, so the
+    // shared-memory pass sums 8 warp partials (GL <= 32) or PL <= 4 pixel lanes (GL > 32) instead of up to 128 terms
+    int terms = PL, slot = threadIdx.x;
+    if (GL <= 32) {
+      for (int off = GL; off < 32; off <<= 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sm[threadIdx.x * 16 + j] = d0[j]; sm[threadIdx.x * 16 + 8 + j] = d1[j]; }
+        for (int j = 0; j < 8; ++j) {
+          d0[j] += __shfl_xor_sync(0xffffffffu, d0[j], off);
+          d1[j] += __shfl_xor_sync(0xffffffffu, d1[j], off);
+        }
+      }
+      terms = 8;
+      slot = (threadIdx.x & 31) < GL ? (threadIdx.x >> 5) * GL + gl : -1;
+    }
+    // sm[(term*GL + gl)*16 + q]
+    if (slot >= 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sm[slot * 16 + j] = d0[j]; sm[slot * 16 + 8 + j] = d1[j]; }
+    }
     __syncthreads();
-    // 16*GL sums of PL terms, spread over the 256 threads
+    // 16*GL sums of `terms` partials, spread over the 256 threads
     for (int o = threadIdx.x; o < 16 * GL; o += 256) {
       const int q = o & 15, gg = o >> 4;
       double r = 0.0;
-      for (int l = 0; l < PL; ++l) r += sm[(l * GL + gg) * 16 + q];
+      for (int l = 0; l < terms; ++l) r += sm[(l * GL + gg) * 16 + q];
       const int gch = g - gl + gg;               // channel group of lane gg in this pass
       if (gch < ng) atomicAdd(acc + (q < 8 ? 0 : x.c) + 8 * gch + (q & 7), r);
     }
@@ -487,6 +503,17 @@ inline int resident_grid(K kern, long long work_items, int per_block) {
   return (int)(b < 1 ? 1 : b);
 }
 
+// blocks of a reduction over P pixels with PL pixel lanes per block: 64 pixels per thread when that still fills the
+// device, down to 16 for small tensors (a thread's pixels are a serial chain of load round trips)
+inline int reduce_blocks(long long P, int pl, int resident) {
+  for (int ppt = 64; ppt > 16; ppt >>= 1) {
+    const long long b = (P + (long long)pl * ppt - 1) / ((long long)pl * ppt);
+    if (b >= resident) return (int)b;
+  }
+  const long long b = (P + (long long)pl * 16 - 1) / ((long long)pl * 16);
+  return (int)(b < 1 ? 1 : b);
+}
+
 inline bool vec8_ok(const dnnca_tensor_t* t) {
   return t->dtype == DNNCA_BF16 && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0 &&
          (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
@@ -516,7 +543,7 @@ extern "C" int dnnca_channel_stats(void* stream, const dnnca_tensor_t* x, double
     ChanLayout G = group_layout(x->c);
     // >= 64 pixels per thread: every block ends with 2*C fp64 atomics, so small tensors get few blocks
     static const int occ0 = resident_grid(reduce_vec8_kernel<0>, 1LL << 40, 1);      // resident blocks on this device
-    const int g0 = grid_for(P, G.pl * 64);
+    const int g0 = reduce_blocks(P, G.pl, occ0);
     reduce_vec8_kernel<0><<<g0 < occ0 ? g0 : occ0, 256, 0, (cudaStream_t)stream>>>(mk(x), mk(x), nullptr, stats, G.cl, G.pl, P);
     DNNCA_LAUNCH_CHECK("channel_stats");
     return DNNCA_OK;
@@ -598,7 +625,7 @@ extern "C" int dnnca_bn_bwd_reduce(void* stream, const dnnca_tensor_t* x, const 
   if (vec8_ok(x) && vec8_ok(dy)) {
     ChanLayout G = group_layout(x->c);
     static const int occ1 = resident_grid(reduce_vec8_kernel<1>, 1LL << 40, 1);
-    const int g1 = grid_for(P, G.pl * 64);
+    const int g1 = reduce_blocks(P, G.pl, occ1);
     reduce_vec8_kernel<1><<<g1 < occ1 ? g1 : occ1, 256, 0, (cudaStream_t)stream>>>(mk(x), mk(dy), mean_invstd, sums, G.cl, G.pl, P);
     DNNCA_LAUNCH_CHECK("bn_bwd_reduce");
     return DNNCA_OK;
