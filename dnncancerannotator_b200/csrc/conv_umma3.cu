@@ -18,6 +18,7 @@
 //          byte of x and dy enters shared memory once per (M tile, N tile) pair.
 // dz box {64 ch, 16 px, 8 rows} is the N operand (MN-major, LBO = next 64 output channels).  Partial sums leave with
 // red.global.add like the first-generation kernel; the bias gradient stays a separate channel-sum pass.
+#include <math.h>
 #include <stdlib.h>
 
 #include "umma_common.cuh"
@@ -282,6 +283,15 @@ static int launch_wgrad_halo(cudaStream_t s, const CUtensorMap& mA, const CUtens
   // red.global.add flush of the accumulators (measured: 2 waves = 1.4x slower at 64 channels)
   long long want = (long long)sm_count() / ((long long)mt * nt * groups);
   if (want > ntiles / 4) want = ntiles / 4;
+  // small problems (mulmo_unet's 64x64 / 32x32 levels): with k slices the CTAs spend ~ntiles/k tile times computing and
+  // the flush pushes k * (CTAs per slice) * (accumulator elements) fp32 atomics through L2 (~28 per clock measured:
+  // 64->64@64, B=32 with 148 slices = 111 us, of which 100 us flush), so k* = sqrt(compute / flush-per-slice)
+  {
+    const double t_tile = MODE == WH_PAIRED ? 2500.0 : (BN > 64 ? 3600.0 : 1900.0);        // MMA cycles per pixel tile
+    const double flush_per_slice = (double)mt * nt * groups * (G::NACC * 128.0 * BN) / 28.0;
+    const long long kopt = (long long)(sqrt((double)ntiles * t_tile / flush_per_slice) + 0.5);
+    if (want > kopt) want = kopt;
+  }
   if (want < 1) want = 1;
   if (groups * want > 65535) want = 65535 / groups;
   a.ksplit = (int)want;
