@@ -148,21 +148,28 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (descriptors in uniform registers; an
+    // `if (lane == 0)` body costs ~100 cycles of issue per MMA, more than these N <= 64 MMAs take) =====
+    {
       constexpr uint32_t idesc = make_idesc(128, BN < 16 ? 16 : BN, 0, 0);
+      // descriptor high word: SBO = 8 rows of SWB bytes, version 1, swizzle mode (see kmajor_desc)
+      constexpr uint32_t dhi = ((8u * SWB) >> 4) | (1u << 14) | ((SWB == 128 ? 2u : (SWB == 64 ? 4u : 6u)) << 29);
+      const uint32_t leader = umma_elect() ? 1u : 0u;
+      const bool committer = umma_elect();
       for (int it = 0; it < kiters; ++it) {
         const int s = it % nst;
         mbar_wait(full + s, (it / nst) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + s * G::STAGE), sb = sa + G::A_BYTES;
-        const uint64_t da = kmajor_desc<SWB>(sa), db = kmajor_desc<SWB>(sb);
+        const uint32_t da = kmajor128_desc_lo(sa), db = kmajor128_desc_lo(sb);
 #pragma unroll
         for (int k = 0; k < KC / 16; ++k)   // +32 bytes per K=16 step inside the swizzle row (start-address field is >>4)
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
-        umma_commit(empty + s);             // frees the stage when these MMAs retire
+          umma_bf16_uniform(tmem_base, da + (uint32_t)(2 * k), dhi, db + (uint32_t)(2 * k), dhi, idesc, (it | k) ? 1u : 0u, leader);
+        if (committer) umma_commit(empty + s);             // frees the stage when these MMAs retire
+        __syncwarp();
       }
-      umma_commit(accum);                   // accumulator complete
+      if (committer) umma_commit(accum);                   // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4).. =====
