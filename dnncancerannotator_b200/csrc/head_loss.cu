@@ -391,6 +391,57 @@ extern "C" int dnnca_label_stats(void* stream, const float* label, int64_t count
   return DNNCA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Label smoothing (losses.py:62-67): tfa.image.gaussian_filter2d(label[..., None], filter_shape, sigma) with the default
+// padding 'REFLECT' -- a separable normalised gaussian on taps range(-size//2 + 1, size//2 + 1) (6 -> -2..3), applied
+// along W then along H, (size-1)//2 reflected samples before and size-1-(size-1)//2 after (index -1 -> 1, n -> n-2).
+// ---------------------------------------------------------------------------------------------------------------
+struct GaussTaps { float g[32]; };
+template <bool VERTICAL>
+__global__ void __launch_bounds__(256) gauss1d_kernel(const float* __restrict__ src, float* __restrict__ dst, long long total,
+                                                      int H, int W, int size, int before, GaussTaps taps) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const long long r = i / W;
+    const int y = (int)(r % H);
+    const int n = VERTICAL ? H : W, c = VERTICAL ? y : x;
+    const float* line = VERTICAL ? src + (r - y) * W + x : src + r * W;
+    const int stride = VERTICAL ? W : 1;
+    float acc = 0.f;
+    for (int k = 0; k < size; ++k) {
+      int j = c + k - before;
+      if (j < 0) j = -j;
+      if (j >= n) j = 2 * n - 2 - j;
+      acc += taps.g[k] * line[(long long)j * stride];
+    }
+    dst[i] = acc;
+  }
+}
+
+extern "C" int dnnca_gaussian_filter2d(void* stream, const float* label, int n, int h, int w, int filter_size, float sigma,
+                                       float* tmp, float* out) {
+  DNNCA_CHECK_ARG(label && tmp && out && n > 0 && h > 0 && w > 0, "gaussian_filter2d: bad arguments");
+  DNNCA_CHECK_ARG(filter_size >= 1 && filter_size <= 32 && sigma > 0.f, "gaussian_filter2d: filter_size in 1..32, sigma > 0");
+  const int before = (filter_size - 1) / 2, after = filter_size - 1 - before;
+  DNNCA_CHECK_ARG(before < h && after < h && before < w && after < w, "gaussian_filter2d: REFLECT padding needs size < image");
+  GaussTaps t;
+  const int k0 = -(filter_size / 2) + 1 - ((filter_size & 1) ? 1 : 0);      // python: -size // 2 + 1 (floor division)
+  float sum = 0.f;
+  for (int k = 0; k < filter_size; ++k) {
+    const float d = (float)(k0 + k);
+    t.g[k] = expf(-(d * d) / (2.0f * sigma * sigma));
+    sum += t.g[k];
+  }
+  for (int k = 0; k < filter_size; ++k) t.g[k] /= sum;
+  const long long total = (long long)n * h * w;
+  const int grid = grid_for(total, 256 * 4, 8);
+  gauss1d_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(label, tmp, total, h, w, filter_size, before, t);
+  DNNCA_LAUNCH_CHECK("gaussian_filter2d (rows)");
+  gauss1d_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(tmp, out, total, h, w, filter_size, before, t);
+  DNNCA_LAUNCH_CHECK("gaussian_filter2d (columns)");
+  return DNNCA_OK;
+}
+
 extern "C" void dnnca_label_stats_decode(const dnnca_label_stats_t* h, double* sum, float* mn, float* mx) {
   auto dec = [](uint32_t k) {
     uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;

@@ -347,12 +347,14 @@ class Model:
         plan.allocate(True)
         self._sync_hyper(lr)
         self._load_batch(plan, x, y)
-        if self.loss.label_smoothing:
-            plan.y_in.copy_(self.loss.prepare_labels(plan.y_in))
+        y_metric = plan.y_in
+        if self.loss.label_smoothing:            # the loss sees the smoothed labels, the metrics the raw ones (keras)
+            y_metric = plan.y_in.clone()
+            plan.y_in.copy_(self.loss.prepare_labels(y_metric))
         loss = self._train_on_static(plan)
         ms = self.metric_set()
         if ms:                                   # keras updates the compiled metrics inside every train step
-            ms.update_state(plan.y_in, plan.probs)
+            ms.update_state(y_metric, plan.probs)
         return loss
 
     def _train_on_static(self, plan):
@@ -460,7 +462,7 @@ class Model:
             self._run(plan, 'eval', seq)
             self.last_logits = plan.logits
             if ms:
-                ms.update_state(plan.y_in, plan.probs)
+                ms.update_state(yb if self.loss.label_smoothing else plan.y_in, plan.probs)
             tot += float(plan.per_sample.sum())
             cnt += plan.batch
         out = {'loss': tot / max(cnt, 1)}

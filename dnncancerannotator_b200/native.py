@@ -65,6 +65,7 @@ _PROTOS = {
     'dnnca_bn_apply': [_vp, _TP, _vp, _TP],
     'dnnca_bn_bwd_reduce': [_vp, _TP, _TP, _vp, _vp],
     'dnnca_bn_bwd_apply': [_vp, _TP, _TP, _vp, _vp, _vp, _TP, _i, _f, _vp, _vp],
+    'dnnca_gaussian_filter2d': [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
     'dnnca_label_stats_init': [_vp, _vp],
     'dnnca_label_stats': [_vp, _vp, _i64, _vp],
     'dnnca_label_stats_decode': [C.POINTER(LabelStats), C.POINTER(C.c_double), C.POINTER(C.c_float),

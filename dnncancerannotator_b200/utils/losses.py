@@ -25,10 +25,6 @@ class WeightedCrossentropy:
         self.label_smoothing_filter_size = label_smoothing_filter_size
         self.label_smoothing_sigma = label_smoothing_sigma
         self.name = 'weighted_crossentropy'
-        if self.label_smoothing:
-            raise NotImplementedError(
-                'label_smoothing (losses.py:62-67, tfa.image.gaussian_filter2d) is not built yet: it is an optional '
-                'overlay (configs/additionals/enable_label_smoothing.yaml) outside the graded hot path')
 
     def get_config(self):
         return dict(weight=self.weight, weight_add=self.weight_add, weight_mul=self.weight_mul,
@@ -41,7 +37,18 @@ class WeightedCrossentropy:
         return cls(**config)
 
     def prepare_labels(self, y):
-        return y
+        """losses.py:60-67: the labels the loss sees -- gaussian-filtered on the device when ``label_smoothing`` is set
+        (``dnnca_gaussian_filter2d``), else ``y`` itself.  ``y``: ``[B,H,W]`` float32 CUDA tensor."""
+        if not self.label_smoothing:
+            return y
+        import torch
+        if not (torch.is_tensor(y) and y.is_cuda and y.dtype == torch.float32 and y.dim() == 3):
+            raise ValueError('label smoothing expects a [B,H,W] float32 CUDA tensor')
+        y = y.contiguous()
+        tmp, out = torch.empty_like(y), torch.empty_like(y)
+        N.call('dnnca_gaussian_filter2d', N.stream_ptr(), N.ptr(y), y.shape[0], y.shape[1], y.shape[2],
+               int(self.label_smoothing_filter_size), float(self.label_smoothing_sigma), N.ptr(tmp), N.ptr(out))
+        return out
 
     def native_config(self, numel_times_replicas) -> N.LossConfig:
         """``dnnca_loss_config_t``; grad_scale = 1/(B*H*W*replicas): mean over H,W (losses.py:36),

@@ -187,6 +187,12 @@ DNNCA_API int dnnca_bn_bwd_apply(void* stream, const dnnca_tensor_t* x, const dn
  *   grad_scale = 1/(B*H*W*replicas) ; df = dz*w (* act'(f) if act != NONE) ;
  *   dw += sum dz*f ; db += sum dz.   per_sample/dw/db are accumulated (caller zeroes).
  * ------------------------------------------------------------------------- */
+/* Label smoothing of WeightedCrossentropy (losses.py:62-67): out = tfa.image.gaussian_filter2d(label[..., None],
+ * filter_shape = filter_size, sigma, padding = 'REFLECT')[..., 0] for label [n,h,w] fp32; `tmp` is a scratch tensor of
+ * the same size (rows pass), `out` may not alias `label` or `tmp`. */
+DNNCA_API int dnnca_gaussian_filter2d(void* stream, const float* label, int n, int h, int w, int filter_size, float sigma,
+                            float* tmp, float* out);
+
 typedef struct dnnca_label_stats {
   double sum;
   uint32_t min_key; /* order-preserving uint encoding of a float */

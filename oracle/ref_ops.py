@@ -185,7 +185,13 @@ def weighted_crossentropy(label, logits, weight=None, weight_add=0.0, weight_mul
     assert float(weight) >= 0.0  # losses.py:30
     mask = label * (weight - 1) + torch.ones_like(label)  # losses.py:31
     z = logits[..., 0]
-    bce = torch.clamp(z, min=0) - z * label + torch.log1p(torch.exp(-z.abs()))
+    # [TF-semantics] tf.nn.sigmoid_cross_entropy_with_logits builds max(z,0) and -|z| with `where(z >= 0, ...)`, so its
+    # autodiff gives sigmoid(z) - y everywhere INCLUDING z == 0 (clamp/abs would give 1 - y there); dead-ReLU pixels of
+    # a zero-bias head sit at z == 0 exactly
+    pos = z >= 0
+    relu_z = torch.where(pos, z, torch.zeros_like(z))
+    neg_abs_z = torch.where(pos, -z, z)
+    bce = relu_z - z * label + torch.log1p(torch.exp(neg_abs_z))
     loss = bce * mask
     return loss.mean(dim=(1, 2))
 

@@ -98,8 +98,10 @@ def test_loss_registry_and_config_keys():
     cfg = l.native_config(1000)
     assert cfg.has_weight == 0 and cfg.weight_mul == 3.0 and abs(cfg.grad_scale - 1e-3) < 1e-9
     assert losses.get('WeightedCrossentropy').weight_mul == 1.0
-    with pytest.raises(NotImplementedError):
-        losses.WeightedCrossentropy(label_smoothing=True)
+    ls = losses.WeightedCrossentropy(label_smoothing=True)         # configs/additionals/enable_label_smoothing.yaml
+    assert ls.get_config()['label_smoothing'] is True and ls.label_smoothing_filter_size == 6
+    with pytest.raises(ValueError):                                 # the smoothing runs on the device only
+        ls.prepare_labels(np.zeros((1, 8, 8), np.float32))
     with pytest.raises(ValueError):
         losses.get('mse')
 

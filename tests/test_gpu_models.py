@@ -342,6 +342,34 @@ def test_wide_configs_fp32_mode_exact(cfgname, C, size, B):
     check_masks(logits, r['logits'].numpy(), exact=True)
 
 
+def test_label_smoothing_overlay_matches_oracle():
+    """configs/additionals/enable_label_smoothing.yaml: the loss sees gaussian-filtered labels (losses.py:62-67); loss and
+    gradients of a UNet step in fp32 mode against the oracle with the same overlay."""
+    from dnncancerannotator_b200.synthetic import make_slices
+    opts = dict(n_filters_first=3, n_downsample=2, rate=2, kernel_size=3, conv_stride=1, padding='same')
+    loss = {'class_name': 'WeightedCrossentropy',
+            'config': dict(weight_mul=3.0, label_smoothing=True, label_smoothing_filter_size=6, label_smoothing_sigma=3)}
+    m = product_model('UNetAnnotator', opts, 'fp32')
+    m.build((None, 32, 32, 3))
+    m.compile(loss=loss)
+    ref = rm.build_model('UNetAnnotator', opts, (None, 32, 32, 3), seed=5)
+    m.set_weights(ref.get_weights())
+    x, y = make_slices(2, 32, 32, 3, seed=21)
+    r = ref.train_step_grads(x, y, dict(loss['config']))
+    plain = ref.train_step_grads(x, y, dict(weight_mul=3.0))
+    assert abs(r['data_loss'] - plain['data_loss']) > 1e-3 * abs(plain['data_loss'])       # the overlay changes the loss
+    m.use_cuda_graph = False
+    per = m.forward_backward(x, y).cpu().numpy()
+    g = m.get_grads()
+    names = [k for k in ref.trainable if not k.endswith('/tconv/bias')]
+    allg = np.concatenate([g[k].ravel() for k in names])
+    allr = np.concatenate([r['grads'][k].numpy().ravel() for k in names])
+    assert abs(per.mean() - r['data_loss']) <= 1e-4 * abs(r['data_loss']), (per.mean(), r['data_loss'])
+    assert rel_l2(allg, allr) <= 5e-3, rel_l2(allg, allr)
+    l1 = float(m.train_step(x, y))                                                        # staged path (train_step) too
+    assert abs(l1 - r['loss']) <= 1e-3 * abs(r['loss']), (l1, r['loss'])
+
+
 def test_uint8_host_contract_matches_float32_inputs():
     """data.py:193-206: the raw uint8 slices (image channels and label) divided by 255 ON THE DEVICE -- staged straight
     into the bf16 input buffer -- must give the same step as float32 [0,1] inputs prepared on the host."""

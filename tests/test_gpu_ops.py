@@ -678,3 +678,18 @@ def test_tconv_row_umma(N, shape):
         lib.dnnca_debug_family_count(fam, 1)
     _tconv_dense(N, 'bf16', shape, np.random.default_rng(sum(shape)))
     assert lib.dnnca_debug_family_count(2, 0) == 4, 'the row-Toeplitz tcgen05 kernels did not take this ConvT shape'
+
+
+@pytest.mark.parametrize('shape,size,sigma', [((3, 32, 40), 6, 3.0), ((2, 17, 9), 5, 1.5), ((1, 256, 256), 6, 3.0), ((4, 8, 8), 3, 0.7)])
+def test_gaussian_label_smoothing(N, shape, size, sigma):
+    """losses.py:62-67 (tfa.image.gaussian_filter2d, REFLECT padding) against the oracle restatement."""
+    from oracle import ref_ops as ops
+    rng = np.random.default_rng(sum(shape) + size)
+    y = (rng.random(shape) > 0.7).astype(np.float32)
+    yd = dev(y)
+    tmp, out = torch.empty_like(yd), torch.empty_like(yd)
+    N.call('dnnca_gaussian_filter2d', None, N.ptr(yd), shape[0], shape[1], shape[2], size, sigma, N.ptr(tmp), N.ptr(out))
+    sync()
+    ref = ops.gaussian_filter2d(torch.tensor(y), size, sigma).numpy()
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+    assert abs(float(out.sum()) - float(ref.sum())) <= 1e-3 * max(1.0, float(ref.sum()))
