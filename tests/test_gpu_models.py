@@ -387,9 +387,13 @@ def test_uint8_host_contract_matches_float32_inputs():
         weights.append(m.get_weights())
     assert losses[0][0] == losses[1][0], (losses[0], losses[1])          # same forward pass, bit for bit
     np.testing.assert_allclose(losses[0], losses[1], rtol=1e-4)          # later steps: fp32 atomics reorder the gradient sums
-    # Adam normalises each gradient by its own running magnitude, so a weight whose gradient is ~0 can move by up to
-    # lr = 1e-3 per step in either run: at most one step's worth anywhere, and 2e-4 for all but a handful of weights
+    # Adam normalises each gradient by its own running magnitude (the first update is lr * sign(g)), so a weight whose
+    # gradient is ~0 -- its sign decided by the order of the fp32 atomics -- can move by lr = 1e-3 per step in opposite
+    # directions in the two runs: the hard bound is 2 * lr * steps, and all but a few percent of the weights agree to 2e-4
+    nbig, ntot = 0, 0
     for k in weights[0]:
         d = np.abs(weights[0][k] - weights[1][k])
-        assert d.max() <= 1e-3, (k, d.max())
-        assert (d > 2e-4).mean() <= 0.01, (k, (d > 2e-4).mean())
+        assert d.max() <= 2 * 1e-3 * 4 + 1e-6, (k, d.max())
+        nbig += int((d > 2e-4).sum())
+        ntot += d.size
+    assert nbig <= 0.03 * ntot, (nbig, ntot)
