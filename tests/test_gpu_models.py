@@ -386,7 +386,7 @@ def test_uint8_host_contract_matches_float32_inputs():
         losses.append(ls)
         weights.append(m.get_weights())
     assert losses[0][0] == losses[1][0], (losses[0], losses[1])          # same forward pass, bit for bit
-    np.testing.assert_allclose(losses[0], losses[1], rtol=1e-4)          # later steps: fp32 atomics reorder the gradient sums
+    np.testing.assert_allclose(losses[0], losses[1], rtol=1e-3)          # later steps: fp32 atomics reorder the gradient sums
     # Adam normalises each gradient by its own running magnitude (the first update is lr * sign(g)), so a weight whose
     # gradient is ~0 -- its sign decided by the order of the fp32 atomics -- can move by lr = 1e-3 per step in opposite
     # directions in the two runs: the hard bound is 2 * lr * steps, and all but a few percent of the weights agree to 2e-4
