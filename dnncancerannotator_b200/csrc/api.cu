@@ -284,3 +284,17 @@ extern "C" int dnnca_convtranspose2x2_wgrad(void* stream, const dnnca_tensor_t* 
   }
   return launch_tconv_wgrad_generic((cudaStream_t)stream, x, dy, dk, db);
 }
+
+// ---- pinned host staging buffers (input tail: data.py:110 prefetch -> H2D) ------------------------------------------
+extern "C" int dnnca_host_alloc(size_t bytes, int write_combined, void** out) {
+  DNNCA_CHECK_ARG(out && bytes > 0, "host_alloc: bad arguments");
+  cudaError_t e = cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+  if (e != cudaSuccess) return cuda_fail(e, "host_alloc: cudaHostAlloc");
+  return DNNCA_OK;
+}
+extern "C" int dnnca_host_free(void* p) {
+  if (!p) return DNNCA_OK;
+  cudaError_t e = cudaFreeHost(p);
+  if (e != cudaSuccess) return cuda_fail(e, "host_free: cudaFreeHost");
+  return DNNCA_OK;
+}

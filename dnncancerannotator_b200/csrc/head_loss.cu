@@ -313,8 +313,12 @@ __global__ void __launch_bounds__(256) head_bce_vec_kernel(View f, const float* 
   for (int j = 0; j < 8; ++j) { wr[j] = w[sub * 8 + j]; dwacc[j] = 0.f; }
   float dbacc = 0.f, lossacc = 0.f;
   const long long base = (long long)blockIdx.y * HW;
-  for (long long q = (long long)blockIdx.x * PPB + pslot; q < HW; q += (long long)gridDim.x * PPB) {
-    const long long p = base + q;
+  // the trip count is warp-uniform (the LPP lanes of a pixel meet in shuffles): lanes past the last pixel of a
+  // ragged tail (H*W not a multiple of 256/LPP) re-read the last pixel and are masked out of every write / sum
+  for (long long q0 = (long long)blockIdx.x * PPB; q0 < HW; q0 += (long long)gridDim.x * PPB) {
+    const long long q = q0 + pslot;
+    const bool live = q < HW;
+    const long long p = base + (live ? q : HW - 1);
     const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(f.data) + p * f.cstride + f.coff + sub * 8);
     const uint32_t wd[4] = {raw.x, raw.y, raw.z, raw.w};
     float fv[8];
@@ -325,6 +329,7 @@ __global__ void __launch_bounds__(256) head_bce_vec_kernel(View f, const float* 
     for (int j = 0; j < 8; ++j) z = fmaf(fv[j], wr[j], z);
 #pragma unroll
     for (int o = 1; o < LPP; o <<= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if (!live) continue;
     z += bias;
     const float y = label[p];
     const float mask = y * (weight - 1.f) + 1.f;
@@ -372,9 +377,38 @@ __global__ void __launch_bounds__(256) head_bce_vec_kernel(View f, const float* 
   }
 }
 
+// d(sum of sigmoid outputs)/d(features): df[p,c] = p(1-p) * w[c] * act'(f[p,c])   (callbacks.py:290-299 takes
+// g.gradient(model(x), x); this seeds the dgrad chain at the head)
+template <typename T>
+__global__ void __launch_bounds__(256) head_input_grad_kernel(View f, const float* __restrict__ w,
+                                                             const float* __restrict__ b, View df, int act, float alpha,
+                                                             long long P) {
+  const int F = f.c;
+  const float bias = b ? b[0] : 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const T* fp = reinterpret_cast<const T*>(f.data) + p * f.cstride + f.coff;
+    T* dp = reinterpret_cast<T*>(df.data) + p * df.cstride + df.coff;
+    float z = bias;
+    for (int c = 0; c < F; ++c) z = fmaf(ldf(fp + c), w[c], z);
+    const float pr = 1.f / (1.f + expf(-z));
+    const float dz = pr * (1.f - pr);
+    for (int c = 0; c < F; ++c) stf(dp + c, dz * w[c] * act_grad(ldf(fp + c), act, alpha));
+  }
+}
+
 }  // namespace dnnca
 
 using namespace dnnca;
+
+extern "C" int dnnca_head_input_grad(void* stream, const dnnca_tensor_t* f, const float* w, const float* b,
+                                     const dnnca_tensor_t* df, int act, float alpha) {
+  DNNCA_CHECK_ARG(view_ok(f) && view_ok(df) && same_shape(f, df) && f->dtype == df->dtype && w, "head_input_grad: bad arguments");
+  const long long P = (long long)f->n * f->h * f->w;
+  const int grid = grid_for(P, 256, 8);
+  DNNCA_DISPATCH_DTYPE(f->dtype, head_input_grad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(mk(f), w, b, mk(df), act, alpha, P);)
+  DNNCA_LAUNCH_CHECK("head_input_grad");
+  return DNNCA_OK;
+}
 
 extern "C" int dnnca_label_stats_init(void* stream, dnnca_label_stats_t* lstats) {
   DNNCA_CHECK_ARG(lstats, "label_stats_init: null");

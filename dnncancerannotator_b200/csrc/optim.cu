@@ -29,9 +29,43 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// loss scalar of one step, on the device (keras Model.train_step: compiled loss + regulariser losses, both taken at
+// the weights the forward pass used): out[0] += scale * (mean_b per_sample[b] + sum_i l2[i]*p[i]^2)
+__global__ void __launch_bounds__(256) loss_total_kernel(const float* __restrict__ per_sample, int batch,
+                                                        const float* __restrict__ p, const float* __restrict__ l2,
+                                                        long long count, float scale, float* __restrict__ out) {
+  float acc = 0.f;
+  if (l2)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+      acc = fmaf(l2[i] * p[i], p[i], acc);
+  if (blockIdx.x == 0) {
+    float s = 0.f;
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) s += per_sample[b];
+    acc += s / (float)batch;
+  }
+  acc = warp_sum(acc);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += ws[i];
+    if (t != 0.f || blockIdx.x == 0) atomicAdd(out, scale * t);
+  }
+}
+
 }  // namespace dnnca
 
 using namespace dnnca;
+
+extern "C" int dnnca_loss_total(void* stream, const float* per_sample, int batch, const float* params, const float* l2,
+                                int64_t count, float scale, float* out) {
+  DNNCA_CHECK_ARG(per_sample && batch > 0 && out && (!l2 || (params && count > 0)), "loss_total: bad arguments");
+  const int grid = l2 ? grid_for(count, 256 * 8, 2) : 1;
+  loss_total_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(per_sample, batch, params, l2, count, scale, out);
+  DNNCA_LAUNCH_CHECK("loss_total");
+  return DNNCA_OK;
+}
 
 extern "C" int dnnca_adam_step(void* stream, float* params, const float* grads, float* m, float* v, int64_t count,
                                const float* hyper, int64_t* step, const float* l2) {

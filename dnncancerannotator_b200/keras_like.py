@@ -33,10 +33,43 @@ class History:
             self.history.setdefault(k, []).append(float(v))
 
 
-def _to_device_f32(a, device):
-    if torch.is_tensor(a):
-        return a.to(device=device, dtype=torch.float32, non_blocking=True)
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device, non_blocking=True)
+def _to_device_unit(a, device):
+    """The ONE input-normalisation door of every entry point (``__call__``, ``predict``, ``evaluate``,
+    ``forward_backward``, ``train_step``): float inputs are the reference's contract (float32 in [0,1],
+    data.py:193-206) and are only cast; raw uint8 slices / labels are divided by 255 ON THE DEVICE
+    (``dnnca_u8_to_unit``, data.py:206), so a model trained on uint8 batches sees the same values when it is
+    evaluated or asked to predict on them."""
+    t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype == torch.uint8:
+        src = t.to(device, non_blocking=True).contiguous()
+        out = torch.empty(src.shape, dtype=torch.float32, device=device)
+        N.call('dnnca_u8_to_unit', N.stream_ptr(), N.ptr(src), src.numel(), N.ptr(out), N.F32)
+        return out
+    if t.dtype not in (torch.float32, torch.float64, torch.float16, torch.bfloat16):
+        raise TypeError(f'inputs must be float in [0,1] or raw uint8 slices, got {t.dtype}')
+    return t.to(device=device, dtype=torch.float32, non_blocking=True)
+
+
+class LoadStatus:
+    """What ``load_weights`` returns: the slice of TF's ``CheckpointLoadStatus`` that ``engine.py:75`` calls."""
+
+    def __init__(self, model_names, file_names):
+        self.missing = sorted(set(model_names) - set(file_names))       # model variables the file does not hold
+        self.unused = sorted(set(file_names) - set(model_names))        # file entries no model variable claimed
+
+    def assert_existing_objects_matched(self):
+        if self.missing:
+            raise AssertionError(f'checkpoint holds no value for {len(self.missing)} model variables: {self.missing[:5]}...')
+        return self
+
+    def assert_consumed(self):
+        self.assert_existing_objects_matched()
+        if self.unused:
+            raise AssertionError(f'{len(self.unused)} checkpoint entries were not used: {self.unused[:5]}...')
+        return self
+
+    def expect_partial(self):
+        return self
 
 
 class Model:
@@ -108,6 +141,13 @@ class Model:
         self.metrics = list(metrics or [])      # keras-style specs (metrics.yaml:1-23) or utils.metrics.Metric instances
         self._metric_set = None                 # utils.metrics.MetricSet, created on first use (needs the device)
         self._hyper_dirty = True
+        self._invalidate_graphs()               # the loss configuration is baked into captured launch sequences
+
+    def _invalidate_graphs(self):
+        """Captured CUDA graphs hold the loss configuration (by value), the replica count and the bucket schedule:
+        re-compiling or changing the data-parallel setup drops them (the next steps warm up and re-capture)."""
+        for plan in self._plans.values():
+            plan.graphs.clear()
 
     def metric_set(self):
         """The compiled pixel-threshold metrics (engine.py:273) as device counters, or None."""
@@ -129,6 +169,7 @@ class Model:
 
     def set_weights(self, weights):
         self.params.set_weights(weights)
+        self._sync_replicas()
 
     def get_grads(self):
         return self.params.get_grads()
@@ -136,6 +177,8 @@ class Model:
     # checkpoints: own format (TF checkpoints need TF), same ckpt-<step> naming as engine.py:52
     def save_weights(self, path):
         os.makedirs(os.path.dirname(os.path.abspath(path)) or '.', exist_ok=True)
+        if self._dp is not None and self.params.device is not None and self._dp.world_size > 1:
+            self._dp.average(self.params.state)     # BN moving statistics are rank-local: saved as the replica mean
         w = self.get_weights()
         extra = {}
         if self.params.device is not None:
@@ -144,14 +187,43 @@ class Model:
         np.savez(path + '.npz' if not path.endswith('.npz') else path, **w, **extra)
 
     def load_weights(self, path):
+        """engine.py:75,197,230.  Returns a status object with ``assert_existing_objects_matched()`` /
+        ``assert_consumed()`` / ``expect_partial()`` like TF's checkpoint loader (engine.py:75 chains the first)."""
         p = path if path.endswith('.npz') else path + '.npz'
+        if os.path.isdir(path) and os.path.exists(os.path.join(path, 'weights.npz')):     # a directory written by save()
+            p = os.path.join(path, 'weights.npz')
         z = np.load(p)
-        self.set_weights({k: z[k] for k in z.files if not k.startswith('__')})
-        if '__step' in z.files and self.params.device is not None:
+        names = [k for k in z.files if not k.startswith('__')]
+        known = [k for k in names if k in self.params.specs]
+        self.set_weights({k: z[k] for k in known})
+        if '__step' in z.files and self.params.device is not None and z['__adam_m'].shape == tuple(self.params.m.shape):
             self.params.m.copy_(torch.from_numpy(z['__adam_m']))
             self.params.v.copy_(torch.from_numpy(z['__adam_v']))
             self.params.step.copy_(torch.from_numpy(z['__step']))
-        return self
+        self._sync_replicas()
+        return LoadStatus(list(self.params.specs), names)
+
+    def save(self, path, **kargs):
+        """engine.py:226 ``model.save(path)``: a directory holding the model's class name + constructor config
+        (``config.json``) and every variable incl. the optimizer slots (``weights.npz``); ``load_model`` rebuilds it."""
+        import json
+        os.makedirs(path, exist_ok=True)
+        cfg = dict(class_name=type(self).__name__, config=self.get_config() if hasattr(self, 'get_config') else {},
+                   input_shape=list(self.input_shape) if self.input_shape else None,
+                   compute_dtype='bf16' if self.compute_dtype == torch.bfloat16 else 'fp32',
+                   loss=dict(class_name='WeightedCrossentropy', config=self.loss.get_config()) if self.loss else None,
+                   optimizer=self.optimizer)
+        with open(os.path.join(path, 'config.json'), 'w') as f:
+            json.dump(cfg, f, indent=1, default=str)
+        self.save_weights(os.path.join(path, 'weights'))
+        return path
+
+    def _sync_replicas(self):
+        """Mirrored variables (engine.py:260-263): after anything that rewrites variables on one replica
+        (set_weights / load_weights / enabling data parallelism) rank 0's copy is broadcast to all."""
+        if self._dp is not None and self.params.device is not None and self._dp.world_size > 1:
+            ps = self.params
+            self._dp.broadcast_parameters(ps.params, ps.state, ps.m, ps.v, ps.step)
 
     @staticmethod
     def list_checkpoints(save_dir):
@@ -166,13 +238,17 @@ class Model:
         return OrderedDict(sorted(out.items()))
 
     # ---- plans -----------------------------------------------------------------
-    def _plan(self, batch, height, width):
-        key = (batch, height, width)
+    def _plan(self, batch, height, width, want_input_grad=False):
+        key = (batch, height, width) if not want_input_grad else (batch, height, width, 'dx')
         if key not in self._plans:
             if not self.built:
                 self.build((None, height, width, self.input_shape[-1] if self.input_shape else None))
+            fresh = self.params.device is None
             self.params.materialize(self.device)
-            plan = R.Plan(self.params, batch, height, width, self.input_shape[-1], self.compute_dtype, self.device)
+            if fresh:
+                self._sync_replicas()
+            plan = R.Plan(self.params, batch, height, width, self.input_shape[-1], self.compute_dtype, self.device,
+                          want_input_grad=want_input_grad)
             self._emit(plan)
             self._plans[key] = plan
         return self._plans[key]
@@ -202,20 +278,52 @@ class Model:
         """``model(x)`` -> probabilities ``[B,H,W,1]`` (fp32 torch tensor on the device);
         the logits of the same call are kept in ``self.last_logits`` (keras caches them as
         ``_keras_logits``, losses.py:61)."""
-        if training:
-            raise NotImplementedError('use train_step for training-mode execution')
-        x = _to_device_f32(x, self.device)
+        x = _to_device_unit(x, self.device)
         plan = self._plan(*x.shape[:3])
-        plan.allocate(False)
+        plan.allocate(bool(training))
+        plan.prestaged = False
+        plan.x_in.copy_(x, non_blocking=True)
+        if training:
+            # keras ``model(x, training=True)``: BatchNormalization normalises with the batch statistics and
+            # updates its moving averages; no gradients, no optimizer
+            if not self.trainable_model:
+                raise NotImplementedError(f'{type(self).__name__} is forward/inference-only in this build')
+
+            def seq():
+                plan.zero_step_state()
+                plan.forward(True)
+                plan.head_forward()
+            self._run(plan, 'call_train', seq)
+        else:
+            def seq():
+                plan.forward(False)
+                plan.head_forward()
+            self._run(plan, 'infer', seq)
+        self.last_logits = plan.logits
+        return plan.probs
+
+    def input_gradient(self, x):
+        """d(sum of output probabilities) / d(input), the quantity ``callbacks.py:290-299`` takes with a
+        ``GradientTape`` around ``self.model(batch['x'])`` for its sensitivity maps.  Inference-mode forward
+        (BatchNormalization with its moving statistics, so its backward is the per-channel scale), then the
+        dgrad chain down to the network input (the first layer's dgrad, which training never needs).
+        Returns ``(probs [B,H,W,1], dx [B,H,W,C])`` as fp32 device tensors."""
+        if not self.trainable_model:
+            raise NotImplementedError(f'{type(self).__name__} has no backward pass in this build')
+        x = _to_device_unit(x, self.device)
+        plan = self._plan(*x.shape[:3], want_input_grad=True)
+        plan.allocate(True)
         plan.prestaged = False
         plan.x_in.copy_(x, non_blocking=True)
 
         def seq():
             plan.forward(False)
             plan.head_forward()
-        self._run(plan, 'infer', seq)
+            plan.head_input_grad()
+            plan.backward_inputs()
+        self._run(plan, 'input_grad', seq)
         self.last_logits = plan.logits
-        return plan.probs
+        return plan.probs, plan.input_grad_f32()
 
     def predict(self, x, batch_size=None, verbose=0):
         if isinstance(x, (np.ndarray, torch.Tensor)):
@@ -234,6 +342,10 @@ class Model:
         SUM-all-reduced over NCCL with the loss pre-scaled by 1/world (== averaging)."""
         from . import parallel
         self._dp = parallel.GradAllReduce(process_group, bucket_bytes)
+        if self.built:
+            self.params.materialize(self.device)
+        self._sync_replicas()                   # params, BN state, Adam slots and step counter from rank 0
+        self._invalidate_graphs()
         return self
 
     def _loss_cfg(self, plan):
@@ -256,6 +368,42 @@ class Model:
         N.call('dnnca_adam_step', N.stream_ptr(), N.ptr(ps.params), N.ptr(ps.grads), N.ptr(ps.m), N.ptr(ps.v),
                ps.n_trainable, N.ptr(ps.hyper), N.ptr(ps.step), N.ptr(ps.l2))
 
+    def _loss_total(self, plan):
+        """Scalar loss of the step into the tail of the flat gradient buffer (zeroed with the gradients, all-reduced
+        with them): mean per-sample loss + L2 terms at the weights of THIS forward pass, scaled by 1/replicas."""
+        ps = self.params
+        world = self._dp.world_size if self._dp else 1
+        N.call('dnnca_loss_total', N.stream_ptr(), N.ptr(plan.per_sample), plan.batch, N.ptr(ps.params), N.ptr(ps.l2),
+               ps.n_trainable, 1.0 / world, N.ptr(ps.loss_slot))
+
+    # ---- label / weight validation (losses.py:30, 91-99) ------------------------------------------
+    def _validate_labels(self, plan):
+        """The reference asserts 0 <= label <= 1 (losses.py:91-92), 0 <= positive rate <= 1 (:97-98) and weight >= 0
+        (:30) inside the loss.  Here the label statistics are reduced on the device anyway; they are read back and
+        checked on the eager warm-up passes of every launch sequence (i.e. for the first batches of every
+        shape), and on every step when ``DNNCA_VALIDATE=always`` (costs a device sync per step)."""
+        import ctypes as C
+        ls = torch.zeros(16, dtype=torch.uint8, device=self.device)
+        N.call('dnnca_label_stats_init', N.stream_ptr(), N.ptr(ls))
+        N.call('dnnca_label_stats', N.stream_ptr(), N.ptr(plan.y_in), plan.y_in.numel(), N.ptr(ls))
+        host = N.LabelStats.from_buffer_copy(ls.cpu().numpy().tobytes())
+        ssum, mn, mx = C.c_double(), C.c_float(), C.c_float()
+        N.lib().dnnca_label_stats_decode(C.byref(host), C.byref(ssum), C.byref(mn), C.byref(mx))
+        if not (mx.value <= 1.0 and mn.value >= 0.0):
+            raise ValueError(f'labels must lie in [0, 1] (losses.py:91-92): min {mn.value}, max {mx.value}; '
+                             'uint8 labels are divided by 255 on the device, float labels are taken as given')
+        r = ssum.value / max(plan.y_in.numel(), 1)
+        w = float(self.loss.weight) if self.loss.weight is not None else (1.0 / r if r > 0 else 1.0)
+        w = self.loss.weight_mul * w + self.loss.weight_add
+        if not w >= 0.0:
+            raise ValueError(f'loss weight must be >= 0 (losses.py:30), got {w}')
+
+    def _maybe_validate(self, plan, key):
+        if os.environ.get('DNNCA_VALIDATE', 'warmup') == 'never':
+            return
+        if os.environ.get('DNNCA_VALIDATE') == 'always' or not self.use_cuda_graph or plan.graphs.get(key) is None:
+            self._validate_labels(plan)
+
     def forward_backward(self, x, y):
         """Forward + loss + backward WITHOUT the optimizer step: leaves the gradients in
         ``get_grads()`` (parity tests, gradient inspection).  Returns the per-sample loss ``[B]``."""
@@ -263,12 +411,15 @@ class Model:
             self.compile()
         if not self.trainable_model:
             raise NotImplementedError(f'{type(self).__name__} is forward/inference-only in this build')
-        x, y = _to_device_f32(x, self.device), _to_device_f32(y, self.device)
+        x, y = _to_device_unit(x, self.device), _to_device_unit(y, self.device)
         plan = self._plan(*x.shape[:3])
         plan.allocate(True)
         plan.prestaged = False
         plan.x_in.copy_(x, non_blocking=True)
-        plan.y_in.copy_(self.loss.prepare_labels(y), non_blocking=True)
+        plan.y_in.copy_(y, non_blocking=True)
+        self._maybe_validate(plan, 'fwdbwd')
+        if self.loss.label_smoothing:
+            plan.y_in.copy_(self.loss.prepare_labels(y), non_blocking=True)
         cfg = self._loss_cfg(plan)
         plan._cfg = cfg   # keep the ctypes struct alive for graph capture
 
@@ -276,6 +427,7 @@ class Model:
             plan.zero_step_state()
             plan.forward(True)
             plan.head_loss(cfg)
+            self._loss_total(plan)
             plan.backward()
         self._run(plan, 'fwdbwd', seq)
         self.last_logits = plan.logits
@@ -307,7 +459,7 @@ class Model:
         return plan
 
     def _load_batch(self, plan, x, y):
-        """Brings (x, y) into the plan's static fp32 input buffers, from the prefetch staging if it holds them."""
+        """Brings (x, y) into the plan's static input buffers, from the prefetch staging if it holds them."""
         st = getattr(plan, '_stage', None)
         if st is not None and st['key'] == (id(x), id(y)):
             cur = torch.cuda.current_stream()
@@ -337,7 +489,7 @@ class Model:
 
     def train_step(self, x, y, lr=None):
         """One optimizer step (keras ``Model.train_step``): returns the scalar loss as a device
-        tensor (mean per-sample loss + L2 regulariser terms)."""
+        tensor (mean per-sample loss + L2 regulariser terms; the global mean under data parallelism)."""
         if self.loss is None:
             self.compile()
         if not self.trainable_model:
@@ -347,43 +499,58 @@ class Model:
         plan.allocate(True)
         self._sync_hyper(lr)
         self._load_batch(plan, x, y)
-        y_metric = plan.y_in
-        if self.loss.label_smoothing:            # the loss sees the smoothed labels, the metrics the raw ones (keras)
-            y_metric = plan.y_in.clone()
-            plan.y_in.copy_(self.loss.prepare_labels(y_metric))
+        self._maybe_validate(plan, self._train_key(plan))
         loss = self._train_on_static(plan)
         ms = self.metric_set()
         if ms:                                   # keras updates the compiled metrics inside every train step
-            ms.update_state(y_metric, plan.probs)
+            ms.update_state(plan.y_metric if self.loss.label_smoothing else plan.y_in, plan.probs)
         return loss
+
+    def _train_key(self, plan):
+        return 'train_u8' if getattr(plan, 'prestaged', False) else 'train'
 
     def _train_on_static(self, plan):
-        """The hot path once the batch sits in ``plan.x_in`` / ``plan.y_in``."""
+        """The hot path once the batch sits in ``plan.x_in`` / ``plan.y_in``: ONE launch sequence = one CUDA graph
+        {zero gradients + statistics, [label smoothing], forward, label statistics, fused head + loss, loss scalar,
+        backward with the gradient buckets all-reduced as they complete, join, fused Adam}."""
         cfg = self._loss_cfg(plan)
         plan._cfg = cfg
+        dp = self._dp if (self._dp is not None and self._dp.world_size > 1) else None
+        ps = self.params
+        if self.loss.label_smoothing and getattr(plan, 'y_metric', None) is None:
+            plan.y_metric = torch.empty_like(plan.y_in)      # raw labels for the metrics (keras: the loss alone smooths)
+            plan.y_tmp = torch.empty_like(plan.y_in)
 
-        if self._dp is None:
-            def seq():
-                plan.zero_step_state()
-                plan.forward(True)
-                plan.head_loss(cfg)
+        def seq():
+            plan.zero_step_state()
+            if self.loss.label_smoothing:        # losses.py:62-67 on the device, inside the step's launch sequence
+                plan.y_metric.copy_(plan.y_in)       # device-to-device copy node of the same graph
+                N.call('dnnca_gaussian_filter2d', N.stream_ptr(), N.ptr(plan.y_metric), plan.batch, plan.height,
+                       plan.width, int(self.loss.label_smoothing_filter_size), float(self.loss.label_smoothing_sigma),
+                       N.ptr(plan.y_tmp), N.ptr(plan.y_in))
+            plan.forward(True)
+            plan.head_loss(cfg)
+            self._loss_total(plan)
+            if dp is None:
                 plan.backward()
-                self._adam()
-            self._run(plan, 'train_u8' if getattr(plan, 'prestaged', False) else 'train', seq)
+            else:
+                ready = plan.ready_frontier()
+                dp.begin(ps.grads_full)
+                dp.launch_ready(plan.pending_before_backward)
+                plan.backward(after_op=lambda i: dp.launch_ready(ready[i]))
+                dp.finish()
+            self._adam()
+        key = self._train_key(plan)
+        if dp is not None and os.environ.get('DNNCA_DP_GRAPH', '1') == '0':
+            saved, self.use_cuda_graph = self.use_cuda_graph, False     # escape hatch: eager launches, NCCL uncaptured
+            try:
+                self._run(plan, key, seq)
+            finally:
+                self.use_cuda_graph = saved
         else:
-            def seq_a():
-                plan.zero_step_state()
-                plan.forward(True)
-                plan.head_loss(cfg)
-                plan.backward()
-            self._run(plan, 'train_fb_u8' if getattr(plan, 'prestaged', False) else 'train_fb', seq_a)
-            self._dp.all_reduce(self.params.grads[:max(self.params.n_trainable, 1)])
-            self._run(plan, 'train_adam', self._adam)
+            self._run(plan, key, seq)
         self.last_logits = plan.logits
-        loss = plan.per_sample.mean()
-        if self.params.l2 is not None:
-            loss = loss + (self.params.l2 * self.params.params * self.params.params).sum()
-        return loss
+        return ps.loss_slot[0].clone()     # the slot is re-zeroed by the next step; callers may read the loss a step late
 
     def fit(self, x=None, y=None, validation_data=None, callbacks=None, steps_per_epoch=None, epochs=1,
             validation_freq=1, initial_epoch=0, verbose=1, lr_schedule=None, **kargs):
@@ -447,12 +614,15 @@ class Model:
         if ms:
             ms.reset_state()
         for xb, yb in x:
-            xb, yb = _to_device_f32(xb, self.device), _to_device_f32(yb, self.device)
+            xb, yb = _to_device_unit(xb, self.device), _to_device_unit(yb, self.device)
             plan = self._plan(*xb.shape[:3])
             plan.allocate(False)
             plan.prestaged = False
             plan.x_in.copy_(xb, non_blocking=True)
-            plan.y_in.copy_(self.loss.prepare_labels(yb), non_blocking=True)
+            plan.y_in.copy_(yb, non_blocking=True)
+            self._maybe_validate(plan, 'eval')
+            if self.loss.label_smoothing:
+                plan.y_in.copy_(self.loss.prepare_labels(yb), non_blocking=True)
             cfg = self._loss_cfg(plan)
             plan._cfg_eval = cfg
 

@@ -59,6 +59,8 @@ class Layer:
     """Minimal stand-in for ``keras.layers.Layer``: a name scope + the shared ParamStore/rng."""
 
     def __init__(self, name=None, **kargs):
+        if kargs:       # keras.layers.Layer would reject them too; silently dropping a config key hides typos
+            raise TypeError(f'{type(self).__name__}: unexpected keyword arguments {sorted(kargs)}')
         self.name = name or type(self).__name__.lower()
         self.built = False
         self._ctx = None
@@ -89,7 +91,11 @@ class Layer:
         ps.add(f'{prefix}/moving_var', np.ones(c, np.float32), trainable=False)
 
 
-def _check_supported(rate, kernel_size, conv_stride, padding):
+def _check_supported(rate, kernel_size, conv_stride, padding, trainable=True):
+    if not trainable:
+        raise NotImplementedError(
+            'trainable=False (frozen Conv/BatchNormalization layers, components.py:47-61) is not implemented: the fused '
+            'optimizer updates every variable of the flat parameter buffer')
     if padding != 'same':
         raise NotImplementedError(
             "padding='valid' is accepted by the reference code (components.py:161-163) but used by none of its "
@@ -123,7 +129,7 @@ class Downsample(Layer):
     def __init__(self, filters, rate, kernel_size, conv_stride, bn, n_conv=2, trainable=True, padding='valid',
                  activation='relu', kernel_regularizer=None, **kargs):
         super().__init__(**kargs)
-        _check_supported(rate, kernel_size, conv_stride, padding)
+        _check_supported(rate, kernel_size, conv_stride, padding, trainable)
         self.configs = dict(filters=filters, rate=rate, kernel_size=kernel_size, conv_stride=conv_stride, bn=bn,
                             n_conv=n_conv, trainable=trainable, padding=padding, activation=activation,
                             kernel_regularizer=kernel_regularizer)
@@ -178,7 +184,7 @@ class Upsample(Layer):
     def __init__(self, filters, rate, kernel_size, conv_stride, bn, trainable, n_conv=2, padding='valid',
                  activation='relu', kernel_regularizer=None, **kargs):
         super().__init__(**kargs)
-        _check_supported(rate, kernel_size, conv_stride, padding)
+        _check_supported(rate, kernel_size, conv_stride, padding, trainable)
         self.configs = dict(filters=filters, rate=rate, kernel_size=kernel_size, conv_stride=conv_stride, bn=bn,
                             trainable=trainable, n_conv=n_conv, padding=padding, activation=activation,
                             kernel_regularizer=kernel_regularizer)

@@ -98,7 +98,7 @@ class MulmoUNet(Layer):
                 xin = x[m]
             else:
                 xin = R.TRef(x.buf, x.coff + m, 1)                                        # inputs[..., m:m+1]
-                xin.needs_grad = False
+                xin.needs_grad = plan.want_input_grad
             res_list, _ = enc.emit(plan, xin, out_dst=R.TRef(bott, m * fb, fb))
             if m == self.reference_index:
                 res_ref = res_list
@@ -148,16 +148,16 @@ class UNetAnnotator(Model):
                 xs = []
                 for m in range(x.c):
                     xm = R.TRef(plan.new_buf(x.h, x.w, 1, f'input_cast{m}', zero=True), 0, 1)
-                    xm.needs_grad = False
+                    xm.needs_grad = plan.want_input_grad
                     src = R.TRef(x.buf, m, 1)
-                    src.needs_grad = False
+                    src.needs_grad = plan.want_input_grad
                     plan.add(R.ConvertOp(plan, src, xm))
                     xs.append(xm)
                 x = xs
             else:
                 cpad = (x.c + 7) // 8 * 8 if wide else x.c            # 16-byte aligned pixels for the TMA
                 xb = R.TRef(plan.new_buf(x.h, x.w, cpad, 'input_cast', zero=True), 0, x.c)
-                xb.needs_grad = False
+                xb.needs_grad = plan.want_input_grad
                 plan.add(R.ConvertOp(plan, x, xb))
                 x = xb
         plan.features = self.unet.emit(plan, x)

@@ -71,6 +71,7 @@ _PROTOS = {
     'dnnca_label_stats_decode': [C.POINTER(LabelStats), C.POINTER(C.c_double), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float)],
     'dnnca_head_fwd': [_vp, _TP, _vp, _vp, _vp, _vp],
+    'dnnca_head_input_grad': [_vp, _TP, _vp, _vp, _TP, _i, _f],
     'dnnca_head_bce_fwd_bwd': [_vp, _TP, _vp, _vp, _vp, _vp, C.POINTER(LossConfig), _vp, _vp, _vp, _TP, _i, _f,
                                _vp, _vp],
     'dnnca_threshold_hist': [_vp, _vp, _vp, _i64, _vp, _i, _vp],
@@ -78,6 +79,9 @@ _PROTOS = {
     'dnnca_u8_to_unit': [_vp, _vp, _i64, _vp, _i],
     'dnnca_convert': [_vp, _TP, _TP],
     'dnnca_adam_step': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    'dnnca_host_alloc': [C.c_size_t, _i, C.POINTER(C.c_void_p)],
+    'dnnca_host_free': [_vp],
+    'dnnca_loss_total': [_vp, _vp, _i, _vp, _vp, _i64, _f, _vp],
 }
 _RESTYPES = {'dnnca_last_error': C.c_char_p, 'dnnca_label_stats_decode': None,
              'dnnca_debug_launch_count': C.c_longlong, 'dnnca_debug_family_count': C.c_longlong,

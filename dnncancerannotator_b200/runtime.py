@@ -78,7 +78,12 @@ class ParamStore:
             s['numel'] = n
         self.n_trainable, self.n_state = off_t, off_s
         self.params = torch.zeros(max(off_t, 4), dtype=torch.float32, device=device)
-        self.grads = torch.zeros_like(self.params)
+        # gradient buffer = [n_trainable gradients | 4-float tail]; tail[0] is the step's loss scalar
+        # (dnnca_loss_total), so that it is zeroed with the gradients and, under data parallelism, travels in the
+        # same SUM all-reduce (keras reports the global mean loss under MirroredStrategy)
+        self.grads_full = torch.zeros(max(off_t, 4) + 4, dtype=torch.float32, device=device)
+        self.grads = self.grads_full[:max(off_t, 4)]
+        self.loss_slot = self.grads_full[max(off_t, 4):max(off_t, 4) + 1]
         self.m = torch.zeros_like(self.params)
         self.v = torch.zeros_like(self.params)
         self.state = torch.zeros(max(off_s, 4), dtype=torch.float32, device=device)
@@ -231,6 +236,11 @@ class Op:
     def bwd(self):
         pass
 
+    def grad_params(self):
+        """Names of the trainable variables whose gradients ``bwd`` writes (the data-parallel all-reduce launches a
+        bucket of the flat gradient buffer as soon as every variable in it has been written)."""
+        return ()
+
 
 class ConvOp(Op):
     """layers.Conv2D (components.py:47-50,123-126; multiresunet.py:51-52).
@@ -256,14 +266,21 @@ class ConvOp(Op):
                ps.ptr(self.kernel), ps.ptr(self.bias), self.y.ct(), self.k, self.act[0], self.act[1],
                self.stats.fwd_ptr() if (self.stats and train) else None, *ws_args(self.ws))
 
+    def grad_params(self):
+        return tuple(n for n in (self.kernel, self.bias) if n)
+
     def bwd(self):
         ps = self.p.params
-        s = N.stream_ptr()
-        N.call('dnnca_conv2d_wgrad', s, self.x.ct(), self.x2.ct() if self.x2 else None, self.y.gct(),
+        N.call('dnnca_conv2d_wgrad', N.stream_ptr(), self.x.ct(), self.x2.ct() if self.x2 else None, self.y.gct(),
                ps.gptr(self.kernel), ps.gptr(self.bias), self.k)
+        self.bwd_input()
+
+    def bwd_input(self):
+        """dgrad only (also the input-gradient chain of callbacks.py:290-299, which needs no parameter gradients)."""
         if self.x.needs_grad:
+            ps = self.p.params
             m, a, al = self.x.mask_args()
-            N.call('dnnca_conv2d_dgrad', s, self.y.gct(), ps.ptr(self.kernel), self.x.gct(),
+            N.call('dnnca_conv2d_dgrad', N.stream_ptr(), self.y.gct(), ps.ptr(self.kernel), self.x.gct(),
                    self.x2.gct() if self.x2 else None, self.k, m, a, al, *ws_args(self.ws))
 
 
@@ -282,14 +299,21 @@ class TConvOp(Op):
         N.call('dnnca_convtranspose2x2_fprop', N.stream_ptr(), self.x.ct(), ps.ptr(self.kernel), ps.ptr(self.bias),
                self.y.ct(), self.stats.fwd_ptr() if (self.stats and train) else None, *ws_args(self.ws))
 
+    def grad_params(self):
+        return tuple(n for n in (self.kernel, self.bias) if n)
+
     def bwd(self):
         ps = self.p.params
-        s = N.stream_ptr()
-        N.call('dnnca_convtranspose2x2_wgrad', s, self.x.ct(), self.y.gct(), ps.gptr(self.kernel), ps.gptr(self.bias))
+        N.call('dnnca_convtranspose2x2_wgrad', N.stream_ptr(), self.x.ct(), self.y.gct(), ps.gptr(self.kernel),
+               ps.gptr(self.bias))
+        self.bwd_input()
+
+    def bwd_input(self):
         if self.x.needs_grad:
+            ps = self.p.params
             m, a, al = self.x.mask_args()
-            N.call('dnnca_convtranspose2x2_dgrad', s, self.y.gct(), ps.ptr(self.kernel), self.x.gct(), m, a, al,
-                   *ws_args(self.ws))
+            N.call('dnnca_convtranspose2x2_dgrad', N.stream_ptr(), self.y.gct(), ps.ptr(self.kernel), self.x.gct(), m, a,
+                   al, *ws_args(self.ws))
 
 
 class PoolOp(Op):
@@ -313,6 +337,9 @@ class PoolOp(Op):
         m, a, al = self.x.mask_args()
         dskip = self.x.gct() if self.x.skip_consumed else None
         N.call('dnnca_maxpool2x2_bwd', N.stream_ptr(), self.y.gct(), N.ptr(self.idx), dskip, self.x.gct(), m, a, al)
+
+    def bwd_input(self):
+        self.bwd()
 
 
 class BNStats:
@@ -359,6 +386,9 @@ class BNOp(Op):
                    ps.ptr(f'{self.prefix}/moving_mean'), ps.ptr(f'{self.prefix}/moving_var'), N.ptr(self.ss))
         N.call('dnnca_bn_apply', s, self.x.ct(), N.ptr(self.ss), self.y.ct())
 
+    def grad_params(self):
+        return tuple(n for n in (self.gamma, f'{self.prefix}/beta') if n)
+
     def bwd(self):
         ps, s = self.p.params, N.stream_ptr()
         N.call('dnnca_bn_bwd_reduce', s, self.x.ct(), self.y.gct(), N.ptr(self.mi), self.stats.bwd_ptr())
@@ -366,6 +396,19 @@ class BNOp(Op):
         N.call('dnnca_bn_bwd_apply', s, self.x.ct(), self.y.gct(), N.ptr(self.mi),
                ps.ptr(self.gamma) if self.gamma else None, self.stats.bwd_ptr(), self.x.gct(), act[0], act[1],
                ps.gptr(self.gamma) if self.gamma else None, ps.gptr(f'{self.prefix}/beta'))
+
+
+    def bwd_input(self):
+        """Backward of an INFERENCE-mode BatchNormalization (moving statistics are constants): dx = dy * scale
+        (* act'(x)) -- ``dnnca_bn_bwd_apply`` with zero batch sums and invstd := the folded scale."""
+        c = self.x.c
+        if getattr(self, 'mi_inf', None) is None:
+            self.mi_inf = torch.zeros(2 * c, dtype=torch.float32, device=self.p.device)
+            self.zero_sums = torch.zeros(2 * c, dtype=torch.float64, device=self.p.device)
+        self.mi_inf[c:].copy_(self.ss[:c])
+        act = self.x.act or (N.ACT_NONE, 0.0)
+        N.call('dnnca_bn_bwd_apply', N.stream_ptr(), self.x.ct(), self.y.gct(), N.ptr(self.mi_inf), None,
+               N.ptr(self.zero_sums), self.x.gct(), act[0], act[1], None, None)
 
 
 class ConvertOp(Op):
@@ -380,6 +423,10 @@ class ConvertOp(Op):
         if getattr(self.plan, 'prestaged', False):
             return                       # the batch was written in the activation dtype by dnnca_u8_to_unit
         N.call('dnnca_convert', N.stream_ptr(), self.x.ct(), self.y.ct())
+
+    def bwd_input(self):
+        if self.y.needs_grad and self.x.buf.grad is not None:       # gradient w.r.t. the fp32 network input
+            N.call('dnnca_convert', N.stream_ptr(), self.y.gct(), self.x.gct())
 
 
 class AddReluAffineOp(Op):
@@ -408,8 +455,9 @@ class CallbackOp(Op):
 # plan
 # ----------------------------------------------------------------------------
 class Plan:
-    def __init__(self, params: ParamStore, batch, height, width, channels, dtype, device):
+    def __init__(self, params: ParamStore, batch, height, width, channels, dtype, device, want_input_grad=False):
         self.params, self.dtype, self.device = params, dtype, device
+        self.want_input_grad = bool(want_input_grad)     # callbacks.py:290-299: d(output)/d(input) on request
         self.bufs: list[Buf] = []
         self.ops: list[Op] = []
         self.stats_len = 0
@@ -419,7 +467,7 @@ class Plan:
         self.x_in = torch.zeros(batch, height, width, channels, dtype=torch.float32, device=device)
         self.y_in = torch.zeros(batch, height, width, dtype=torch.float32, device=device)
         self.input = TRef(Buf(self, batch, height, width, channels, 'input', torch.float32, external=self.x_in))
-        self.input.needs_grad = False
+        self.input.needs_grad = self.want_input_grad
         self.features = None          # TRef feeding the head
         self.head = None              # (kernel name, bias name)
         self.allocated_training = None
@@ -486,11 +534,53 @@ class Plan:
                f.gct() if with_grads else None, act[0], act[1], ps.gptr(self.head[0]) if with_grads else None,
                ps.gptr(self.head[1]) if with_grads else None)
 
-    def backward(self):
+    def head_input_grad(self):
+        f = self.features
+        act = f.act or (N.ACT_NONE, 0.0)
+        N.call('dnnca_head_input_grad', N.stream_ptr(), f.ct(), self.params.ptr(self.head[0]), self.params.ptr(self.head[1]),
+               f.gct(), act[0], act[1])
+
+    def backward_inputs(self):
+        """dgrad chain only, down to the network input (no parameter gradients are touched)."""
         for op in reversed(self.ops):
+            if hasattr(op, 'bwd_input'):
+                op.bwd_input()
+
+    def input_grad_f32(self):
+        g = self.input.buf.grad
+        if g is None:
+            raise RuntimeError('this plan was not built with want_input_grad=True')
+        return g
+
+    def backward(self, after_op=None):
+        """The tape: forward list reversed.  ``after_op(i)`` is called after the i-th backward op was launched
+        (data parallelism: launches the gradient buckets that just became complete)."""
+        for i, op in enumerate(reversed(self.ops)):
             op.bwd()
+            if after_op is not None:
+                after_op(i)
+
+    def ready_frontier(self):
+        """ready[i] = lowest offset R of the flat gradient buffer such that every gradient in [R, end) has been
+        written once backward op i has run: the highest end (offset + numel) over the variables still to be written
+        by later backward ops (earlier layers sit at lower offsets, so R falls as the backward pass proceeds)."""
+        specs = self.params.specs
+        ends = []
+        for op in reversed(self.ops):
+            e = 0
+            for n in op.grad_params():
+                sp = specs[n]
+                if sp['trainable']:
+                    e = max(e, sp['offset'] + sp['numel'])
+            ends.append(e)
+        ready, pending = [0] * len(ends), 0
+        for i in range(len(ends) - 1, -1, -1):
+            ready[i] = pending
+            pending = max(pending, ends[i])
+        self.pending_before_backward = pending      # frontier before the first backward op (head gradients are done)
+        return ready
 
     def zero_step_state(self):
-        self.params.grads.zero_()
+        self.params.grads_full.zero_()
         if self.stats_len:
             self.stats.zero_()

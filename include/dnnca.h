@@ -214,6 +214,11 @@ DNNCA_API void dnnca_label_stats_decode(const dnnca_label_stats_t* host_copy, do
 
 DNNCA_API int dnnca_head_fwd(void* stream, const dnnca_tensor_t* f, const float* w, const float* b, float* logits,
                    float* probs);
+/* Seed of the input-gradient chain: df = d(sum_p sigmoid(f.w + b)) / df = p(1-p) * w (* act'(f)).  Replaces the
+ * GradientTape of callbacks.py:290-299 (g.gradient(model(x), x), "sensitivity" maps) at the head; the dgrad entry
+ * points above carry it down to the network input. */
+DNNCA_API int dnnca_head_input_grad(void* stream, const dnnca_tensor_t* f, const float* w, const float* b,
+                                    const dnnca_tensor_t* df, int act, float alpha);
 DNNCA_API int dnnca_head_bce_fwd_bwd(void* stream, const dnnca_tensor_t* f, const float* w, const float* b,
                            const float* label, const dnnca_label_stats_t* lstats, const dnnca_loss_config_t* cfg,
                            float* logits, float* probs, float* per_sample, const dnnca_tensor_t* df, int act,
@@ -258,6 +263,25 @@ DNNCA_API int dnnca_convert(void* stream, const dnnca_tensor_t* src, const dnnca
  * ------------------------------------------------------------------------- */
 DNNCA_API int dnnca_adam_step(void* stream, float* params, const float* grads, float* m, float* v, int64_t count,
                     const float* hyper, int64_t* step, const float* l2);
+
+/* ---------------------------------------------------------------------------
+ * Scalar training loss of one step, on the device (keras Model.train_step as driven by engine.py:126-135: compiled
+ * loss, losses.py:60-72 reduced over the batch, plus the kernel_regularizer terms of kernel_regularizer.yaml:1-4,
+ * both at the weights the forward pass used):
+ *   out[0] += scale * (mean_b per_sample[b] + sum_i l2[i]*params[i]^2)      (l2 may be NULL; caller zeroes out)
+ * `scale` = 1/replicas: the SUM all-reduce of engine.py:260-263 then yields the global mean keras reports.
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_loss_total(void* stream, const float* per_sample, int batch, const float* params, const float* l2,
+                               int64_t count, float scale, float* out);
+
+/* ---------------------------------------------------------------------------
+ * Page-locked host staging buffers for the input tail (the reference's tf.data pipeline ends with prefetch,
+ * data.py:110; here the H2D copy of batch i+1 runs from these buffers while batch i computes).
+ * write_combined != 0 -> cudaHostAllocWriteCombined: DMA reads are not snooped through the CPU caches (for buffers
+ * the CPU only writes).  The one place where the library allocates: HOST memory, on explicit request.
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_host_alloc(size_t bytes, int write_combined, void** out);
+DNNCA_API int dnnca_host_free(void* ptr);
 
 #ifdef __cplusplus
 }

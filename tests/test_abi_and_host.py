@@ -217,3 +217,91 @@ def test_bind_host_to_gpu_is_a_noop_without_nvml_or_gpu():
     before = os.sched_getaffinity(0)
     assert bind_host_to_gpu(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+# ---- round 2: boundary completions ---------------------------------------------------------
+def test_load_status_and_model_save(tmp_path):
+    """engine.py:75 ``load_weights(...).assert_existing_objects_matched()`` and engine.py:226 ``model.save``."""
+    import json
+    from dnncancerannotator_b200.models import tf_models
+    m = tf_models.UNetAnnotator(4, 2, 2, 3, 1, bn=True, padding='same')
+    m.build((None, 32, 32, 3))
+    m.compile(loss={'class_name': 'WeightedCrossentropy', 'config': {'weight_mul': 3.0}})
+    d = m.save(str(tmp_path / 'saved'))
+    cfg = json.load(open(os.path.join(d, 'config.json')))
+    assert cfg['class_name'] == 'UNetAnnotator' and cfg['config']['n_filters_first'] == 4
+    assert cfg['loss']['config']['weight_mul'] == 3.0 and cfg['input_shape'] == [None, 32, 32, 3]
+    m2 = getattr(tf_models, cfg['class_name'])(**cfg['config'], seed=5)
+    m2.build(tuple(cfg['input_shape']))
+    st = m2.load_weights(d)                                      # the directory written by save()
+    assert st.assert_existing_objects_matched() is st and st.assert_consumed() is st
+    for k, v in m.get_weights().items():
+        np.testing.assert_array_equal(v, m2.get_weights()[k])
+    # a checkpoint that lacks variables of the model / holds foreign ones
+    w = m.get_weights()
+    del w['head/bias']
+    np.savez(str(tmp_path / 'partial.npz'), **w, extra=np.zeros(3, np.float32))
+    st = m2.load_weights(str(tmp_path / 'partial'))
+    assert st.missing == ['head/bias'] and st.unused == ['extra']
+    with pytest.raises(AssertionError):
+        st.assert_existing_objects_matched()
+    assert st.expect_partial() is st
+
+
+def test_unknown_layer_kwargs_and_frozen_layers_are_rejected():
+    from dnncancerannotator_b200.models.tf_models import components
+    with pytest.raises(TypeError, match='unexpected keyword'):
+        components.Downsample(4, 2, 3, 1, False, padding='same', dilation=2)
+    with pytest.raises(NotImplementedError, match='trainable=False'):
+        components.Downsample(4, 2, 3, 1, False, padding='same', trainable=False)
+
+
+def test_ready_frontier_and_bucket_schedule():
+    """Data-parallel overlap schedule: a bucket of the flat gradient buffer is issued once every gradient in it has
+    been written; the frontier falls monotonically through the backward pass and ends at 0."""
+    from dnncancerannotator_b200.models import tf_models
+    from dnncancerannotator_b200.parallel import GradAllReduce, bucket_ranges
+    from dnncancerannotator_b200.utils.load import load_config
+    for cfgname in ('unet', 'unet_big', 'mulmo_unet'):
+        cfg = load_config(os.path.join(ROOT, 'configs', cfgname + '.yaml'))
+        m = getattr(tf_models, cfg['model'])(**cfg['model_options'])
+        plan = cpu_plan(m, 1, 32, 3)
+        ready = plan.ready_frontier()
+        ps = m.params
+        assert len(ready) == len(plan.ops)
+        assert all(a >= b for a, b in zip(ready, ready[1:])) and ready[-1] == 0
+        # before the backward pass only the head's gradients (the highest offsets) are complete
+        head_off = ps.specs['head/kernel']['offset']
+        assert plan.pending_before_backward <= head_off
+        # replay the schedule with a recording stand-in for the collective
+        dp = GradAllReduce.__new__(GradAllReduce)
+        dp.world_size, dp.bucket_elems, dp.min_buckets, dp.group = 2, (8 << 20) // 4, 4, None
+        issued = []
+
+        class W:
+            def wait(self):
+                pass
+        import torch.distributed as dist
+        orig = dist.all_reduce
+        dist.all_reduce = lambda t, op=None, group=None, async_op=False: (issued.append(t.numel()), W())[1]
+        try:
+            flat = ps.grads_full
+            dp.begin(flat)
+            written = set()
+            dp.launch_ready(plan.pending_before_backward)
+            for i, op in enumerate(reversed(plan.ops)):
+                written.update(op.grad_params())
+                dp.launch_ready(ready[i])
+                # every gradient inside an issued bucket has been written (or is the head's / the loss slot)
+                for _, (a, b) in dp.launch_log:
+                    for n, sp in ps.specs.items():
+                        if sp['trainable'] and a <= sp['offset'] < b and not n.startswith('head/'):
+                            assert n in written, (cfgname, n, a, b)
+            early = len(dp.launch_log)
+            dp.finish()
+        finally:
+            dist.all_reduce = orig
+        assert sum(issued) == flat.numel() and len(issued) >= 4
+        assert early >= len(issued) - 1, (cfgname, early, len(issued))      # only the last bucket waits for the end
+        covered = sorted(i for _, (a, b) in dp.launch_log for i in (a, b))
+        assert covered[0] == 0 and covered[-1] == flat.numel()

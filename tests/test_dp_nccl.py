@@ -1,0 +1,118 @@
+"""Data parallelism of the CUDA path on real GPUs (engine.py:260-263): two ranks over NCCL on one box.
+
+Parity statement: an R-rank run with per-rank batches must equal the oracle evaluated on R independent sub-batches
+(rank-local BatchNorm statistics, rank-local positive-rate loss weight) whose gradients are averaged; variables are
+mirrored from rank 0; the reported loss is the global mean.  Run with ``gpurun --gpus 2 -- python -m pytest
+tests/test_dp_nccl.py -m gpu`` (skipped on a single-GPU box)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+OPTS = dict(n_filters_first=4, n_downsample=2, rate=2, kernel_size=3, conv_stride=1, bn=True, padding='same')
+LOSS = dict(weight_mul=3.0)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, mode, graph, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    os.environ['DNNCA_DP_GRAPH'] = '1' if graph else '0'
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from dnncancerannotator_b200.models import tf_models
+        from dnncancerannotator_b200.synthetic import make_slices
+        from oracle import ref_models as rm
+        from oracle import ref_ops as ops
+        H = 32
+        m = tf_models.UNetAnnotator(**OPTS, dtype=mode, seed=rank)          # replicas start DIFFERENT ...
+        m.build((None, H, H, 3))
+        m.compile(loss=dict(class_name='WeightedCrossentropy', config=LOSS))
+        ref0 = rm.build_model('UNetAnnotator', OPTS, (None, H, H, 3), seed=10 + rank)
+        ref0.randomize_bn(seed=3 + rank)
+        m.set_weights(ref0.get_weights())
+        m.enable_data_parallel(bucket_bytes=1024)                            # ... and are mirrored from rank 0; many buckets
+        w_after_sync = m.get_weights()
+        batches = [make_slices(3, H, H, 3, seed=1234 + r) for r in range(world)]
+        x, y = batches[rank]
+        # oracle: every replica's sub-batch on its own (own BN statistics, own loss weight), gradients averaged
+        ref = rm.build_model('UNetAnnotator', OPTS, (None, H, H, 3), seed=10)
+        ref.randomize_bn(seed=3)
+        per = [ref.train_step_grads(bx, by, LOSS) for bx, by in batches]
+        avg = {k: sum(p['grads'][k] for p in per) / world for k in ref.trainable}
+        mean_loss = float(np.mean([p['loss'] for p in per]))
+        losses = [float(m.train_step(x, y)) for _ in range(4)]              # eager, eager, capture + replay, replay
+        g = m.get_grads()                                                    # all-reduced gradients of the LAST step
+        w = m.get_weights()
+        # oracle weights after ONE Adam step with the averaged gradient
+        w1 = {}
+        for k in ref.trainable:
+            w1[k], _, _ = ops.adam_step(ref.weights[k], avg[k], torch.zeros_like(avg[k]), torch.zeros_like(avg[k]), 1)
+        res = dict(w_sync=w_after_sync, losses=losses, mean_loss=mean_loss,
+                         log=[(f, b) for f, b in m._dp.launch_log], grads=g, w=w,
+                         avg={k: v.numpy() for k, v in avg.items()}, w1={k: v.numpy() for k, v in w1.items()},
+                         ref_w0={k: v.numpy() for k, v in ref.weights.items()})
+        # first-step weights: re-run one step from the synced weights
+        m2 = tf_models.UNetAnnotator(**OPTS, dtype=mode, seed=0)
+        m2.build((None, H, H, 3))
+        m2.compile(loss=dict(class_name='WeightedCrossentropy', config=LOSS))
+        m2.set_weights(ref.get_weights())
+        m2.enable_data_parallel(bucket_bytes=1024)
+        l1 = float(m2.train_step(x, y))
+        res.update(l1=l1, g1=m2.get_grads(), w_step1=m2.get_weights())
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64).ravel() - np.asarray(b, np.float64).ravel()) /
+                 max(np.linalg.norm(np.asarray(b, np.float64).ravel()), 1e-30))
+
+
+@pytest.mark.parametrize('mode,graph', [('fp32', True), ('fp32', False), ('bf16', True)])
+def test_two_rank_nccl_step_matches_oracle_subbatch_average(mode, graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), mode, graph, out), nprocs=world, join=True)
+    a, b = out[0], out[1]
+    tol = 2e-3 if mode == 'fp32' else 0.3
+    # mirrored variables: rank 1 took rank 0's values when data parallelism was enabled
+    for k in a['w_sync']:
+        np.testing.assert_array_equal(a['w_sync'][k], b['w_sync'][k])
+        np.testing.assert_array_equal(a['w_sync'][k], a['ref_w0'][k])
+    # one step from the oracle's weights: all-reduced gradients == average of the oracle's per-replica gradients
+    names = [k for k in a['avg'] if not k.endswith('/tconv/bias')]
+    got = np.concatenate([a['g1'][k].ravel() for k in names])
+    want = np.concatenate([a['avg'][k].ravel() for k in names])
+    assert _rel(got, want) <= tol, _rel(got, want)
+    for k in names:
+        np.testing.assert_array_equal(a['g1'][k], b['g1'][k])              # both ranks hold the same reduced gradient
+    assert abs(a['l1'] - a['mean_loss']) <= (1e-4 if mode == 'fp32' else 2e-2) * abs(a['mean_loss'])
+    assert a['l1'] == b['l1']                                              # the loss scalar travels in the all-reduce
+    if mode == 'fp32':
+        for k in names:
+            assert _rel(a['w_step1'][k], a['w1'][k]) < 5e-3 or np.abs(a['w_step1'][k] - a['w1'][k]).max() < 2e-4, k
+    # replicas stay mirrored over the four steps (eager, eager, captured graph, replay)
+    for k in a['w']:
+        np.testing.assert_array_equal(a['w'][k], b['w'][k]) if 'moving' not in k else None
+    assert all(np.isfinite(a['losses'])) and a['losses'] == b['losses']
+    # overlap schedule: several buckets, all but the last issued before the backward pass ended (frontier > 0)
+    log = a['log']
+    assert len(log) >= 4 and sum(1 for f, _ in log if f > 0) >= len(log) - 1, log
