@@ -42,6 +42,9 @@ def parse():
                     help='batch of the CPU arm (measured on the B200 host, 16 threads: 181 slices/s at 4, 318 at 8, 405 at 16, 492 at 32)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--forward', action='store_true',
+                    help='forward-only (inference) batch sweep: --config multiresunet --forward --batches 1,2,...')
+    ap.add_argument('--batches', default='1,2,4,8,16,32,64,128,256')
     ap.add_argument('--no-secondary', dest='secondary', action='store_false',
                     help='skip the short unet_big / mulmo_unet runs appended to the default (unet.yaml) line')
     ap.add_argument('--no-f32-e2e', action='store_true', help='skip the float32-input variant of the e2e loop')
@@ -331,6 +334,113 @@ def secondary_line(cfgname, B, args, world, rank, local):
     return line
 
 
+def run_forward_sweep(args):
+    """BASELINE configs[4]: configs/multiresunet.yaml evaluate / inference sweep, forward only, batch 1..256.
+    Per batch size: W untimed calls (fold + pack pass, eager warm-ups, graph capture), then K graph replays with the
+    batch resident in HBM (CUDA events), and the same through the public call with HOST uint8 slices in and the
+    probability maps read back (e2e).  With N ranks every rank runs its own replica (no communication)."""
+    import gc
+    import torch
+    import torch.distributed as dist
+    from dnncancerannotator_b200 import native as N
+    from dnncancerannotator_b200 import hostmem
+    from dnncancerannotator_b200.models import tf_models
+    from dnncancerannotator_b200.synthetic import make_slices
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    cfg = load_cfg(args.config)
+    S = args.size
+    Cc = cfg['model_options'].get('n_channels', args.channels)
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
+    lib = N.lib()
+    rows = []
+    for B in [int(b) for b in args.batches.split(',')]:
+        m = getattr(tf_models, cfg['model'])(**cfg['model_options'], dtype=args.dtype)
+        m.build((None, S, S, Cc))
+        x8, _ = make_slices(B, S, S, Cc, seed=1234 + rank, as_uint8=True)
+        xh = hostmem.pinned_like(x8, write_combined=False)
+        xd = torch.from_numpy(x8).cuda().float().div_(255.0)
+        for _ in range(max(args.warmup, 4)):
+            m(xd)
+        plan = m._plan(B, S, S)
+        torch.cuda.synchronize()
+        steps = args.steps if B >= 16 else args.steps * 4
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g = plan.graphs['infer']
+        e0.record()
+        for _ in range(steps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        # e2e: host uint8 -> device (/255 on the device) -> forward -> probabilities back on the host
+        out_h = torch.empty((B, S, S, 1), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            out_h.copy_(m(xh), non_blocking=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(max(steps // 4, 3)):
+            out_h.copy_(m(xh), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1) / max(steps // 4, 3)
+        # launches and tensor-core share (one eager pass)
+        m.use_cuda_graph = False
+        for f in range(3):
+            lib.dnnca_debug_family_count(f, 1)
+        lib.dnnca_debug_launch_count(1)
+        with N.Profiler() as prof:
+            m(xd)
+        launches = int(lib.dnnca_debug_launch_count(1))
+        fam = [int(lib.dnnca_debug_family_count(f, 0)) for f in range(3)]
+        agg = prof.summary()
+        conv_ms = sum(v['ms'] for v in agg.values() if v['flops'])
+        tot_ms = sum(v['ms'] for v in agg.values())
+        # FLOP convention of SURVEY 8d: LOGICAL channel counts (the physically padded channels do not count)
+        conv_fl = 0
+        for op in plan.ops:
+            if type(op).__name__ == '_FoldedConv':
+                conv_fl += 2 * op.x.n * op.x.h * op.x.w * op.xs.c * op.cout * op.k * op.k
+            elif type(op).__name__ == '_FoldedTConv':
+                conv_fl += 2 * op.x.n * op.x.h * op.x.w * op.xs.c * op.cout * 4
+        t = torch.tensor([ms, e2e_ms], device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        rows.append({'batch': B, 'ms_per_forward': round(ms, 4), 'slices_per_s': round(B * world / (ms / 1e3), 1),
+                     'e2e_slices_per_s': round(B * world / (e2e_ms / 1e3), 1), 'launches': launches,
+                     'conv_launches_generic_small_tcgen05': fam,
+                     'whole_forward_tflops': round(conv_fl / (ms * 1e9), 1),
+                     'conv_kernels_tflops': round(conv_fl / conv_ms / 1e9, 1) if conv_ms else None,
+                     'conv_share_of_forward': round(conv_ms / tot_ms, 3) if tot_ms else None,
+                     'gflop_per_slice_logical': round(conv_fl / B / 1e9, 2),
+                     'breakdown': [{'kernel': k, 'ms': round(d['ms'], 4), 'calls': d['calls'],
+                                    'gbs': round(d['bytes'] / d['ms'] / 1e6, 1) if d['ms'] else None}
+                                   for k, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])[:14]]})
+        del m, plan, g, xd, xh, out_h
+        gc.collect()
+        torch.cuda.empty_cache()
+    if rank == 0:
+        best = max(rows, key=lambda r: r['slices_per_s'])
+        line = {'metric': 'forward_slices_per_sec', 'value': best['slices_per_s'], 'unit': UNIT, 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': best['ms_per_forward'], 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+                'config': {'workload': f'configs/{args.config}.yaml {cfg["model"]} forward (inference, BatchNorm folded), '
+                                       f'{S}x{S}x{Cc} slices, batch sweep {args.batches}; value = best batch ({best["batch"]})',
+                           'parallelism': f'replicas x{world}', 'cuda_graph': True},
+                'e2e': {'value': best['e2e_slices_per_s'], 'unit': UNIT, 'h2d_bytes_per_step': best['batch'] * S * S * Cc,
+                        'd2h_bytes_per_step': best['batch'] * S * S * 4},
+                'gpu_launches': best['launches'] * args.steps, 'sweep': rows,
+                'peaks': {'bf16_tflops_burst': peaks.get('bf16_tflops'), 'hbm_gbs': peaks.get('hbm_gbs')}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -455,5 +565,7 @@ if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.forward:
+        run_forward_sweep(a)
     else:
         run_ours(a)

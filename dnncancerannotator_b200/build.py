@@ -32,6 +32,7 @@ UNITS = [
     ('optim.cu', 'optim', []),
     ('metrics.cu', 'metrics', []),
     ('tconv_small.cu', 'tconv_small', []),
+    ('input_tail.cu', 'input_tail', []),
 ]
 for dt in (0, 1):
     for kind in (0, 1, 2):

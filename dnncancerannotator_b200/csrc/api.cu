@@ -87,6 +87,8 @@ int try_tconv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const float*, cons
 int try_tconv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float, void*, size_t);
 int try_conv_wgrad_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*, int);
 int try_tconv_wgrad_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
+int prepack_conv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, int, void*, size_t);
+int prepack_tconv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, void*, size_t);
 // tcgen05 row-Toeplitz family for few-channel 3x3 convs (conv_row_umma.cu)
 int try_conv_fprop_row(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, float);
 int try_conv_dgrad_row(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float);
@@ -150,13 +152,20 @@ extern "C" size_t dnnca_conv_workspace_bytes(int taps, int cin, int cout) {
 extern "C" int dnnca_conv2d_fprop(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w,
                                   const float* bias, const dnnca_tensor_t* y, int ksize, int act, float alpha,
                                   double* stats, void* workspace, size_t workspace_bytes) {
-  DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && w, "conv2d_fprop: bad tensor arguments");
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && (w || workspace), "conv2d_fprop: bad tensor arguments");
   DNNCA_CHECK_ARG(same_nhw(x, y) && x->dtype == y->dtype, "conv2d_fprop: x and y must share n,h,w and dtype ('same' padding, stride 1)");
   DNNCA_CHECK_ARG(second_ok(x, x2), "conv2d_fprop: x2 must share n,h,w and dtype with x");
   DNNCA_CHECK_ARG(act_ok(act), "conv2d_fprop: unknown activation %d", act);
   if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_fprop: kernel size %d (only 1 and 3 are used by the reference models)", ksize);
   cudaStream_t s = (cudaStream_t)stream;
   int r = 0;
+  if (!w) {     // prepacked: `workspace` still holds the tensor-core packing of an earlier call with the same weights
+    r = g_force_generic ? 0 : try_conv_fprop_umma(s, x, x2, nullptr, bias, y, ksize, act, alpha, workspace, workspace_bytes, stats);
+    if (r < 0) return r;
+    if (r == 0) DNNCA_UNSUPPORTED("conv2d_fprop: w == NULL (prepacked weights) needs a shape the tensor-core kernels serve");
+    if (r == 1 && stats) return dnnca_channel_stats(stream, y, stats);
+    return DNNCA_OK;
+  }
   if (!g_force_generic && ksize == 3 && x->dtype == DNNCA_BF16) {
     r = try_conv_fprop_row(s, x, x2, w, bias, y, act, alpha);
     if (r < 0) return r;
@@ -238,9 +247,15 @@ extern "C" int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const d
 extern "C" int dnnca_convtranspose2x2_fprop(void* stream, const dnnca_tensor_t* x, const float* k, const float* bias,
                                             const dnnca_tensor_t* y, double* stats, void* workspace,
                                             size_t workspace_bytes) {
-  DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && k, "convtranspose2x2_fprop: bad tensor arguments");
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && (k || workspace), "convtranspose2x2_fprop: bad tensor arguments");
   DNNCA_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && x->dtype == y->dtype,
                   "convtranspose2x2_fprop: y must be [n,2h,2w,cout] with x's dtype");
+  if (!k) {     // prepacked (see conv2d_fprop)
+    int rp = g_force_generic ? 0 : try_tconv_fprop_umma((cudaStream_t)stream, x, nullptr, bias, y, workspace, workspace_bytes);
+    if (rp < 0) return rp;
+    if (rp == 0) DNNCA_UNSUPPORTED("convtranspose2x2_fprop: k == NULL (prepacked weights) needs a shape the tensor-core kernels serve");
+    return stats ? dnnca_channel_stats(stream, y, stats) : DNNCA_OK;
+  }
   int r = (g_force_generic || x->dtype != DNNCA_BF16) ? 0 : try_tconv_fprop_row((cudaStream_t)stream, x, k, bias, y);
   if (r == 0 && !g_force_generic) r = try_tconv_fprop_small((cudaStream_t)stream, x, k, bias, y);
   if (r == 0 && !g_force_generic) r = try_tconv_fprop_umma((cudaStream_t)stream, x, k, bias, y, workspace, workspace_bytes);
@@ -296,5 +311,24 @@ extern "C" int dnnca_host_free(void* p) {
   if (!p) return DNNCA_OK;
   cudaError_t e = cudaFreeHost(p);
   if (e != cudaSuccess) return cuda_fail(e, "host_free: cudaFreeHost");
+  return DNNCA_OK;
+}
+
+// ---- weight packing for prepacked (w == NULL) inference calls ---------------------------------------------------------
+extern "C" int dnnca_conv2d_prepack(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w,
+                                    const dnnca_tensor_t* y, int ksize, void* workspace, size_t workspace_bytes) {
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && w && workspace && second_ok(x, x2), "conv2d_prepack: bad arguments");
+  if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_prepack: kernel size %d", ksize);
+  const int r = g_force_generic ? 0 : prepack_conv_fprop_umma((cudaStream_t)stream, x, x2, w, y, ksize, workspace, workspace_bytes);
+  if (r < 0) return r;
+  if (r == 0) DNNCA_UNSUPPORTED("conv2d_prepack: this shape is not served by the tensor-core kernels (pass w to conv2d_fprop instead)");
+  return DNNCA_OK;
+}
+extern "C" int dnnca_convtranspose2x2_prepack(void* stream, const dnnca_tensor_t* x, const float* k, const dnnca_tensor_t* y,
+                                              void* workspace, size_t workspace_bytes) {
+  DNNCA_CHECK_ARG(view_ok(x) && view_ok(y) && k && workspace, "convtranspose2x2_prepack: bad arguments");
+  const int r = g_force_generic ? 0 : prepack_tconv_fprop_umma((cudaStream_t)stream, x, k, y, workspace, workspace_bytes);
+  if (r < 0) return r;
+  if (r == 0) DNNCA_UNSUPPORTED("convtranspose2x2_prepack: this shape is not served by the tensor-core kernels");
   return DNNCA_OK;
 }

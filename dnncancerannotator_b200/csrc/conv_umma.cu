@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
       tmem_ld_wait();
       const int ncol = n0 + c0;               // first GEMM column of this chunk
       if (!inside || ncol >= a.n_total) continue;
-      epilogue_chunk<CH>(a, v, n, gy, gx, ncol);
+      epilogue_chunk<CH>(a, v, n, gy, gx, ncol, a.n_total - ncol);
     }
   }
   tc_fence_before();
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
 }
 
 static bool bf16_view16(const dnnca_tensor_t* t);
+static bool bf16_view8(const dnnca_tensor_t* t);
 static bool bf16_view_in(const dnnca_tensor_t* t);
 
 // ---------------------------------------------------------------- wgrad
@@ -515,10 +516,33 @@ static int pick_bn(int unit, int ntotal) {
 }
 
 static int pad16(int c) { return (c + 15) / 16 * 16; }
-size_t umma_pack_bytes(int taps, int cin, int cout) { return (size_t)taps * pad16(cin) * pad16(cout) * 2; }
+static int pad64(int c) { return (c + 63) / 64 * 64; }
+// room for either K padding (multiples of 16, or of 64 when pick_kchunk prefers 64-channel chunks)
+size_t umma_pack_bytes(int taps, int cin, int cout) { return (size_t)taps * pad64(cin) * pad16(cout) * 2; }
 
-static int pack(cudaStream_t s, const float* w, void* out, int mode, int taps, int cin, int cout) {
-  const int kp = pad16(cin);
+// K chunk (TMA box / swizzle width) of a single-input operand with ANY channel count: channels beyond the tensor are
+// zero-filled by the TMA (activations) and by the pack kernel (weights), so K may be padded up to whole chunks.
+// cost = chunks * (fixed per-chunk pipeline step ~ 32 channels of work + chunk width); MultiResUnet's 8/24/40/72/120/144
+// /216/432/864-channel tensors otherwise fall to 16-channel chunks (9 of them for 144 channels)
+static int pick_kchunk(int c, int* kp) {
+  int best = 0, bestcost = 1 << 30;
+  for (int kc : {64, 32, 16}) {
+    const int n = (c + kc - 1) / kc, cost = n * (32 + kc);
+    if (cost < bestcost) { bestcost = cost; best = kc; *kp = n * kc; }
+  }
+  return best;
+}
+// N tile of fprop / ConvT fprop for any N that is a multiple of 8: the smallest of 16..256 covering it, 256-column tiles
+// beyond (the weight TMA zero-fills rows >= N, the epilogue stores 8-column groups below N only)
+static int pick_bn_cover(int n) {
+  for (int bn : {16, 32, 64, 128, 256})
+    if (n <= bn) return bn;
+  return 256;
+}
+
+static int pack(cudaStream_t s, const float* w, void* out, int mode, int taps, int cin, int cout, int kp = 0) {
+  if (!w) return DNNCA_OK;          // workspace still holds the packing of an earlier call (dnnca.h: inference with unchanged weights)
+  if (kp <= 0) kp = pad16(cin);
   const long long total = (long long)taps * kp * cout;
   pack_weights_kernel<<<grid_for(total, 256 * 4, 4), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(out), mode, taps, cin, cout, kp);
   DNNCA_LAUNCH_CHECK("pack_weights");
@@ -527,6 +551,11 @@ static int pack(cudaStream_t s, const float* w, void* out, int mode, int taps, i
 
 static bool bf16_view16(const dnnca_tensor_t* t) {
   return t && t->dtype == DNNCA_BF16 && t->c % 16 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
+}
+// output written in 16-byte groups of 8 channels
+static bool bf16_view8(const dnnca_tensor_t* t) {
+  return t && t->dtype == DNNCA_BF16 && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0 &&
          (reinterpret_cast<uintptr_t>(t->data) & 15) == 0;
 }
 // operand that is only READ through the TMA: any channel count (missing channels are zero-filled out of bounds)
@@ -544,32 +573,37 @@ static bool halo_enabled() {
   return v == 1;
 }
 
+static thread_local bool g_pack_only = false;
+
 // returns 1 handled / 0 not covered / <0 error
 // returns 2 when the kernel also accumulated the BatchNorm statistics into `stats` (else the caller runs channel_stats)
 int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w, const float* bias,
                         const dnnca_tensor_t* y, int k, int act, float alpha, void* ws, size_t ws_bytes, double* stats) {
-  if (!ws || !bf16_view16(y)) return 0;
-  if (x2 ? (!bf16_view16(x) || !bf16_view16(x2)) : !bf16_view_in(x)) return 0;
+  if (!ws || !bf16_view8(y)) return 0;
+  if (x2 ? (!bf16_view16(x) || !bf16_view16(x2) || !bf16_view16(y)) : !bf16_view_in(x)) return 0;
   const int ca = x->c, cb = x2 ? x2->c : 0, cin = ca + cb, cout = y->c, taps = k * k;
   if (ws_bytes < umma_pack_bytes(taps, cin, cout)) return 0;
-  const int kc = cb ? gcd_kc(pick_kc(ca), pick_kc(cb)) : pick_kc(pad16(ca));
-  const int bn = pick_bn(cout, cout);
+  int kp = cin;
+  const int kc = cb ? gcd_kc(pick_kc(ca), pick_kc(cb)) : pick_kchunk(ca, &kp);
+  const int exact = pick_bn(cout, cout);
+  const int bn = (exact >= 32 || exact == cout) ? exact : pick_bn_cover(cout);      // a dividing tile of >= 32 columns, else one covering tile
   if (!kc || !bn) return 0;
-  int r = pack(s, w, ws, 0, taps, cin, cout);
-  if (r != DNNCA_OK) return r;
   CUtensorMap mA, mB, mW;
   if (!act_map(&mA, x, kc, 1)) return 0;
   mB = mA;
   if (x2 && !act_map(&mB, x2, kc, 1)) return 0;
-  if (!weight_map(&mW, ws, pad16(cin), cout, taps, kc, bn)) return 0;
+  if (!weight_map(&mW, ws, kp, cout, taps, kc, bn)) return 0;
+  int r = pack(s, w, ws, 0, taps, cin, cout, kp);
+  if (r != DNNCA_OK) return r;
+  if (g_pack_only) return 1;            // dnnca_conv2d_prepack: the packing a later w == NULL call of this layer expects
   UArgs a{};
-  a.taps = taps; a.ktap = k; a.sx = 1; a.offbase = -(k / 2); a.c_a = cb ? ca : pad16(ca); a.c_b = cb; a.H = x->h; a.W = x->w;
+  a.taps = taps; a.ktap = k; a.sx = 1; a.offbase = -(k / 2); a.c_a = cb ? ca : kp; a.c_b = cb; a.H = x->h; a.W = x->w;
   a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + 7) / 8; a.epi = EPI_FPROP; a.act = act; a.alpha = alpha; a.bias = bias;
   a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
   a.mask = nullptr; a.n_total = cout; a.cout_t = cout; a.nimg = x->n;
   if (k == 3 && (kc == 64 || (!x2 && ca < 64)) && halo_enabled()) {
     a.stats = stats;
-    r = try_conv3x3_halo(s, x, x2, ws, kc == 64 ? cin : pad16(cin), cout, a);
+    r = try_conv3x3_halo(s, x, x2, ws, kp, cout, a);
     if (r != 0) return (r == 1 && stats) ? 2 : r;
     a.stats = nullptr;
   }
@@ -610,23 +644,25 @@ int try_conv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dz, const float* w
 
 int try_tconv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const float* kw, const float* bias, const dnnca_tensor_t* y,
                          void* ws, size_t ws_bytes) {
-  if (!ws || !bf16_view16(x) || !bf16_view16(y)) return 0;
+  if (!ws || !bf16_view_in(x) || !bf16_view16(y)) return 0;
   const int cin = x->c, cout = y->c;
   if (ws_bytes < umma_pack_bytes(4, cin, cout)) return 0;
-  const int kc = pick_kc(cin);
+  int kp = cin;
+  const int kc = cin % 16 == 0 ? pick_kc(cin) : pick_kchunk(cin, &kp);      // any input width: K padded with zeros
   const int bn = pick_bn(cout, 4 * cout);
   if (!kc || !bn) return 0;
-  int r = pack(s, kw, ws, 2, 4, cin, cout);       // [tap*Cout + co][Cin]: one GEMM with N = 4*Cout
-  if (r != DNNCA_OK) return r;
   CUtensorMap mA, mW;
   if (!act_map(&mA, x, kc, 1)) return 0;
-  if (!weight_map(&mW, ws, cin, 4 * cout, 1, kc, bn)) return 0;
+  if (!weight_map(&mW, ws, kp, 4 * cout, 1, kc, bn)) return 0;
+  int r = pack(s, kw, ws, 2, 4, cin, cout, kp);   // [tap*Cout + co][Cin]: one GEMM with N = 4*Cout
+  if (r != DNNCA_OK) return r;
+  if (g_pack_only) return 1;
   UArgs a{};
-  a.taps = 1; a.ktap = 1; a.sx = 1; a.offbase = 0; a.c_a = cin; a.c_b = 0; a.H = x->h; a.W = x->w;
+  a.taps = 1; a.ktap = 1; a.sx = 1; a.offbase = 0; a.c_a = kp; a.c_b = 0; a.H = x->h; a.W = x->w;
   a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + 7) / 8; a.epi = EPI_TCONV; a.act = DNNCA_ACT_NONE; a.alpha = 0.f; a.bias = bias;
   a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = 4 * cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
   a.mask = nullptr; a.n_total = 4 * cout; a.cout_t = cout;
-  if (kc == 64 && halo_enabled()) {
+  if (kc == 64 && kp == cin && halo_enabled()) {
     r = try_tconv_fprop_halo(s, x, ws, cin, cout, a);
     if (r != 0) return r;
   }
@@ -661,6 +697,22 @@ int try_tconv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dy, const float* 
   if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, dx->n, bn);
   if (kc == 32) return dispatch_bn<32>(s, mA, mA, mW, a, dx->n, bn);
   return dispatch_bn<16>(s, mA, mA, mW, a, dx->n, bn);
+}
+
+// packing only: what dnnca_conv2d_prepack / dnnca_convtranspose2x2_prepack run (1 packed / 0 shape not served / <0 error)
+int prepack_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w,
+                            const dnnca_tensor_t* y, int k, void* ws, size_t ws_bytes) {
+  g_pack_only = true;
+  const int r = try_conv_fprop_umma(s, x, x2, w, nullptr, y, k, DNNCA_ACT_NONE, 0.f, ws, ws_bytes, nullptr);
+  g_pack_only = false;
+  return r;
+}
+int prepack_tconv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const float* kw, const dnnca_tensor_t* y, void* ws,
+                             size_t ws_bytes) {
+  g_pack_only = true;
+  const int r = try_tconv_fprop_umma(s, x, kw, nullptr, y, ws, ws_bytes);
+  g_pack_only = false;
+  return r;
 }
 
 }  // namespace dnnca

@@ -307,6 +307,44 @@ __device__ __forceinline__ uint4* vptr_w(const View& v, long long p, int g) {
   return reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(v.data) + p * v.cstride + v.coff + 8 * g);
 }
 
+// 8 channels (one 16-byte access) per thread-iteration; the three affine tables sit in shared memory
+__global__ void __launch_bounds__(256) add_relu_affine_vec8_kernel(View a, const float* __restrict__ fa, View b,
+                                                                  const float* __restrict__ fb,
+                                                                  const float* __restrict__ fo, View y, long long P) {
+  extern __shared__ float tab[];                    // [6][C]: sa ta sb tb so to
+  const int C = a.c, ng = C / 8;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    tab[i] = fa ? fa[i] : 1.f;          tab[C + i] = fa ? fa[C + i] : 0.f;
+    tab[2 * C + i] = fb ? fb[i] : 1.f;  tab[3 * C + i] = fb ? fb[C + i] : 0.f;
+    tab[4 * C + i] = fo ? fo[i] : 1.f;  tab[5 * C + i] = fo ? fo[C + i] : 0.f;
+  }
+  __syncthreads();
+  const long long total = P * ng;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / ng;
+    const int g = (int)(e - p * ng);
+    const uint4 ra = __ldg(vptr(a, p, g)), rb = __ldg(vptr(b, p, g));
+    const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = 8 * g + j;
+      const float va = __uint_as_float((j & 1) ? (wa[j >> 1] & 0xffff0000u) : (wa[j >> 1] << 16));
+      const float vb = __uint_as_float((j & 1) ? (wb[j >> 1] & 0xffff0000u) : (wb[j >> 1] << 16));
+      float v = fmaf(va, tab[c], tab[C + c]) + fmaf(vb, tab[2 * C + c], tab[3 * C + c]);
+      v = fmaxf(v, 0.f);
+      o[j] = fmaf(v, tab[4 * C + c], tab[5 * C + c]);
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 q = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&q);
+    }
+    *vptr_w(y, p, g) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // MODE 0: channel stats (x)            -> acc[0..C) += sum x, acc[C..2C) += sum x^2
 // MODE 1: BN backward reduce (x, dy)   -> acc[0..C) += sum dy, acc[C..2C) += sum dy*xhat
 template <int MODE>
@@ -493,6 +531,53 @@ __global__ void __launch_bounds__(256) map_vec8_kernel(View x, View dy, const fl
 // grid of a grid-stride kernel: enough blocks for the work, at most ONE resident wave (a block count that is not a multiple
 // of the resident slots leaves a partial last wave: the 118-register BN backward reduction held 2 blocks per SM and ran
 // 1024 blocks = 3.46 waves)
+// ---------------------------------------------------------------------------
+// Inference-time weight folding with physical channel padding (MultiResUnet: 8/17/26/... channel tensors live in
+// buffers padded to multiples of 8 so the tensor-core kernels take them; holes carry zero weights and stay zero)
+__global__ void __launch_bounds__(256) fold_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, int layout,
+                                                          const int* __restrict__ in_map, int cin_p,
+                                                          const int* __restrict__ out_map, int cout_p,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ mm, const float* __restrict__ mv, float eps,
+                                                          float* __restrict__ w_out, float* __restrict__ b_out) {
+  const long long total = (long long)taps * cin_p * cout_p;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int tap, cip, cop;
+    if (layout == 0) { cop = (int)(e % cout_p); const long long t = e / cout_p; cip = (int)(t % cin_p); tap = (int)(t / cin_p); }
+    else { cip = (int)(e % cin_p); const long long t = e / cin_p; cop = (int)(t % cout_p); tap = (int)(t / cout_p); }
+    const int ci = in_map ? in_map[cip] : cip, co = out_map ? out_map[cop] : cop;
+    float v = 0.f;
+    if (ci >= 0 && co >= 0 && ci < cin && co < cout) {
+      v = layout == 0 ? w[((long long)tap * cin + ci) * cout + co] : w[((long long)tap * cout + co) * cin + ci];
+      if (mv) v *= (gamma ? gamma[co] : 1.f) * rsqrtf(mv[co] + eps);
+    }
+    w_out[e] = v;
+    if (b_out && tap == 0 && cip == 0) {
+      float b = 0.f;
+      if (co >= 0 && co < cout) {
+        if (mv) { const float sc = (gamma ? gamma[co] : 1.f) * rsqrtf(mv[co] + eps); b = (beta ? beta[co] : 0.f) - mm[co] * sc; }
+        else b = beta ? beta[co] : 0.f;
+      }
+      b_out[cop] = b;
+    }
+  }
+}
+
+__global__ void bn_inference_params_mapped_kernel(int CP, const int* __restrict__ map, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, float eps, const float* __restrict__ mm,
+                                                  const float* __restrict__ mv, float* __restrict__ scale_shift) {
+  const int cp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cp >= CP) return;
+  const int c = map ? map[cp] : cp;
+  float scale = 0.f, shift = 0.f;
+  if (c >= 0) {
+    scale = (gamma ? gamma[c] : 1.f) * rsqrtf(mv[c] + eps);
+    shift = beta[c] - mm[c] * scale;
+  }
+  scale_shift[cp] = scale;
+  scale_shift[CP + cp] = shift;
+}
+
 template <typename K>
 inline int resident_grid(K kern, long long work_items, int per_block) {
   int per_sm = 0;
@@ -704,8 +789,14 @@ extern "C" int dnnca_add_relu_affine(void* stream, const dnnca_tensor_t* a, cons
                                      const dnnca_tensor_t* y) {
   DNNCA_CHECK_ARG(view_ok(a) && view_ok(b) && view_ok(y) && same_shape(a, b) && same_shape(a, y), "add_relu_affine: bad arguments");
   DNNCA_CHECK_ARG(a->dtype == b->dtype && a->dtype == y->dtype, "add_relu_affine: dtype mismatch");
-  ChanLayout L = chan_layout(a->c);
   long long P = (long long)a->n * a->h * a->w;
+  if (vec8_ok(a) && vec8_ok(b) && vec8_ok(y) && a->c * 6 * 4 <= 48 * 1024) {
+    add_relu_affine_vec8_kernel<<<grid_for(P * (a->c / 8), 256 * 4, 8), 256, (size_t)a->c * 6 * 4, (cudaStream_t)stream>>>(
+        mk(a), affine_a, mk(b), affine_b, affine_out, mk(y), P);
+    DNNCA_LAUNCH_CHECK("add_relu_affine");
+    return DNNCA_OK;
+  }
+  ChanLayout L = chan_layout(a->c);
   int grid = grid_for(P, L.pl * 4);
   DNNCA_DISPATCH_DTYPE(a->dtype, add_relu_affine_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
       mk(a), affine_a, mk(b), affine_b, affine_out, mk(y), L.cl, L.pl, P);)
@@ -722,5 +813,31 @@ extern "C" int dnnca_u8_to_unit(void* stream, const uint8_t* src, int64_t count,
   else
     u8_to_unit_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, count, (__nv_bfloat16*)dst);
   DNNCA_LAUNCH_CHECK("u8_to_unit");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_fold_weights(void* stream, const float* w, int taps, int cin, int cout, int layout,
+                                  const int32_t* in_map, int cin_phys, const int32_t* out_map, int cout_phys,
+                                  const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
+                                  float eps, float* w_out, float* b_out) {
+  DNNCA_CHECK_ARG(w && w_out && taps > 0 && cin > 0 && cout > 0 && cin_phys > 0 && cout_phys > 0 && (layout == 0 || layout == 1),
+                  "fold_weights: bad arguments");
+  DNNCA_CHECK_ARG((in_map || cin_phys == cin) && (out_map || cout_phys == cout), "fold_weights: a NULL map needs equal logical / physical counts");
+  DNNCA_CHECK_ARG((moving_mean == nullptr) == (moving_var == nullptr), "fold_weights: moving statistics come in pairs");
+  const long long total = (long long)taps * cin_phys * cout_phys;
+  fold_weights_kernel<<<grid_for(total, 256 * 4, 4), 256, 0, (cudaStream_t)stream>>>(w, taps, cin, cout, layout, in_map, cin_phys,
+                                                                                    out_map, cout_phys, gamma, beta, moving_mean,
+                                                                                    moving_var, eps, w_out, b_out);
+  DNNCA_LAUNCH_CHECK("fold_weights");
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_bn_inference_params_mapped(void* stream, int c_phys, const int32_t* map, const float* gamma,
+                                                const float* beta, float eps, const float* moving_mean,
+                                                const float* moving_var, float* scale_shift) {
+  DNNCA_CHECK_ARG(c_phys > 0 && beta && moving_mean && moving_var && scale_shift, "bn_inference_params_mapped: bad arguments");
+  bn_inference_params_mapped_kernel<<<(c_phys + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c_phys, map, gamma, beta, eps,
+                                                                                           moving_mean, moving_var, scale_shift);
+  DNNCA_LAUNCH_CHECK("bn_inference_params_mapped");
   return DNNCA_OK;
 }

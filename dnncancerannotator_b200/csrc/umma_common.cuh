@@ -254,8 +254,11 @@ __device__ __forceinline__ void epilogue_chunk32(const UArgs& a, uint32_t (&v)[3
   }
 }
 
+// `nvalid`: GEMM columns of this chunk below N (a multiple of 8; >= CH for full chunks): columns at or beyond it belong
+// to the zero-padded part of a covering N tile and are neither biased nor stored
 template <int CH>
-__device__ __forceinline__ void epilogue_chunk(const UArgs& a, const uint32_t (&v)[32], int n, int gy, int gx, int ncol) {
+__device__ __forceinline__ void epilogue_chunk(const UArgs& a, const uint32_t (&v)[32], int n, int gy, int gx, int ncol,
+                                               int nvalid = CH) {
   __nv_bfloat16* dst;
   int ch;
   long long pix;
@@ -291,7 +294,7 @@ __device__ __forceinline__ void epilogue_chunk(const UArgs& a, const uint32_t (&
     const int bch = a.epi == EPI_TCONV ? ch : ncol;
     if (a.bias) {
 #pragma unroll
-      for (int j = 0; j < CH; ++j) f[j] = act_slope_apply(f[j] + __ldg(a.bias + bch + j), slope);
+      for (int j = 0; j < CH; ++j) f[j] = act_slope_apply(f[j] + (j < nvalid ? __ldg(a.bias + bch + j) : 0.f), slope);
     } else {
 #pragma unroll
       for (int j = 0; j < CH; ++j) f[j] = act_slope_apply(f[j], slope);
@@ -309,7 +312,7 @@ __device__ __forceinline__ void epilogue_chunk(const UArgs& a, const uint32_t (&
     o.y = *reinterpret_cast<uint32_t*>(&p1);
     o.z = *reinterpret_cast<uint32_t*>(&p2);
     o.w = *reinterpret_cast<uint32_t*>(&p3);
-    d4[q] = o;
+    if (q * 8 < nvalid) d4[q] = o;
   }
 }
 

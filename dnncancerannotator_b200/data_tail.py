@@ -1,0 +1,76 @@
+"""Device side of the reference's input pipeline tail (``annotator/data.py``).
+
+``prepare_batch`` takes the RAW combined uint8 slices ``[B, Hin, Win, S]`` (every slice type incl. the label as one
+channel -- what ``tf_prepare_combined_slices`` / the TFRecord reader yield before ``base`` touches them) and runs, in one
+kernel (``dnnca_input_tail``): the centre crop of ``base`` (data.py:182-197), the displaced crop of ``random_crop``
+(data.py:677-689), ``tf.image.random_flip_left_right`` (data.py:620-625), the float cast and ``/255`` (data.py:198-199)
+and the feature / label split of ``to_feature_label`` (data.py:766-788).  The random draws stay on the host
+(``draw_augmentation`` restates the reference's distributions); the pixels never exist as float32 on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import native as N
+
+DEFAULT_SLICE_TYPES = ('TRA', 'ADC', 'DWI', 'DCEE', 'DCEL', 'label')     # data.py:30-41 / data_options.yaml:7
+
+
+def draw_augmentation(rng: np.random.Generator, batch, in_size, out_size, random_crop=True, random_flip=True,
+                      stddev=4, max_=6, min_=-6):
+    """Per-sample crop origins ``[B,2]`` (row, column) and flip flags ``[B]``.
+
+    ``random_crop`` (data.py:677-689): origin = (in - out)//2 + clip(int(normal(0, stddev)), min_, max_) per axis
+    (``tf.cast(..., tf.int32)`` truncates towards zero); ``random_flip_left_right`` flips with probability 1/2."""
+    hin, win = in_size
+    hout, wout = out_size
+    base = np.array([(hin - hout) // 2, (win - wout) // 2], np.int64)
+    if random_crop:
+        diff = np.clip(np.trunc(rng.normal(0.0, stddev, (batch, 2))).astype(np.int64), min_, max_)
+    else:
+        diff = np.zeros((batch, 2), np.int64)
+    origin = base[None, :] + diff
+    origin[:, 0] = np.clip(origin[:, 0], 0, hin - hout)      # crop_to_bounding_box would raise outside the image
+    origin[:, 1] = np.clip(origin[:, 1], 0, win - wout)
+    flip = (rng.random(batch) < 0.5) if random_flip else np.zeros(batch, bool)
+    return origin.astype(np.int32), flip.astype(np.uint8)
+
+
+def prepare_batch(combined, slice_types=DEFAULT_SLICE_TYPES, output_size=(256, 256), crop_yx=None, flip=None,
+                  dtype=torch.float32, x_out=None, y_out=None, device=None):
+    """-> ``(x [B,H,W,nf] dtype, y [B,H,W] float32)`` on the device.
+
+    ``combined``: uint8 ``[B,Hin,Win,S]`` (numpy, CPU or CUDA tensor; a pinned CPU tensor is copied asynchronously).
+    ``crop_yx`` / ``flip``: outputs of ``draw_augmentation`` (None = centre crop / no flip = the evaluation pipeline,
+    data.py:114-144).  ``x_out`` may be a wider pre-allocated buffer ``[B,H,W,Cpad]`` (e.g. the padded bf16 input of the
+    first conv): only its first nf channels are written."""
+    device = device or torch.device('cuda', torch.cuda.current_device())
+    t = combined if torch.is_tensor(combined) else torch.from_numpy(np.ascontiguousarray(combined))
+    if t.dtype != torch.uint8 or t.dim() != 4:
+        raise TypeError('combined slices must be uint8 [B,Hin,Win,S]')
+    t = t.to(device, non_blocking=True).contiguous()
+    B, hin, win, S = t.shape
+    slice_types = list(slice_types)
+    if len(slice_types) != S:
+        raise ValueError(f'{S} channels but {len(slice_types)} slice types')
+    fidx = [i for i, n in enumerate(slice_types) if n != 'label']                     # data.py:770
+    lidx = slice_types.index('label') if 'label' in slice_types else -1                # data.py:771
+    hout, wout = output_size
+    if x_out is None:
+        x_out = torch.empty(B, hout, wout, len(fidx), dtype=dtype, device=device)
+    if y_out is None:
+        y_out = torch.empty(B, hout, wout, dtype=torch.float32, device=device)
+    assert x_out.is_contiguous() and tuple(x_out.shape[:3]) == (B, hout, wout) and x_out.shape[3] >= len(fidx)
+    cy = None if crop_yx is None else torch.as_tensor(np.ascontiguousarray(crop_yx, np.int32)).to(device)
+    fl = None if flip is None else torch.as_tensor(np.ascontiguousarray(flip, np.uint8)).to(device)
+    if cy is not None:
+        c = np.asarray(crop_yx)
+        if c.shape != (B, 2) or (c < 0).any() or (c[:, 0] > hin - hout).any() or (c[:, 1] > win - wout).any():
+            raise ValueError('crop origins must be [B,2] and keep the window inside the image')
+    arr = (C.c_int32 * len(fidx))(*fidx)
+    N.call('dnnca_input_tail', N.stream_ptr(), N.ptr(t), B, hin, win, S, N.ptr(cy), N.ptr(fl), hout, wout, arr, len(fidx),
+           lidx, N.ptr(x_out), N.dtype_code(x_out.dtype), x_out.shape[3], N.ptr(y_out))
+    return x_out, y_out

@@ -273,6 +273,10 @@ class Model:
             plan.graphs[key] = g
         g.replay()
 
+    def _before_inference(self, plan):
+        """Hook run with the batch already in ``plan.x_in``, before an inference launch sequence (models that cache
+        folded / packed weights refresh them here)."""
+
     # ---- inference -------------------------------------------------------------
     def __call__(self, x, training=False):
         """``model(x)`` -> probabilities ``[B,H,W,1]`` (fp32 torch tensor on the device);
@@ -283,6 +287,7 @@ class Model:
         plan.allocate(bool(training))
         plan.prestaged = False
         plan.x_in.copy_(x, non_blocking=True)
+        self._before_inference(plan)
         if training:
             # keras ``model(x, training=True)``: BatchNormalization normalises with the batch statistics and
             # updates its moving averages; no gradients, no optimizer
@@ -365,6 +370,7 @@ class Model:
 
     def _adam(self):
         ps = self.params
+        ps.version += 1
         N.call('dnnca_adam_step', N.stream_ptr(), N.ptr(ps.params), N.ptr(ps.grads), N.ptr(ps.m), N.ptr(ps.v),
                ps.n_trainable, N.ptr(ps.hyper), N.ptr(ps.step), N.ptr(ps.l2))
 
@@ -620,6 +626,7 @@ class Model:
             plan.prestaged = False
             plan.x_in.copy_(xb, non_blocking=True)
             plan.y_in.copy_(yb, non_blocking=True)
+            self._before_inference(plan)
             self._maybe_validate(plan, 'eval')
             if self.loss.label_smoothing:
                 plan.y_in.copy_(self.loss.prepare_labels(yb), non_blocking=True)

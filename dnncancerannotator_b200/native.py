@@ -51,6 +51,8 @@ _PROTOS = {
     'dnnca_debug_launch_count': [_i],
     'dnnca_debug_family_count': [_i, _i],
     'dnnca_conv_workspace_bytes': [_i, _i, _i],
+    'dnnca_conv2d_prepack': [_vp, _TP, _TP, _vp, _TP, _i, _vp, C.c_size_t],
+    'dnnca_convtranspose2x2_prepack': [_vp, _TP, _vp, _TP, _vp, C.c_size_t],
     'dnnca_conv2d_fprop': [_vp, _TP, _TP, _vp, _vp, _TP, _i, _i, _f, _vp, _vp, C.c_size_t],
     'dnnca_conv2d_dgrad': [_vp, _TP, _vp, _TP, _TP, _i, _TP, _i, _f, _vp, C.c_size_t],
     'dnnca_conv2d_wgrad': [_vp, _TP, _TP, _TP, _vp, _vp, _i],
@@ -63,6 +65,8 @@ _PROTOS = {
     'dnnca_bn_finalize': [_vp, _vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp],
     'dnnca_bn_inference_params': [_vp, _i, _vp, _vp, _f, _vp, _vp, _vp],
     'dnnca_bn_apply': [_vp, _TP, _vp, _TP],
+    'dnnca_fold_weights': [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp],
+    'dnnca_bn_inference_params_mapped': [_vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp],
     'dnnca_bn_bwd_reduce': [_vp, _TP, _TP, _vp, _vp],
     'dnnca_bn_bwd_apply': [_vp, _TP, _TP, _vp, _vp, _vp, _TP, _i, _f, _vp, _vp],
     'dnnca_gaussian_filter2d': [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
@@ -77,6 +81,7 @@ _PROTOS = {
     'dnnca_threshold_hist': [_vp, _vp, _vp, _i64, _vp, _i, _vp],
     'dnnca_add_relu_affine': [_vp, _TP, _vp, _TP, _vp, _vp, _TP],
     'dnnca_u8_to_unit': [_vp, _vp, _i64, _vp, _i],
+    'dnnca_input_tail': [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, C.POINTER(C.c_int32), _i, _i, _vp, _i, _i, _vp],
     'dnnca_convert': [_vp, _TP, _TP],
     'dnnca_adam_step': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     'dnnca_host_alloc': [C.c_size_t, _i, C.POINTER(C.c_void_p)],

@@ -51,6 +51,7 @@ class ParamStore:
         self._gviews = {}
         self.n_trainable = 0
         self.n_state = 0
+        self.version = 0          # bumped whenever variables are (re)written: inference plans cache folded / packed weights
 
     def add(self, name, array, trainable=True, l2=0.0):
         assert self.device is None, 'variables must be created before the store is materialised'
@@ -100,6 +101,7 @@ class ParamStore:
                     self.l2[s['offset']:s['offset'] + s['numel']] = s['l2']
             s['init'] = None
         # Adam hyper-parameters and step counter live on the device (graph replay)
+        self.version += 1
         self.hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-7], dtype=torch.float32, device=device)
         self.step = torch.zeros(1, dtype=torch.int64, device=device)
 
@@ -125,6 +127,7 @@ class ParamStore:
         return out
 
     def set_weights(self, weights):
+        self.version += 1
         for name, arr in weights.items():
             if name not in self.specs:
                 raise KeyError(f'unknown variable {name}')
@@ -213,11 +216,12 @@ class TRef:
 # ----------------------------------------------------------------------------
 # ops
 # ----------------------------------------------------------------------------
-def conv_workspace(plan, taps, inputs, y):
+def conv_workspace(plan, taps, inputs, y, out_multiple=16):
     """bf16 weight-repack workspace of the tcgen05 kernels (dnnca_conv_workspace_bytes), or None when the layer
-    cannot take the tensor-core path (fp32 mode, channel counts that are not multiples of 16)."""
+    cannot take the tensor-core path (fp32 mode, output channel counts that are not multiples of ``out_multiple``:
+    16 in general, 8 for single-input Conv2D fprop, whose epilogue stores 8-channel groups)."""
     ins = [t for t in inputs if t is not None]
-    if plan.dtype != torch.bfloat16 or y.c % 16 or any(t.buf.c % 8 or t.coff % 8 for t in ins):
+    if plan.dtype != torch.bfloat16 or y.c % out_multiple or y.coff % 8 or y.buf.c % 8 or any(t.buf.c % 8 or t.coff % 8 for t in ins):
         return None                       # (the library re-checks; narrow inputs only need 16-byte aligned pixels)
     if len(ins) > 1 and any(t.c % 16 for t in ins):
         return None
@@ -328,7 +332,8 @@ class PoolOp(Op):
             self.idx = torch.empty(self.y.n, self.y.h, self.y.w, self.y.c, dtype=torch.uint8, device=self.p.device)
 
     def fwd(self, train):
-        N.call('dnnca_maxpool2x2_fwd', N.stream_ptr(), self.x.ct(), self.y.ct(), N.ptr(self.idx) if train else None,
+        keep = train or self.p.want_input_grad       # the input-gradient chain runs an inference forward but needs the argmax
+        N.call('dnnca_maxpool2x2_fwd', N.stream_ptr(), self.x.ct(), self.y.ct(), N.ptr(self.idx) if keep else None,
                self.stats.fwd_ptr() if (self.stats and train) else None)
 
     def bwd(self):
@@ -529,6 +534,13 @@ class Plan:
             N.call('dnnca_label_stats', s, N.ptr(self.y_in), self.y_in.numel(), N.ptr(self.lstats))
         f = self.features
         act = f.act or (N.ACT_NONE, 0.0)
+        if self.head is None:       # inference-only model whose head weights are folded (MultiResUnet conv10 + BN)
+            assert not with_grads, 'a folded head has no gradient path'
+            wf, bf = self._head_fold[0], self._head_fold[1]
+            N.call('dnnca_head_bce_fwd_bwd', s, f.ct(), N.ptr(wf), N.ptr(bf), N.ptr(self.y_in), N.ptr(self.lstats),
+                   C.byref(loss_cfg), N.ptr(self.logits), N.ptr(self.probs), N.ptr(self.per_sample), None, act[0], act[1],
+                   None, None)
+            return
         N.call('dnnca_head_bce_fwd_bwd', s, f.ct(), ps.ptr(self.head[0]), ps.ptr(self.head[1]), N.ptr(self.y_in),
                N.ptr(self.lstats), C.byref(loss_cfg), N.ptr(self.logits), N.ptr(self.probs), N.ptr(self.per_sample),
                f.gct() if with_grads else None, act[0], act[1], ps.gptr(self.head[0]) if with_grads else None,

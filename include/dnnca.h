@@ -77,8 +77,17 @@ DNNCA_API long long dnnca_debug_family_count(int family, int reset);
  * weights, `taps * cin * cout * 2` bytes (taps = k*k, or 4 for ConvT).  The caller owns it (one per
  * layer or one shared scratch on a single stream); every fprop/dgrad call re-packs from the fp32
  * masters, so nothing in it is state.  workspace == NULL selects the CUDA-core kernels.
+ * Inference with unchanged weights (model.evaluate / predict sweeps, engine.py:198-203, 222): an fprop call with
+ * w == NULL (k == NULL for ConvT) re-uses the packing the SAME layer's previous fprop call left in `workspace`
+ * (caller's contract: a per-layer workspace nothing else wrote); it fails with DNNCA_ERR_UNSUPPORTED when the
+ * shape is not served by the tensor-core kernels.  dnnca_conv2d_prepack / dnnca_convtranspose2x2_prepack write
+ * exactly that packing (no convolution is launched): call them once per weight version, then fprop with w == NULL.
  * ------------------------------------------------------------------------- */
 DNNCA_API size_t dnnca_conv_workspace_bytes(int taps, int cin, int cout);
+DNNCA_API int dnnca_conv2d_prepack(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w,
+                                   const dnnca_tensor_t* y, int ksize, void* workspace, size_t workspace_bytes);
+DNNCA_API int dnnca_convtranspose2x2_prepack(void* stream, const dnnca_tensor_t* x, const float* k, const dnnca_tensor_t* y,
+                                             void* workspace, size_t workspace_bytes);
 
 /* ---------------------------------------------------------------------------
  * Conv2D, stride 1, 'same' zero padding, k in {1,3}
@@ -247,9 +256,40 @@ DNNCA_API int dnnca_add_relu_affine(void* stream, const dnnca_tensor_t* a, const
                           const float* affine_b, const float* affine_out, const dnnca_tensor_t* y);
 
 /* ---------------------------------------------------------------------------
+ * Inference-time weight folding with physical channel padding (MultiResUnet, multiresunet.py:31-60, 89-126):
+ *   conv2d_bn = Conv2D(use_bias=False) -> BatchNormalization(scale=False) [-> activation] evaluated with the moving
+ *   statistics is a conv with kernel K*s and bias beta - mean*s, s = gamma*rsqrt(var+eps) (gamma NULL -> 1).
+ *   The model's odd channel counts (8/17/26/35/51/53/71/...) are stored in buffers whose concat segments are padded
+ *   to multiples of 8 so that the tcgen05 kernels take every layer; `in_map[ci_phys]` / `out_map[co_phys]` give the
+ *   logical channel of a physical one or -1 for a hole (NULL = identity).  Holes get zero weights and zero bias.
+ *   layout 0: w [taps,Cin,Cout] (Conv2D HWIO) ; layout 1: w [taps,Cout,Cin] (Conv2DTranspose).  moving_var == NULL:
+ *   no BatchNorm, `beta` is the layer's bias (or NULL).  w_out is fp32 in the same layout with physical extents.
+ * bn_inference_params_mapped: scale|shift of an inference BatchNorm laid out over physical channels (holes: 0 | 0).
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_fold_weights(void* stream, const float* w, int taps, int cin, int cout, int layout,
+                                 const int32_t* in_map, int cin_phys, const int32_t* out_map, int cout_phys,
+                                 const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
+                                 float eps, float* w_out, float* b_out);
+DNNCA_API int dnnca_bn_inference_params_mapped(void* stream, int c_phys, const int32_t* map, const float* gamma,
+                                               const float* beta, float eps, const float* moving_mean,
+                                               const float* moving_var, float* scale_shift);
+
+/* ---------------------------------------------------------------------------
  * Input tail: uint8 -> /255 -> activation dtype (data.py:193-206 `base`, 766-788)
  * ------------------------------------------------------------------------- */
 DNNCA_API int dnnca_u8_to_unit(void* stream, const uint8_t* src, int64_t count, void* dst, int dtype);
+/* The whole input tail in one pass over the RAW combined uint8 slices [n,hin,win,s] (all slice types incl. the label
+ * as channels, what the TFRecord / PNG decoder yields): crop to [hout,wout] at crop_yx[b] = (row, column) (device int32
+ * [n,2]; NULL = the centre crop of data.py:182-197; the random crop of data.py:677-689 is the centre origin plus the
+ * host-drawn offset), left-right flip of the cropped window where flip[b] != 0 (tf.image.random_flip_left_right,
+ * data.py:620-625; NULL = none), cast and /255 (data.py:198-199), and the feature / label split of to_feature_label
+ * (data.py:766-788): x[b,y,x,i] = src[..., feature_idx[i]]/255 in `x_dtype` with `x_cstride` elements per pixel
+ * (>= nf: the padded bf16 input buffer of the first conv can be written directly), y[b,y,x] = src[..., label_idx]/255
+ * (fp32; y_out may be NULL, label_idx < 0 writes zeros).  feature_idx is a HOST array (nf <= 16). */
+DNNCA_API int dnnca_input_tail(void* stream, const uint8_t* combined, int n, int hin, int win, int s,
+                               const int32_t* crop_yx, const uint8_t* flip, int hout, int wout,
+                               const int32_t* feature_idx, int nf, int label_idx, void* x_out, int x_dtype,
+                               int x_cstride, float* y_out);
 /* dtype conversion between two views of equal logical shape (fp32 <-> bf16, slice copies) */
 DNNCA_API int dnnca_convert(void* stream, const dnnca_tensor_t* src, const dnnca_tensor_t* dst);
 

@@ -16,23 +16,43 @@ import torch
 from . import ref_ops as ops
 
 
+_MANTISSA = 7     # stored mantissa bits of the emulated format: 7 = bfloat16, 10 = TF32 / fp16, 23 = fp32 (no rounding)
+
+
+def round_mantissa(x, bits=None):
+    """Round-to-nearest-even of a float32 tensor to ``bits`` stored mantissa bits (exponent range kept): bits=7 is
+    exactly ``x.bfloat16().float()``; bits=10 is what a TF32 tensor-core multiply sees of its operands."""
+    bits = _MANTISSA if bits is None else bits
+    if bits >= 23:
+        return x
+    if bits == 7:
+        return x.bfloat16().float()
+    drop = 23 - bits
+    i = x.detach().contiguous().view(torch.int32)
+    lsb = (i >> drop) & 1
+    i = (i + ((1 << (drop - 1)) - 1) + lsb) & ~((1 << drop) - 1)
+    return i.view(torch.float32)
+
+
 class _Round(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        return x.bfloat16().float()
+        return round_mantissa(x)
 
     @staticmethod
     def backward(ctx, g):
-        return g.bfloat16().float()
+        return round_mantissa(g)
 
 
 def _rw(k):
-    """bf16 copy of a weight with a straight-through gradient to the fp32 master."""
-    return k + (k.detach().bfloat16().float() - k.detach())
+    """low-precision copy of a weight with a straight-through gradient to the fp32 master."""
+    return k + (round_mantissa(k.detach()) - k.detach())
 
 
 @contextlib.contextmanager
-def emulate_bf16(round_weights_min_channels=16):
+def emulate_bf16(round_weights_min_channels=16, mantissa_bits=7):
+    global _MANTISSA
+    saved_bits, _MANTISSA = _MANTISSA, mantissa_bits
     oc, ot, ob, oa = ops.conv2d, ops.conv2d_transpose, ops.batchnorm, ops.activation
     r = _Round.apply
 
@@ -57,3 +77,4 @@ def emulate_bf16(round_weights_min_channels=16):
         yield
     finally:
         ops.conv2d, ops.conv2d_transpose, ops.batchnorm, ops.activation = oc, ot, ob, oa
+        _MANTISSA = saved_bits

@@ -71,11 +71,21 @@ class _Base:
         self.regularized: list[str] = []
         self.l2 = None
         self.dtype = torch.float32
+        self.device = torch.device('cpu')
+
+    def to(self, device):
+        """Evaluate the SAME restatement with torch on another device (tools/parity_real_shapes.py runs the fp32
+        oracle at the configs' full sizes on the GPU box's device with TF32 disabled; checked against the CPU
+        evaluation at a small size there).  Test infrastructure only."""
+        self.device = torch.device(device)
+        for k in self.weights:
+            self.weights[k] = self.weights[k].to(self.device)
+        return self
 
     # -- variable creation ----------------------------------------------------
     def _add(self, name, array, trainable=True, regularized=False):
         assert name not in self.weights, name
-        self.weights[name] = torch.tensor(np.asarray(array), dtype=self.dtype)
+        self.weights[name] = torch.tensor(np.asarray(array), dtype=self.dtype, device=self.device)
         if trainable:
             self.trainable.append(name)
         if regularized and self.l2 is not None:
@@ -109,13 +119,13 @@ class _Base:
 
     # -- public ---------------------------------------------------------------
     def get_weights(self):
-        return OrderedDict((k, v.detach().numpy().copy()) for k, v in self.weights.items())
+        return OrderedDict((k, v.detach().cpu().numpy().copy()) for k, v in self.weights.items())
 
     def set_weights(self, weights):
         for k, v in weights.items():
             assert k in self.weights, k
             assert tuple(self.weights[k].shape) == tuple(np.shape(v)), (k, self.weights[k].shape, np.shape(v))
-            self.weights[k] = torch.tensor(np.asarray(v), dtype=self.dtype)
+            self.weights[k] = torch.tensor(np.asarray(v), dtype=self.dtype, device=self.device)
 
     def randomize_bn(self, seed=1):
         """Non-trivial BN parameters for tests (gamma~U[.5,1.5], beta~N(0,.1))."""
@@ -123,15 +133,15 @@ class _Base:
         for k in self.weights:
             c = self.weights[k].shape[0]
             if k.endswith('/gamma'):
-                self.weights[k] = torch.tensor(rng.uniform(0.5, 1.5, c), dtype=self.dtype)
+                self.weights[k] = torch.tensor(rng.uniform(0.5, 1.5, c), dtype=self.dtype, device=self.device)
             elif k.endswith('/beta'):
-                self.weights[k] = torch.tensor(rng.normal(0, 0.1, c), dtype=self.dtype)
+                self.weights[k] = torch.tensor(rng.normal(0, 0.1, c), dtype=self.dtype, device=self.device)
             elif k.endswith('/moving_mean'):
-                self.weights[k] = torch.tensor(rng.normal(0, 0.1, c), dtype=self.dtype)
+                self.weights[k] = torch.tensor(rng.normal(0, 0.1, c), dtype=self.dtype, device=self.device)
             elif k.endswith('/moving_var'):
-                self.weights[k] = torch.tensor(rng.uniform(0.5, 1.5, c), dtype=self.dtype)
+                self.weights[k] = torch.tensor(rng.uniform(0.5, 1.5, c), dtype=self.dtype, device=self.device)
             elif k.endswith('/bias'):
-                self.weights[k] = torch.tensor(rng.normal(0, 0.05, c), dtype=self.dtype)
+                self.weights[k] = torch.tensor(rng.normal(0, 0.05, c), dtype=self.dtype, device=self.device)
 
     def __call__(self, x, training=False):
         return self.forward(x, training=training)['probs']
@@ -139,7 +149,7 @@ class _Base:
     def forward(self, x, training=False, weights=None):
         ctx = dict(w=self.weights if weights is None else weights, training=training,
                    new_moving=OrderedDict(), pool_idx=[], tensors=OrderedDict())
-        x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(self.dtype)
+        x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device=self.device, dtype=self.dtype)
         logits = self._graph(ctx, x)
         return dict(logits=logits, probs=torch.sigmoid(logits), new_moving=ctx['new_moving'],
                     pool_idx=ctx['pool_idx'], tensors=ctx['tensors'])
@@ -152,7 +162,7 @@ class _Base:
         loss_config = dict(loss_config or {})
         w = OrderedDict((k, v.clone().requires_grad_(k in self.trainable)) for k, v in self.weights.items())
         out = self.forward(x, training=True, weights=w)
-        y = torch.as_tensor(np.asarray(y) if not torch.is_tensor(y) else y).to(self.dtype)
+        y = torch.as_tensor(np.asarray(y) if not torch.is_tensor(y) else y).to(device=self.device, dtype=self.dtype)
         if loss_config.pop('label_smoothing', False):
             y = ops.gaussian_filter2d(y, loss_config.pop('label_smoothing_filter_size', 6),
                                       loss_config.pop('label_smoothing_sigma', 3))

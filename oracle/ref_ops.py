@@ -155,7 +155,7 @@ def gaussian_filter2d(label, filter_size=6, sigma=3.0):
     ``filter_size`` taps centred at (size-1)/2 ... for an even size TFA pads
     (size-1)//2 before and size - 1 - (size-1)//2 after."""
     # TFA builds the kernel on range(-size//2 + 1, size//2 + 1) (6 -> -2..3)
-    k = torch.arange(-filter_size // 2 + 1, filter_size // 2 + 1, dtype=label.dtype)
+    k = torch.arange(-filter_size // 2 + 1, filter_size // 2 + 1, dtype=label.dtype, device=label.device)
     g = torch.exp(-(k ** 2) / (2.0 * sigma ** 2))
     g = g / g.sum()
     pad_before = (filter_size - 1) // 2
@@ -180,7 +180,7 @@ def weighted_crossentropy(label, logits, weight=None, weight_add=0.0, weight_mul
         return logits.new_zeros([0])
     if weight is None:  # losses.py:25-27
         r = positive_rate(label)
-        weight = 1.0 / r if float(r) > 0.0 else torch.tensor(1.0, dtype=label.dtype)
+        weight = 1.0 / r if float(r) > 0.0 else torch.tensor(1.0, dtype=label.dtype, device=label.device)
     weight = weight_mul * weight + weight_add  # losses.py:29
     assert float(weight) >= 0.0  # losses.py:30
     mask = label * (weight - 1) + torch.ones_like(label)  # losses.py:31

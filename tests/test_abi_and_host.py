@@ -177,7 +177,31 @@ def test_multiresunet_lowering_structure():
     plan = cpu_plan(m, 1, 32, 5, training=False)
     assert m.count_params() == 7262996
     c = op_counts(plan)
-    assert c['_FoldedConv'] == 56 and c['TConvOp'] == 4 and c['PoolOp'] == 4 and c['AddReluAffineOp'] == 19
+    assert c['_FoldedConv'] == 56 and c['_FoldedTConv'] == 4 and c['PoolOp'] == 4 and c['AddReluAffineOp'] == 19
+    # odd block widths live in buffers whose concat segments are padded to multiples of 8 channels
+    # (51 = 8|17|26 -> 8|24|32 = 64, ..., 853 -> 864) so that every conv can take the tensor-core path
+    from dnncancerannotator_b200.models.tf_models.multiresunet import _FoldedConv, _FoldedTConv
+    convs = [op for op in plan.ops if isinstance(op, _FoldedConv)]
+    assert all(op.x.c % 8 == 0 and op.y.c % 8 == 0 and op.y.coff % 8 == 0 for op in convs)
+    widths = sorted({b.c for b in plan.bufs if b.name == 'mres_out'})
+    assert widths == [64, 120, 224, 432, 864]
+    assert [op.xs.c for op in plan.ops if isinstance(op, _FoldedTConv)] == [853, 426, 212, 105]
+    m0 = convs[1].xs.chmap()                                     # the network input: 5 modalities in 8 physical channels
+    assert list(m0) == [0, 1, 2, 3, 4, -1, -1, -1]
+    cat = [op for op in plan.ops if type(op).__name__ == 'AddReluAffineOp'][0]
+    assert cat.b.c == 64 and cat.a.c == 64
+
+
+def test_multiresblock_is_exported_and_usable():
+    """tf_models/__init__.py:2 exports MultiResBlock(U, inp, alpha) as a graph-building helper."""
+    from dnncancerannotator_b200.models import tf_models
+    from dnncancerannotator_b200.models.tf_models import multiresunet as mr
+    m = tf_models.MultiResUnet(None, None, 5)
+    b = mr._Builder(m)
+    out = tf_models.MultiResBlock(32, mr.Sym(b, None, 5))
+    assert out.c == 51 and m.params.count() > 0
+    with pytest.raises(TypeError):
+        tf_models.MultiResBlock(32, object())
 
 
 def test_unsupported_geometry_is_rejected():

@@ -181,12 +181,37 @@ def test_multiresunet_forward(mode):
     m.build((None, 32, 32, 5))
     assert m.count_params() == 7262996
     m.set_weights(ref.get_weights())
-    for _ in range(3):
+    from dnncancerannotator_b200 import native as N
+    lib = N.lib()
+    for f in range(3):
+        lib.dnnca_debug_family_count(f, 1)
+    for _ in range(4):                         # fold + pack pass, eager warm-ups (prepacked), graph capture, replay
         m(z['x'])
+    fam = [int(lib.dnnca_debug_family_count(f, 0)) for f in range(3)]
     logits = m.last_logits.cpu().numpy()
-    REPORT[f'multires/{mode}/eval'] = dict(logits_rel_l2=rel_l2(logits, z['eval_logits']), logits_rel_max=rel_inf(logits, z['eval_logits']))
+    REPORT[f'multires/{mode}/eval'] = dict(logits_rel_l2=rel_l2(logits, z['eval_logits']), logits_rel_max=rel_inf(logits, z['eval_logits']),
+                                           launches_generic=fam[0], launches_small=fam[1], launches_tcgen05=fam[2])
     assert rel_l2(logits, z['eval_logits']) <= (2e-2 if mode == 'bf16' else 5e-4), rel_l2(logits, z['eval_logits'])
     assert rel_inf(logits, z['eval_logits']) <= (6e-2 if mode == 'bf16' else 5e-4), rel_inf(logits, z['eval_logits'])
+    if mode == 'bf16':                         # every conv / ConvT (odd widths padded to multiples of 8) on the tensor cores
+        assert fam[0] == 0 and fam[1] == 0 and fam[2] >= 60, fam
+    # new weights are honoured: the folded / packed copies are refreshed when the variables change
+    w2 = ref.get_weights()
+    w2['conv0/kernel'] = w2['conv0/kernel'] * 0.5
+    m.set_weights(w2)
+    ref2 = rm.build_model('MultiResUnet', dict(height=None, width=None, n_channels=5), None, seed=0)
+    ref2.set_weights(w2)
+    want = ref2.forward(z['x'], training=False)['logits'].numpy()
+    m(z['x'])
+    got = m.last_logits.cpu().numpy()
+    assert rel_l2(got, want) <= (2e-2 if mode == 'bf16' else 5e-4), rel_l2(got, want)
+    assert rel_l2(want, z['eval_logits']) > 1e-3                 # the change was visible at all
+    # evaluate() through the folded head
+    y = (np.random.default_rng(0).random((z['x'].shape[0], 32, 32)) > 0.9).astype(np.float32)
+    ev = m.evaluate([(z['x'], y)])['loss']
+    from oracle import ref_ops as ops
+    wl = float(ops.weighted_crossentropy(torch.tensor(y), torch.tensor(want)).mean())
+    assert abs(ev - wl) <= (3e-2 if mode == 'bf16' else 1e-4) * abs(wl), (ev, wl)
     with pytest.raises(NotImplementedError):
         m.train_step(z['x'], np.zeros((1, 32, 32), np.float32))
 
