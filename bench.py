@@ -328,6 +328,7 @@ def secondary_line(cfgname, B, args, world, rank, local):
             'roofline': r['roofline'], 'categories': r['categories'], 'loss_first': r['loss_first'],
             'loss_last': r['loss_last']}
     m = r.pop('model')
+    m.release_graphs()
     del r, m
     gc.collect()
     torch.cuda.empty_cache()
@@ -513,6 +514,7 @@ def run_ours(args):
 
     secondary = []
     if args.secondary and args.config == 'unet':
+        m.release_graphs()
         del m, plan, xh, yh, x8h, y8h
         r.pop('model'); r.pop('plan'); r.pop('xh'); r.pop('yh')
         import gc
@@ -525,6 +527,8 @@ def run_ours(args):
                 line2 = {'config': f'configs/{name}.yaml', 'error': f'{type(exc).__name__}: {exc}'[:300]}
             secondary.append(line2)
 
+    if 'model' in r:
+        r['model'].release_graphs()          # captured NCCL collectives must be gone before the communicator is destroyed
     if world > 1:
         dist.barrier()
     if rank != 0:

@@ -33,6 +33,8 @@ UNITS = [
     ('metrics.cu', 'metrics', []),
     ('tconv_small.cu', 'tconv_small', []),
     ('input_tail.cu', 'input_tail', []),
+    ('bn_fold.cu', 'bn_fold', []),
+    ('p2p_adam.cu', 'p2p_adam', []),
 ]
 for dt in (0, 1):
     for kind in (0, 1, 2):

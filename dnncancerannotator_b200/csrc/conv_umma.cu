@@ -30,8 +30,12 @@ namespace dnnca {
 //                                 -> dgrad pack  [tap][Cin][Cout]           (MODE 3)
 // K (the contiguous axis) is padded to a multiple of 16 with zeros in modes 0/2 (`kp` >= cin): layers whose input
 // has fewer than 16 channels (first convs: 1, 3 or 5 modalities) still feed whole K=16 MMAs.
+// `sa` / `sb` (mode 0 only, may be NULL): per-input-channel scale of a BatchNorm folded into the conv's input
+// (channels [0, ca) of the first tensor, [ca, cin) of the second): the packed weight is bf16(w * scale[ci])
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                                          int mode, int taps, int cin, int cout, int kp) {
+                                                          int mode, int taps, int cin, int cout, int kp,
+                                                          const float* __restrict__ sa, int ca,
+                                                          const float* __restrict__ sb) {
   const long long total = (mode == 0 || mode == 2) ? (long long)taps * cout * kp : (long long)taps * cin * cout;
   const int kk = taps == 9 ? 3 : (taps == 4 ? 2 : 1);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -41,6 +45,8 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
       const long long t = e / kp;
       const int co = (int)(t % cout), tap = (int)(t / cout);
       v = ci < cin ? w[((long long)tap * cin + ci) * cout + co] : 0.f;
+      if (ci < ca) { if (sa) v *= sa[ci]; }
+      else if (ci < cin && sb) v *= sb[ci - ca];
     } else if (mode == 1) {     // e = (tap', ci, co), source tap = rot180
       const int co = (int)(e % cout);
       const long long t = e / cout;
@@ -540,11 +546,13 @@ static int pick_bn_cover(int n) {
   return 256;
 }
 
-static int pack(cudaStream_t s, const float* w, void* out, int mode, int taps, int cin, int cout, int kp = 0) {
+static int pack(cudaStream_t s, const float* w, void* out, int mode, int taps, int cin, int cout, int kp = 0,
+                const float* sa = nullptr, int ca = 0, const float* sb = nullptr) {
   if (!w) return DNNCA_OK;          // workspace still holds the packing of an earlier call (dnnca.h: inference with unchanged weights)
   if (kp <= 0) kp = pad16(cin);
   const long long total = (long long)taps * kp * cout;
-  pack_weights_kernel<<<grid_for(total, 256 * 4, 4), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(out), mode, taps, cin, cout, kp);
+  pack_weights_kernel<<<grid_for(total, 256 * 4, 4), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(out), mode, taps, cin, cout, kp,
+                                                                  sa, sa || sb ? ca : cin, sb);
   DNNCA_LAUNCH_CHECK("pack_weights");
   return DNNCA_OK;
 }
@@ -566,6 +574,7 @@ static bool bf16_view_in(const dnnca_tensor_t* t) {
 int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tensor_t* xb, const void* wpack, int ktot, int ntot,
                      UArgs a);
 int try_tconv_fprop_halo(cudaStream_t s, const dnnca_tensor_t* x, const void* wpack, int cin, int cout, UArgs a);
+int try_conv1x1_halo(cudaStream_t s, const dnnca_tensor_t* x, const void* wpack, int ktot, int ntot, UArgs a);
 int try_tconv_dgrad_halo(cudaStream_t s, const dnnca_tensor_t* dy, const void* wpack, int cin, int cout, UArgs a);
 static bool halo_enabled() {
   static int v = -1;
@@ -574,6 +583,11 @@ static bool halo_enabled() {
 }
 
 static thread_local bool g_pack_only = false;
+// BatchNorm folded into the conv input (dnnca_conv2d_fprop_affine): scale vectors for the weight packing and the
+// per-border-class bias table for the epilogue; set by fprop_umma_affine around one try_conv_fprop_umma call.  With a
+// fold active only the persistent halo kernel may serve the layer (it alone carries the class-bias epilogue).
+struct FoldCtx { const float* sa; const float* sb; const float* bias9; };
+static thread_local const FoldCtx* g_fold = nullptr;
 
 // returns 1 handled / 0 not covered / <0 error
 // returns 2 when the kernel also accumulated the BatchNorm statistics into `stats` (else the caller runs channel_stats)
@@ -593,7 +607,7 @@ int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_ten
   mB = mA;
   if (x2 && !act_map(&mB, x2, kc, 1)) return 0;
   if (!weight_map(&mW, ws, kp, cout, taps, kc, bn)) return 0;
-  int r = pack(s, w, ws, 0, taps, cin, cout, kp);
+  int r = g_fold ? pack(s, w, ws, 0, taps, cin, cout, kp, g_fold->sa, ca, g_fold->sb) : pack(s, w, ws, 0, taps, cin, cout, kp);
   if (r != DNNCA_OK) return r;
   if (g_pack_only) return 1;            // dnnca_conv2d_prepack: the packing a later w == NULL call of this layer expects
   UArgs a{};
@@ -601,11 +615,17 @@ int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_ten
   a.tiles_x = (x->w + 15) / 16; a.tiles_y = (x->h + 7) / 8; a.epi = EPI_FPROP; a.act = act; a.alpha = alpha; a.bias = bias;
   a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
   a.mask = nullptr; a.n_total = cout; a.cout_t = cout; a.nimg = x->n;
+  a.bias9 = g_fold ? g_fold->bias9 : nullptr;
   if (k == 3 && (kc == 64 || (!x2 && ca < 64)) && halo_enabled()) {
     a.stats = stats;
     r = try_conv3x3_halo(s, x, x2, ws, kp, cout, a);
     if (r != 0) return (r == 1 && stats) ? 2 : r;
     a.stats = nullptr;
+  }
+  if (g_fold) return 0;                 // no other kernel applies the folded input affine
+  if (k == 1 && !x2 && kc == 64 && halo_enabled()) {      // 1x1 convs (MultiResUnet shortcuts) as a persistent plain GEMM
+    r = try_conv1x1_halo(s, x, ws, kp, cout, a);
+    if (r != 0) return r;
   }
   if (kc == 64) return dispatch_bn<64>(s, mA, mB, mW, a, x->n, bn);
   if (kc == 32) return dispatch_bn<32>(s, mA, mB, mW, a, x->n, bn);
@@ -697,6 +717,27 @@ int try_tconv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dy, const float* 
   if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, dx->n, bn);
   if (kc == 32) return dispatch_bn<32>(s, mA, mA, mW, a, dx->n, bn);
   return dispatch_bn<16>(s, mA, mA, mW, a, dx->n, bn);
+}
+
+// Conv2D 3x3 fprop whose input(s) carry a folded BatchNorm affine; 1 / 2 (statistics taken) handled, 0 not served
+int fprop_umma_affine(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w, const dnnca_tensor_t* y,
+                      int act, float alpha, void* ws, size_t ws_bytes, double* stats, const float* scale_a,
+                      const float* scale_b, const float* bias9) {
+  FoldCtx f{scale_a, scale_b, bias9};
+  g_fold = &f;
+  const int r = try_conv_fprop_umma(s, x, x2, w, nullptr, y, 3, act, alpha, ws, ws_bytes, stats);
+  g_fold = nullptr;
+  return r;
+}
+// would fprop_umma_affine serve this shape? (host-side checks only; mirrors try_conv_fprop_umma + try_conv3x3_halo)
+int fprop_umma_affine_supported(const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* y) {
+  if (!halo_enabled() || !bf16_view8(y)) return 0;
+  if (x2 ? (!bf16_view16(x) || !bf16_view16(x2) || !bf16_view16(y) || x->c % 64 || x2->c % 64) : !bf16_view_in(x)) return 0;
+  if (x->h < 2 || x->w < 2) return 0;
+  int kp = x->c;
+  const int kc = x2 ? 64 : pick_kchunk(x->c, &kp);
+  if (!(kc == 64 || (!x2 && x->c < 64))) return 0;
+  return (x2 || x->c < 64 || kp % 64 == 0) ? 1 : 0;
 }
 
 // packing only: what dnnca_conv2d_prepack / dnnca_convtranspose2x2_prepack run (1 packed / 0 shape not served / <0 error)

@@ -45,7 +45,12 @@ struct HGeom {
   static constexpr int A_SBO = HPX * 128;                  // bytes between consecutive tile rows (8-pixel core groups)
   static constexpr int B_TAP = BN * 128;                   // one tap of one 64-channel chunk
   static constexpr int A_SLOTS = TAPS == 9 ? 3 : 4;
-  static constexpr int CTRL = 6144;                        // barriers + TMEM slot + bias slice (BN floats at +256) + BN-statistics accumulators (2*BN doubles at +2048)
+  // control block: barriers + TMEM slot (256 B) | bias table: 9 border classes x BN floats (3x3 fprop with a folded
+  // BatchNorm on its input: the bias depends on which taps fall into the zero padding) | BN-statistics accumulators
+  // (2*BN doubles)
+  static constexpr int BIAS_OFF = 256;
+  static constexpr int STAT_OFF = (BIAS_OFF + 9 * BN * 4 + 15) & ~15;
+  static constexpr int CTRL = (STAT_OFF + 2 * BN * 8 + 1023) & ~1023;
   // resident: all TAPS * (Cin/64) weight blocks stay in shared memory for the CTA's lifetime
   static constexpr int smem_resident(int kchunks) { return CTRL + A_SLOTS * A_SLOT + TAPS * kchunks * B_TAP + 1024; }
   static constexpr int B_STAGES = BN > 128 ? 3 : 4;
@@ -81,8 +86,11 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
   uint64_t* tfull = emptyB + 8;                              // [2] accumulator ready
   uint64_t* tempty = tfull + 2;                              // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sbias = reinterpret_cast<float*>(smem + 256);      // [BN] bias slice of this CTA's N tile (fprop)
-  double* sstat = reinterpret_cast<double*>(smem + 2048);   // [2*BN] per-channel sum | sum of squares (fprop + stats)
+  // bias slice of this CTA's N tile per border class (row class * 3 + column class; class 0 = first row / column,
+  // 1 = interior, 2 = last): all nine rows equal `bias` unless a BatchNorm is folded into the input (UArgs::bias9)
+  constexpr int NCLS = (EPI == EPI_FPROP && TAPS == 9) ? 9 : 1;
+  float* sbias = reinterpret_cast<float*>(smem + G::BIAS_OFF);
+  double* sstat = reinterpret_cast<double*>(smem + G::STAT_OFF);   // [2*BN] per-channel sum | sum of squares (fprop + stats)
   const bool do_stats = EPI == EPI_FPROP && a.stats != nullptr;
   unsigned char* aring = smem + G::CTRL;
   unsigned char* bring = aring + G::A_SLOTS * A_SLOT;
@@ -101,8 +109,15 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
-  for (int i = threadIdx.x; i < BN; i += blockDim.x)
-    sbias[i] = (a.bias && EPI != EPI_DGRAD && n0 + i < a.n_total) ? a.bias[EPI == EPI_TCONV ? (n0 + i) % a.cout_t : n0 + i] : 0.f;
+  for (int i = threadIdx.x; i < NCLS * BN; i += blockDim.x) {
+    const int cls = i / BN, col = i - cls * BN;
+    float b = 0.f;
+    if (EPI != EPI_DGRAD && n0 + col < a.n_total) {
+      if (NCLS == 9 && a.bias9) b = a.bias9[cls * a.n_total + n0 + col];
+      else if (a.bias) b = a.bias[EPI == EPI_TCONV ? (n0 + col) % a.cout_t : n0 + col];
+    }
+    sbias[i] = b;
+  }
   for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sstat[i] = 0.0;
   tc_fence_before();
   __syncthreads();
@@ -245,6 +260,8 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
       const int gy = tw_.tiy * 16 + ty, gx = tw_.tix * 8 + tx;
       const bool inside = gy < a.H && gx < a.W;
       const int buf = ti & 1;
+      const float* sb = sbias;
+      if (NCLS == 9) sb += ((gy == 0 ? 0 : (gy == a.H - 1 ? 2 : 1)) * 3 + (gx == 0 ? 0 : (gx == a.W - 1 ? 2 : 1))) * BN;
       ChunkAddr ca[NCHUNK];
       uint4 m[NMASK][4];
 #pragma unroll
@@ -270,11 +287,12 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
         }
         if (EPI != EPI_FPROP || !do_stats) {
           if (inside && n0 + col < a.n_total)
-            epilogue_chunk32<false, EPI>(a, v, ca[c], m[EPI == EPI_DGRAD ? c : 0], sbias + col, !(a.dbg & 1));
+            epilogue_chunk32<false, EPI>(a, v, ca[c], m[EPI == EPI_DGRAD ? c : 0], sb + col, !(a.dbg & 1),
+                                         a.n_total - (n0 + col));
         } else {
           // BatchNormalization statistics of the stored tensor (components.py:57-58,130-132) in the epilogue: rows of
           // the tile are lanes, so a column sum is a 31-shuffle warp reduction; one shared fp64 atomic per lane
-          epilogue_chunk32<true, EPI>(a, v, ca[c], m[0], sbias + col, inside && n0 + col < a.n_total);
+          epilogue_chunk32<true, EPI>(a, v, ca[c], m[0], sb + col, inside && n0 + col < a.n_total, a.n_total - (n0 + col));
           if (REG_STATS) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -385,7 +403,7 @@ template <int BN, bool RESIDENT, int TAPS = 9>
 static int launch_halo(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mW, const UArgs& a,
                        int kchunks) {
   if (a.epi == EPI_DGRAD) return launch_halo_epi<BN, RESIDENT, TAPS, EPI_DGRAD>(s, mA, mB, mW, a, kchunks);
-  if (TAPS == 9) return launch_halo_epi<BN, RESIDENT, TAPS, EPI_FPROP>(s, mA, mB, mW, a, kchunks);
+  if (TAPS == 9 || a.epi == EPI_FPROP) return launch_halo_epi<BN, RESIDENT, TAPS, EPI_FPROP>(s, mA, mB, mW, a, kchunks);   // TAPS 1 + FPROP: 1x1 conv
   if (BN == 256) return launch_halo_epi<256, RESIDENT, TAPS, EPI_TCONV>(s, mA, mB, mW, a, kchunks);
   return 0;
 }
@@ -396,11 +414,16 @@ int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tenso
   // a single input with fewer than 64 channels (first layers) is one K chunk whose missing channels are zero-filled by
   // the TMA (activations and packed weights alike)
   const bool narrow = !xb && xa->c < 64;
-  // N (output channels) in multiples of 32: the last N tile may be half empty (the weight TMA zero-fills the missing rows,
-  // the epilogue skips 32-column chunks at or beyond n_total)
-  if ((!narrow && (xa->c % 64 || (xb && xb->c % 64))) || ntot % 32) return 0;
-  const int bn = ntot % 256 == 0 ? 256 : (ntot % 128 == 0 ? 128 : 64);
-  if (a.split % 32) return 0;               // the epilogue routes 32-column chunks to the two dgrad destinations
+  // K: two inputs need whole 64-channel chunks each; a single input of any width runs ceil(C/64) chunks whose tail
+  // channels the TMA zero-fills (activations out of bounds, weights packed with K padded to `ktot`)
+  if (xb && (xa->c % 64 || xb->c % 64)) return 0;
+  if (!narrow && ktot % 64) return 0;
+  // N (output channels) in multiples of 8: the last N tile may be partly empty (the weight TMA zero-fills the missing
+  // rows, the epilogue stores 8-column groups below n_total only); dgrad routes whole 32-column chunks to its two
+  // destinations and keeps the multiple-of-32 rule
+  if (ntot % 8) return 0;
+  if (a.epi == EPI_DGRAD && (ntot % 32 || a.split % 32)) return 0;
+  const int bn = ntot % 256 == 0 ? 256 : (ntot % 128 == 0 ? 128 : (ntot <= 64 ? 64 : 128));
   CUtensorMap mA, mB, mW;
   if (!halo_map(&mA, xa)) return 0;
   mB = mA;
@@ -411,7 +434,7 @@ int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tenso
   a.dbg = getenv("DNNCA_HALO_DBG") ? atoi(getenv("DNNCA_HALO_DBG")) : 0;
   const int kchunks = narrow ? 1 : ktot / 64;
   if (narrow) a.c_a = 64;
-  const size_t limit = 220 * 1024;
+  const size_t limit = 226 * 1024;
   if (bn == 64) {
     if ((size_t)HGeom<64>::smem_resident(kchunks) <= limit) return launch_halo<64, true>(s, mA, mB, mW, a, kchunks);
     return launch_halo<64, false>(s, mA, mB, mW, a, kchunks);
@@ -421,6 +444,33 @@ int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tenso
     return launch_halo<128, false>(s, mA, mB, mW, a, kchunks);
   }
   return launch_halo<256, false>(s, mA, mB, mW, a, kchunks);
+}
+
+// Conv2D 1x1 fprop (pack mode 0 with one tap already in `wpack`: [N][K]) as a plain GEMM over the 16x8 pixel tile on the
+// persistent kernel (TAPS = 1, fprop epilogue); single input of any width.  returns 1 / 0 / <0
+int try_conv1x1_halo(cudaStream_t s, const dnnca_tensor_t* x, const void* wpack, int ktot, int ntot, UArgs a) {
+  if (ktot % 64 || ntot % 8) return 0;
+  const int bn = ntot % 256 == 0 ? 256 : (ntot % 128 == 0 ? 128 : (ntot <= 64 ? 64 : 128));
+  CUtensorMap mA, mW;
+  if (!halo_map(&mA, x, 8, 16)) return 0;
+  if (!weight_map64(&mW, wpack, ktot, ntot, bn, 1)) return 0;
+  a.tiles_x = (a.W + 7) / 8;
+  a.tiles_y = (a.H + 15) / 16;
+  a.nimg = x->n;
+  a.taps = 1; a.sx = 1; a.c_a = ktot; a.c_b = 0;
+  a.dbg = getenv("DNNCA_HALO_DBG") ? atoi(getenv("DNNCA_HALO_DBG")) : 0;
+  const int kchunks = ktot / 64;
+  const size_t limit = 226 * 1024;
+  if (bn == 64) {
+    if ((size_t)HGeom<64, 1>::smem_resident(kchunks) <= limit) return launch_halo<64, true, 1>(s, mA, mA, mW, a, kchunks);
+    return launch_halo<64, false, 1>(s, mA, mA, mW, a, kchunks);
+  }
+  if (bn == 128) {
+    if ((size_t)HGeom<128, 1>::smem_resident(kchunks) <= limit) return launch_halo<128, true, 1>(s, mA, mA, mW, a, kchunks);
+    return launch_halo<128, false, 1>(s, mA, mA, mW, a, kchunks);
+  }
+  if ((size_t)HGeom<256, 1>::smem_resident(kchunks) <= limit) return launch_halo<256, true, 1>(s, mA, mA, mW, a, kchunks);
+  return launch_halo<256, false, 1>(s, mA, mA, mW, a, kchunks);
 }
 
 // ConvT 2x2/s2 fprop as ONE GEMM with N = 4*Cout (pack mode 2 already in `wpack`: [tap*Cout + co][Cin]) on the persistent
@@ -436,7 +486,7 @@ int try_tconv_fprop_halo(cudaStream_t s, const dnnca_tensor_t* x, const void* wp
   a.taps = 1; a.sx = 1;
   a.dbg = getenv("DNNCA_HALO_DBG") ? atoi(getenv("DNNCA_HALO_DBG")) : 0;
   const int kchunks = cin / 64;
-  if ((size_t)HGeom<256, 1>::smem_resident(kchunks) <= 220 * 1024) return launch_halo<256, true, 1>(s, mA, mA, mW, a, kchunks);
+  if ((size_t)HGeom<256, 1>::smem_resident(kchunks) <= 226 * 1024) return launch_halo<256, true, 1>(s, mA, mA, mW, a, kchunks);
   return launch_halo<256, false, 1>(s, mA, mA, mW, a, kchunks);
 }
 
@@ -453,7 +503,7 @@ int try_tconv_dgrad_halo(cudaStream_t s, const dnnca_tensor_t* dy, const void* w
   a.taps = 4; a.sx = 2; a.c_a = cout; a.c_b = 0;
   a.dbg = getenv("DNNCA_HALO_DBG") ? atoi(getenv("DNNCA_HALO_DBG")) : 0;
   const int kchunks = 4 * (cout / 64);
-  const size_t limit = 220 * 1024;
+  const size_t limit = 226 * 1024;
   if (bn == 64) {
     if ((size_t)HGeom<64, 1>::smem_resident(kchunks) <= limit) return launch_halo<64, true, 1>(s, mA, mA, mW, a, kchunks);
     return launch_halo<64, false, 1>(s, mA, mA, mW, a, kchunks);

@@ -172,10 +172,12 @@ __device__ __forceinline__ void unpack8f(const uint4& v, float* f) {
   for (int j = 0; j < 4; ++j) { f[2 * j] = bf_lo(w[j]); f[2 * j + 1] = bf_hi(w[j]); }
 }
 
-template <bool STATS>
+// AFF: the input carries a folded BatchNorm affine s*a + t (bn_fold.cu): the window is searched for the max of a where
+// s >= 0 and for the min where s < 0 (compare sign*a), the stored output / statistics are those of s*a_sel + t
+template <bool STATS, bool AFF = false>
 __global__ void __launch_bounds__(256) maxpool_fwd_vec8_kernel(PV x, __nv_bfloat16* y, long long ycs, uint8_t* __restrict__ idx,
                                                               double* __restrict__ stats, int C, int Ho, int Wo, long long PO,
-                                                              int GL, int PL) {
+                                                              int GL, int PL, const float* __restrict__ aff = nullptr) {
   __shared__ double sm[STATS ? 256 * 16 : 1];
   const int gl = threadIdx.x & (GL - 1), pl = threadIdx.x / GL;
   const int ng = C / 8;
@@ -189,6 +191,11 @@ __global__ void __launch_bounds__(256) maxpool_fwd_vec8_kernel(PV x, __nv_bfloat
     for (int j = 0; j < 8; ++j) d0[j] = d1[j] = 0.0;
     if (g < ng) {
       int cnt = 0;
+      float sc[8], sh[8], sg[8];
+      if (AFF) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = aff[8 * g + j]; sh[j] = aff[C + 8 * g + j]; sg[j] = sc[j] < 0.f ? -1.f : 1.f; }
+      }
       for (long long p = (long long)blockIdx.x * PL + pl; p < PO; p += (long long)gridDim.x * PL) {
         const int ox = (int)(p % Wo);
         const long long t = p / Wo;
@@ -203,12 +210,24 @@ __global__ void __launch_bounds__(256) maxpool_fwd_vec8_kernel(PV x, __nv_bfloat
         float best[8], v[8];
         uint32_t bi[2] = {0u, 0u};
         unpack8f(r[0], best);
+        if (AFF) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) best[j] *= sg[j];
+        }
 #pragma unroll
         for (int k = 1; k < 4; ++k) {
           unpack8f(r[k], v);
+          if (AFF) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= sg[j];
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (v[j] > best[j]) { best[j] = v[j]; bi[j >> 2] = (bi[j >> 2] & ~(0xffu << ((j & 3) * 8))) | ((uint32_t)k << ((j & 3) * 8)); }
+        }
+        if (AFF) {       // affine of the selected element, rounded like the stored tensor (statistics are taken on stored values)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) best[j] = __bfloat162float(__float2bfloat16_rn(fmaf(sg[j] * best[j], sc[j], sh[j])));
         }
         __stcs(reinterpret_cast<uint4*>(y + p * ycs + 8 * g),
                make_uint4(pack2(best[0], best[1]), pack2(best[2], best[3]), pack2(best[4], best[5]), pack2(best[6], best[7])));
@@ -299,6 +318,25 @@ static int vec_grid(long long threads) {
   long long b = (threads + 255) / 256, cap = (long long)sm_count() * 16;
   if (b > cap) b = cap;
   return (int)(b < 1 ? 1 : b);
+}
+
+// MaxPool of a tensor with a folded BatchNorm affine; 1 handled / 0 not covered
+int try_maxpool_fwd_affine_vec(cudaStream_t s, const dnnca_tensor_t* x, const float* aff, const dnnca_tensor_t* y, uint8_t* idx,
+                               double* stats) {
+  if (!(vec8_view(x) && vec8_view(y) && (!idx || (reinterpret_cast<uintptr_t>(idx) & 7) == 0))) return 0;
+  const int C = x->c;
+  int gl = 1;
+  while (gl < C / 8 && gl < 256) gl <<= 1;
+  const int pl = 256 / gl;
+  const long long PO = (long long)y->n * y->h * y->w;
+  long long b = (PO + (long long)pl * (stats ? 32 : 4) - 1) / ((long long)pl * (stats ? 32 : 4)), cap = (long long)sm_count() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff;
+  if (stats) maxpool_fwd_vec8_kernel<true, true><<<(int)b, 256, 0, s>>>(pv(x), yp, y->cstride, idx, stats, C, y->h, y->w, PO, gl, pl, aff);
+  else maxpool_fwd_vec8_kernel<false, true><<<(int)b, 256, 0, s>>>(pv(x), yp, y->cstride, idx, stats, C, y->h, y->w, PO, gl, pl, aff);
+  DNNCA_LAUNCH_CHECK("maxpool_fwd_affine_vec8");
+  return 1;
 }
 
 // returns 1 when handled, 0 when the shape is not covered

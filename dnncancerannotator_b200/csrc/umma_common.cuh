@@ -114,6 +114,7 @@ struct UArgs {
   int epi, act;
   float alpha;
   const float* bias;
+  const float* bias9;        // 3x3 fprop with a BatchNorm folded into the input: [9][n_total] bias per border class, or NULL
   // outputs: channel-slice views (bf16).  ya: columns [0, split); yb: columns [split, N)
   __nv_bfloat16* ya; long long ya_cs; int split;
   __nv_bfloat16* yb; long long yb_cs;
@@ -196,9 +197,11 @@ __device__ __forceinline__ void warp_colsum32(float (&v)[32], int lane) {
 }
 
 // STATS: on return v[] holds the values as they read back from the bf16 tensor (fp32 bit patterns)
+// `nvalid`: columns of this chunk below N (a multiple of 8): 8-column groups at or beyond it belong to the zero-padded
+// tail of a partially filled N tile and are not stored
 template <bool STATS = false, int EPI = -1>
 __device__ __forceinline__ void epilogue_chunk32(const UArgs& a, uint32_t (&v)[32], const ChunkAddr& ca, const uint4 (&m)[4],
-                                                 const float* sbias, bool store = true) {
+                                                 const float* sbias, bool store = true, int nvalid = 32) {
   const int epi = EPI >= 0 ? EPI : a.epi;
   float f[32];
 #pragma unroll
@@ -241,7 +244,7 @@ __device__ __forceinline__ void epilogue_chunk32(const UArgs& a, uint32_t (&v)[3
     o.y = *reinterpret_cast<uint32_t*>(&p1);
     o.z = *reinterpret_cast<uint32_t*>(&p2);
     o.w = *reinterpret_cast<uint32_t*>(&p3);
-    if (store) d4[q] = o;                     // (a streaming st.global.cs here measured 3 % slower: the consumer kernel
+    if (store && q * 8 < nvalid) d4[q] = o;   // (a streaming st.global.cs here measured 3 % slower: the consumer kernel
                                               // that follows finds part of this output in L2)
     if (STATS) {                              // the values as they read back from the bf16 tensor
       const uint32_t ow[4] = {o.x, o.y, o.z, o.w};

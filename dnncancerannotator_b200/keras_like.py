@@ -101,6 +101,7 @@ class Model:
         self.trainable_model = True     # MultiResUnet (inference-only in this build) sets False
         # data parallel (engine.py:260-263 MirroredStrategy): set by enable_data_parallel()
         self._dp = None
+        self._p2p = None
 
     # ---- to be provided by subclasses ------------------------------------------
     def _build_variables(self, input_shape):
@@ -142,6 +143,23 @@ class Model:
         self._metric_set = None                 # utils.metrics.MetricSet, created on first use (needs the device)
         self._hyper_dirty = True
         self._invalidate_graphs()               # the loss configuration is baked into captured launch sequences
+
+    def release_graphs(self):
+        """Destroys every captured CUDA graph (they are re-captured on demand).  Call before
+        ``torch.distributed.destroy_process_group()``: NCCL does not tear a communicator down while a live graph still
+        holds collectives captured on it (the destroy call blocks)."""
+        if self.params.device is not None:
+            torch.cuda.synchronize()
+        self._invalidate_graphs()
+        if self.params.device is not None:
+            torch.cuda.synchronize()
+
+    def close(self):
+        """Releases captured graphs and peer-memory mappings (call before destroying the process group)."""
+        self.release_graphs()
+        if getattr(self, '_p2p', None) is not None:
+            self._p2p.check()
+            self._p2p.close()
 
     def _invalidate_graphs(self):
         """Captured CUDA graphs hold the loss configuration (by value), the replica count and the bucket schedule:
@@ -246,10 +264,13 @@ class Model:
             fresh = self.params.device is None
             self.params.materialize(self.device)
             if fresh:
+                self._setup_p2p()
                 self._sync_replicas()
             plan = R.Plan(self.params, batch, height, width, self.input_shape[-1], self.compute_dtype, self.device,
                           want_input_grad=want_input_grad)
             self._emit(plan)
+            if os.environ.get('DNNCA_BN_FOLD', '1') != '0' and not want_input_grad:
+                plan.fold_batchnorms()
             self._plans[key] = plan
         return self._plans[key]
 
@@ -347,11 +368,29 @@ class Model:
         SUM-all-reduced over NCCL with the loss pre-scaled by 1/world (== averaging)."""
         from . import parallel
         self._dp = parallel.GradAllReduce(process_group, bucket_bytes)
+        self._p2p = None
         if self.built:
             self.params.materialize(self.device)
+            self._setup_p2p()
         self._sync_replicas()                   # params, BN state, Adam slots and step counter from rank 0
         self._invalidate_graphs()
         return self
+
+    def _setup_p2p(self):
+        """Small models (whole gradient <= 4 MB) exchange gradients through NVLink peer memory inside the Adam kernel
+        (csrc/p2p_adam.cu) instead of NCCL; larger ones keep the bucketed NCCL all-reduce overlapped with backward."""
+        from . import parallel
+        ps = self.params
+        if self._dp is None or getattr(self, '_p2p', None) is not None or ps.device is None:
+            return
+        n = max(ps.n_trainable, 4) + 4
+        if not parallel.P2PAdam.usable(n * 4, self._dp.world_size):
+            return
+        p2p = parallel.P2PAdam(self._dp.group)
+        full = p2p.setup(n, self.device)
+        ps.rebind_grads(full, p2p.reduced)
+        self._p2p = p2p
+        self._invalidate_graphs()
 
     def _loss_cfg(self, plan):
         world = self._dp.world_size if self._dp else 1
@@ -522,12 +561,15 @@ class Model:
         cfg = self._loss_cfg(plan)
         plan._cfg = cfg
         dp = self._dp if (self._dp is not None and self._dp.world_size > 1) else None
+        p2p = getattr(self, '_p2p', None) if dp is not None else None
         ps = self.params
         if self.loss.label_smoothing and getattr(plan, 'y_metric', None) is None:
             plan.y_metric = torch.empty_like(plan.y_in)      # raw labels for the metrics (keras: the loss alone smooths)
             plan.y_tmp = torch.empty_like(plan.y_in)
 
         def seq():
+            if p2p is not None:
+                p2p.wait_done()                  # no peer may still be reading the gradients the next line zeroes
             plan.zero_step_state()
             if self.loss.label_smoothing:        # losses.py:62-67 on the device, inside the step's launch sequence
                 plan.y_metric.copy_(plan.y_in)       # device-to-device copy node of the same graph
@@ -539,13 +581,18 @@ class Model:
             self._loss_total(plan)
             if dp is None:
                 plan.backward()
+                self._adam()
+            elif p2p is not None:
+                plan.backward()
+                ps.version += 1
+                p2p.adam_step(ps)                # all-reduce over NVLink peer memory fused into the Adam kernel
             else:
                 ready = plan.ready_frontier()
                 dp.begin(ps.grads_full)
                 dp.launch_ready(plan.pending_before_backward)
                 plan.backward(after_op=lambda i: dp.launch_ready(ready[i]))
                 dp.finish()
-            self._adam()
+                self._adam()
         key = self._train_key(plan)
         if dp is not None and os.environ.get('DNNCA_DP_GRAPH', '1') == '0':
             saved, self.use_cuda_graph = self.use_cuda_graph, False     # escape hatch: eager launches, NCCL uncaptured

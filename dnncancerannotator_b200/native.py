@@ -53,6 +53,11 @@ _PROTOS = {
     'dnnca_conv_workspace_bytes': [_i, _i, _i],
     'dnnca_conv2d_prepack': [_vp, _TP, _TP, _vp, _TP, _i, _vp, C.c_size_t],
     'dnnca_convtranspose2x2_prepack': [_vp, _TP, _vp, _TP, _vp, C.c_size_t],
+    'dnnca_conv2d_fold_supported': [_TP, _TP, _TP, _i],
+    'dnnca_conv2d_fold_scratch_bytes': [_i],
+    'dnnca_conv2d_fprop_affine': [_vp, _TP, _TP, _vp, _vp, _vp, _vp, _TP, _i, _f, _vp, _vp, C.c_size_t, _vp],
+    'dnnca_conv2d_wgrad_affine': [_vp, _TP, _TP, _vp, _vp, _TP, _vp, _vp, _vp],
+    'dnnca_maxpool2x2_fwd_affine': [_vp, _TP, _vp, _TP, _vp, _vp],
     'dnnca_conv2d_fprop': [_vp, _TP, _TP, _vp, _vp, _TP, _i, _i, _f, _vp, _vp, C.c_size_t],
     'dnnca_conv2d_dgrad': [_vp, _TP, _vp, _TP, _TP, _i, _TP, _i, _f, _vp, C.c_size_t],
     'dnnca_conv2d_wgrad': [_vp, _TP, _TP, _TP, _vp, _vp, _i],
@@ -84,13 +89,20 @@ _PROTOS = {
     'dnnca_input_tail': [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, C.POINTER(C.c_int32), _i, _i, _vp, _i, _i, _vp],
     'dnnca_convert': [_vp, _TP, _TP],
     'dnnca_adam_step': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    'dnnca_p2p_alloc': [C.c_size_t, C.POINTER(C.c_void_p)],
+    'dnnca_p2p_free': [_vp],
+    'dnnca_p2p_export': [_vp, C.c_char_p],
+    'dnnca_p2p_import': [C.c_char_p, C.POINTER(C.c_void_p)],
+    'dnnca_p2p_close': [_vp],
+    'dnnca_p2p_wait_done': [_vp, _vp, _i, _vp],
+    'dnnca_p2p_adam_step': [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     'dnnca_host_alloc': [C.c_size_t, _i, C.POINTER(C.c_void_p)],
     'dnnca_host_free': [_vp],
     'dnnca_loss_total': [_vp, _vp, _i, _vp, _vp, _i64, _f, _vp],
 }
 _RESTYPES = {'dnnca_last_error': C.c_char_p, 'dnnca_label_stats_decode': None,
              'dnnca_debug_launch_count': C.c_longlong, 'dnnca_debug_family_count': C.c_longlong,
-             'dnnca_conv_workspace_bytes': C.c_size_t}
+             'dnnca_conv_workspace_bytes': C.c_size_t, 'dnnca_conv2d_fold_scratch_bytes': C.c_size_t}
 
 _lib = None
 
@@ -176,9 +188,14 @@ class Profiler:
         byt = sum(v.n * v.h * v.w * v.c * esz(v) for v in vs)
         flops = 0
         label = name.replace('dnnca_', '')
+        if name in ('dnnca_conv2d_prepack', 'dnnca_conv2d_fold_supported'):
+            return dict(label=label, bytes=0, flops=0)
         if name.startswith('dnnca_conv2d_') and len(vs) >= 2:
-            k = [a for a in args if isinstance(a, int)][0]
+            affine = name.endswith('_affine')      # BatchNorm folded into the input(s): same conv, k = 3
+            k = 3 if affine else [a for a in args if isinstance(a, int)][0]
             a = vs[0]
+            name = name[:-len('_affine')] if affine else name
+            label = name.replace('dnnca_', '')
             if name.endswith('fprop'):      # x [x2] y
                 cin, cout = sum(v.c for v in vs[:-1]), vs[-1].c
             elif name.endswith('wgrad'):    # x [x2] dz

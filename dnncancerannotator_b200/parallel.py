@@ -116,3 +116,91 @@ class GradAllReduce:
         for t in flat_buffers:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
             t.div_(self.world_size)
+
+
+class _DevMem:
+    """Zero-copy torch view of raw device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, nbytes, typestr, shape):
+        self.__cuda_array_interface__ = dict(shape=shape, typestr=typestr, data=(int(ptr), False), version=3, strides=None)
+        self.ptr, self.nbytes = ptr, nbytes
+
+
+class P2PAdam:
+    """All-reduce fused into Adam over NVLink peer memory (``csrc/p2p_adam.cu``) for models whose whole gradient is small
+    (configs/unet.yaml: 35 KB): the flat gradient buffer of every rank is peer-mapped through CUDA IPC and ONE kernel per
+    rank sums the peers' gradients in place of an NCCL all-reduce and applies the Adam update.  ``torch.distributed`` is
+    used only to exchange the 64-byte IPC handles at set-up."""
+
+    MAX_BYTES = 4 << 20
+
+    def __init__(self, group=None):
+        import ctypes as C
+        from . import native as N
+        self.N, self.C = N, C
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.local = self.peers_g = self.peers_f = None
+        self.opened = []
+
+    @classmethod
+    def usable(cls, nbytes, world):
+        import os
+        return os.environ.get('DNNCA_P2P', '1') != '0' and 1 < world <= 8 and nbytes <= cls.MAX_BYTES and torch.cuda.is_available()
+
+    def setup(self, numel, device):
+        """Allocates this rank's shared gradient buffer [numel] fp32 + flag array, exchanges IPC handles, opens the peers'.
+        Returns the gradient buffer as a torch tensor (to replace ParamStore.grads_full)."""
+        N, C = self.N, self.C
+        lib = N.lib()
+        gp, fp = C.c_void_p(), C.c_void_p()
+        N.check(lib.dnnca_p2p_alloc(C.c_size_t(numel * 4), C.byref(gp)), 'p2p_alloc')
+        N.check(lib.dnnca_p2p_alloc(C.c_size_t(256), C.byref(fp)), 'p2p_alloc')
+        hg, hf = C.create_string_buffer(64), C.create_string_buffer(64)
+        N.check(lib.dnnca_p2p_export(gp, hg), 'p2p_export')
+        N.check(lib.dnnca_p2p_export(fp, hf), 'p2p_export')
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, (hg.raw, hf.raw), group=self.group)
+        G, Fl = (C.c_void_p * self.world_size)(), (C.c_void_p * self.world_size)()
+        for r, (a, b) in enumerate(handles):
+            if r == self.rank:
+                G[r], Fl[r] = gp.value, fp.value
+                continue
+            pa, pb = C.c_void_p(), C.c_void_p()
+            N.check(lib.dnnca_p2p_import(a, C.byref(pa)), 'p2p_import')
+            N.check(lib.dnnca_p2p_import(b, C.byref(pb)), 'p2p_import')
+            self.opened += [pa, pb]
+            G[r], Fl[r] = pa.value, pb.value
+        self.peers_g, self.peers_f = G, Fl
+        self.local = (gp, fp)
+        self.numel = numel
+        self.grads = torch.as_tensor(_DevMem(gp.value, numel * 4, '<f4', (numel,)), device=device)
+        self.flags = torch.as_tensor(_DevMem(fp.value, 256, '<i8', (32,)), device=device)
+        self.reduced = torch.zeros(numel, dtype=torch.float32, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        self.done_blocks = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group=self.group)        # every peer mapping exists before the first exchange
+        return self.grads
+
+    def wait_done(self):
+        N = self.N
+        N.call('dnnca_p2p_wait_done', N.stream_ptr(), self.local[1], self.world_size, N.ptr(self.epoch))
+
+    def adam_step(self, ps):
+        N = self.N
+        N.call('dnnca_p2p_adam_step', N.stream_ptr(), self.peers_g, self.peers_f, self.rank, self.world_size, N.ptr(ps.params),
+               N.ptr(ps.m), N.ptr(ps.v), ps.n_trainable, self.numel, N.ptr(self.reduced), N.ptr(ps.hyper), N.ptr(ps.step),
+               N.ptr(self.epoch), N.ptr(ps.l2), N.ptr(self.done_blocks))
+
+    def check(self):
+        """Raises if a peer wait timed out (sticky device flag)."""
+        if int(self.flags[16]) != 0:
+            raise RuntimeError('p2p_adam: a wait for a peer GPU timed out (a rank died or fell out of lockstep)')
+
+    def close(self):
+        lib = self.N.lib()
+        torch.cuda.synchronize()
+        for p in self.opened:
+            lib.dnnca_p2p_close(p)
+        self.opened = []

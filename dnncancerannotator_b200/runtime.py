@@ -105,6 +105,24 @@ class ParamStore:
         self.hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-7], dtype=torch.float32, device=device)
         self.step = torch.zeros(1, dtype=torch.int64, device=device)
 
+    def rebind_grads(self, full, reduced=None):
+        """Moves the flat gradient buffer to other device memory (data parallelism over NVLink peer memory: the buffer
+        must be an IPC-exportable allocation).  ``reduced``: where the cross-replica sums land (``get_grads`` / the loss
+        scalar read from there); None = the buffer itself."""
+        n = max(self.n_trainable, 4)
+        assert full.numel() == n + 4 and full.dtype == torch.float32
+        full.zero_()
+        self.grads_full = full
+        self.grads = full[:n]
+        self.grads_reduced = reduced
+        res = reduced if reduced is not None else full
+        self.loss_slot = res[n:n + 1]
+        for name, s in self.specs.items():
+            if s['trainable']:
+                self._gviews[name] = self.grads[s['offset']:s['offset'] + s['numel']].view(s['shape'])
+        self._rviews = None if reduced is None else {
+            name: reduced[s['offset']:s['offset'] + s['numel']].view(s['shape']) for name, s in self.specs.items() if s['trainable']}
+
     def view(self, name):
         return self._views[name]
 
@@ -141,7 +159,8 @@ class ParamStore:
                 self._views[name].copy_(torch.from_numpy(arr))
 
     def get_grads(self):
-        return OrderedDict((k, self._gviews[k].detach().cpu().numpy().copy()) for k in self._gviews)
+        views = getattr(self, '_rviews', None) or self._gviews      # cross-replica sums when they live in their own buffer
+        return OrderedDict((k, views[k].detach().cpu().numpy().copy()) for k in views)
 
     def count(self, trainable=None):
         return int(sum(int(np.prod(s['shape'])) for s in self.specs.values()
@@ -159,11 +178,12 @@ class Buf:
         self.data = external
         self.grad = None
         self.want_grad = False
+        self.virtual = False          # output of a BatchNorm folded into its consumers: never materialised (gradient only)
         plan.bufs.append(self)
 
     def allocate(self, training):
         dev = self.plan.device
-        if self.data is None:
+        if self.data is None and not self.virtual:
             alloc = torch.zeros if self.zero else torch.empty
             self.data = alloc(self.n, self.h, self.w, self.c, dtype=self.dtype, device=dev)
         if training and self.want_grad and self.grad is None:
@@ -182,6 +202,7 @@ class TRef:
         self.act = None            # (code, alpha) when this tensor IS the output of conv+activation
         self.skip_consumed = False  # a second consumer (skip concat) adds into its gradient first
         self.needs_grad = True
+        self.fold = None           # (pre-BN TRef, BNOp) when this tensor is the never-materialised output of a folded BatchNorm
         self._ct = self._gct = None
 
     n = property(lambda s: s.buf.n)
@@ -191,8 +212,17 @@ class TRef:
 
     def ct(self):
         if self._ct is None:
+            assert self.buf.data is not None, f'{self.buf.name} is the output of a folded BatchNorm and has no storage'
             self._ct = N.tensor_view(self.buf.data, self.coff, self.c)
         return C.byref(self._ct)
+
+    def src(self):
+        """(tensor view to READ, [2C] scale|shift pointer or None): the pre-BN tensor and the BatchNorm's affine when this
+        tensor is a folded BatchNorm output, else the tensor itself."""
+        if self.fold is None:
+            return self.ct(), None
+        a, bn = self.fold
+        return a.ct(), N.ptr(bn.ss)
 
     def gct(self):
         if self._gct is None:
@@ -229,6 +259,14 @@ def conv_workspace(plan, taps, inputs, y, out_multiple=16):
     return torch.empty(nbytes, dtype=torch.uint8, device=plan.device)
 
 
+def conv_workspace_ok(plan, inputs, y):
+    """Would ``conv_workspace`` hand this layer a tensor-core workspace? (same conditions, no allocation)"""
+    ins = [t for t in inputs if t is not None]
+    if plan.dtype != torch.bfloat16 or y.c % 16 or y.coff % 8 or y.buf.c % 8 or any(t.buf.c % 8 or t.coff % 8 for t in ins):
+        return False
+    return not (len(ins) > 1 and any(t.c % 16 for t in ins))
+
+
 def ws_args(ws):
     return (N.ptr(ws), ws.numel()) if ws is not None else (None, 0)
 
@@ -261,22 +299,40 @@ class ConvOp(Op):
         if act and act[0] != N.ACT_NONE:
             y.act = act
 
+    def folded(self):
+        return self.x.fold is not None or (self.x2 is not None and self.x2.fold is not None)
+
     def allocate(self, training):
         self.ws = conv_workspace(self.p, self.k * self.k, [self.x, self.x2], self.y) if self.ws is None else self.ws
+        if self.folded() and getattr(self, 'scratch', None) is None:
+            self.scratch = torch.empty(N.lib().dnnca_conv2d_fold_scratch_bytes(self.y.c) // 4, dtype=torch.float32,
+                                       device=self.p.device)
 
     def fwd(self, train):
         ps = self.p.params
+        st = self.stats.fwd_ptr() if (self.stats and train) else None
+        if self.folded():           # BatchNorm of the input(s) folded into this conv (bn_fold.cu)
+            xa, fa = self.x.src()
+            xb, fb = self.x2.src() if self.x2 else (None, None)
+            N.call('dnnca_conv2d_fprop_affine', N.stream_ptr(), xa, xb, fa, fb, ps.ptr(self.kernel), ps.ptr(self.bias),
+                   self.y.ct(), self.act[0], self.act[1], st, *ws_args(self.ws), N.ptr(self.scratch))
+            return
         N.call('dnnca_conv2d_fprop', N.stream_ptr(), self.x.ct(), self.x2.ct() if self.x2 else None,
-               ps.ptr(self.kernel), ps.ptr(self.bias), self.y.ct(), self.k, self.act[0], self.act[1],
-               self.stats.fwd_ptr() if (self.stats and train) else None, *ws_args(self.ws))
+               ps.ptr(self.kernel), ps.ptr(self.bias), self.y.ct(), self.k, self.act[0], self.act[1], st, *ws_args(self.ws))
 
     def grad_params(self):
         return tuple(n for n in (self.kernel, self.bias) if n)
 
     def bwd(self):
         ps = self.p.params
-        N.call('dnnca_conv2d_wgrad', N.stream_ptr(), self.x.ct(), self.x2.ct() if self.x2 else None, self.y.gct(),
-               ps.gptr(self.kernel), ps.gptr(self.bias), self.k)
+        if self.folded():
+            xa, fa = self.x.src()
+            xb, fb = self.x2.src() if self.x2 else (None, None)
+            N.call('dnnca_conv2d_wgrad_affine', N.stream_ptr(), xa, xb, fa, fb, self.y.gct(), ps.gptr(self.kernel),
+                   ps.gptr(self.bias), N.ptr(self.scratch))
+        else:
+            N.call('dnnca_conv2d_wgrad', N.stream_ptr(), self.x.ct(), self.x2.ct() if self.x2 else None, self.y.gct(),
+                   ps.gptr(self.kernel), ps.gptr(self.bias), self.k)
         self.bwd_input()
 
     def bwd_input(self):
@@ -333,8 +389,12 @@ class PoolOp(Op):
 
     def fwd(self, train):
         keep = train or self.p.want_input_grad       # the input-gradient chain runs an inference forward but needs the argmax
-        N.call('dnnca_maxpool2x2_fwd', N.stream_ptr(), self.x.ct(), self.y.ct(), N.ptr(self.idx) if keep else None,
-               self.stats.fwd_ptr() if (self.stats and train) else None)
+        st = self.stats.fwd_ptr() if (self.stats and train) else None
+        if self.x.fold is not None:
+            xa, fa = self.x.src()
+            N.call('dnnca_maxpool2x2_fwd_affine', N.stream_ptr(), xa, fa, self.y.ct(), N.ptr(self.idx) if keep else None, st)
+            return
+        N.call('dnnca_maxpool2x2_fwd', N.stream_ptr(), self.x.ct(), self.y.ct(), N.ptr(self.idx) if keep else None, st)
 
     def bwd(self):
         if not self.x.needs_grad:
@@ -370,6 +430,7 @@ class BNOp(Op):
         self.p, self.x, self.y, self.prefix, self.stats = plan, x, y, prefix, stats
         self.gamma = f'{prefix}/gamma' if scale else None
         self.fused_stats = fused_stats
+        self.folded = False        # Plan.fold_batchnorms: the consumers read `x` + the affine, `y` is never written
         self.ss = self.mi = None   # scale|shift and mean|invstd, fp32 [2C] each
 
     def allocate(self, training):
@@ -389,7 +450,8 @@ class BNOp(Op):
         else:
             N.call('dnnca_bn_inference_params', s, c, g, ps.ptr(f'{self.prefix}/beta'), BN_EPSILON,
                    ps.ptr(f'{self.prefix}/moving_mean'), ps.ptr(f'{self.prefix}/moving_var'), N.ptr(self.ss))
-        N.call('dnnca_bn_apply', s, self.x.ct(), N.ptr(self.ss), self.y.ct())
+        if not self.folded:
+            N.call('dnnca_bn_apply', s, self.x.ct(), N.ptr(self.ss), self.y.ct())
 
     def grad_params(self):
         return tuple(n for n in (self.gamma, f'{self.prefix}/beta') if n)
@@ -485,6 +547,50 @@ class Plan:
         self.ops.append(op)
         return op
 
+    def fold_batchnorms(self, min_channels=32):
+        """Folds every BatchNorm whose output is read only by 3x3 convs the folded tensor-core kernel serves and by
+        max-pools into those consumers (bn_fold.cu): the BN's apply pass and its output tensor disappear, the consumers
+        read the pre-BN tensor + the [2C] scale|shift the BN's finalize wrote.  A BN feeding the head, a transposed conv,
+        a concat slice (MulmoUNet's bottleneck) or a layer narrower than ``min_channels`` (those run on the
+        row-Toeplitz kernels) keeps its materialised output.  Returns the number of folded BatchNorms."""
+        if self.dtype != torch.bfloat16 or self.allocated_training is not None:
+            return 0
+        lib = N.lib()
+        n = 0
+        for bn in [op for op in self.ops if isinstance(op, BNOp)]:
+            t, a = bn.y, bn.x
+            if t is self.features or t.coff != 0 or t.c != t.buf.c or a.c < min_channels or t.c % 8:
+                continue
+            users = [op for op in self.ops if getattr(op, 'x', None) is t or getattr(op, 'x2', None) is t]
+            if not users or any(op is bn for op in users):
+                continue
+            ok = True
+            for op in users:
+                if isinstance(op, PoolOp):
+                    continue
+                if not (isinstance(op, ConvOp) and op.k == 3):
+                    ok = False
+                    break
+                # shape query with stand-in views (no storage yet): same n,h,w,c / strides as the real tensors
+                def view(tr):
+                    if tr is None:
+                        return None
+                    src = tr.fold[0] if tr.fold else (a if tr is t else tr)
+                    v = N.Tensor(256, src.n, src.h, src.w, src.c, src.buf.c, src.coff, N.BF16)
+                    return C.byref(v)
+                if not lib.dnnca_conv2d_fold_supported(view(op.x), view(op.x2), view(op.y), 3) or \
+                        conv_workspace_ok(self, [op.x, op.x2], op.y) is False:
+                    ok = False
+                    break
+            if not ok:
+                continue
+            t.fold = (a, bn)
+            t.buf.virtual = True
+            bn.folded = True
+            n += 1
+        self.n_folded_bn = n
+        return n
+
     def allocate(self, training):
         if self.allocated_training is not None and (self.allocated_training or not training):
             return
@@ -511,7 +617,8 @@ class Plan:
         self.allocated_training = training or bool(self.allocated_training)
 
     def activation_bytes(self):
-        return sum(b.nbytes() * (2 if b.grad is not None else 1) for b in self.bufs)
+        """Bytes of activation + activation-gradient storage actually allocated by this plan."""
+        return sum(t.numel() * t.element_size() for b in self.bufs for t in (b.data, b.grad) if t is not None)
 
     # ---- launch sequences ----------------------------------------------------
     def forward(self, train=False):

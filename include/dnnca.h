@@ -183,6 +183,31 @@ DNNCA_API int dnnca_bn_bwd_apply(void* stream, const dnnca_tensor_t* x, const dn
                        float* dgamma, float* dbeta);
 
 /* ---------------------------------------------------------------------------
+ * BatchNormalization folded into its consumer (the reference's block order is Conv -> act -> BN -> Conv,
+ * components.py:46-61 and 118-134, BN -> MaxPool at :54-59): instead of materialising y = s*a + t (bn_apply), the
+ * consumer reads the pre-BN tensor `a` together with the [2C] scale|shift array bn_finalize / bn_inference_params
+ * wrote.  Exact, including the zero padding that follows the BN (nine border-class bias vectors).
+ *   conv2d_fold_supported : 1 when conv2d_fprop_affine serves this (x, x2, y) shape (3x3, bf16, tensor-core kernel).
+ *   conv2d_fprop_affine   : y = act(conv3x3([s*x+t | s2*x2+t2] zero-padded, w) + bias); affine_* may be NULL
+ *                           (identity).  `scratch`: dnnca_conv2d_fold_scratch_bytes(cout) bytes owned by the layer,
+ *                           shared between the fprop and the wgrad call of a step.  stats as in conv2d_fprop.
+ *   conv2d_wgrad_affine   : gradients w.r.t. w and bias of that layer: dW = s*dW_raw + t*S (S = sums of dz over the
+ *                           pixels whose tap stays inside the image); db is required.
+ *   maxpool2x2_fwd_affine : MaxPool2D of s*x + t (max of x where s >= 0, min where s < 0), y / idx / stats as in
+ *                           maxpool2x2_fwd; the backward pass is maxpool2x2_bwd unchanged.
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_conv2d_fold_supported(const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* y, int ksize);
+DNNCA_API size_t dnnca_conv2d_fold_scratch_bytes(int cout);
+DNNCA_API int dnnca_conv2d_fprop_affine(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* affine_x,
+                                        const float* affine_x2, const float* w, const float* bias, const dnnca_tensor_t* y,
+                                        int act, float alpha, double* stats, void* workspace, size_t workspace_bytes,
+                                        float* scratch);
+DNNCA_API int dnnca_conv2d_wgrad_affine(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* affine_x,
+                                        const float* affine_x2, const dnnca_tensor_t* dz, float* dw, float* db, float* scratch);
+DNNCA_API int dnnca_maxpool2x2_fwd_affine(void* stream, const dnnca_tensor_t* x, const float* affine, const dnnca_tensor_t* y,
+                                          uint8_t* idx, double* stats);
+
+/* ---------------------------------------------------------------------------
  * Head Conv2D(filters=1, k=1, 'sigmoid') + WeightedCrossentropy
  *   replaces layers.Conv2D at unet.py:241-244 and losses.py:17-37, 60-72, 87-102.
  * label_stats: lstats = {sum(label) fp64, min, max} over the whole per-replica
@@ -313,6 +338,32 @@ DNNCA_API int dnnca_adam_step(void* stream, float* params, const float* grads, f
  * ------------------------------------------------------------------------- */
 DNNCA_API int dnnca_loss_total(void* stream, const float* per_sample, int batch, const float* params, const float* l2,
                                int64_t count, float scale, float* out);
+
+/* ---------------------------------------------------------------------------
+ * Gradient all-reduce fused into the Adam step over NVLink peer memory (replaces, for small models, MirroredStrategy's
+ * NCCL all-reduce + the per-variable ResourceApplyAdam that follow the backward pass: engine.py:260-263, 276-284).
+ * One process per GPU on one box; every rank's flat gradient buffer and a 17-word flag array are allocated with
+ * p2p_alloc (cudaMalloc), exported / imported through CUDA IPC handles (64 bytes each, exchanged by the host side) and
+ * p2p_adam_step launches ONE kernel per rank that (1) publishes "gradients complete" to all peers and waits for theirs,
+ * (2) sums element i over all ranks' buffers straight from peer memory in rank order and applies the Keras-form Adam
+ * update of adam_step to the local parameters, (3) publishes "done reading".  p2p_wait_done is the first kernel of the
+ * next step: it holds this rank's gradient zeroing back until every peer has finished reading.
+ *   count        = trainable parameters (Adam runs over [0, count));
+ *   reduce_count = elements summed (>= count: the 4-float tail of the gradient buffer carries the loss scalar);
+ *   reduced_out  = LOCAL buffer [reduce_count] receiving the sums (may be NULL);  p2p_epoch = device int64 exchange
+ *   counter (starts at 0, identical on all ranks);  done_blocks = device uint32, zero.
+ *   flags[16] becomes non-zero if a wait timed out (a peer died): the step's result is then undefined.
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_p2p_alloc(size_t bytes, void** out);
+DNNCA_API int dnnca_p2p_free(void* ptr);
+DNNCA_API int dnnca_p2p_export(void* ptr, unsigned char* handle64);
+DNNCA_API int dnnca_p2p_import(const unsigned char* handle64, void** out);
+DNNCA_API int dnnca_p2p_close(void* ptr);
+DNNCA_API int dnnca_p2p_wait_done(void* stream, void* local_flags, int world, const int64_t* p2p_epoch);
+DNNCA_API int dnnca_p2p_adam_step(void* stream, const void* const* peer_grads, void* const* peer_flags, int rank, int world,
+                                  float* params, float* m, float* v, int64_t count, int64_t reduce_count, float* reduced_out,
+                                  const float* hyper, int64_t* step, int64_t* p2p_epoch, const float* l2,
+                                  unsigned int* done_blocks);
 
 /* ---------------------------------------------------------------------------
  * Page-locked host staging buffers for the input tail (the reference's tf.data pipeline ends with prefetch,

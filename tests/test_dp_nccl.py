@@ -25,10 +25,21 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, mode, graph, out):
+def _worker(rank, world, port, mode, graph, p2p, out):
+    import faulthandler
+    import sys
     import torch.distributed as dist
+    logdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    os.makedirs(logdir, exist_ok=True)
+    log = open(os.path.join(logdir, f'dp_test_{mode}_{int(graph)}{int(p2p)}_rank{rank}.log'), 'w')
+    faulthandler.dump_traceback_later(90, file=log, exit=True)      # a hung collective must not eat the GPU budget
+
+    def say(msg):
+        log.write(msg + '\n')
+        log.flush()
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     os.environ['DNNCA_DP_GRAPH'] = '1' if graph else '0'
+    os.environ['DNNCA_P2P'] = '1' if p2p else '0'      # gradient exchange: NVLink peer memory inside Adam / bucketed NCCL
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
@@ -43,7 +54,9 @@ def _worker(rank, world, port, mode, graph, out):
         ref0 = rm.build_model('UNetAnnotator', OPTS, (None, H, H, 3), seed=10 + rank)
         ref0.randomize_bn(seed=3 + rank)
         m.set_weights(ref0.get_weights())
+        say('model built')
         m.enable_data_parallel(bucket_bytes=1024)                            # ... and are mirrored from rank 0; many buckets
+        say('dp enabled')
         w_after_sync = m.get_weights()
         batches = [make_slices(3, H, H, 3, seed=1234 + r) for r in range(world)]
         x, y = batches[rank]
@@ -53,7 +66,11 @@ def _worker(rank, world, port, mode, graph, out):
         per = [ref.train_step_grads(bx, by, LOSS) for bx, by in batches]
         avg = {k: sum(p['grads'][k] for p in per) / world for k in ref.trainable}
         mean_loss = float(np.mean([p['loss'] for p in per]))
-        losses = [float(m.train_step(x, y)) for _ in range(4)]              # eager, eager, capture + replay, replay
+        say('oracle done')
+        losses = []
+        for i in range(4):                                                   # eager, eager, capture + replay, replay
+            losses.append(float(m.train_step(x, y)))
+            say(f'step {i} loss {losses[-1]}')
         g = m.get_grads()                                                    # all-reduced gradients of the LAST step
         w = m.get_weights()
         # oracle weights after ONE Adam step with the averaged gradient
@@ -70,11 +87,20 @@ def _worker(rank, world, port, mode, graph, out):
         m2.compile(loss=dict(class_name='WeightedCrossentropy', config=LOSS))
         m2.set_weights(ref.get_weights())
         m2.enable_data_parallel(bucket_bytes=1024)
+        say('m2 ready')
         l1 = float(m2.train_step(x, y))
+        say('m2 stepped')
         res.update(l1=l1, g1=m2.get_grads(), w_step1=m2.get_weights())
         out[rank] = res
+        say('results stored')
+        assert (m._p2p is not None) == bool(p2p)
+        m.close()                              # graphs holding captured NCCL collectives / peer mappings go before the communicator
+        m2.close()
+        say('graphs released')
     finally:
         dist.destroy_process_group()
+        say('group destroyed')
+        faulthandler.cancel_dump_traceback_later()
 
 
 def _rel(a, b):
@@ -82,15 +108,16 @@ def _rel(a, b):
                  max(np.linalg.norm(np.asarray(b, np.float64).ravel()), 1e-30))
 
 
-@pytest.mark.parametrize('mode,graph', [('fp32', True), ('fp32', False), ('bf16', True)])
-def test_two_rank_nccl_step_matches_oracle_subbatch_average(mode, graph):
+@pytest.mark.parametrize('mode,graph,p2p', [('fp32', True, False), ('fp32', False, False), ('fp32', True, True), ('fp32', False, True),
+                                            ('bf16', True, True), ('bf16', True, False)])
+def test_two_rank_step_matches_oracle_subbatch_average(mode, graph, p2p):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs (gpurun --gpus 2)')
     import torch.multiprocessing as mp
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), mode, graph, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), mode, graph, p2p, out), nprocs=world, join=True)
     a, b = out[0], out[1]
     tol = 2e-3 if mode == 'fp32' else 0.3
     # mirrored variables: rank 1 took rank 0's values when data parallelism was enabled
@@ -115,4 +142,8 @@ def test_two_rank_nccl_step_matches_oracle_subbatch_average(mode, graph):
     assert all(np.isfinite(a['losses'])) and a['losses'] == b['losses']
     # overlap schedule: several buckets, all but the last issued before the backward pass ended (frontier > 0)
     log = a['log']
-    assert len(log) >= 4 and sum(1 for f, _ in log if f > 0) >= len(log) - 1, log
+    if p2p:
+        assert log == []                       # no NCCL collective on the step path at all
+        return
+    # (with these 256-element test buckets the first layer's kernel + bias spill into the last two)
+    assert len(log) >= 4 and sum(1 for f, _ in log if f > 0) >= len(log) - 2, log
