@@ -18,7 +18,9 @@
 
 namespace dnnca {
 
-// T[tap][co] += sum_{ci in this block's slice} w[tap,ci,co] * shift[ci]      grid (taps, co tiles, ci slices)
+// Tpart[slice][tap][co] = sum_{ci in this block's slice} w[tap,ci,co] * shift[ci]      grid (taps, co tiles, ci slices)
+// (partial sums per slice, added in slice order by bias9_kernel: no atomics, so a step is reproducible bit for bit --
+// a last-bit difference in a bias flips bf16 roundings downstream and these BN nets amplify that to 1e-3 in the logits)
 __global__ void __launch_bounds__(128) fold_shift_kernel(const float* __restrict__ w, int cin, int cout,
                                                         const float* __restrict__ ta, int ca, const float* __restrict__ tb,
                                                         float* __restrict__ T) {
@@ -36,13 +38,13 @@ __global__ void __launch_bounds__(128) fold_shift_kernel(const float* __restrict
   float acc = 0.f;
 #pragma unroll 8
   for (int i = 0; i < c1 - c0; ++i) acc = fmaf(__ldg(wp + (long long)i * cout), st[i], acc);
-  atomicAdd(T + tap * cout + co, acc);
+  T[((long long)blockIdx.z * 9 + tap) * cout + co] = acc;
 }
 
 // bias9[cls][co] = bias[co] + sum over the taps that stay inside the image for border class cls = (row class)*3 + (column
 // class), class 0 = first row/column (tap offset -1 is outside), 1 = interior, 2 = last (offset +1 is outside)
-__global__ void __launch_bounds__(256) bias9_kernel(const float* __restrict__ T, const float* __restrict__ bias, int cout,
-                                                   float* __restrict__ bias9) {
+__global__ void __launch_bounds__(256) bias9_kernel(const float* __restrict__ T, int slices, const float* __restrict__ bias,
+                                                   int cout, float* __restrict__ bias9) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 9 * cout; i += gridDim.x * blockDim.x) {
     const int cls = i / cout, co = i - cls * cout;
     const int ry = cls / 3, rx = cls % 3;
@@ -53,7 +55,11 @@ __global__ void __launch_bounds__(256) bias9_kernel(const float* __restrict__ T,
       for (int dx = 0; dx < 3; ++dx) {
         const bool out_y = (ry == 0 && dy == 0) || (ry == 2 && dy == 2);
         const bool out_x = (rx == 0 && dx == 0) || (rx == 2 && dx == 2);
-        if (!out_y && !out_x) b += T[(dy * 3 + dx) * cout + co];
+        if (!out_y && !out_x) {
+          float t = 0.f;
+          for (int z = 0; z < slices; ++z) t += T[((long long)z * 9 + dy * 3 + dx) * cout + co];
+          b += t;
+        }
       }
     bias9[i] = b;
   }
@@ -219,9 +225,13 @@ extern "C" int dnnca_conv2d_fold_supported(const dnnca_tensor_t* x, const dnnca_
   return fprop_umma_affine_supported(x, x2, y);
 }
 
-extern "C" size_t dnnca_conv2d_fold_scratch_bytes(int cout) { return cout > 0 ? (size_t)(9 + 9 + 8) * cout * sizeof(float) : 0; }
+static inline int fold_slices(int cin) { return (cin + 31) / 32; }   // 32 input channels per block (<= 64: fold_shift_kernel's smem slice)
 
-// scratch layout (floats): T [9*cout] | bias9 [9*cout] | E [8*cout]
+extern "C" size_t dnnca_conv2d_fold_scratch_bytes(int cin, int cout) {
+  return (cin > 0 && cout > 0) ? (size_t)(9 + 8 + 9 * fold_slices(cin)) * cout * sizeof(float) : 0;
+}
+
+// scratch layout (floats): bias9 [9*cout] | E [8*cout] | Tpart [slices][9*cout]
 extern "C" int dnnca_conv2d_fprop_affine(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* affine_x,
                                          const float* affine_x2, const float* w, const float* bias, const dnnca_tensor_t* y,
                                          int act, float alpha, double* stats, void* workspace, size_t workspace_bytes,
@@ -232,16 +242,13 @@ extern "C" int dnnca_conv2d_fprop_affine(void* stream, const dnnca_tensor_t* x, 
     DNNCA_UNSUPPORTED("conv2d_fprop_affine: shape not served by the folded tensor-core kernel (query dnnca_conv2d_fold_supported)");
   cudaStream_t s = (cudaStream_t)stream;
   const int ca = x->c, cb = x2 ? x2->c : 0, cin = ca + cb, cout = y->c;
-  float* T = scratch;
-  float* bias9 = scratch + 9 * cout;
-  cudaError_t e = cudaMemsetAsync(T, 0, sizeof(float) * 9 * cout, s);
-  if (e != cudaSuccess) return cuda_fail(e, "conv2d_fprop_affine: memset");
-  note_launch(1);
-  const int zs = (cin + 31) / 32;                 // 32 input channels per block (<= 64: fold_shift_kernel's smem slice)
+  float* bias9 = scratch;
+  float* T = scratch + 17 * cout;
+  const int zs = fold_slices(cin);
   dim3 grid(9, (cout + 127) / 128, zs);
   fold_shift_kernel<<<grid, 128, 0, s>>>(w, cin, cout, affine_x ? affine_x + ca : nullptr, ca, affine_x2 ? affine_x2 + cb : nullptr, T);
   DNNCA_LAUNCH_CHECK("fold_shift");
-  bias9_kernel<<<(9 * cout + 255) / 256, 256, 0, s>>>(T, bias, cout, bias9);
+  bias9_kernel<<<(9 * cout + 255) / 256, 256, 0, s>>>(T, zs, bias, cout, bias9);
   DNNCA_LAUNCH_CHECK("bias9");
   const int r = fprop_umma_affine(s, x, x2, w, y, act, alpha, workspace, workspace_bytes, stats, affine_x, affine_x2, bias9);
   if (r < 0) return r;
@@ -257,7 +264,7 @@ extern "C" int dnnca_conv2d_wgrad_affine(void* stream, const dnnca_tensor_t* x, 
   if (r != DNNCA_OK) return r;
   cudaStream_t s = (cudaStream_t)stream;
   const int ca = x->c, cb = x2 ? x2->c : 0, cin = ca + cb, cout = dz->c;
-  float* E = scratch + 18 * cout;
+  float* E = scratch + 9 * cout;
   cudaError_t e = cudaMemsetAsync(E, 0, sizeof(float) * 8 * cout, s);
   if (e != cudaSuccess) return cuda_fail(e, "conv2d_wgrad_affine: memset");
   note_launch(1);

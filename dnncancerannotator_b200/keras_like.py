@@ -419,7 +419,7 @@ class Model:
         ps = self.params
         world = self._dp.world_size if self._dp else 1
         N.call('dnnca_loss_total', N.stream_ptr(), N.ptr(plan.per_sample), plan.batch, N.ptr(ps.params), N.ptr(ps.l2),
-               ps.n_trainable, 1.0 / world, N.ptr(ps.loss_slot))
+               ps.n_trainable, 1.0 / world, N.ptr(ps.loss_in))
 
     # ---- label / weight validation (losses.py:30, 91-99) ------------------------------------------
     def _validate_labels(self, plan):

@@ -54,7 +54,7 @@ _PROTOS = {
     'dnnca_conv2d_prepack': [_vp, _TP, _TP, _vp, _TP, _i, _vp, C.c_size_t],
     'dnnca_convtranspose2x2_prepack': [_vp, _TP, _vp, _TP, _vp, C.c_size_t],
     'dnnca_conv2d_fold_supported': [_TP, _TP, _TP, _i],
-    'dnnca_conv2d_fold_scratch_bytes': [_i],
+    'dnnca_conv2d_fold_scratch_bytes': [_i, _i],
     'dnnca_conv2d_fprop_affine': [_vp, _TP, _TP, _vp, _vp, _vp, _vp, _TP, _i, _f, _vp, _vp, C.c_size_t, _vp],
     'dnnca_conv2d_wgrad_affine': [_vp, _TP, _TP, _vp, _vp, _TP, _vp, _vp, _vp],
     'dnnca_maxpool2x2_fwd_affine': [_vp, _TP, _vp, _TP, _vp, _vp],

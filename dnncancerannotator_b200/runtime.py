@@ -84,7 +84,8 @@ class ParamStore:
         # same SUM all-reduce (keras reports the global mean loss under MirroredStrategy)
         self.grads_full = torch.zeros(max(off_t, 4) + 4, dtype=torch.float32, device=device)
         self.grads = self.grads_full[:max(off_t, 4)]
-        self.loss_slot = self.grads_full[max(off_t, 4):max(off_t, 4) + 1]
+        self.loss_slot = self.grads_full[max(off_t, 4):max(off_t, 4) + 1]       # where the step's loss is READ
+        self.loss_in = self.loss_slot                                             # where dnnca_loss_total WRITES it
         self.m = torch.zeros_like(self.params)
         self.v = torch.zeros_like(self.params)
         self.state = torch.zeros(max(off_s, 4), dtype=torch.float32, device=device)
@@ -117,6 +118,7 @@ class ParamStore:
         self.grads_reduced = reduced
         res = reduced if reduced is not None else full
         self.loss_slot = res[n:n + 1]
+        self.loss_in = full[n:n + 1]       # the local term goes into the exchanged buffer, the cross-replica sum is read from `res`
         for name, s in self.specs.items():
             if s['trainable']:
                 self._gviews[name] = self.grads[s['offset']:s['offset'] + s['numel']].view(s['shape'])
@@ -305,7 +307,7 @@ class ConvOp(Op):
     def allocate(self, training):
         self.ws = conv_workspace(self.p, self.k * self.k, [self.x, self.x2], self.y) if self.ws is None else self.ws
         if self.folded() and getattr(self, 'scratch', None) is None:
-            self.scratch = torch.empty(N.lib().dnnca_conv2d_fold_scratch_bytes(self.y.c) // 4, dtype=torch.float32,
+            self.scratch = torch.empty(N.lib().dnnca_conv2d_fold_scratch_bytes(self.x.c + (self.x2.c if self.x2 else 0), self.y.c) // 4, dtype=torch.float32,
                                        device=self.p.device)
 
     def fwd(self, train):

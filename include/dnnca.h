@@ -189,7 +189,7 @@ DNNCA_API int dnnca_bn_bwd_apply(void* stream, const dnnca_tensor_t* x, const dn
  * wrote.  Exact, including the zero padding that follows the BN (nine border-class bias vectors).
  *   conv2d_fold_supported : 1 when conv2d_fprop_affine serves this (x, x2, y) shape (3x3, bf16, tensor-core kernel).
  *   conv2d_fprop_affine   : y = act(conv3x3([s*x+t | s2*x2+t2] zero-padded, w) + bias); affine_* may be NULL
- *                           (identity).  `scratch`: dnnca_conv2d_fold_scratch_bytes(cout) bytes owned by the layer,
+ *                           (identity).  `scratch`: dnnca_conv2d_fold_scratch_bytes(cin, cout) bytes owned by the layer,
  *                           shared between the fprop and the wgrad call of a step.  stats as in conv2d_fprop.
  *   conv2d_wgrad_affine   : gradients w.r.t. w and bias of that layer: dW = s*dW_raw + t*S (S = sums of dz over the
  *                           pixels whose tap stays inside the image); db is required.
@@ -197,7 +197,7 @@ DNNCA_API int dnnca_bn_bwd_apply(void* stream, const dnnca_tensor_t* x, const dn
  *                           maxpool2x2_fwd; the backward pass is maxpool2x2_bwd unchanged.
  * ------------------------------------------------------------------------- */
 DNNCA_API int dnnca_conv2d_fold_supported(const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* y, int ksize);
-DNNCA_API size_t dnnca_conv2d_fold_scratch_bytes(int cout);
+DNNCA_API size_t dnnca_conv2d_fold_scratch_bytes(int cin, int cout);
 DNNCA_API int dnnca_conv2d_fprop_affine(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* affine_x,
                                         const float* affine_x2, const float* w, const float* bias, const dnnca_tensor_t* y,
                                         int act, float alpha, double* stats, void* workspace, size_t workspace_bytes,

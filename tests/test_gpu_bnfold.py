@@ -68,7 +68,7 @@ def test_conv_fprop_and_wgrad_with_folded_input_affine(N, shape, act):
     va, vb, vy, vdz = N.tensor_view(xa), (N.tensor_view(xb) if cx2 else None), N.tensor_view(y), N.tensor_view(dzd)
     assert lib.dnnca_conv2d_fold_supported(C.byref(va), C.byref(vb) if vb else None, C.byref(vy), 3) == 1
     ws = torch.empty(lib.dnnca_conv_workspace_bytes(9, cin, cout), dtype=torch.uint8, device='cuda')
-    scratch = torch.zeros(lib.dnnca_conv2d_fold_scratch_bytes(cout) // 4, dtype=torch.float32, device='cuda')
+    scratch = torch.zeros(lib.dnnca_conv2d_fold_scratch_bytes(cin, cout) // 4, dtype=torch.float32, device='cuda')
     stats = torch.zeros(2 * cout, dtype=torch.float64, device='cuda')
     code, alpha = (N.ACT_RELU, 0.0) if act == 'relu' else (N.ACT_LEAKY, 0.3)
     N.call('dnnca_conv2d_fprop_affine', None, C.byref(va), C.byref(vb) if vb else None, N.ptr(fa), N.ptr(fb), N.ptr(wd), N.ptr(bd),
