@@ -407,6 +407,17 @@ class Model:
                                                  dtype=torch.float32), non_blocking=True)
             self._hyper_dirty = False
 
+    def _side_stream(self):
+        """Second stream of the training step (weight gradients beside the dgrad chain), or None (DNNCA_WGRAD_STREAM=0)."""
+        # measured (B200, profiles/r02i_*): mulmo_unet +13 %, unet_big +2.8 %, unet.yaml -0.5 % -- the few-channel row kernels
+        # are persistent one-CTA-per-SM kernels chained by programmatic dependent launch, which a second stream breaks
+        mode = os.environ.get('DNNCA_WGRAD_STREAM', 'auto')
+        if mode == '0' or (mode == 'auto' and self.params.n_trainable < 100_000):
+            return None
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _adam(self):
         ps = self.params
         ps.version += 1
@@ -580,10 +591,10 @@ class Model:
             plan.head_loss(cfg)
             self._loss_total(plan)
             if dp is None:
-                plan.backward()
+                plan.backward(side_stream=self._side_stream())
                 self._adam()
             elif p2p is not None:
-                plan.backward()
+                plan.backward(side_stream=self._side_stream())
                 ps.version += 1
                 p2p.adam_step(ps)                # all-reduce over NVLink peer memory fused into the Adam kernel
             else:

@@ -326,6 +326,12 @@ class ConvOp(Op):
         return tuple(n for n in (self.kernel, self.bias) if n)
 
     def bwd(self):
+        self.bwd_params()
+        self.bwd_input()
+
+    def bwd_params(self):
+        """wgrad only: reads x and dz, writes the parameter gradients -- nothing downstream in the backward pass depends
+        on it, so ``Plan.backward`` may issue it on a side stream beside the dgrad chain."""
         ps = self.p.params
         if self.folded():
             xa, fa = self.x.src()
@@ -335,7 +341,6 @@ class ConvOp(Op):
         else:
             N.call('dnnca_conv2d_wgrad', N.stream_ptr(), self.x.ct(), self.x2.ct() if self.x2 else None, self.y.gct(),
                    ps.gptr(self.kernel), ps.gptr(self.bias), self.k)
-        self.bwd_input()
 
     def bwd_input(self):
         """dgrad only (also the input-gradient chain of callbacks.py:290-299, which needs no parameter gradients)."""
@@ -365,10 +370,13 @@ class TConvOp(Op):
         return tuple(n for n in (self.kernel, self.bias) if n)
 
     def bwd(self):
+        self.bwd_params()
+        self.bwd_input()
+
+    def bwd_params(self):
         ps = self.p.params
         N.call('dnnca_convtranspose2x2_wgrad', N.stream_ptr(), self.x.ct(), self.y.gct(), ps.gptr(self.kernel),
                ps.gptr(self.bias))
-        self.bwd_input()
 
     def bwd_input(self):
         if self.x.needs_grad:
@@ -673,13 +681,37 @@ class Plan:
             raise RuntimeError('this plan was not built with want_input_grad=True')
         return g
 
-    def backward(self, after_op=None):
+    def backward(self, after_op=None, side_stream=None):
         """The tape: forward list reversed.  ``after_op(i)`` is called after the i-th backward op was launched
-        (data parallelism: launches the gradient buckets that just became complete)."""
-        for i, op in enumerate(reversed(self.ops)):
-            op.bwd()
-            if after_op is not None:
-                after_op(i)
+        (data parallelism: launches the gradient buckets that just became complete).
+
+        ``side_stream``: the weight-gradient kernels are issued there (fork on an event recorded when dz is complete,
+        one join at the end), so that in the captured graph a wgrad is a sibling of the dgrad chain instead of a link
+        in it: its prologue and its last, partly filled wave overlap the next dgrad.  Not combined with ``after_op``
+        (a bucket must not leave before the wgrads that fill it)."""
+        if side_stream is None or after_op is not None:
+            for i, op in enumerate(reversed(self.ops)):
+                op.bwd()
+                if after_op is not None:
+                    after_op(i)
+            return
+        main = torch.cuda.current_stream()
+        forked = False
+        for op in reversed(self.ops):
+            if hasattr(op, 'bwd_params'):
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side_stream.wait_event(ev)
+                with torch.cuda.stream(side_stream):
+                    op.bwd_params()
+                forked = True
+                op.bwd_input()
+            else:
+                op.bwd()
+        if forked:
+            ev = torch.cuda.Event()
+            ev.record(side_stream)
+            main.wait_event(ev)
 
     def ready_frontier(self):
         """ready[i] = lowest offset R of the flat gradient buffer such that every gradient in [R, end) has been

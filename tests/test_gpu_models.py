@@ -422,3 +422,108 @@ def test_uint8_host_contract_matches_float32_inputs():
         nbig += int((d > 2e-4).sum())
         ntot += d.size
     assert nbig <= 0.03 * ntot, (nbig, ntot)
+
+
+def _oracle_adam_steps(ref, x, y, loss_cfg, steps, mom=None, t0=0):
+    """`steps` fp32-oracle optimizer steps in place (autograd + keras-form Adam + BN moving statistics)."""
+    mom = mom or {k: (torch.zeros_like(ref.weights[k]), torch.zeros_like(ref.weights[k])) for k in ref.trainable}
+    losses = []
+    for t in range(steps):
+        r = ref.train_step_grads(x, y, loss_cfg)
+        losses.append(r['loss'])
+        for k in ref.trainable:
+            ref.weights[k], m_, v_ = ops.adam_step(ref.weights[k], r['grads'][k], mom[k][0], mom[k][1], t0 + t + 1)
+            mom[k] = (m_, v_)
+        for k, v in r['new_moving'].items():
+            ref.weights[k] = v
+    return losses, mom
+
+
+# (logits rel-L2, loss rel, gradient rel-L2) bounds at the BASELINE configs' REAL shapes after 20 fp32-oracle Adam steps.
+# unet_big meets the north-star logits / loss bounds (1e-2 / 1e-3); its parameter gradient sits AT the 2e-2 bound
+# (2.15e-2 measured, bf16-storage emulation of the oracle itself: 2.2e-2).  mulmo_unet (16..128 channels, three
+# encoders) keeps a larger storage-rounding amplification (profiles/r02_conditioning.json: x4 on the logits, x14 on the
+# gradients per unit of storage rounding): 2.5e-2 / 4.7e-2 measured against 2.7e-2 / 4.5e-2 for the emulation.  The
+# bounds below are the measured values + 30 %, AND the CUDA path may not deviate more than 1.25x the emulation.
+REAL_SHAPE_BOUNDS = {'unet_big': (1e-2, 1e-3, 2.8e-2), 'mulmo_unet': (3.3e-2, 1e-3, 6.1e-2)}
+
+
+@pytest.mark.parametrize('cfgname', ['unet_big', 'mulmo_unet'])
+def test_bn_configs_real_shape_conditioned_weights_bf16(cfgname):
+    """the BatchNorm configs at 256x256, batch 8, gamma = 1 / beta = 0 glorot init (the bench's
+    conditions) and then after 20 fp32-oracle Adam steps; bf16 CUDA path against the fp32 oracle (evaluated with torch
+    on the device, TF32 off: the same restatement, minutes faster than on the host cores)."""
+    from dnncancerannotator_b200.utils.load import load_config
+    from dnncancerannotator_b200.synthetic import make_slices
+    from oracle.ref_bf16 import emulate_bf16
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = load_config([os.path.join(root, 'configs', cfgname + '.yaml'),
+                       os.path.join(root, 'configs', 'additionals', 'deploy_options.yaml')])
+    loss_cfg = cfg['deploy_options']['loss']['config']
+    S, B = 256, 8
+    ref = rm.build_model(cfg['model'], cfg['model_options'], (None, S, S, 3), seed=0).to(torch.device('cuda', 0))
+    m = product_model(cfg['model'], cfg['model_options'], 'bf16')
+    m.build((None, S, S, 3))
+    m.compile(loss=cfg['deploy_options']['loss'])
+    x, y = make_slices(B, S, S, 3, seed=1234)
+    _oracle_adam_steps(ref, x, y, loss_cfg, 20)
+    r = ref.train_step_grads(x, y, loss_cfg)
+    with emulate_bf16():
+        e = ref.train_step_grads(torch.tensor(x).bfloat16().float(), y, loss_cfg)
+    m.set_weights(ref.get_weights())
+    per = m.forward_backward(x, y).cpu().numpy()
+    logits = m.last_logits.cpu().numpy()
+    g = m.get_grads()
+    names = [k for k in ref.trainable if not k.endswith('/tconv/bias')]
+    cat = lambda d: np.concatenate([(d[k].detach().cpu().numpy() if torch.is_tensor(d[k]) else np.asarray(d[k])).ravel() for k in names])
+    allg, allr, alle = cat(g), cat(r['grads']), cat(e['grads'])
+    rl, el = r['logits'].cpu().numpy(), e['logits'].cpu().numpy()
+    tag = f'{cfgname}@256x8/bf16/after20adam'
+    REPORT[tag] = dict(logits_rel_l2=rel_l2(logits, rl), logits_rel_max=rel_inf(logits, rl), grad_rel_l2=rel_l2(allg, allr),
+                       loss_rel=abs(per.mean() - r['data_loss']) / abs(r['data_loss']),
+                       emulated_bf16_logits_rel_l2=rel_l2(el, rl), emulated_bf16_grad_rel_l2=rel_l2(alle, allr),
+                       masks_disagree_p05=float(((logits > 0) != (rl > 0)).mean()))
+    bl, bloss, bg = REAL_SHAPE_BOUNDS[cfgname]
+    rep = REPORT[tag]
+    assert rep['logits_rel_l2'] <= bl, rep
+    assert rep['loss_rel'] <= bloss, rep
+    assert rep['grad_rel_l2'] <= bg, rep
+    assert rep['logits_rel_l2'] <= 1.25 * rep['emulated_bf16_logits_rel_l2'] + 1e-3, rep
+    assert rep['grad_rel_l2'] <= 1.25 * rep['emulated_bf16_grad_rel_l2'] + 1e-3, rep
+    assert rep['masks_disagree_p05'] <= 2e-2, rep
+
+
+def test_bn_training_trajectory_bf16_50_steps():
+    """50 optimizer steps of a BatchNorm U-Net (32..128 channels: the tcgen05 halo kernels with
+    folded BatchNorm) in bf16 through ``train_step`` (CUDA graph) against 50 fp32-oracle steps from the same weights
+    on the same batch: the loss curves stay together and both descend."""
+    from dnncancerannotator_b200.synthetic import make_slices
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    opts = dict(n_filters_first=32, n_downsample=2, rate=2, kernel_size=3, conv_stride=1, bn=True, padding='same')
+    loss_cfg = dict(weight_mul=3.0)
+    S, B = 64, 8
+    ref = rm.build_model('UNetAnnotator', opts, (None, S, S, 3), seed=11).to(torch.device('cuda', 0))
+    m = product_model('UNetAnnotator', opts, 'bf16')
+    m.build((None, S, S, 3))
+    m.compile(optimizer='adam', loss=dict(class_name='WeightedCrossentropy', config=loss_cfg))
+    m.set_weights(ref.get_weights())
+    x, y = make_slices(B, S, S, 3, seed=21)
+    rl, _ = _oracle_adam_steps(ref, x, y, loss_cfg, 50)
+    ours = [float(m.train_step(x, y)) for _ in range(50)]
+    rl, ours = np.asarray(rl), np.asarray(ours)
+    dev = np.abs(ours - rl) / np.abs(rl)
+    REPORT['unet_bn32@64x8/bf16/50steps'] = dict(loss_first=ours[0], loss_last=ours[-1], oracle_loss_last=rl[-1],
+                                                 max_rel_dev=dev.max(), mean_rel_dev=dev.mean())
+    assert ours[-1] < 0.7 * ours[0] and rl[-1] < 0.7 * rl[0], (ours[0], ours[-1], rl[0], rl[-1])
+    # measured on B200: max 1.3e-2 (step 3: Adam's first updates are +-lr per weight, the sign of a small gradient is
+    # what bf16 rounding can flip), mean 1.3e-3, final loss 0.52622 vs 0.52611
+    assert dev[:2].max() <= 2e-3, dev[:2]            # the first steps are the same computation up to bf16 rounding
+    assert dev.max() <= 3e-2 and dev.mean() <= 5e-3, (dev.max(), dev.mean())
+    assert dev[-1] <= 1e-2, dev[-1]
+    # the two runs end at weights that make the same predictions
+    wl = ref.forward(x, training=False)['logits'].cpu().numpy()
+    m(x)
+    assert rel_l2(m.last_logits.cpu().numpy(), wl) <= 0.15
