@@ -601,7 +601,9 @@ class Model:
                 ready = plan.ready_frontier()
                 dp.begin(ps.grads_full)
                 dp.launch_ready(plan.pending_before_backward)
-                plan.backward(after_op=lambda i: dp.launch_ready(ready[i]))
+                plan.backward(after_op=lambda i: dp.launch_ready(ready[i], before=plan.join_side_streams),
+                              side_stream=self._side_stream())
+                plan.join_side_streams()
                 dp.finish()
                 self._adam()
         key = self._train_key(plan)

@@ -99,7 +99,9 @@ class MulmoUNet(Layer):
             else:
                 xin = R.TRef(x.buf, x.coff + m, 1)                                        # inputs[..., m:m+1]
                 xin.needs_grad = plan.want_input_grad
+            op0 = len(plan.ops)
             res_list, _ = enc.emit(plan, xin, out_dst=R.TRef(bott, m * fb, fb))
+            plan.branches.append((op0, len(plan.ops)))          # the per-modality encoders are independent of each other
             if m == self.reference_index:
                 res_ref = res_list
         return self.decoder.emit(plan, R.TRef(bott), res_ref)

@@ -80,10 +80,14 @@ class GradAllReduce:
         self._works, self._next = [], 0
         self.launch_log = []
 
-    def launch_ready(self, frontier):
-        """Issues every not-yet-issued bucket that lies entirely in [frontier, end)."""
+    def launch_ready(self, frontier, before=None):
+        """Issues every not-yet-issued bucket that lies entirely in [frontier, end).  ``before()`` runs once ahead of
+        the first bucket issued by this call (the step joins its side streams there: a bucket must not leave before the
+        weight-gradient kernels that fill it)."""
         if self.world_size == 1:
             return
+        if before is not None and self._next < len(self._buckets) and self._buckets[self._next][0] >= frontier:
+            before()
         while self._next < len(self._buckets) and self._buckets[self._next][0] >= frontier:
             a, b = self._buckets[self._next]
             self._works.append(dist.all_reduce(self._flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))

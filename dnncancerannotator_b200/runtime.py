@@ -549,6 +549,7 @@ class Plan:
         self.head = None              # (kernel name, bias name)
         self.allocated_training = None
         self.graphs = {}
+        self.branches = []            # [(first op, end op)] of mutually independent, adjacent op ranges (set by the model)
 
     def new_buf(self, h, w, c, name, n=None, zero=False):
         return Buf(self, n or self.batch, h, w, c, name, zero=zero)
@@ -631,8 +632,50 @@ class Plan:
         return sum(t.numel() * t.element_size() for b in self.bufs for t in (b.data, b.grad) if t is not None)
 
     # ---- launch sequences ----------------------------------------------------
+    def _branch_streams(self):
+        """One extra stream per independent branch beyond the first (MulmoUNet's per-modality encoders, unet.py:182-186)
+        or None when the plan has no branches / DNNCA_BRANCH_STREAMS=0."""
+        import os
+        if len(self.branches) < 2 or os.environ.get('DNNCA_BRANCH_STREAMS', '1') == '0':
+            return None
+        if getattr(self, '_bstreams', None) is None:
+            self._bstreams = [torch.cuda.Stream(device=self.device) for _ in self.branches[1:]]
+            self._bsides = [torch.cuda.Stream(device=self.device) for _ in self.branches[1:]]
+            for (s0, e0), (s1, e1) in zip(self.branches[:-1], self.branches[1:]):
+                assert e0 == s1, 'branches must be adjacent op ranges'
+        return self._bstreams
+
     def forward(self, train=False):
-        for op in self.ops:
+        bs = self._branch_streams()
+        if bs is None:
+            for op in self.ops:
+                op.fwd(train)
+            return
+        # independent branches run side by side in the captured graph: branch 0 stays on the launching stream, the
+        # others fork from an event recorded after the ops in front of them and join before the first op behind them
+        first, last = self.branches[0][0], self.branches[-1][1]
+        main = torch.cuda.current_stream()
+        for op in self.ops[:first]:
+            op.fwd(train)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        joins = []
+        for k, (s, e) in enumerate(self.branches):
+            if k == 0:
+                for op in self.ops[s:e]:
+                    op.fwd(train)
+                continue
+            st = bs[k - 1]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                for op in self.ops[s:e]:
+                    op.fwd(train)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            joins.append(ev)
+        for ev in joins:
+            main.wait_event(ev)
+        for op in self.ops[last:]:
             op.fwd(train)
 
     def head_forward(self):
@@ -681,37 +724,70 @@ class Plan:
             raise RuntimeError('this plan was not built with want_input_grad=True')
         return g
 
-    def backward(self, after_op=None, side_stream=None):
-        """The tape: forward list reversed.  ``after_op(i)`` is called after the i-th backward op was launched
-        (data parallelism: launches the gradient buckets that just became complete).
-
-        ``side_stream``: the weight-gradient kernels are issued there (fork on an event recorded when dz is complete,
-        one join at the end), so that in the captured graph a wgrad is a sibling of the dgrad chain instead of a link
-        in it: its prologue and its last, partly filled wave overlap the next dgrad.  Not combined with ``after_op``
-        (a bucket must not leave before the wgrads that fill it)."""
-        if side_stream is None or after_op is not None:
-            for i, op in enumerate(reversed(self.ops)):
-                op.bwd()
-                if after_op is not None:
-                    after_op(i)
-            return
-        main = torch.cuda.current_stream()
-        forked = False
-        for op in reversed(self.ops):
-            if hasattr(op, 'bwd_params'):
+    def _bwd_range(self, ops, side_stream, main, after_op=None, base=0):
+        """Backward of ``ops`` (already reversed) on stream ``main`` (the current one); weight gradients go to
+        ``side_stream`` when given (noted in ``_open_sides`` until the next join)."""
+        for i, op in enumerate(ops):
+            if side_stream is not None and hasattr(op, 'bwd_params'):
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side_stream.wait_event(ev)
                 with torch.cuda.stream(side_stream):
                     op.bwd_params()
-                forked = True
+                if side_stream not in self._open_sides:
+                    self._open_sides.append(side_stream)
                 op.bwd_input()
             else:
                 op.bwd()
-        if forked:
+            if after_op is not None:
+                after_op(base + i)
+
+    def backward(self, after_op=None, side_stream=None):
+        """The tape: forward list reversed.  ``after_op(i)`` is called after the i-th backward op was launched
+        (data parallelism: launches the gradient buckets that just became complete; the callback joins the side
+        streams itself before a bucket leaves, see ``join_side_streams``).
+
+        ``side_stream``: the weight-gradient kernels are issued there (fork on an event recorded when dz is complete,
+        join at the end), so that in the captured graph a wgrad is a sibling of the dgrad chain instead of a link in
+        it: its prologue and its last, partly filled wave overlap the next dgrad.  Independent branches
+        (``self.branches``) run their backward chains on their own streams."""
+        main = torch.cuda.current_stream()
+        self._open_sides = []
+        bs = self._branch_streams() if side_stream is not None else None
+        rev = list(reversed(self.ops))
+        n = len(rev)
+        if bs is None:
+            self._bwd_range(rev, side_stream, main, after_op)
+            self.join_side_streams()
+            return
+        first, last = self.branches[0][0], self.branches[-1][1]
+        self._bwd_range(rev[:n - last], side_stream, main, after_op)          # everything behind the branches (decoder)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        # branches in reverse order: the last branch's ops come first on the tape; branch 0 stays on the launching stream
+        for k in range(len(self.branches) - 1, -1, -1):
+            s, e = self.branches[k]
+            ops = rev[n - e:n - s]
+            if k == 0:
+                # (every other branch has been issued by now: a bucket leaving from here joins them first)
+                self._bwd_range(ops, side_stream, main, after_op, base=n - e)
+                continue
+            st, sd = bs[k - 1], self._bsides[k - 1]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                self._bwd_range(ops, sd, st, None)
+            self._open_sides.append(st)
+        self._bwd_range(rev[n - first:], None, main, after_op, base=n - first)
+        self.join_side_streams()
+
+    def join_side_streams(self):
+        """The launching stream waits for everything issued so far on the side streams of this backward pass."""
+        main = torch.cuda.current_stream()
+        for st in getattr(self, '_open_sides', []):
             ev = torch.cuda.Event()
-            ev.record(side_stream)
+            ev.record(st)
             main.wait_event(ev)
+        self._open_sides = []
 
     def ready_frontier(self):
         """ready[i] = lowest offset R of the flat gradient buffer such that every gradient in [R, end) has been
