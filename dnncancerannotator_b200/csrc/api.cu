@@ -85,6 +85,10 @@ int try_conv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_
 int try_conv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, const dnnca_tensor_t*, int, float, void*, size_t);
 int try_tconv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, void*, size_t);
 int try_tconv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float, void*, size_t);
+int conv_dgrad_umma_bnreduce(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, void*, size_t,
+                             const dnnca_tensor_t*, const float*, double*, bool*);
+int tconv_dgrad_umma_bnreduce(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, void*, size_t, const dnnca_tensor_t*,
+                              const float*, double*, bool*);
 int try_conv_wgrad_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*, int);
 int try_tconv_wgrad_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, float*, float*);
 int prepack_conv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, int, void*, size_t);
@@ -216,6 +220,58 @@ extern "C" int dnnca_conv2d_dgrad(void* stream, const dnnca_tensor_t* dz, const 
     if (r == 1) return DNNCA_OK;
   }
   return launch_conv_dgrad_generic(s, dz, w, dx, dx2, ksize, mask, act, alpha);
+}
+
+// dgrad whose destination `dx` is the output gradient of a BatchNormalization (input tensor `bn_x`): the BN backward
+// sums are taken in the dgrad epilogue where the tensor-core halo kernel serves the layer, by bn_bwd_reduce otherwise
+extern "C" int dnnca_conv2d_dgrad_bnreduce(void* stream, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
+                                           const dnnca_tensor_t* dx2, int ksize, const dnnca_tensor_t* bn_x,
+                                           const float* mean_invstd, double* sums, void* workspace, size_t workspace_bytes) {
+  DNNCA_CHECK_ARG(view_ok(dz) && view_ok(dx) && w && view_ok(bn_x) && mean_invstd && sums, "conv2d_dgrad_bnreduce: bad arguments");
+  DNNCA_CHECK_ARG(same_nhw(dz, dx) && dz->dtype == dx->dtype, "conv2d_dgrad_bnreduce: dz and dx must share n,h,w and dtype");
+  DNNCA_CHECK_ARG(second_ok(dx, dx2), "conv2d_dgrad_bnreduce: dx2 must share n,h,w and dtype with dx");
+  DNNCA_CHECK_ARG(same_shape(bn_x, dx) && bn_x->dtype == dx->dtype, "conv2d_dgrad_bnreduce: bn_x must have dx's shape and dtype");
+  if (ksize != 1 && ksize != 3) DNNCA_UNSUPPORTED("conv2d_dgrad_bnreduce: kernel size %d", ksize);
+  cudaStream_t s = (cudaStream_t)stream;
+  bool fused = false;
+  int r = 0;
+  if (!g_force_generic && ksize == 3 && dx->dtype == DNNCA_BF16) r = try_conv_dgrad_row(s, dz, w, dx, dx2, nullptr, DNNCA_ACT_NONE, 0.f);
+  if (r == 0 && !g_force_generic && ksize == 3)
+    r = dx->dtype == DNNCA_F32 ? try_conv_dgrad_small_f32(s, dz, w, dx, dx2, nullptr, DNNCA_ACT_NONE, 0.f)
+                               : try_conv_dgrad_small_bf16(s, dz, w, dx, dx2, nullptr, DNNCA_ACT_NONE, 0.f);
+  if (r == 0 && !g_force_generic)
+    r = conv_dgrad_umma_bnreduce(s, dz, w, dx, dx2, ksize, workspace, workspace_bytes, bn_x, mean_invstd, sums, &fused);
+  if (r < 0) return r;
+  if (r == 0) {
+    r = launch_conv_dgrad_generic(s, dz, w, dx, dx2, ksize, nullptr, DNNCA_ACT_NONE, 0.f);
+    if (r != DNNCA_OK) return r;
+  }
+  if (!fused) return dnnca_bn_bwd_reduce(stream, bn_x, dx, mean_invstd, sums);
+  return DNNCA_OK;
+}
+
+extern "C" int dnnca_convtranspose2x2_dgrad_bnreduce(void* stream, const dnnca_tensor_t* dy, const float* k, const dnnca_tensor_t* dx,
+                                                     const dnnca_tensor_t* bn_x, const float* mean_invstd, double* sums,
+                                                     void* workspace, size_t workspace_bytes) {
+  DNNCA_CHECK_ARG(view_ok(dy) && view_ok(dx) && k && view_ok(bn_x) && mean_invstd && sums, "convtranspose2x2_dgrad_bnreduce: bad arguments");
+  DNNCA_CHECK_ARG(dy->n == dx->n && dy->h == 2 * dx->h && dy->w == 2 * dx->w && dx->dtype == dy->dtype,
+                  "convtranspose2x2_dgrad_bnreduce: dy must be [n,2h,2w,cout]");
+  DNNCA_CHECK_ARG(same_shape(bn_x, dx) && bn_x->dtype == dx->dtype, "convtranspose2x2_dgrad_bnreduce: bn_x must have dx's shape and dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  bool fused = false;
+  int r = 0;
+  if (!g_force_generic) {
+    r = dx->dtype == DNNCA_BF16 ? try_tconv_dgrad_row(s, dy, k, dx, nullptr, DNNCA_ACT_NONE, 0.f) : 0;
+    if (r == 0) r = try_tconv_dgrad_small(s, dy, k, dx, nullptr, DNNCA_ACT_NONE, 0.f);
+    if (r == 0) r = tconv_dgrad_umma_bnreduce(s, dy, k, dx, workspace, workspace_bytes, bn_x, mean_invstd, sums, &fused);
+    if (r < 0) return r;
+  }
+  if (r == 0) {
+    r = launch_tconv_dgrad_generic(s, dy, k, dx, nullptr, DNNCA_ACT_NONE, 0.f);
+    if (r != DNNCA_OK) return r;
+  }
+  if (!fused) return dnnca_bn_bwd_reduce(stream, bn_x, dx, mean_invstd, sums);
+  return DNNCA_OK;
 }
 
 extern "C" int dnnca_conv2d_wgrad(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2,

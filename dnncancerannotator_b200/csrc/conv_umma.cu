@@ -589,6 +589,23 @@ static thread_local bool g_pack_only = false;
 struct FoldCtx { const float* sa; const float* sb; const float* bias9; };
 static thread_local const FoldCtx* g_fold = nullptr;
 
+// BatchNorm backward reduction fused into a dgrad epilogue (dnnca_conv2d_dgrad_bnreduce / dnnca_convtranspose2x2_dgrad_bnreduce):
+// the BN's input tensor, its [2C] mean|invstd and the [2C] fp64 sums; `done` is set when the persistent halo kernel took it
+struct BnrCtx { const dnnca_tensor_t* x; const float* mi; double* sums; bool done; };
+static thread_local BnrCtx* g_bnr = nullptr;
+static void bnr_arm(UArgs& a, const dnnca_tensor_t* dx) {
+  a.epi = EPI_DGRAD_BNR; a.act = DNNCA_ACT_NONE; a.alpha = 0.f;
+  a.mask = reinterpret_cast<const __nv_bfloat16*>(g_bnr->x->data) + g_bnr->x->coff; a.mask_cs = g_bnr->x->cstride;
+  a.stats = g_bnr->sums; a.bnr_mi = g_bnr->mi;
+  (void)dx;
+}
+static void bnr_disarm(UArgs& a) { a.epi = EPI_DGRAD; a.mask = nullptr; a.mask_cs = 0; a.stats = nullptr; a.bnr_mi = nullptr; }
+static bool bnr_usable(const dnnca_tensor_t* dx, const dnnca_tensor_t* mask) {
+  return g_bnr && !mask && g_bnr->x->dtype == DNNCA_BF16 && g_bnr->x->c == dx->c && g_bnr->x->n == dx->n && g_bnr->x->h == dx->h &&
+         g_bnr->x->w == dx->w && g_bnr->x->coff % 8 == 0 && g_bnr->x->cstride % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(g_bnr->x->data) & 15) == 0;
+}
+
 // returns 1 handled / 0 not covered / <0 error
 // returns 2 when the kernel also accumulated the BatchNorm statistics into `stats` (else the caller runs channel_stats)
 int try_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* w, const float* bias,
@@ -654,7 +671,10 @@ int try_conv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dz, const float* w
   a.mask = mask ? reinterpret_cast<const __nv_bfloat16*>(mask->data) + mask->coff : nullptr; a.mask_cs = mask ? mask->cstride : 0;
   a.n_total = cin; a.cout_t = cin; a.nimg = dx->n;
   if (k == 3 && (kc == 64 || cout < 64) && halo_enabled()) {     // cout < 64: one K chunk, missing channels zero-filled
+    const bool bnr = bnr_usable(dx, mask);
+    if (bnr) bnr_arm(a, dx);
     r = try_conv3x3_halo(s, dz, nullptr, ws, cout, cin, a);
+    if (bnr) { g_bnr->done = r == 1; bnr_disarm(a); }
     if (r != 0) return r;
   }
   if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, dx->n, bn);
@@ -711,7 +731,10 @@ int try_tconv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dy, const float* 
   a.mask = mask ? reinterpret_cast<const __nv_bfloat16*>(mask->data) + mask->coff : nullptr; a.mask_cs = mask ? mask->cstride : 0;
   a.n_total = cin; a.cout_t = cin; a.nimg = dx->n;
   if (kc == 64 && halo_enabled()) {
+    const bool bnr = bnr_usable(dx, mask);
+    if (bnr) bnr_arm(a, dx);
     r = try_tconv_dgrad_halo(s, dy, ws, cin, cout, a);
+    if (bnr) { g_bnr->done = r == 1; bnr_disarm(a); }
     if (r != 0) return r;
   }
   if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, dx->n, bn);
@@ -729,6 +752,28 @@ int fprop_umma_affine(cudaStream_t s, const dnnca_tensor_t* x, const dnnca_tenso
   g_fold = nullptr;
   return r;
 }
+// dgrad with the BatchNorm backward reduction of destination A in its epilogue: returns what the plain try_* returns and
+// sets *fused when the sums were taken (else the caller runs bn_bwd_reduce)
+int conv_dgrad_umma_bnreduce(cudaStream_t s, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
+                             const dnnca_tensor_t* dx2, int k, void* ws, size_t ws_bytes, const dnnca_tensor_t* bn_x,
+                             const float* mi, double* sums, bool* fused) {
+  BnrCtx c{bn_x, mi, sums, false};
+  g_bnr = &c;
+  const int r = try_conv_dgrad_umma(s, dz, w, dx, dx2, k, nullptr, DNNCA_ACT_NONE, 0.f, ws, ws_bytes);
+  g_bnr = nullptr;
+  *fused = c.done;
+  return r;
+}
+int tconv_dgrad_umma_bnreduce(cudaStream_t s, const dnnca_tensor_t* dy, const float* kw, const dnnca_tensor_t* dx, void* ws,
+                              size_t ws_bytes, const dnnca_tensor_t* bn_x, const float* mi, double* sums, bool* fused) {
+  BnrCtx c{bn_x, mi, sums, false};
+  g_bnr = &c;
+  const int r = try_tconv_dgrad_umma(s, dy, kw, dx, nullptr, DNNCA_ACT_NONE, 0.f, ws, ws_bytes);
+  g_bnr = nullptr;
+  *fused = c.done;
+  return r;
+}
+
 // would fprop_umma_affine serve this shape? (host-side checks only; mirrors try_conv_fprop_umma + try_conv3x3_halo)
 int fprop_umma_affine_supported(const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* y) {
   if (!halo_enabled() || !bf16_view8(y)) return 0;

@@ -52,8 +52,15 @@ struct HGeom {
   static constexpr int STAT_OFF = (BIAS_OFF + 9 * BN * 4 + 15) & ~15;
   static constexpr int CTRL = (STAT_OFF + 2 * BN * 8 + 1023) & ~1023;
   // resident: all TAPS * (Cin/64) weight blocks stay in shared memory for the CTA's lifetime
-  static constexpr int smem_resident(int kchunks) { return CTRL + A_SLOTS * A_SLOT + TAPS * kchunks * B_TAP + 1024; }
+  // staged epilogue: every epilogue warp owns STG_BUFS swizzled [32 px][64 ch] bf16 blocks (4 KB each) that leave through
+  // its own TMA stores
+  static constexpr int STG_BUFS = BN > 128 ? 1 : 2;
+  static constexpr int STG_BYTES = 8 * STG_BUFS * 4096;
+  static constexpr int smem_resident(int kchunks, bool staged = false) {
+    return CTRL + A_SLOTS * A_SLOT + TAPS * kchunks * B_TAP + (staged ? STG_BYTES : 0) + 1024;
+  }
   static constexpr int B_STAGES = BN > 128 ? 3 : 4;
+  static constexpr int smem_stream(bool staged) { return CTRL + A_SLOTS * A_SLOT + B_STAGES * B_TAP + (staged ? STG_BYTES : 0) + 1024; }
   static constexpr int SMEM_STREAM = CTRL + A_SLOTS * A_SLOT + B_STAGES * B_TAP + 1024;
 };
 
@@ -70,10 +77,70 @@ __device__ __forceinline__ uint64_t kmajor128_desc(uint32_t saddr, uint32_t sbo_
   return d;
 }
 
-template <int BN, bool RESIDENT, int TAPS, int EPI>
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// Staged epilogue of one 32-column chunk of one accumulator row: bias + activation (fprop) or act'(mask) (dgrad), bf16
+// rounding, then four 16-byte stores into the warp's swizzled staging block: pixel row `lane` (128 bytes), 16-byte
+// chunk j lands at position j ^ (lane & 7) -- the SWIZZLE_128B pattern the TMA store expects; conflict-free.
+template <int EPI>
+__device__ __forceinline__ void stage_chunk32(const UArgs& a, const uint32_t (&v)[32], const float* sbias,
+                                              const __nv_bfloat16* msk, uint32_t srow, int chunk0, uint32_t sw) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  const float slope = act_slope(a.act, a.alpha);
+  if (EPI == EPI_DGRAD) {
+    if (msk) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 m = reinterpret_cast<const uint4*>(msk)[q];
+        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[q * 8 + 2 * j] *= __uint_as_float(mw[j] << 16) > 0.f ? 1.f : slope;
+          f[q * 8 + 2 * j + 1] *= __uint_as_float(mw[j] & 0xffff0000u) > 0.f ? 1.f : slope;
+        }
+      }
+    }
+  } else if (EPI == EPI_FPROP) {
+    const float4* sb4 = reinterpret_cast<const float4*>(sbias);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = sb4[j];
+      f[4 * j + 0] = act_slope_apply(f[4 * j + 0] + b4.x, slope);
+      f[4 * j + 1] = act_slope_apply(f[4 * j + 1] + b4.y, slope);
+      f[4 * j + 2] = act_slope_apply(f[4 * j + 2] + b4.z, slope);
+      f[4 * j + 3] = act_slope_apply(f[4 * j + 3] + b4.w, slope);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[q * 8 + 0], f[q * 8 + 1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(f[q * 8 + 2], f[q * 8 + 3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[q * 8 + 4], f[q * 8 + 5]);
+    __nv_bfloat162 p3 = __floats2bfloat162_rn(f[q * 8 + 6], f[q * 8 + 7]);
+    sts_v4(srow + ((((uint32_t)(chunk0 + q)) ^ sw) << 4), *reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+           *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+  }
+}
+
+// STAGED: epilogue through shared memory + TMA stores (fprop / dgrad kinds); the two epilogue warp groups take alternate
+// tiles, each warp owns its 32 accumulator rows over ALL columns of the tile.  Measured motive (B200, B = 32): with the
+// per-thread 64-byte global stores removed 256->256@64 fprop ran 115 -> 96 us, 128->128@128 136 -> 124 us; BatchNorm
+// statistics as per-tile warp shuffles cost another 37 us at 128->128@128.
+template <int BN, bool RESIDENT, int TAPS, int EPI, bool STAGED>
 __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_constant__ CUtensorMap mapA,
                                                             const __grid_constant__ CUtensorMap mapB,
-                                                            const __grid_constant__ CUtensorMap mapW, UArgs a) {
+                                                            const __grid_constant__ CUtensorMap mapW,
+                                                            const __grid_constant__ CUtensorMap mapYa,
+                                                            const __grid_constant__ CUtensorMap mapYb, UArgs a) {
   using G = HGeom<BN, TAPS>;
   constexpr int B_STAGES = RESIDENT ? 1 : G::B_STAGES;
   constexpr int A_SLOT = G::A_SLOT, A_SLOTS = G::A_SLOTS;
@@ -89,9 +156,11 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
   // bias slice of this CTA's N tile per border class (row class * 3 + column class; class 0 = first row / column,
   // 1 = interior, 2 = last): all nine rows equal `bias` unless a BatchNorm is folded into the input (UArgs::bias9)
   constexpr int NCLS = (EPI == EPI_FPROP && TAPS == 9) ? 9 : 1;
+  constexpr bool BNR = EPI == EPI_DGRAD_BNR, IS_DGRAD = EPI == EPI_DGRAD || BNR;
+  constexpr int EPI_ADDR = IS_DGRAD ? EPI_DGRAD : EPI;     // addressing / store code of the epilogue helpers
   float* sbias = reinterpret_cast<float*>(smem + G::BIAS_OFF);
   double* sstat = reinterpret_cast<double*>(smem + G::STAT_OFF);   // [2*BN] per-channel sum | sum of squares (fprop + stats)
-  const bool do_stats = EPI == EPI_FPROP && a.stats != nullptr;
+  const bool do_stats = (EPI == EPI_FPROP || BNR) && a.stats != nullptr;
   unsigned char* aring = smem + G::CTRL;
   unsigned char* bring = aring + G::A_SLOTS * A_SLOT;
 
@@ -104,7 +173,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < A_SLOTS; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, STAGED ? 4 : 8); }
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(fullB + s, 1); mbar_init(emptyB + s, 1); }
     fence_mbar_init();
   }
@@ -112,7 +181,9 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
   for (int i = threadIdx.x; i < NCLS * BN; i += blockDim.x) {
     const int cls = i / BN, col = i - cls * BN;
     float b = 0.f;
-    if (EPI != EPI_DGRAD && n0 + col < a.n_total) {
+    if (BNR) {                              // the BatchNorm's batch mean of this column (destination A only)
+      if (n0 + col < a.split) b = a.bnr_mi[n0 + col];
+    } else if (!IS_DGRAD && n0 + col < a.n_total) {
       if (NCLS == 9 && a.bias9) b = a.bias9[cls * a.n_total + n0 + col];
       else if (a.bias) b = a.bias[EPI == EPI_TCONV ? (n0 + col) % a.cout_t : n0 + col];
     }
@@ -235,6 +306,125 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
       if ((a.dbg & 16) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
         HALO_PRINT("mma: total %lld wait fullA %lld wait tempty %lld tiles %d\n", HALO_CLOCK() - t00, twa, twt, ti);
     }
+  } else if (STAGED) {
+    // ===== staged epilogue: warps 2..5 take the even tiles of this CTA, warps 6..9 the odd ones (TMEM buffer = tile parity);
+    // a warp reads its 32 accumulator rows (TMEM lanes 32*(warp%4)..+31) 64 columns at a time, writes them as a swizzled
+    // [32 px][64 ch] bf16 block and hands the block to the TMA (box {64 ch, 8 px, 4 rows}); BatchNorm sums are taken from
+    // the staged block with lanes mapped to channel pairs =====
+    const int grp = (warp - 2) >> 2, lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const int ty = r >> 3, tx = r & 7;
+    constexpr int NBLK = BN / 64;
+    constexpr int STG_BUFS = G::STG_BUFS;
+    unsigned char* stg = bring + (RESIDENT ? TAPS * kchunks * G::B_TAP : B_STAGES * G::B_TAP) + (warp - 2) * (STG_BUFS * 4096);
+    const uint32_t stg_u = smem_u32(stg);
+    const uint32_t sw = (uint32_t)(lane & 7);
+    // column pass: lane l owns channels 2l, 2l+1 of a 64-column block = one 4-byte word per pixel row
+    const uint32_t cword = (uint32_t)((lane & 3) << 2);
+    const uint32_t cchunk = (uint32_t)(lane >> 2);
+    float s0[NBLK][2], s1[NBLK][2], mean2[NBLK][2];
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) {
+      s0[b][0] = s0[b][1] = s1[b][0] = s1[b][1] = 0.f;
+      mean2[b][0] = mean2[b][1] = 0.f;
+      if (BNR && do_stats) {
+        const int ch = n0 + b * 64 + 2 * lane;
+        if (ch < a.split) { mean2[b][0] = a.bnr_mi[ch]; mean2[b][1] = a.bnr_mi[ch + 1]; }
+      }
+    }
+    int sbuf = 0;
+    int ti = grp;
+    TileWalk tw_(blockIdx.x + grp * gridDim.x, 2 * gridDim.x, a.tiles_x, a.tiles_y);
+    for (int t = blockIdx.x + grp * gridDim.x; t < ntiles; t += 2 * gridDim.x, ti += 2, tw_.next()) {
+      const int n = tw_.n;
+      const int gy = tw_.tiy * 16 + ty, gx = tw_.tix * 8 + tx;
+      const bool inside = gy < a.H && gx < a.W;
+      const int by0 = tw_.tiy * 16 + lg * 4, bx0 = tw_.tix * 8;       // this warp's 4 rows x 8 pixels of the tile
+      const int buf = ti & 1;
+      const float* sb = sbias;
+      if (NCLS == 9) sb += ((gy == 0 ? 0 : (gy == a.H - 1 ? 2 : 1)) * 3 + (gx == 0 ? 0 : (gx == a.W - 1 ? 2 : 1))) * BN;
+      const long long pix = ((long long)n * a.H + (inside ? gy : 0)) * a.W + (inside ? gx : 0);
+      mbar_wait(tfull + buf, (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
+        const int colb = blk * 64, ncol = n0 + colb;
+        const bool blk_live = ncol < a.n_total;
+        const bool in_a = ncol < a.split;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN + colb), v0);
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN + colb + 32), v1);
+        // BatchNorm backward sums: the BN input at this block's pixels, lanes over channel pairs (coalesced 128-byte rows)
+        uint32_t xw[(BNR ? 32 : 1)];
+        if (BNR && do_stats && blk_live && in_a) {
+          const __nv_bfloat16* xb = a.mask + ncol + 2 * lane;
+          const bool lane_ok = ncol + 2 * lane < a.split;          // a partly filled block: channels beyond the tensor
+#pragma unroll
+          for (int p = 0; p < 32; ++p) {
+            const int py = by0 + (p >> 3), px = bx0 + (p & 7);
+            xw[BNR ? p : 0] = (lane_ok && py < a.H && px < a.W)
+                                  ? __ldg(reinterpret_cast<const unsigned int*>(xb + (((long long)n * a.H + py) * a.W + px) * a.mask_cs))
+                                  : 0u;
+          }
+        }
+        tmem_ld_wait();
+        if (blk == NBLK - 1) {                 // the accumulator now lives in registers: the MMA warp may reuse it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty + buf);
+        }
+        if (lane == 0) {                       // staging block free again? (its previous TMA store has read it)
+          if (STG_BUFS == 2) tma_store_wait_read1();
+          else tma_store_wait_read();
+        }
+        __syncwarp();
+        const uint32_t sblock = stg_u + (uint32_t)(sbuf * 4096);
+        const uint32_t srow = sblock + (uint32_t)(lane * 128);
+        const __nv_bfloat16* mk = nullptr;
+        if (EPI == EPI_DGRAD && a.mask && in_a && inside && blk_live) mk = a.mask + pix * a.mask_cs + ncol;
+        stage_chunk32<EPI_ADDR>(a, v0, sb + colb, mk, srow, 0, sw);
+        stage_chunk32<EPI_ADDR>(a, v1, sb + colb + 32, (mk && ncol + 32 < a.n_total) ? mk + 32 : nullptr, srow, 4, sw);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && blk_live) {
+          if (in_a) tma_store_4d(&mapYa, stg + sbuf * 4096, ncol, bx0, by0, n);
+          else tma_store_4d(&mapYb, stg + sbuf * 4096, ncol - a.split, bx0, by0, n);
+          tma_store_commit();
+        }
+        if (do_stats && blk_live && (!BNR || in_a)) {
+          // sums of the values as they read back from the bf16 tensor, from the staged block
+#pragma unroll
+          for (int p = 0; p < 32; ++p) {
+            const bool pv = (by0 + (p >> 3) < a.H) && (bx0 + (p & 7) < a.W);
+            const uint32_t w = lds_u32(sblock + (uint32_t)(p * 128) + ((cchunk ^ (uint32_t)(p & 7)) << 4) + cword);
+            const float lo = pv ? __uint_as_float(w << 16) : 0.f, hi = pv ? __uint_as_float(w & 0xffff0000u) : 0.f;
+            if (BNR) {
+              const uint32_t xv = xw[BNR ? p : 0];
+              s0[blk][0] += lo;
+              s0[blk][1] += hi;
+              s1[blk][0] = fmaf(lo, __uint_as_float(xv << 16) - mean2[blk][0], s1[blk][0]);
+              s1[blk][1] = fmaf(hi, __uint_as_float(xv & 0xffff0000u) - mean2[blk][1], s1[blk][1]);
+            } else {
+              s0[blk][0] += lo;
+              s0[blk][1] += hi;
+              s1[blk][0] = fmaf(lo, lo, s1[blk][0]);
+              s1[blk][1] = fmaf(hi, hi, s1[blk][1]);
+            }
+          }
+        }
+        if (STG_BUFS == 2) sbuf ^= 1;
+      }
+    }
+    if (do_stats) {
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          atomicAdd(sstat + b * 64 + 2 * lane + e, (double)s0[b][e]);
+          atomicAdd(sstat + BN + b * 64 + 2 * lane + e, (double)s1[b][e]);
+        }
+    }
+    if (lane == 0) tma_store_wait_all();       // the staging blocks must outlive their stores
   } else {
     // ===== epilogue: warps 2..9.  A warp may only touch TMEM lanes 32*(warp%4)..+31, so two warps share each lane
     // quarter and split the columns; the mask row (dgrad) is prefetched before the accumulator is ready =====
@@ -245,8 +435,8 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
     constexpr int NCHUNK = BN / 64;         // 32-column chunks per warp
     // BN statistics: for BN = 64 every thread keeps per-column partial sums of ITS tile row in registers over all of
     // the CTA's tiles and the warp reduction runs once at the end; wider tiles reduce per tile (register budget)
-    constexpr bool REG_STATS = BN <= 64 && EPI == EPI_FPROP;
-    constexpr int NMASK = EPI == EPI_DGRAD ? NCHUNK : 1;     // mask rows are prefetched only by dgrad
+    constexpr bool REG_STATS = BN <= 64 && (EPI == EPI_FPROP || BNR);
+    constexpr int NMASK = IS_DGRAD ? NCHUNK : 1;             // mask rows are prefetched only by dgrad
     float acc1[REG_STATS ? NCHUNK : 1][32], acc2[REG_STATS ? NCHUNK : 1][32];
 #pragma unroll
     for (int c = 0; c < (REG_STATS ? NCHUNK : 1); ++c)
@@ -267,10 +457,13 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
         const int col = half * (BN / 2) + c * 32;
-        ca[c] = chunk_addr<EPI>(a, n, inside ? gy : 0, inside ? gx : 0, n0 + col);
-        if (EPI == EPI_DGRAD && ca[c].msk && inside && n0 + col < a.n_total) {
+        ca[c] = chunk_addr<EPI_ADDR>(a, n, inside ? gy : 0, inside ? gx : 0, n0 + col);
+        if (IS_DGRAD && ca[c].msk && inside && n0 + col < a.n_total) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) m[EPI == EPI_DGRAD ? c : 0][q] = reinterpret_cast<const uint4*>(ca[c].msk)[q];
+          for (int q = 0; q < 4; ++q) m[IS_DGRAD ? c : 0][q] = reinterpret_cast<const uint4*>(ca[c].msk)[q];
+        } else if (BNR) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m[IS_DGRAD ? c : 0][q] = make_uint4(0u, 0u, 0u, 0u);
         }
       }
       const long long tq = HALO_CLOCK();
@@ -285,10 +478,45 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
           tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN + col), v);
           tmem_ld_wait();
         }
-        if (EPI != EPI_FPROP || !do_stats) {
+        if (BNR && do_stats) {
+          // BatchNormalization backward sums of the gradient as it reads back from the bf16 tensor (components.py:57-59,
+          // 130-131 under GradientTape): r1 = dy, r2 = dy * (x - mean); invstd is applied once per CTA at the end
+          const bool live = inside && ca[c].msk != nullptr && n0 + col < a.n_total;
+          epilogue_chunk32<true, EPI_DGRAD>(a, v, ca[c], m[IS_DGRAD ? c : 0], sb + col, inside && n0 + col < a.n_total,
+                                            a.n_total - (n0 + col));
+          float r1[32], r2[32];
+          const float4* mean4 = reinterpret_cast<const float4*>(sbias + col);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 mq = m[IS_DGRAD ? c : 0][q];
+            const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
+            const float4 ma = mean4[2 * q], mb = mean4[2 * q + 1];
+            const float mean8[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float g0 = live ? __uint_as_float(v[q * 8 + 2 * j]) : 0.f;
+              const float g1 = live ? __uint_as_float(v[q * 8 + 2 * j + 1]) : 0.f;
+              r1[q * 8 + 2 * j] = g0;
+              r1[q * 8 + 2 * j + 1] = g1;
+              r2[q * 8 + 2 * j] = g0 * (__uint_as_float(mw[j] << 16) - mean8[2 * j]);
+              r2[q * 8 + 2 * j + 1] = g1 * (__uint_as_float(mw[j] & 0xffff0000u) - mean8[2 * j + 1]);
+            }
+          }
+          if (REG_STATS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { acc1[REG_STATS ? c : 0][j] += r1[j]; acc2[REG_STATS ? c : 0][j] += r2[j]; }
+          } else {
+            warp_colsum32(r1, lane);
+            warp_colsum32(r2, lane);
+            if (n0 + col + lane < a.split) {
+              atomicAdd(sstat + col + lane, (double)r1[0]);
+              atomicAdd(sstat + BN + col + lane, (double)r2[0]);
+            }
+          }
+        } else if (EPI != EPI_FPROP || !do_stats) {
           if (inside && n0 + col < a.n_total)
-            epilogue_chunk32<false, EPI>(a, v, ca[c], m[EPI == EPI_DGRAD ? c : 0], sb + col, !(a.dbg & 1),
-                                         a.n_total - (n0 + col));
+            epilogue_chunk32<false, EPI_ADDR>(a, v, ca[c], m[IS_DGRAD ? c : 0], sb + col, !(a.dbg & 1),
+                                              a.n_total - (n0 + col));
         } else {
           // BatchNormalization statistics of the stored tensor (components.py:57-58,130-132) in the epilogue: rows of
           // the tile are lanes, so a column sum is a 31-shuffle warp reduction; one shared fp64 atomic per lane
@@ -339,11 +567,17 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
   if (do_stats)
-    for (int i = threadIdx.x; i < BN; i += blockDim.x)
-      if (n0 + i < a.n_total) {
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+      if (BNR) {
+        if (n0 + i < a.split) {               // sum dy | sum dy*xhat = invstd * sum dy*(x - mean)
+          atomicAdd(a.stats + n0 + i, sstat[i]);
+          atomicAdd(a.stats + a.split + n0 + i, sstat[BN + i] * (double)a.bnr_mi[a.split + n0 + i]);
+        }
+      } else if (n0 + i < a.n_total) {
         atomicAdd(a.stats + n0 + i, sstat[i]);
         atomicAdd(a.stats + a.n_total + n0 + i, sstat[BN + i]);
       }
+    }
 }
 
 // ---------------------------------------------------------------- host side
@@ -373,12 +607,40 @@ static bool weight_map64(CUtensorMap* m, const void* wp, int ktot, int ntot, int
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, bool RESIDENT, int TAPS, int EPI>
-static int launch_halo_epi(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mW, const UArgs& a,
-                           int kchunks) {
+static bool halo_staged_enabled() {
+  static int v = -1;
+  if (v < 0) v = (getenv("DNNCA_HALO_STAGED") && atoi(getenv("DNNCA_HALO_STAGED")) == 0) ? 0 : 1;      // A/B switch
+  return v == 1;
+}
+
+// do the resident weights (+ the staging blocks of a staged epilogue) fit into shared memory?
+template <int BN, int TAPS>
+static bool resident_fits(int kchunks, const UArgs& a) {
+  // (resident weights win over the staged epilogue where only one of them fits: [64+64]->64@256 fprop measured 290 us
+  // resident + per-thread stores against 444 us streamed + staged)
+  (void)a;
+  return (size_t)HGeom<BN, TAPS>::smem_resident(kchunks, false) <= 226 * 1024;
+}
+
+// output views of a staged epilogue: 4-D {C, W, H, N}, box {64 ch, 8 px, 4 rows, 1}, SWIZZLE_128B
+static bool out_map(CUtensorMap* m, __nv_bfloat16* base, int c, long long cstride, int w, int h, int n) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc || c <= 0) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (cstride * 2) % 16) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)cstride * 2, (cuuint64_t)w * cstride * 2, (cuuint64_t)h * w * cstride * 2};
+  cuuint32_t box[4] = {64, 8, 4, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, bool RESIDENT, int TAPS, int EPI, bool STAGED>
+static int launch_halo_st(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mW, const CUtensorMap& mYa,
+                          const CUtensorMap& mYb, const UArgs& a, int kchunks) {
   using G = HGeom<BN, TAPS>;
-  const int smem = RESIDENT ? G::smem_resident(kchunks) : G::SMEM_STREAM;
-  auto kern = conv_umma_halo_kernel<BN, RESIDENT, TAPS, EPI>;
+  const int smem = RESIDENT ? G::smem_resident(kchunks, STAGED) : G::smem_stream(STAGED);
+  auto kern = conv_umma_halo_kernel<BN, RESIDENT, TAPS, EPI, STAGED>;
   static int smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -391,10 +653,27 @@ static int launch_halo_epi(cudaStream_t s, const CUtensorMap& mA, const CUtensor
   if (per < 1) per = 1;
   if (per > ntiles) per = ntiles;
   dim3 grid((unsigned)per, (unsigned)nt);
-  kern<<<grid, 320, smem, s>>>(mA, mB, mW, a);
+  kern<<<grid, 320, smem, s>>>(mA, mB, mW, mYa, mYb, a);
   DNNCA_LAUNCH_CHECK("conv_umma_halo");
   note_family(2);
   return 1;
+}
+
+template <int BN, bool RESIDENT, int TAPS, int EPI>
+static int launch_halo_epi(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mW, const UArgs& a,
+                           int kchunks) {
+  using G = HGeom<BN, TAPS>;
+  // staged epilogue (fprop / dgrad kinds): needs whole 64-column blocks per destination and room for the staging blocks
+  if (EPI != EPI_TCONV && halo_staged_enabled() && (a.split % 64 == 0 || a.split >= a.n_total) &&
+      (size_t)(RESIDENT ? G::smem_resident(kchunks, true) : G::smem_stream(true)) <= 226 * 1024) {
+    CUtensorMap mYa, mYb;
+    const int ca = a.split < a.n_total ? a.split : a.n_total, cb = a.n_total - ca;
+    bool ok = out_map(&mYa, a.ya, ca, a.ya_cs, a.W, a.H, a.nimg);
+    mYb = mYa;
+    if (ok && cb > 0) ok = out_map(&mYb, a.yb, cb, a.yb_cs, a.W, a.H, a.nimg);
+    if (ok) return launch_halo_st<BN, RESIDENT, TAPS, EPI == EPI_TCONV ? EPI_FPROP : EPI, true>(s, mA, mB, mW, mYa, mYb, a, kchunks);
+  }
+  return launch_halo_st<BN, RESIDENT, TAPS, EPI, false>(s, mA, mB, mW, mA, mA, a, kchunks);
 }
 
 // the epilogue kind is a template parameter (the fprop instantiation carries BatchNorm-statistics registers, the dgrad one
@@ -403,6 +682,7 @@ template <int BN, bool RESIDENT, int TAPS = 9>
 static int launch_halo(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mW, const UArgs& a,
                        int kchunks) {
   if (a.epi == EPI_DGRAD) return launch_halo_epi<BN, RESIDENT, TAPS, EPI_DGRAD>(s, mA, mB, mW, a, kchunks);
+  if (a.epi == EPI_DGRAD_BNR) return launch_halo_epi<BN, RESIDENT, TAPS, EPI_DGRAD_BNR>(s, mA, mB, mW, a, kchunks);
   if (TAPS == 9 || a.epi == EPI_FPROP) return launch_halo_epi<BN, RESIDENT, TAPS, EPI_FPROP>(s, mA, mB, mW, a, kchunks);   // TAPS 1 + FPROP: 1x1 conv
   if (BN == 256) return launch_halo_epi<256, RESIDENT, TAPS, EPI_TCONV>(s, mA, mB, mW, a, kchunks);
   return 0;
@@ -422,7 +702,7 @@ int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tenso
   // rows, the epilogue stores 8-column groups below n_total only); dgrad routes whole 32-column chunks to its two
   // destinations and keeps the multiple-of-32 rule
   if (ntot % 8) return 0;
-  if (a.epi == EPI_DGRAD && (ntot % 32 || a.split % 32)) return 0;
+  if ((a.epi == EPI_DGRAD || a.epi == EPI_DGRAD_BNR) && (ntot % 32 || a.split % 32)) return 0;
   const int bn = ntot % 256 == 0 ? 256 : (ntot % 128 == 0 ? 128 : (ntot <= 64 ? 64 : 128));
   CUtensorMap mA, mB, mW;
   if (!halo_map(&mA, xa)) return 0;
@@ -436,11 +716,11 @@ int try_conv3x3_halo(cudaStream_t s, const dnnca_tensor_t* xa, const dnnca_tenso
   if (narrow) a.c_a = 64;
   const size_t limit = 226 * 1024;
   if (bn == 64) {
-    if ((size_t)HGeom<64>::smem_resident(kchunks) <= limit) return launch_halo<64, true>(s, mA, mB, mW, a, kchunks);
+    if (resident_fits<64, 9>(kchunks, a)) return launch_halo<64, true>(s, mA, mB, mW, a, kchunks);
     return launch_halo<64, false>(s, mA, mB, mW, a, kchunks);
   }
   if (bn == 128) {
-    if ((size_t)HGeom<128>::smem_resident(kchunks) <= limit) return launch_halo<128, true>(s, mA, mB, mW, a, kchunks);
+    if (resident_fits<128, 9>(kchunks, a)) return launch_halo<128, true>(s, mA, mB, mW, a, kchunks);
     return launch_halo<128, false>(s, mA, mB, mW, a, kchunks);
   }
   return launch_halo<256, false>(s, mA, mB, mW, a, kchunks);
@@ -462,14 +742,14 @@ int try_conv1x1_halo(cudaStream_t s, const dnnca_tensor_t* x, const void* wpack,
   const int kchunks = ktot / 64;
   const size_t limit = 226 * 1024;
   if (bn == 64) {
-    if ((size_t)HGeom<64, 1>::smem_resident(kchunks) <= limit) return launch_halo<64, true, 1>(s, mA, mA, mW, a, kchunks);
+    if (resident_fits<64, 1>(kchunks, a)) return launch_halo<64, true, 1>(s, mA, mA, mW, a, kchunks);
     return launch_halo<64, false, 1>(s, mA, mA, mW, a, kchunks);
   }
   if (bn == 128) {
-    if ((size_t)HGeom<128, 1>::smem_resident(kchunks) <= limit) return launch_halo<128, true, 1>(s, mA, mA, mW, a, kchunks);
+    if (resident_fits<128, 1>(kchunks, a)) return launch_halo<128, true, 1>(s, mA, mA, mW, a, kchunks);
     return launch_halo<128, false, 1>(s, mA, mA, mW, a, kchunks);
   }
-  if ((size_t)HGeom<256, 1>::smem_resident(kchunks) <= limit) return launch_halo<256, true, 1>(s, mA, mA, mW, a, kchunks);
+  if (resident_fits<256, 1>(kchunks, a)) return launch_halo<256, true, 1>(s, mA, mA, mW, a, kchunks);
   return launch_halo<256, false, 1>(s, mA, mA, mW, a, kchunks);
 }
 
@@ -486,7 +766,7 @@ int try_tconv_fprop_halo(cudaStream_t s, const dnnca_tensor_t* x, const void* wp
   a.taps = 1; a.sx = 1;
   a.dbg = getenv("DNNCA_HALO_DBG") ? atoi(getenv("DNNCA_HALO_DBG")) : 0;
   const int kchunks = cin / 64;
-  if ((size_t)HGeom<256, 1>::smem_resident(kchunks) <= 226 * 1024) return launch_halo<256, true, 1>(s, mA, mA, mW, a, kchunks);
+  if (resident_fits<256, 1>(kchunks, a)) return launch_halo<256, true, 1>(s, mA, mA, mW, a, kchunks);
   return launch_halo<256, false, 1>(s, mA, mA, mW, a, kchunks);
 }
 
@@ -505,14 +785,14 @@ int try_tconv_dgrad_halo(cudaStream_t s, const dnnca_tensor_t* dy, const void* w
   const int kchunks = 4 * (cout / 64);
   const size_t limit = 226 * 1024;
   if (bn == 64) {
-    if ((size_t)HGeom<64, 1>::smem_resident(kchunks) <= limit) return launch_halo<64, true, 1>(s, mA, mA, mW, a, kchunks);
+    if (resident_fits<64, 1>(kchunks, a)) return launch_halo<64, true, 1>(s, mA, mA, mW, a, kchunks);
     return launch_halo<64, false, 1>(s, mA, mA, mW, a, kchunks);
   }
   if (bn == 128) {
-    if ((size_t)HGeom<128, 1>::smem_resident(kchunks) <= limit) return launch_halo<128, true, 1>(s, mA, mA, mW, a, kchunks);
+    if (resident_fits<128, 1>(kchunks, a)) return launch_halo<128, true, 1>(s, mA, mA, mW, a, kchunks);
     return launch_halo<128, false, 1>(s, mA, mA, mW, a, kchunks);
   }
-  if ((size_t)HGeom<256, 1>::smem_resident(kchunks) <= limit) return launch_halo<256, true, 1>(s, mA, mA, mW, a, kchunks);
+  if (resident_fits<256, 1>(kchunks, a)) return launch_halo<256, true, 1>(s, mA, mA, mW, a, kchunks);
   return launch_halo<256, false, 1>(s, mA, mA, mW, a, kchunks);
 }
 

@@ -34,6 +34,7 @@ struct WHArgs {
   int ksplit, mt_a;            // pixel-tile slices; M tiles that belong to x (the rest to x2)
   float* dw;
   float* db;                   // PAIRED: bias gradient from the all-ones block paired with the ninth tap (or NULL)
+  int acc_major;               // experiment switch: MMA order accumulator-major (the first version) instead of K-step-major
 };
 
 __device__ __forceinline__ bool wh_elect() {
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
     } else if (warp == 1) {
       const uint32_t leader = wh_elect() ? 1u : 0u;
       const bool committer = wh_elect();
-      const uint32_t idesc128 = make_idesc(128, BN, 1, 1), idesc64 = make_idesc(64, BN, 1, 1);
+      const uint32_t idesc128 = make_idesc(128, BN, 1, 1);
       const uint32_t ring_addr = smem_u32(ring);
       int s = 0;
       uint32_t ph = 0;
@@ -176,11 +177,11 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
         const uint32_t xaddr = ring_addr + (uint32_t)(s * G::STAGE);
         const uint32_t z_lo0 = wh_desc_lo(xaddr + G::NXA * G::XATOM, WH_ZATOM);
         const uint32_t accf = it ? 1u : 0u;
+        // per accumulator: first pixel row of its (first) tap and the distance to its second 64-row block
+        uint32_t x_lo0[NACC], z_lo[NACC];
 #pragma unroll
         for (int j = 0; j < NACC; ++j) {
-          // first pixel row of the accumulator's (first) tap, and the distance to its second 64-row block
           uint32_t row0, lbo;
-          bool m64 = false;
           if (PAIRED) {
             const int ta = 2 * j, tb = 2 * j + 1;
             row0 = (uint32_t)((ta / 3) * WH_PW + ta % 3);
@@ -190,13 +191,25 @@ __global__ void __launch_bounds__(192) wgrad_halo_kernel(const __grid_constant__
             row0 = TCONV ? 0u : (uint32_t)j;          // FULL: dx = j (the box is already shifted by dy)
             lbo = G::XATOM;
           }
-          const uint32_t x_lo0 = wh_desc_lo(xaddr + row0 * 128, lbo);
-          const uint32_t idesc = m64 ? idesc64 : idesc128;
-          const uint32_t dcol = tmem_base + (uint32_t)(j * BN);
-          const uint32_t z_lo = TCONV ? z_lo0 + (uint32_t)(j * G::NZA * (WH_ZATOM >> 4)) : z_lo0;     // ConvT: tap j's dy tile
+          x_lo0[j] = wh_desc_lo(xaddr + row0 * 128, lbo);
+          z_lo[j] = TCONV ? z_lo0 + (uint32_t)(j * G::NZA * (WH_ZATOM >> 4)) : z_lo0;     // ConvT: tap j's dy tile
+        }
+        // K step outermost, accumulators innermost: consecutive MMAs go to DIFFERENT accumulators (DNNCA_WGRAD_ORDER=1
+        // restores accumulator-major order, 8 dependent MMAs in a row)
+        if (!a.acc_major) {
 #pragma unroll
           for (int r = 0; r < WH_R; ++r)               // one tile row = 16 pixels = one K step
-            wh_umma(dcol, x_lo0 + (uint32_t)(r * G::PW * 8), z_lo + (uint32_t)(r * 128), idesc, r ? 1u : accf, leader);
+#pragma unroll
+            for (int j = 0; j < NACC; ++j)
+              wh_umma(tmem_base + (uint32_t)(j * BN), x_lo0[j] + (uint32_t)(r * G::PW * 8), z_lo[j] + (uint32_t)(r * 128), idesc128,
+                      r ? 1u : accf, leader);
+        } else {
+#pragma unroll
+          for (int j = 0; j < NACC; ++j)
+#pragma unroll
+            for (int r = 0; r < WH_R; ++r)
+              wh_umma(tmem_base + (uint32_t)(j * BN), x_lo0[j] + (uint32_t)(r * G::PW * 8), z_lo[j] + (uint32_t)(r * 128), idesc128,
+                      r ? 1u : accf, leader);
         }
         if (committer) umma_commit(empty + s);
         __syncwarp();
@@ -295,6 +308,7 @@ static int launch_wgrad_halo(cudaStream_t s, const CUtensorMap& mA, const CUtens
   if (want < 1) want = 1;
   if (groups * want > 65535) want = 65535 / groups;
   a.ksplit = (int)want;
+  a.acc_major = getenv("DNNCA_WGRAD_ORDER") ? atoi(getenv("DNNCA_WGRAD_ORDER")) : 0;
   dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)(groups * a.ksplit));
   kern<<<grid, 192, G::SMEM, s>>>(mA, mB, mG, a);
   DNNCA_LAUNCH_CHECK("wgrad_halo");

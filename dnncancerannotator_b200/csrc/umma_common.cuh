@@ -103,7 +103,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_
 }
 
 
-enum { EPI_FPROP = 0, EPI_DGRAD = 1, EPI_TCONV = 2 };
+// EPI_DGRAD_BNR (persistent halo kernels only): dgrad whose destination A is the output of a BatchNormalization -- `mask`
+// points at the BN's INPUT tensor and the epilogue also accumulates the BN backward sums (sum dy, sum dy*xhat) of the
+// gradient it stores, so the separate bn_bwd_reduce pass over (x, dy) disappears
+enum { EPI_FPROP = 0, EPI_DGRAD = 1, EPI_TCONV = 2, EPI_DGRAD_BNR = 3 };
 
 struct UArgs {
   int taps, ktap;            // filter taps; ktap = sqrt(taps)
@@ -124,6 +127,8 @@ struct UArgs {
   int nimg;                  // images (persistent kernels)
   int dbg;                   // experiment switch (descriptor variants)
   double* stats;             // fprop (persistent halo kernel): per-channel sum | sum of squares of the STORED output, or NULL
+                             // EPI_DGRAD_BNR: [2*split] sum dy | sum dy*xhat of the BatchNorm whose output gradient is destination A
+  const float* bnr_mi;       // EPI_DGRAD_BNR: that BatchNorm's [2*split] mean | invstd
 };
 
 // epilogue of one 32-(or 16-)column chunk of one accumulator row: bias+act (fprop / ConvT) or act'(mask) (dgrad),

@@ -271,6 +271,7 @@ class Model:
             self._emit(plan)
             if os.environ.get('DNNCA_BN_FOLD', '1') != '0' and not want_input_grad:
                 plan.fold_batchnorms()
+            plan.fuse_bn_reductions()
             self._plans[key] = plan
         return self._plans[key]
 

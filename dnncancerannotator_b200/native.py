@@ -60,6 +60,8 @@ _PROTOS = {
     'dnnca_maxpool2x2_fwd_affine': [_vp, _TP, _vp, _TP, _vp, _vp],
     'dnnca_conv2d_fprop': [_vp, _TP, _TP, _vp, _vp, _TP, _i, _i, _f, _vp, _vp, C.c_size_t],
     'dnnca_conv2d_dgrad': [_vp, _TP, _vp, _TP, _TP, _i, _TP, _i, _f, _vp, C.c_size_t],
+    'dnnca_conv2d_dgrad_bnreduce': [_vp, _TP, _vp, _TP, _TP, _i, _TP, _vp, _vp, _vp, C.c_size_t],
+    'dnnca_convtranspose2x2_dgrad_bnreduce': [_vp, _TP, _vp, _TP, _TP, _vp, _vp, _vp, C.c_size_t],
     'dnnca_conv2d_wgrad': [_vp, _TP, _TP, _TP, _vp, _vp, _i],
     'dnnca_convtranspose2x2_fprop': [_vp, _TP, _vp, _vp, _TP, _vp, _vp, C.c_size_t],
     'dnnca_convtranspose2x2_dgrad': [_vp, _TP, _vp, _TP, _TP, _i, _f, _vp, C.c_size_t],
@@ -190,6 +192,9 @@ class Profiler:
         label = name.replace('dnnca_', '')
         if name in ('dnnca_conv2d_prepack', 'dnnca_conv2d_fold_supported'):
             return dict(label=label, bytes=0, flops=0)
+        if name.endswith('_bnreduce'):              # dgrad + the BatchNorm backward sums in its epilogue: same conv
+            name = name[:-len('_bnreduce')]
+            label = name.replace('dnnca_', '')
         if name.startswith('dnnca_conv2d_') and len(vs) >= 2:
             affine = name.endswith('_affine')      # BatchNorm folded into the input(s): same conv, k = 3
             k = 3 if affine else [a for a in args if isinstance(a, int)][0]

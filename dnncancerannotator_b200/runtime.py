@@ -346,6 +346,12 @@ class ConvOp(Op):
         """dgrad only (also the input-gradient chain of callbacks.py:290-299, which needs no parameter gradients)."""
         if self.x.needs_grad:
             ps = self.p.params
+            bn = getattr(self.x, 'bnr', None)
+            if bn is not None and self.p.train_bn:     # x is a BatchNorm output read by this conv alone: its backward sums
+                N.call('dnnca_conv2d_dgrad_bnreduce', N.stream_ptr(), self.y.gct(), ps.ptr(self.kernel), self.x.gct(),
+                       self.x2.gct() if self.x2 else None, self.k, bn.x.ct(), N.ptr(bn.mi), bn.stats.bwd_ptr(),
+                       *ws_args(self.ws))
+                return
             m, a, al = self.x.mask_args()
             N.call('dnnca_conv2d_dgrad', N.stream_ptr(), self.y.gct(), ps.ptr(self.kernel), self.x.gct(),
                    self.x2.gct() if self.x2 else None, self.k, m, a, al, *ws_args(self.ws))
@@ -381,6 +387,11 @@ class TConvOp(Op):
     def bwd_input(self):
         if self.x.needs_grad:
             ps = self.p.params
+            bn = getattr(self.x, 'bnr', None)
+            if bn is not None and self.p.train_bn:
+                N.call('dnnca_convtranspose2x2_dgrad_bnreduce', N.stream_ptr(), self.y.gct(), ps.ptr(self.kernel), self.x.gct(),
+                       bn.x.ct(), N.ptr(bn.mi), bn.stats.bwd_ptr(), *ws_args(self.ws))
+                return
             m, a, al = self.x.mask_args()
             N.call('dnnca_convtranspose2x2_dgrad', N.stream_ptr(), self.y.gct(), ps.ptr(self.kernel), self.x.gct(), m, a,
                    al, *ws_args(self.ws))
@@ -441,6 +452,7 @@ class BNOp(Op):
         self.gamma = f'{prefix}/gamma' if scale else None
         self.fused_stats = fused_stats
         self.folded = False        # Plan.fold_batchnorms: the consumers read `x` + the affine, `y` is never written
+        self.reduce_fused = False  # Plan.fuse_bn_reductions: the sole consumer's dgrad takes the backward sums
         self.ss = self.mi = None   # scale|shift and mean|invstd, fp32 [2C] each
 
     def allocate(self, training):
@@ -468,7 +480,8 @@ class BNOp(Op):
 
     def bwd(self):
         ps, s = self.p.params, N.stream_ptr()
-        N.call('dnnca_bn_bwd_reduce', s, self.x.ct(), self.y.gct(), N.ptr(self.mi), self.stats.bwd_ptr())
+        if not self.reduce_fused:      # else the dgrad that wrote y's gradient left the sums (dnnca_*_dgrad_bnreduce)
+            N.call('dnnca_bn_bwd_reduce', s, self.x.ct(), self.y.gct(), N.ptr(self.mi), self.stats.bwd_ptr())
         act = self.x.act or (N.ACT_NONE, 0.0)
         N.call('dnnca_bn_bwd_apply', s, self.x.ct(), self.y.gct(), N.ptr(self.mi),
                ps.ptr(self.gamma) if self.gamma else None, self.stats.bwd_ptr(), self.x.gct(), act[0], act[1],
@@ -549,6 +562,7 @@ class Plan:
         self.head = None              # (kernel name, bias name)
         self.allocated_training = None
         self.graphs = {}
+        self.train_bn = True          # BatchNorm layers run in training mode in the backward pass being launched
         self.branches = []            # [(first op, end op)] of mutually independent, adjacent op ranges (set by the model)
 
     def new_buf(self, h, w, c, name, n=None, zero=False):
@@ -600,6 +614,33 @@ class Plan:
             bn.folded = True
             n += 1
         self.n_folded_bn = n
+        return n
+
+    def fuse_bn_reductions(self):
+        """BatchNorm backward sums taken by the dgrad that writes the BN output's gradient: applies to every BatchNorm
+        whose output has exactly ONE reader, a Conv2D (as its first input) or a transposed conv -- then that reader's
+        dgrad is the only writer of the gradient and `bn_bwd_reduce` (a full read of x and dy) is dropped.  Skip tensors
+        (read by the pool and by the decoder) and the BN feeding the head keep the separate pass."""
+        import os
+        # OFF by default: measured on B200 (profiles/r02p_*) it does not pay -- unet_big B=32 12.396 -> 12.383 ms, mulmo_unet
+        # 5.64 -> 5.74 ms.  The 64-channel dgrads at 256^2 already move 3.7 TB/s; reading the BN input as well makes them
+        # HBM-bound, so the pass only moves from one kernel into another.  DNNCA_BN_REDUCE_FUSE=1 enables it.
+        if os.environ.get('DNNCA_BN_REDUCE_FUSE', '0') != '1' or self.want_input_grad:
+            return 0
+        n = 0
+        for bn in [op for op in self.ops if isinstance(op, BNOp)]:
+            t = bn.y
+            if t is self.features:
+                continue
+            users = [op for op in self.ops if op is not bn and (getattr(op, 'x', None) is t or getattr(op, 'x2', None) is t)]
+            if len(users) != 1 or not isinstance(users[0], (ConvOp, TConvOp)) or users[0].x is not t:
+                continue
+            if t.coff != 0 or t.c != t.buf.c or bn.x.c != t.c:
+                continue
+            t.bnr = bn
+            bn.reduce_fused = True
+            n += 1
+        self.n_fused_bn_reduce = n
         return n
 
     def allocate(self, training):

@@ -196,6 +196,17 @@ DNNCA_API int dnnca_bn_bwd_apply(void* stream, const dnnca_tensor_t* x, const dn
  *   maxpool2x2_fwd_affine : MaxPool2D of s*x + t (max of x where s >= 0, min where s < 0), y / idx / stats as in
  *                           maxpool2x2_fwd; the backward pass is maxpool2x2_bwd unchanged.
  * ------------------------------------------------------------------------- */
+/* dgrad whose destination dx is the gradient of a BatchNormalization OUTPUT (the reference's Conv -> act -> BN -> Conv
+ * chain, components.py:46-61,118-134, differentiated by GradientTape): besides dx (and dx2) the call leaves the BN's
+ * backward sums (sum dy | sum dy*xhat over n,h,w, fp64 [2C], accumulated: zero them per step) in `sums`, taken in the
+ * dgrad epilogue on the tensor-core path and by dnnca_bn_bwd_reduce otherwise.  bn_x: the BN's input; mean_invstd: what
+ * dnnca_bn_finalize wrote.  dnnca_bn_bwd_apply follows unchanged. */
+DNNCA_API int dnnca_conv2d_dgrad_bnreduce(void* stream, const dnnca_tensor_t* dz, const float* w, const dnnca_tensor_t* dx,
+                                          const dnnca_tensor_t* dx2, int ksize, const dnnca_tensor_t* bn_x,
+                                          const float* mean_invstd, double* sums, void* workspace, size_t workspace_bytes);
+DNNCA_API int dnnca_convtranspose2x2_dgrad_bnreduce(void* stream, const dnnca_tensor_t* dy, const float* k, const dnnca_tensor_t* dx,
+                                                    const dnnca_tensor_t* bn_x, const float* mean_invstd, double* sums,
+                                                    void* workspace, size_t workspace_bytes);
 DNNCA_API int dnnca_conv2d_fold_supported(const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const dnnca_tensor_t* y, int ksize);
 DNNCA_API size_t dnnca_conv2d_fold_scratch_bytes(int cin, int cout);
 DNNCA_API int dnnca_conv2d_fprop_affine(void* stream, const dnnca_tensor_t* x, const dnnca_tensor_t* x2, const float* affine_x,

@@ -201,3 +201,114 @@ def test_folded_plan_matches_unfolded_plan_and_oracle():
     for k in wf:
         if 'moving' in k:
             np.testing.assert_allclose(wf[k], wu[k], rtol=2e-2, atol=2e-3)
+
+
+# (n, h, w, cout of the layer = K of the dgrad GEMM, ca = channels of dx (the BN output), cb = channels of dx2)
+BNR_SHAPES = [(2, 32, 24, 64, 64, 0), (1, 16, 40, 64, 128, 0), (2, 18, 22, 64, 64, 64), (1, 34, 16, 128, 128, 128),
+              (2, 16, 16, 256, 256, 0), (2, 16, 16, 32, 32, 0), (2, 8, 8, 12, 12, 0)]
+
+
+@pytest.mark.parametrize('shape', BNR_SHAPES)
+def test_conv_dgrad_with_bn_backward_sums(N, shape):
+    """dnnca_conv2d_dgrad_bnreduce == dnnca_conv2d_dgrad followed by dnnca_bn_bwd_reduce over (bn_x, dx): the gradient
+    is bit-identical (same kernel arithmetic) and the sums agree to fp32 partial-sum round-off."""
+    n, h, w, cout, ca, cb = shape
+    rng = np.random.default_rng(abs(hash(shape)) % 2 ** 31)
+    lib = N.lib()
+    cin = ca + cb
+    d = lambda t, dt=torch.bfloat16: torch.as_tensor(t).to('cuda').to(dt).contiguous()
+    dz = d(rng.normal(0, 1.0, (n, h, w, cout)).astype(np.float32))
+    wt = d((rng.normal(0, 1.0, (3, 3, cin, cout)) / np.sqrt(9 * cout)).astype(np.float32), torch.float32)
+    bn_x = d(np.maximum(rng.normal(0.4, 1.0, (n, h, w, ca)), 0).astype(np.float32))
+    mi = d(np.concatenate([rng.normal(0.5, 0.2, ca), rng.uniform(0.5, 2.0, ca)]).astype(np.float32), torch.float32)
+    ws = torch.empty(lib.dnnca_conv_workspace_bytes(9, cin, cout), dtype=torch.uint8, device='cuda')
+    outs = []
+    for fused in (False, True):
+        dx = torch.full((n, h, w, ca), 7.0, dtype=torch.bfloat16, device='cuda')
+        dx2 = torch.full((n, h, w, cb), 7.0, dtype=torch.bfloat16, device='cuda') if cb else None
+        sums = torch.zeros(2 * ca, dtype=torch.float64, device='cuda')
+        vdz, vdx, vx = N.tensor_view(dz), N.tensor_view(dx), N.tensor_view(bn_x)
+        vdx2 = N.tensor_view(dx2) if cb else None
+        if fused:
+            N.call('dnnca_conv2d_dgrad_bnreduce', None, C.byref(vdz), N.ptr(wt), C.byref(vdx), C.byref(vdx2) if cb else None, 3,
+                   C.byref(vx), N.ptr(mi), N.ptr(sums), N.ptr(ws), ws.numel())
+        else:
+            N.call('dnnca_conv2d_dgrad', None, C.byref(vdz), N.ptr(wt), C.byref(vdx), C.byref(vdx2) if cb else None, 3, None,
+                   N.ACT_NONE, 0.0, N.ptr(ws), ws.numel())
+            N.call('dnnca_bn_bwd_reduce', None, C.byref(vx), C.byref(vdx), N.ptr(mi), N.ptr(sums))
+        torch.cuda.synchronize()
+        outs.append((dx.float().cpu().numpy(), dx2.float().cpu().numpy() if cb else None, sums.cpu().numpy()))
+    (dx0, dxb0, s0), (dx1, dxb1, s1) = outs
+    np.testing.assert_array_equal(dx0, dx1)
+    if cb:
+        np.testing.assert_array_equal(dxb0, dxb1)
+    # independent fp64 sums from the stored gradient
+    xh = (bn_x.float().cpu().numpy().astype(np.float64) - mi[:ca].cpu().numpy()) * mi[ca:].cpu().numpy()
+    want = np.concatenate([dx0.astype(np.float64).sum((0, 1, 2)), (dx0.astype(np.float64) * xh).sum((0, 1, 2))])
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(s1, want, rtol=2e-4, atol=2e-5 * scale)
+    np.testing.assert_allclose(s0, want, rtol=2e-4, atol=2e-5 * scale)
+
+
+@pytest.mark.parametrize('shape', [(2, 8, 12, 64, 128), (1, 16, 16, 128, 256), (2, 8, 8, 12, 12)])
+def test_tconv_dgrad_with_bn_backward_sums(N, shape):
+    n, h, w, cout, cin = shape                  # ConvT cin -> cout, x [n,h,w,cin], dy [n,2h,2w,cout]
+    rng = np.random.default_rng(abs(hash(shape)) % 2 ** 31)
+    lib = N.lib()
+    d = lambda t, dt=torch.bfloat16: torch.as_tensor(t).to('cuda').to(dt).contiguous()
+    dy = d(rng.normal(0, 1.0, (n, 2 * h, 2 * w, cout)).astype(np.float32))
+    kt = d((rng.normal(0, 1.0, (2, 2, cout, cin)) / np.sqrt(4 * cout)).astype(np.float32), torch.float32)
+    bn_x = d(np.maximum(rng.normal(0.4, 1.0, (n, h, w, cin)), 0).astype(np.float32))
+    mi = d(np.concatenate([rng.normal(0.5, 0.2, cin), rng.uniform(0.5, 2.0, cin)]).astype(np.float32), torch.float32)
+    ws = torch.empty(lib.dnnca_conv_workspace_bytes(4, cin, cout), dtype=torch.uint8, device='cuda')
+    outs = []
+    for fused in (False, True):
+        dx = torch.full((n, h, w, cin), 7.0, dtype=torch.bfloat16, device='cuda')
+        sums = torch.zeros(2 * cin, dtype=torch.float64, device='cuda')
+        vdy, vdx, vx = N.tensor_view(dy), N.tensor_view(dx), N.tensor_view(bn_x)
+        if fused:
+            N.call('dnnca_convtranspose2x2_dgrad_bnreduce', None, C.byref(vdy), N.ptr(kt), C.byref(vdx), C.byref(vx), N.ptr(mi),
+                   N.ptr(sums), N.ptr(ws), ws.numel())
+        else:
+            N.call('dnnca_convtranspose2x2_dgrad', None, C.byref(vdy), N.ptr(kt), C.byref(vdx), None, N.ACT_NONE, 0.0, N.ptr(ws),
+                   ws.numel())
+            N.call('dnnca_bn_bwd_reduce', None, C.byref(vx), C.byref(vdx), N.ptr(mi), N.ptr(sums))
+        torch.cuda.synchronize()
+        outs.append((dx.float().cpu().numpy(), sums.cpu().numpy()))
+    (dx0, s0), (dx1, s1) = outs
+    np.testing.assert_array_equal(dx0, dx1)
+    xh = (bn_x.float().cpu().numpy().astype(np.float64) - mi[:cin].cpu().numpy()) * mi[cin:].cpu().numpy()
+    want = np.concatenate([dx0.astype(np.float64).sum((0, 1, 2)), (dx0.astype(np.float64) * xh).sum((0, 1, 2))])
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(s1, want, rtol=2e-4, atol=2e-5 * scale)
+
+
+def test_plan_fuses_bn_backward_reductions():
+    """Every BatchNorm whose output has one reader loses its bn_bwd_reduce pass; gradients agree with the unfused plan."""
+    from dnncancerannotator_b200 import runtime as R
+    from dnncancerannotator_b200.models import tf_models
+    from dnncancerannotator_b200.synthetic import make_slices
+    ref = rm.build_model('UNetAnnotator', OPTS, (None, 64, 64, 3), seed=4)
+    ref.randomize_bn(seed=6)
+    x, y = make_slices(4, 64, 64, 3, seed=9)
+    res = {}
+    for fuse in ('1', '0'):
+        os.environ['DNNCA_BN_REDUCE_FUSE'] = fuse
+        try:
+            m = tf_models.UNetAnnotator(**OPTS, dtype='bf16')
+            m.build((None, 64, 64, 3))
+            m.compile(loss=dict(class_name='WeightedCrossentropy', config=dict(weight_mul=3.0)))
+            m.set_weights(ref.get_weights())
+            m.forward_backward(x, y)
+            plan = m._plan(4, 64, 64)
+            res[fuse] = (m.get_grads(), sum(1 for op in plan.ops if isinstance(op, R.BNOp) and op.reduce_fused),
+                         sum(1 for op in plan.ops if isinstance(op, R.BNOp)))
+        finally:
+            os.environ.pop('DNNCA_BN_REDUCE_FUSE', None)
+    (g1, n1, nb), (g0, n0, _) = res['1'], res['0']      # (the fusion is opt-in: DNNCA_BN_REDUCE_FUSE=1)
+    # n_downsample=2: enc 2 x (bn0, pool_bn) + dec 2 x (tconv_bn, bn0) + dec u0 bn1 (read by the next ConvT); skips and the last BN are not
+    assert n0 == 0 and n1 >= 8 and n1 < nb, (n1, nb)
+    names = [k for k in g1 if not k.endswith('/tconv/bias')]
+    a = np.concatenate([g1[k].ravel() for k in names])
+    b = np.concatenate([g0[k].ravel() for k in names])
+    assert rel_l2(a, b) <= 2e-3, rel_l2(a, b)
