@@ -193,8 +193,16 @@ class Model:
         return self.params.get_grads()
 
     # checkpoints: own format (TF checkpoints need TF), same ckpt-<step> naming as engine.py:52
-    def save_weights(self, path):
+    def save_weights(self, path, save_format=None):
+        """Own ``.npz`` format by default; ``save_format='tf'`` writes a TensorFlow object-based checkpoint
+        (``<path>.index`` + ``<path>.data-00000-of-00001``) laid out like the file the reference's
+        ``ModelCheckpoint(save_weights_only=True)`` writes (engine.py:105), see ``utils/tf_checkpoint.py``."""
         os.makedirs(os.path.dirname(os.path.abspath(path)) or '.', exist_ok=True)
+        if save_format == 'tf':
+            from .utils import tf_checkpoint
+            if self._dp is not None and self.params.device is not None and self._dp.world_size > 1:
+                self._dp.average(self.params.state)
+            return tf_checkpoint.export_from(self, path)
         if self._dp is not None and self.params.device is not None and self._dp.world_size > 1:
             self._dp.average(self.params.state)     # BN moving statistics are rank-local: saved as the replica mean
         w = self.get_weights()
@@ -207,6 +215,15 @@ class Model:
     def load_weights(self, path):
         """engine.py:75,197,230.  Returns a status object with ``assert_existing_objects_matched()`` /
         ``assert_consumed()`` / ``expect_partial()`` like TF's checkpoint loader (engine.py:75 chains the first)."""
+        tf_prefix = path[:-len('.index')] if path.endswith('.index') else path
+        if os.path.exists(tf_prefix + '.index') and not os.path.exists(tf_prefix + '.npz'):
+            # a TensorFlow checkpoint written by the reference (engine.py:105): read without TensorFlow
+            from .utils import tf_checkpoint
+            loaded, missing, unused = tf_checkpoint.load_into(self, tf_prefix)
+            self._sync_replicas()
+            st = LoadStatus(loaded + missing, loaded)
+            st.unused = unused
+            return st
         p = path if path.endswith('.npz') else path + '.npz'
         if os.path.isdir(path) and os.path.exists(os.path.join(path, 'weights.npz')):     # a directory written by save()
             p = os.path.join(path, 'weights.npz')
@@ -250,9 +267,9 @@ class Model:
         d = os.path.join(save_dir, 'checkpoints')
         if os.path.isdir(d):
             for f in os.listdir(d):
-                m = re.fullmatch(r'ckpt-(\d+)\.npz', f)
+                m = re.fullmatch(r'ckpt-(\d+)\.(npz|index)', f)       # own format, or the reference's TF checkpoints
                 if m:
-                    out[int(m.group(1))] = os.path.join(d, f[:-4])
+                    out[int(m.group(1))] = os.path.join(d, f[:-len(m.group(2)) - 1])
         return OrderedDict(sorted(out.items()))
 
     # ---- plans -----------------------------------------------------------------
