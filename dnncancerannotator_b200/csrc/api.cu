@@ -83,7 +83,7 @@ int try_tconv_wgrad_small(cudaStream_t, const dnnca_tensor_t*, const dnnca_tenso
 size_t umma_pack_bytes(int taps, int cin, int cout);
 int try_conv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, int, int, float, void*, size_t, double*);
 int try_conv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, const dnnca_tensor_t*, int, float, void*, size_t);
-int try_tconv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, void*, size_t);
+int try_tconv_fprop_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const float*, const dnnca_tensor_t*, void*, size_t, double*);
 int try_tconv_dgrad_umma(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, float, void*, size_t);
 int conv_dgrad_umma_bnreduce(cudaStream_t, const dnnca_tensor_t*, const float*, const dnnca_tensor_t*, const dnnca_tensor_t*, int, void*, size_t,
                              const dnnca_tensor_t*, const float*, double*, bool*);
@@ -307,19 +307,20 @@ extern "C" int dnnca_convtranspose2x2_fprop(void* stream, const dnnca_tensor_t* 
   DNNCA_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && x->dtype == y->dtype,
                   "convtranspose2x2_fprop: y must be [n,2h,2w,cout] with x's dtype");
   if (!k) {     // prepacked (see conv2d_fprop)
-    int rp = g_force_generic ? 0 : try_tconv_fprop_umma((cudaStream_t)stream, x, nullptr, bias, y, workspace, workspace_bytes);
+    int rp = g_force_generic ? 0 : try_tconv_fprop_umma((cudaStream_t)stream, x, nullptr, bias, y, workspace, workspace_bytes, stats);
     if (rp < 0) return rp;
     if (rp == 0) DNNCA_UNSUPPORTED("convtranspose2x2_fprop: k == NULL (prepacked weights) needs a shape the tensor-core kernels serve");
-    return stats ? dnnca_channel_stats(stream, y, stats) : DNNCA_OK;
+    return (stats && rp != 2) ? dnnca_channel_stats(stream, y, stats) : DNNCA_OK;
   }
   int r = (g_force_generic || x->dtype != DNNCA_BF16) ? 0 : try_tconv_fprop_row((cudaStream_t)stream, x, k, bias, y);
   if (r == 0 && !g_force_generic) r = try_tconv_fprop_small((cudaStream_t)stream, x, k, bias, y);
-  if (r == 0 && !g_force_generic) r = try_tconv_fprop_umma((cudaStream_t)stream, x, k, bias, y, workspace, workspace_bytes);
+  if (r == 0 && !g_force_generic) r = try_tconv_fprop_umma((cudaStream_t)stream, x, k, bias, y, workspace, workspace_bytes, stats);
   if (r < 0) return r;
+  const bool stats_taken = r == 2;
   if (r == 0) r = launch_tconv_fprop_generic((cudaStream_t)stream, x, k, bias, y);
   else r = DNNCA_OK;
   if (r != DNNCA_OK) return r;
-  if (stats) return dnnca_channel_stats(stream, y, stats);
+  if (stats && !stats_taken) return dnnca_channel_stats(stream, y, stats);
   return DNNCA_OK;
 }
 

@@ -682,8 +682,9 @@ int try_conv_dgrad_umma(cudaStream_t s, const dnnca_tensor_t* dz, const float* w
   return dispatch_bn<16>(s, mA, mA, mW, a, dx->n, bn);
 }
 
+// returns 2 when the kernel also accumulated the BatchNorm statistics of y into `stats`
 int try_tconv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const float* kw, const float* bias, const dnnca_tensor_t* y,
-                         void* ws, size_t ws_bytes) {
+                         void* ws, size_t ws_bytes, double* stats) {
   if (!ws || !bf16_view_in(x) || !bf16_view16(y)) return 0;
   const int cin = x->c, cout = y->c;
   if (ws_bytes < umma_pack_bytes(4, cin, cout)) return 0;
@@ -703,8 +704,10 @@ int try_tconv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const float* k
   a.ya = reinterpret_cast<__nv_bfloat16*>(y->data) + y->coff; a.ya_cs = y->cstride; a.split = 4 * cout; a.yb = a.ya; a.yb_cs = a.ya_cs;
   a.mask = nullptr; a.n_total = 4 * cout; a.cout_t = cout;
   if (kc == 64 && kp == cin && halo_enabled()) {
+    a.stats = stats;
     r = try_tconv_fprop_halo(s, x, ws, cin, cout, a);
     if (r != 0) return r;
+    a.stats = nullptr;
   }
   if (kc == 64) return dispatch_bn<64>(s, mA, mA, mW, a, x->n, bn);
   if (kc == 32) return dispatch_bn<32>(s, mA, mA, mW, a, x->n, bn);
@@ -796,7 +799,7 @@ int prepack_conv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const dnnca
 int prepack_tconv_fprop_umma(cudaStream_t s, const dnnca_tensor_t* x, const float* kw, const dnnca_tensor_t* y, void* ws,
                              size_t ws_bytes) {
   g_pack_only = true;
-  const int r = try_tconv_fprop_umma(s, x, kw, nullptr, y, ws, ws_bytes);
+  const int r = try_tconv_fprop_umma(s, x, kw, nullptr, y, ws, ws_bytes, nullptr);
   g_pack_only = false;
   return r;
 }

@@ -109,7 +109,7 @@ __device__ __forceinline__ void stage_chunk32(const UArgs& a, const uint32_t (&v
         }
       }
     }
-  } else if (EPI == EPI_FPROP) {
+  } else if (EPI == EPI_FPROP || EPI == EPI_TCONV) {
     const float4* sb4 = reinterpret_cast<const float4*>(sbias);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
   constexpr int EPI_ADDR = IS_DGRAD ? EPI_DGRAD : EPI;     // addressing / store code of the epilogue helpers
   float* sbias = reinterpret_cast<float*>(smem + G::BIAS_OFF);
   double* sstat = reinterpret_cast<double*>(smem + G::STAT_OFF);   // [2*BN] per-channel sum | sum of squares (fprop + stats)
-  const bool do_stats = (EPI == EPI_FPROP || BNR) && a.stats != nullptr;
+  const bool do_stats = (EPI == EPI_FPROP || BNR || (EPI == EPI_TCONV && STAGED)) && a.stats != nullptr;
   unsigned char* aring = smem + G::CTRL;
   unsigned char* bring = aring + G::A_SLOTS * A_SLOT;
 
@@ -387,8 +387,16 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
         fence_proxy_async();
         __syncwarp();
         if (lane == 0 && blk_live) {
-          if (in_a) tma_store_4d(&mapYa, stg + sbuf * 4096, ncol, bx0, by0, n);
-          else tma_store_4d(&mapYb, stg + sbuf * 4096, ncol - a.split, bx0, by0, n);
+          if (EPI == EPI_TCONV) {
+            // ConvT 2x2/s2: column block = (filter tap, 64 output channels); tap (ty, tx) of input pixel (y, x) is output
+            // pixel (2y + ty, 2x + tx): the output is described to the TMA as {C, 2, W, 2, H*N} (mapYa), one box per tap
+            const int tap = ncol / a.cout_t, ch = ncol - tap * a.cout_t;
+            if (by0 < a.H) tma_store_5d(&mapYa, stg + sbuf * 4096, ch, tap & 1, bx0, tap >> 1, n * a.H + by0);
+          } else if (in_a) {
+            tma_store_4d(&mapYa, stg + sbuf * 4096, ncol, bx0, by0, n);
+          } else {
+            tma_store_4d(&mapYb, stg + sbuf * 4096, ncol - a.split, bx0, by0, n);
+          }
           tma_store_commit();
         }
         if (do_stats && blk_live && (!BNR || in_a)) {
@@ -573,6 +581,11 @@ __global__ void __launch_bounds__(320) conv_umma_halo_kernel(const __grid_consta
           atomicAdd(a.stats + n0 + i, sstat[i]);
           atomicAdd(a.stats + a.split + n0 + i, sstat[BN + i] * (double)a.bnr_mi[a.split + n0 + i]);
         }
+      } else if (EPI == EPI_TCONV) {
+        if (n0 + i < a.n_total) {             // the four filter taps of a channel are four column blocks
+          atomicAdd(a.stats + (n0 + i) % a.cout_t, sstat[i]);
+          atomicAdd(a.stats + a.cout_t + (n0 + i) % a.cout_t, sstat[BN + i]);
+        }
       } else if (n0 + i < a.n_total) {
         atomicAdd(a.stats + n0 + i, sstat[i]);
         atomicAdd(a.stats + a.n_total + n0 + i, sstat[BN + i]);
@@ -605,6 +618,21 @@ static bool weight_map64(CUtensorMap* m, const void* wp, int ktot, int ntot, int
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ConvT 2x2/s2 output [N, 2H, 2W, C] seen from the INPUT pixel grid: {C, 2 (tx), W, 2 (ty), H*N}; box {64 ch, 1, 8 px, 1, 4 rows}.
+// (H and N share one dimension: a 4-row box never straddles two images when H % 4 == 0.)
+static bool tconv_out_map(CUtensorMap* m, __nv_bfloat16* base, int c, long long cstride, int w, int h, int n) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc || c <= 0) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (cstride * 2) % 16) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)c, 2, (cuuint64_t)w, 2, (cuuint64_t)h * n};
+  cuuint64_t strides[4] = {(cuuint64_t)cstride * 2, (cuuint64_t)2 * cstride * 2, (cuuint64_t)2 * w * cstride * 2,
+                           (cuuint64_t)4 * w * cstride * 2};
+  cuuint32_t box[5] = {64, 1, 8, 1, 4};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static bool halo_staged_enabled() {
@@ -663,6 +691,14 @@ template <int BN, bool RESIDENT, int TAPS, int EPI>
 static int launch_halo_epi(cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mW, const UArgs& a,
                            int kchunks) {
   using G = HGeom<BN, TAPS>;
+  if (EPI == EPI_TCONV && halo_staged_enabled() && a.cout_t % 64 == 0 && a.H % 4 == 0 &&
+      (size_t)(RESIDENT ? G::smem_resident(kchunks, true) : G::smem_stream(true)) <= 226 * 1024) {
+    CUtensorMap mY;
+    if (tconv_out_map(&mY, a.ya, a.cout_t, a.ya_cs, a.W, a.H, a.nimg)) {
+      const int r = launch_halo_st<BN, RESIDENT, TAPS, EPI, true>(s, mA, mB, mW, mY, mY, a, kchunks);
+      return (r == 1 && a.stats) ? 2 : r;      // 2: the BatchNorm statistics of the output were taken as well
+    }
+  }
   // staged epilogue (fprop / dgrad kinds): needs whole 64-column blocks per destination and room for the staging blocks
   if (EPI != EPI_TCONV && halo_staged_enabled() && (a.split % 64 == 0 || a.split >= a.n_total) &&
       (size_t)(RESIDENT ? G::smem_resident(kchunks, true) : G::smem_stream(true)) <= 226 * 1024) {
