@@ -31,6 +31,7 @@ UNITS = [
     ('head_loss.cu', 'head_loss', []),
     ('optim.cu', 'optim', []),
     ('metrics.cu', 'metrics', []),
+    ('region_metrics.cu', 'region_metrics', []),
     ('tconv_small.cu', 'tconv_small', []),
     ('input_tail.cu', 'input_tail', []),
     ('bn_fold.cu', 'bn_fold', []),

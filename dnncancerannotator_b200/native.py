@@ -86,6 +86,11 @@ _PROTOS = {
     'dnnca_head_bce_fwd_bwd': [_vp, _TP, _vp, _vp, _vp, _vp, C.POINTER(LossConfig), _vp, _vp, _vp, _TP, _i, _f,
                                _vp, _vp],
     'dnnca_threshold_hist': [_vp, _vp, _vp, _i64, _vp, _i, _vp],
+    'dnnca_resize_bilinear': [_vp, _vp, _i, _i, _i, _vp, _i, _i],
+    'dnnca_grey_open': [_vp, _vp, _i, _i, _i, _i, _vp],
+    'dnnca_connected_components': [_vp, _vp, _i, _i, _i, _vp],
+    'dnnca_region_workspace_bytes': [_i, _i, _i, _i, _i],
+    'dnnca_region_confusion': [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _f, _i, _vp, C.c_size_t, _i, _vp, _vp, _vp],
     'dnnca_add_relu_affine': [_vp, _TP, _vp, _TP, _vp, _vp, _TP],
     'dnnca_u8_to_unit': [_vp, _vp, _i64, _vp, _i],
     'dnnca_input_tail': [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, C.POINTER(C.c_int32), _i, _i, _vp, _i, _i, _vp],
@@ -104,7 +109,8 @@ _PROTOS = {
 }
 _RESTYPES = {'dnnca_last_error': C.c_char_p, 'dnnca_label_stats_decode': None,
              'dnnca_debug_launch_count': C.c_longlong, 'dnnca_debug_family_count': C.c_longlong,
-             'dnnca_conv_workspace_bytes': C.c_size_t, 'dnnca_conv2d_fold_scratch_bytes': C.c_size_t}
+             'dnnca_conv_workspace_bytes': C.c_size_t, 'dnnca_conv2d_fold_scratch_bytes': C.c_size_t,
+             'dnnca_region_workspace_bytes': C.c_size_t}
 
 _lib = None
 

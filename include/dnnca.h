@@ -283,6 +283,46 @@ DNNCA_API int dnnca_threshold_hist(void* stream, const float* probs, const float
                                    const float* thresholds, int nthr, uint64_t* hist);
 
 /* ---------------------------------------------------------------------------
+ * Region-based detection counters ("later" row)
+ *   replaces the update_state of RegionBasedRecall / Precision / TruePositives / FalsePositives / FalseNegatives /
+ *   FBetaScore / ConfusionMatrix (annotator/utils/metrics.py:80-520; get_tp_fn :206-227, get_tp_fp :229-252,
+ *   get_tp_fn_fp :254-288) as configured by configs/additionals/metrics.yaml:24-59 and by the Visualizer's region PR
+ *   curve (callbacks.py:226-230), together with the third-party ops those call:
+ *     dnnca_resize_bilinear        tf.image.resize(image, [oh, ow]) of metrics.py:194-204 (TF2 bilinear, half-pixel
+ *                                  centres, no antialias) for single-channel fp32 planes [n,h,w] -> [n,oh,ow];
+ *     dnnca_grey_open              annotator/utils/image.py:12-29 morph_open (tf.nn.erosion2d then tf.nn.dilation2d, zero
+ *                                  structuring element, 'SAME': out-of-image taps do not take part) applied to the
+ *                                  PROBABILITIES: 1[open(p) >= t] == morph_open(1[p >= t]) for every t, so one pass
+ *                                  serves all thresholds; filter_size 1..15; dst may not alias src;
+ *     dnnca_connected_components   tfa.image.connected_components (4-neighbourhood) of n uint8 masks [n,h,w]:
+ *                                  roots[b,y,x] = row-major index (y*w + x) of the FIRST pixel of the component the
+ *                                  pixel belongs to, -1 for background -- the rank of a root among the roots of the
+ *                                  batch in (image, row, column) order, plus one, is the id tfa assigns;
+ *     dnnca_region_confusion       the whole per-batch update for labels [n,h,w] / probabilities [n,h,w] (fp32) and
+ *                                  nthr thresholds (device fp32, any order): label regions = components of
+ *                                  label > 0.5, prediction regions at threshold t = components of
+ *                                  open(p) >= t (metrics.py:126-141), IoU over all (label, prediction) pairs in fp32
+ *                                  (metrics.py:189-191), a pair counts when IoU > iou_threshold.  Counters, each
+ *                                  [4][nthr] in the order { labels detected (tp of get_tp_fn), labels missed (fn),
+ *                                  predictions without a hit (fp), predictions with a hit (tp of get_tp_fp) }:
+ *                                  per_slice int32 [n][4][nthr] (may be NULL; the caller zeroes it: it is the
+ *                                  return_raw=True form) and totals uint64 [4][nthr] (may be NULL; ACCUMULATED).
+ *                                  workspace: dnnca_region_workspace_bytes(n,h,w,nthr,table_slots) bytes, caller-owned;
+ *                                  table_slots (power of two >= 64) bounds the number of distinct overlapping
+ *                                  (label region, prediction region) pairs per slice and threshold; *overflow
+ *                                  (device int32, caller zeroes) is set to 1 if a table filled up -- the counters
+ *                                  are then invalid and the call must be repeated with a larger table.
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_resize_bilinear(void* stream, const float* src, int n, int h, int w, float* dst, int oh, int ow);
+DNNCA_API int dnnca_grey_open(void* stream, const float* src, int n, int h, int w, int filter_size, float* dst);
+DNNCA_API int dnnca_connected_components(void* stream, const uint8_t* mask, int n, int h, int w, int32_t* roots);
+DNNCA_API size_t dnnca_region_workspace_bytes(int n, int h, int w, int nthr, int table_slots);
+DNNCA_API int dnnca_region_confusion(void* stream, const float* labels, const float* probs, int n, int h, int w,
+                                     const float* thresholds, int nthr, float iou_threshold, int morph_filter_size,
+                                     void* workspace, size_t workspace_bytes, int table_slots, int32_t* per_slice,
+                                     uint64_t* totals, int32_t* overflow);
+
+/* ---------------------------------------------------------------------------
  * MultiResUnet elementwise tail (inference): y = s2*relu(a*sa+ta + b*sb+tb)+t2
  *   replaces BatchNormalization -> add -> Activation('relu') -> BatchNormalization
  *   at multiresunet.py:120-124 and add -> relu -> BN at :148-150, :160-162.

@@ -63,7 +63,7 @@ def test_host_metric_formulas_match_the_oracle(seed):
     assert rm.auc_roc(*rm.confusion(yy, pp, thr)) == pytest.approx(1.0)
     tp, fp, fn, tn = rm.confusion(yy, np.array([0.9, 0.1, 0.9, 0.1], np.float32), [0.8])
     assert (tp[0], fp[0], fn[0], tn[0]) == (1, 1, 1, 1)
-    assert M.solve_metric({'RegionBasedRecall': {'thresholds': 0.8}}) is None
+    assert isinstance(M.solve_metric({'RegionBasedRecall': {'thresholds': 0.8}}), M.RegionBasedRecall)
 
 
 @pytest.mark.gpu
@@ -100,4 +100,7 @@ def test_model_evaluate_reports_compiled_metrics():
     tp, fp, fn, tn = rm.confusion(y, probs, [0.5])
     assert out['pixel/precision'] == pytest.approx(float(rm.precision(tp, fp)[0]), abs=1e-12)
     assert out['pixel/AUROC'] == pytest.approx(rm.auc_roc(*rm.confusion(y, probs, rm.auc_thresholds(50))), abs=1e-12)
-    assert 'region/recall' not in out and 'loss' in out
+    from oracle import ref_region as rr
+    pr = m._plan(4, 32, 32).probs.cpu().numpy()
+    rtp, rfn, rfp, rtpp = rr.get_tp_fn_fp(y, pr, [0.8])
+    assert out['region/recall'] == pytest.approx(float(rtp[0]) / (float(rtp[0] + rfn[0]) + 1e-7), rel=1e-6, abs=1e-7) and 'loss' in out
