@@ -34,6 +34,7 @@ UNITS = [
     ('region_metrics.cu', 'region_metrics', []),
     ('tconv_small.cu', 'tconv_small', []),
     ('input_tail.cu', 'input_tail', []),
+    ('tps_warp.cu', 'tps_warp', []),
     ('bn_fold.cu', 'bn_fold', []),
     ('p2p_adam.cu', 'p2p_adam', []),
 ]

@@ -74,3 +74,63 @@ def prepare_batch(combined, slice_types=DEFAULT_SLICE_TYPES, output_size=(256, 2
     N.call('dnnca_input_tail', N.stream_ptr(), N.ptr(t), B, hin, win, S, N.ptr(cy), N.ptr(fl), hout, wout, arr, len(fidx),
            lidx, N.ptr(x_out), N.dtype_code(x_out.dtype), x_out.shape[3], N.ptr(y_out))
     return x_out, y_out
+
+
+# ---- thin-plate-spline warp augmentation (data.py:628-645, 718-763) ---------------------------------------------------
+
+def draw_control_points(rng: np.random.Generator, n_images, width, n_points=100, max_diff=5, stddev=2.0):
+    """``random_warp``'s random draws (data.py:742-746): source points ~ U[0, width)^2, displacement ~ N(0, stddev)
+    clipped to +-max_diff.  -> (source, dest) float32 ``[n_images, n_points, 2]`` in (row, column) pixels."""
+    raw = rng.uniform(0.0, float(width), (n_images, n_points, 2)).astype(np.float32)
+    diff = np.clip(rng.normal(0.0, stddev, (n_images, n_points, 2)), -float(max_diff), float(max_diff)).astype(np.float32)
+    return raw, raw + diff
+
+
+def sparse_image_warp(image, source_control_point_locations, dest_control_point_locations, interpolation_order=2,
+                      regularization_weight=0.0, num_boundary_points=0, return_flow=True):
+    """``tfa.image.sparse_image_warp`` as the reference calls it (data.py:749-753) -> ``(warped image, dense flow)``.
+
+    ``image``: float32 ``[B,H,W,C]`` (numpy / CPU / CUDA tensor); control points ``[B,P,2]`` (row, column).  Only the
+    arguments the reference uses are implemented (thin-plate order 2, no regularisation, no boundary points); the fit
+    and the dense flow run in FP64 in normalised coordinates (``csrc/tps_warp.cu``)."""
+    if interpolation_order != 2 or regularization_weight != 0.0 or num_boundary_points != 0:
+        raise NotImplementedError('sparse_image_warp: the reference uses interpolation_order=2, regularization_weight=0, '
+                                  'num_boundary_points=0 (data.py:749-753); nothing else is built')
+    dev = image.device if torch.is_tensor(image) and image.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    img = torch.as_tensor(image).to(device=dev, dtype=torch.float32).contiguous()
+    src = torch.as_tensor(source_control_point_locations).to(device=dev, dtype=torch.float32).contiguous()
+    dst = torch.as_tensor(dest_control_point_locations).to(device=dev, dtype=torch.float32).contiguous()
+    if img.dim() != 4 or src.shape != dst.shape or src.dim() != 3 or src.shape[0] != img.shape[0] or src.shape[2] != 2:
+        raise ValueError('image [B,H,W,C]; control points [B,P,2]')
+    B, H, W, Cc = img.shape
+    P = src.shape[1]
+    lib = N.lib()
+    ws = torch.empty(int(lib.dnnca_tps_workspace_bytes(B, P)) // 8 + 1, dtype=torch.float64, device=dev)
+    coef = torch.empty(B, P + 3, 2, dtype=torch.float64, device=dev)
+    singular = torch.zeros(1, dtype=torch.int32, device=dev)
+    extent = float(max(H, W))
+    N.call('dnnca_tps_fit', N.stream_ptr(), N.ptr(src), N.ptr(dst), B, P, extent, N.ptr(ws), ws.numel() * 8, N.ptr(coef),
+           N.ptr(singular))
+    out = torch.empty_like(img)
+    flow = torch.empty(B, H, W, 2, dtype=torch.float32, device=dev) if return_flow else None
+    N.call('dnnca_tps_warp', N.stream_ptr(), N.ptr(img), B, H, W, Cc, N.ptr(dst), N.ptr(coef), P, extent, N.ptr(out), N.ptr(flow))
+    if int(singular.item()):
+        raise N.DnncaError('sparse_image_warp: singular spline system (coincident control points)')
+    return out, flow
+
+
+def random_warp(image, n_points=100, max_diff=5, stddev=2.0, process_in_batch=None, rng=None):
+    """``random_warp`` (data.py:718-763): a single image ``[H,W,C]`` (``process_in_batch=None``) or a batch
+    ``[process_in_batch,H,W,C]``, square images only (data.py:741).  Random draws come from ``rng`` on the host."""
+    rng = rng or np.random.default_rng()
+    img = torch.as_tensor(image)
+    single = process_in_batch is None
+    if single:
+        img = img[None]
+    elif img.shape[0] != process_in_batch:
+        raise ValueError(f'batch of {img.shape[0]} images but process_in_batch={process_in_batch}')
+    if img.shape[1] != img.shape[2]:
+        raise ValueError('random_warp: only square images are supported (data.py:741)')
+    src, dst = draw_control_points(rng, img.shape[0], img.shape[1], n_points, max_diff, stddev)
+    out, _ = sparse_image_warp(img, src, dst, return_flow=False)
+    return out[0] if single else out

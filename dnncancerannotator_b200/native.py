@@ -94,6 +94,9 @@ _PROTOS = {
     'dnnca_add_relu_affine': [_vp, _TP, _vp, _TP, _vp, _vp, _TP],
     'dnnca_u8_to_unit': [_vp, _vp, _i64, _vp, _i],
     'dnnca_input_tail': [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, C.POINTER(C.c_int32), _i, _i, _vp, _i, _i, _vp],
+    'dnnca_tps_workspace_bytes': [_i, _i],
+    'dnnca_tps_fit': [_vp, _vp, _vp, _i, _i, _f, _vp, C.c_size_t, _vp, _vp],
+    'dnnca_tps_warp': [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp],
     'dnnca_convert': [_vp, _TP, _TP],
     'dnnca_adam_step': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     'dnnca_p2p_alloc': [C.c_size_t, C.POINTER(C.c_void_p)],
@@ -110,7 +113,7 @@ _PROTOS = {
 _RESTYPES = {'dnnca_last_error': C.c_char_p, 'dnnca_label_stats_decode': None,
              'dnnca_debug_launch_count': C.c_longlong, 'dnnca_debug_family_count': C.c_longlong,
              'dnnca_conv_workspace_bytes': C.c_size_t, 'dnnca_conv2d_fold_scratch_bytes': C.c_size_t,
-             'dnnca_region_workspace_bytes': C.c_size_t}
+             'dnnca_region_workspace_bytes': C.c_size_t, 'dnnca_tps_workspace_bytes': C.c_size_t}
 
 _lib = None
 

@@ -366,6 +366,27 @@ DNNCA_API int dnnca_input_tail(void* stream, const uint8_t* combined, int n, int
                                const int32_t* crop_yx, const uint8_t* flip, int hout, int wout,
                                const int32_t* feature_idx, int nf, int label_idx, void* x_out, int x_dtype,
                                int x_cstride, float* y_out);
+/* Thin-plate-spline warp augmentation ("later" row): random_warp (data.py:718-763) =
+ * tfa.image.sparse_image_warp(image, source_control_point_locations, dest_control_point_locations) with its defaults
+ * (interpolation_order 2, regularization_weight 0, num_boundary_points 0).  Control points are device fp32 [n,npoints,2]
+ * in (row, column) pixel coordinates, drawn by the host (data.py:742-746).
+ *   dnnca_tps_fit   solves the polyharmonic-spline system of every image (interpolate_spline._solve_interpolation; train
+ *                   points = DEST locations, values = dest - source) in FP64 by partial-pivoting elimination, in
+ *                   coordinates divided by `extent` (the image side; any positive scale gives the same interpolant).
+ *                   coef: FP64 [n][npoints+3][2] (w rows, then v rows for row, column, 1), to be used with the same
+ *                   dest_points and extent.  workspace: dnnca_tps_workspace_bytes(n, npoints), 8-byte aligned.
+ *                   *singular (device int32, caller zeroes) is set to 1 if a system had no usable pivot (coincident
+ *                   control points): the coefficients of that call are invalid.
+ *   dnnca_tps_warp  evaluates the dense flow at every pixel (interpolate_spline._apply_interpolation, in FP64: close
+ *                   control points carry large weights of opposite sign) and resamples
+ *                   image fp32 [n,h,w,c] at (row, column) - flow bilinearly with tfa's clamping
+ *                   (dense_image_warp.interpolate_bilinear: floor in [0, size-2], weights in [0, 1]) into out (same
+ *                   shape, may not alias image).  flow_out: fp32 [n,h,w,2] or NULL (sparse_image_warp's second result). */
+DNNCA_API size_t dnnca_tps_workspace_bytes(int n, int npoints);
+DNNCA_API int dnnca_tps_fit(void* stream, const float* source_points, const float* dest_points, int n, int npoints,
+                            float extent, void* workspace, size_t workspace_bytes, double* coef, int32_t* singular);
+DNNCA_API int dnnca_tps_warp(void* stream, const float* image, int n, int h, int w, int c, const float* dest_points,
+                             const double* coef, int npoints, float extent, float* out, float* flow_out);
 /* dtype conversion between two views of equal logical shape (fp32 <-> bf16, slice copies) */
 DNNCA_API int dnnca_convert(void* stream, const dnnca_tensor_t* src, const dnnca_tensor_t* dst);
 
