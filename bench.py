@@ -304,10 +304,20 @@ def measure_training(cfgname, B, S, Cc, dtype, steps, warmup, world, rank, local
     ms_per_step = float(t) / steps
     out = dict(model=m, plan=plan, cfg=cfg, xh=xh, yh=yh, barrier=barrier, ms_per_step=ms_per_step,
                value=B * world / (ms_per_step / 1e3), loss_first=loss0, loss_last=float(loss), wall=wall, clocks=clocks,
-               warmup_done=W, e0=e0, e1=e1)
+               warmup_done=W, e0=e0, e1=e1, exchange=exchange_kind(m, world))
     if profile:        # every rank runs the pass (it contains the gradient all-reduce); rank 0 reports
         out.update(profile_step(m, plan, cfg, world))
     return out
+
+
+def exchange_kind(m, world):
+    """Which gradient exchange the step graph of this model contains (parallel.py)."""
+    if world <= 1:
+        return None
+    if getattr(m, '_p2p', None) is not None:
+        return ('all-reduce fused into the Adam kernel over NVLink peer memory (csrc/p2p_adam.cu: every rank reads the '
+                'peers\' gradient buffers; no NCCL call in the step)')
+    return 'NCCL buckets issued inside the step graph as the backward pass completes them'
 
 
 def secondary_line(cfgname, B, args, world, rank, local):
@@ -320,7 +330,7 @@ def secondary_line(cfgname, B, args, world, rank, local):
     step_tf = r['conv_flops_per_step'] / (r['ms_per_step'] * 1e9)      # conv FLOPs of a step / whole step time
     line = {'config': f'configs/{cfgname}.yaml', 'per_gpu_batch': B, 'value': r['value'], 'unit': UNIT,
             'ms_per_step': r['ms_per_step'], 'steps': min(args.steps, 10), 'warmup': 3, 'n_gpus': world,
-            'launches_per_step': r['launches_per_step'],
+            'launches_per_step': r['launches_per_step'], 'allreduce': r.get('exchange'),
             'conv_tensor_pipe': {'tflops': conv['tflops'], 'frac_of_burst_peak': conv['frac_of_bf16_burst_peak'],
                                  'frac_of_sustained_peak': conv['frac_of_bf16_sustained_peak'],
                                  'share_of_step': conv['share_of_step']},
@@ -552,8 +562,7 @@ def run_ours(args):
                    'global_batch': B * world, 'parallelism': f'dp{world}',
                    'l2': 'working set per step (>1 GB of activations) exceeds the 126 MB L2; no flush needed',
                    'cuda_graph': True,
-                   'allreduce': ('NCCL buckets issued inside the step graph as the backward pass completes them'
-                                 if world > 1 else None),
+                   'allreduce': r.get('exchange'),
                    'host_numa_cpus': (f'{len(numa_cpus)} CPUs local to the GPU' if numa_cpus else None)},
         'e2e': e2e, 'gpu_launches': (lps or 0) * args.steps, 'launches_per_step': lps,
         'clocks': r['clocks'], 'roofline': r.get('roofline'), 'cpu_baseline': cpu, 'breakdown': r.get('breakdown'),
