@@ -186,6 +186,11 @@ def profile_step(m, plan, cfg, world):
     m._train_on_static(plan)
     torch.cuda.synchronize()
     launches_per_step = int(lib.dnnca_debug_launch_count(1))
+    # per-kernel times are taken with every kernel ALONE on the device: the step graph runs weight gradients and
+    # MulmoUNet's encoder branches on side streams, where the events around a call would time it sharing the SMs
+    saved_env = {k: os.environ.get(k) for k in ('DNNCA_WGRAD_STREAM', 'DNNCA_BRANCH_STREAMS')}
+    os.environ['DNNCA_WGRAD_STREAM'] = '0'
+    os.environ['DNNCA_BRANCH_STREAMS'] = '0'
     peaks = {}
     pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(pk):
@@ -195,6 +200,11 @@ def profile_step(m, plan, cfg, world):
         for _ in range(3):
             m._train_on_static(plan)
     agg = prof.summary()
+    for k, v in saved_env.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
     m.use_cuda_graph = True
     tot = sum(d['ms'] for d in agg.values())
     rows = sorted(agg.items(), key=lambda kv: -kv[1]['ms'])
@@ -250,7 +260,8 @@ def profile_step(m, plan, cfg, world):
                                       'tflops': round(conv_fl / conv_ms / 1e9, 1) if conv_ms else None,
                                       'frac_of_bf16_sustained_peak': round(conv_fl / conv_ms / 1e9 / tens_sus, 4) if conv_ms else None,
                                       'frac_of_bf16_burst_peak': round(conv_fl / conv_ms / 1e9 / tens_burst, 4) if conv_ms else None},
-                     'note': 'CUDA events around each C-ABI call in an eager pass after the timed region; '
+                     'note': 'CUDA events around each C-ABI call in an eager single-stream pass after the timed region '
+                             '(the step graph itself overlaps weight gradients / encoder branches on side streams); '
                              'algorithmic bytes = every operand read once + result written once at its storage dtype'})
     return dict(launches_per_step=launches_per_step, roofline=roofline, breakdown=breakdown, categories=categories,
                 conv_flops_per_step=step_flops, tens_burst=tens_burst, tens_sus=tens_sus)

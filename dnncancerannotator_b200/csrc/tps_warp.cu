@@ -10,8 +10,8 @@
 //      clamped to [0, 1]).
 //
 // B200 formulation:
-//   * `tps_solve_kernel`: one CTA per image, the (P+3) x (P+5) augmented system in FP64 in L2-resident scratch,
-//     Gaussian elimination with partial pivoting (the matrix is symmetric indefinite: zero trailing block).
+//   * `tps_solve_kernel`: one CTA per image, the (P+3) x (P+5) augmented system in FP64 in shared memory (P <= 165; L2-
+//     resident scratch beyond), Gaussian elimination with partial pivoting (symmetric indefinite: zero trailing block).
 //   * coordinates are divided by the image extent before the fit.  Under the side conditions B^T w = 0 the interpolant
 //     is invariant to that scaling (the extra r^2 log s^2 terms collapse into the affine part), and phi stays O(1)
 //     instead of O(1e6).
@@ -19,8 +19,7 @@
 //     the test set) and then carry weights of 1e5 with opposite signs: the flow is a difference of nearly equal phi
 //     terms.  Measured: fp32 phi leaves 2e-2 px of error there, fp32 coefficients alone 1e-3 px; the reference's own
 //     float32 graph (distances by the |x|^2 - 2xy + |y|^2 expansion in pixel units) sits 0.1-0.3 px from the exact
-//     interpolant.  FP64 costs about 40 DFMA-class instructions per (pixel, control point): ~15 us per 256^2 image
-//     with 100 points on the B200's FP64 pipe -- small against the step the batch feeds.
+//     interpolant.  The FP64 log is table driven (`tps_log`: 2 shared-memory words + 8 DFMA).
 //   * `tps_warp_kernel` fuses steps 2 and 3: the control points of an image sit in shared memory (y, x, w_y, w_x as
 //     doubles), every thread evaluates the flow of its pixel and resamples all channels at once; the dense flow never
 //     goes through HBM unless the caller asks for it.  HBM traffic = image in (gathered, within max_diff pixels of
@@ -35,12 +34,45 @@ __device__ __forceinline__ double tps_phi(double r2_norm, double eps_norm) {
   return 0.5 * r2_norm * log(fmax(r2_norm, eps_norm));
 }
 
-// scratch per image: m x (m + 2) doubles, m = P + 3.  coef per image: [m][2] doubles (w rows then v rows, normalised space)
-__global__ void __launch_bounds__(256) tps_solve_kernel(const float* __restrict__ src, const float* __restrict__ dst, int npts,
-                                                        float inv_extent, double* __restrict__ scratch, double* __restrict__ coef,
-                                                        int* __restrict__ singular) {
+// ---- FP64 log from a 128-entry table: x = 2^e * m, m in [1, 2); m = m_j (1 + t) with m_j the midpoint of the j-th of 128
+// mantissa intervals, |t| <= 2^-8; log x = e ln 2 - log(inv_j) + log1p(t), inv_j = fl(1 / m_j), log1p by a degree-6
+// polynomial (t^7 / 7 < 2e-18).  2 shared-memory words + 8 DFMA instead of the ~100 instruction slots of log().
+struct TpsLogTab {
+  double inv[128];
+  double nlg[128];       // -log(inv[j])
+};
+__device__ __forceinline__ void tps_log_tab_init(TpsLogTab* t) {
+  for (int j = threadIdx.x; j < 128; j += blockDim.x) {
+    const double inv = 1.0 / (1.0 + ((double)j + 0.5) / 128.0);
+    t->inv[j] = inv;
+    t->nlg[j] = -log(inv);
+  }
+}
+__device__ __forceinline__ double tps_log(double x, const TpsLogTab* t) {      // x > 0 and normal
+  const long long bits = __double_as_longlong(x);
+  const int e = (int)(bits >> 52) - 1023;
+  const int j = (int)(bits >> 45) & 127;
+  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double u = fma(m, t->inv[j], -1.0);
+  double p = fma(u, -1.0 / 6.0, 0.2);
+  p = fma(u, p, -0.25);
+  p = fma(u, p, 1.0 / 3.0);
+  p = fma(u, p, -0.5);
+  p = fma(u, p, 1.0);
+  return fma((double)e, 0.69314718055994530942, fma(u, p, t->nlg[j]));
+}
+
+// one CTA per image.  The (m x (m + 2)) augmented system, m = P + 3, lives in shared memory when it fits (P <= 165), else
+// in the caller's scratch (L2).  coef per image: [m][2] doubles (w rows then v rows, normalised space)
+constexpr int TPS_SOLVE_THREADS = 512;
+
+template <bool IN_SMEM>
+__global__ void __launch_bounds__(TPS_SOLVE_THREADS) tps_solve_kernel(const float* __restrict__ src, const float* __restrict__ dst,
+                                                                      int npts, float inv_extent, double* __restrict__ scratch,
+                                                                      double* __restrict__ coef, int* __restrict__ singular) {
+  extern __shared__ double sm_mat[];
   const int b = blockIdx.x, m = npts + 3, ld = m + 2;
-  double* a = scratch + (size_t)b * m * ld;
+  double* a = IN_SMEM ? sm_mat : scratch + (size_t)b * m * ld;
   const float* s = src + (size_t)b * npts * 2;
   const float* d = dst + (size_t)b * npts * 2;
   const double inv = (double)inv_extent, eps = TPS_EPSILON * inv * inv;
@@ -62,9 +94,10 @@ __global__ void __launch_bounds__(256) tps_solve_kernel(const float* __restrict_
   }
   __syncthreads();
   // ---- elimination with partial pivoting
-  __shared__ double red_v[256];
-  __shared__ int red_i[256];
-  __shared__ int bad;
+  __shared__ double red_v[TPS_SOLVE_THREADS / 32];
+  __shared__ int red_i[TPS_SOLVE_THREADS / 32];
+  __shared__ int piv_s, bad;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) bad = 0;
   for (int k = 0; k < m; ++k) {
     double best = -1.0;
@@ -73,36 +106,45 @@ __global__ void __launch_bounds__(256) tps_solve_kernel(const float* __restrict_
       const double v = fabs(a[(size_t)i * ld + k]);
       if (v > best) { best = v; bi = i; }
     }
-    red_v[threadIdx.x] = best; red_i[threadIdx.x] = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double v2 = __shfl_xor_sync(0xffffffffu, best, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (v2 > best || (v2 == best && i2 < bi)) { best = v2; bi = i2; }
+    }
+    if (lane == 0) { red_v[wid] = best; red_i[wid] = bi; }
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) {
-        const double v2 = red_v[threadIdx.x + o];
-        const int i2 = red_i[threadIdx.x + o];
-        if (v2 > red_v[threadIdx.x] || (v2 == red_v[threadIdx.x] && i2 < red_i[threadIdx.x])) {
-          red_v[threadIdx.x] = v2; red_i[threadIdx.x] = i2;
-        }
+    if (wid == 0) {
+      best = lane < TPS_SOLVE_THREADS / 32 ? red_v[lane] : -1.0;
+      bi = lane < TPS_SOLVE_THREADS / 32 ? red_i[lane] : k;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (v2 > best || (v2 == best && i2 < bi)) { best = v2; bi = i2; }
       }
-      __syncthreads();
+      if (lane == 0) {
+        piv_s = bi;
+        if (!(best > 1e-13)) bad = 1;        // entries are O(1) in normalised coordinates: coincident control points
+      }
     }
-    const int piv = red_i[0];
-    if (!(red_v[0] > 1e-13)) {          // entries are O(1) in normalised coordinates: coincident control points
-      if (threadIdx.x == 0) bad = 1;
-    }
+    __syncthreads();
+    const int piv = piv_s;
     if (piv != k) {
       for (int j = k + threadIdx.x; j < ld; j += blockDim.x) {
         const double t = a[(size_t)k * ld + j];
         a[(size_t)k * ld + j] = a[(size_t)piv * ld + j];
         a[(size_t)piv * ld + j] = t;
       }
+      __syncthreads();
     }
-    __syncthreads();
     const double pk = a[(size_t)k * ld + k];
     const int rows = m - k - 1, cols = ld - k - 1;
     if (pk != 0.0) {
+      const double rp = 1.0 / pk;
       for (int e = threadIdx.x; e < rows * cols; e += blockDim.x) {
         const int i = k + 1 + e / cols, j = k + 1 + e % cols;
-        a[(size_t)i * ld + j] -= a[(size_t)i * ld + k] / pk * a[(size_t)k * ld + j];
+        a[(size_t)i * ld + j] = fma(-(a[(size_t)i * ld + k] * rp), a[(size_t)k * ld + j], a[(size_t)i * ld + j]);
       }
     }
     __syncthreads();
@@ -128,6 +170,8 @@ __global__ void __launch_bounds__(256) tps_warp_kernel(const float* __restrict__
                                                        const float* __restrict__ dst, const double* __restrict__ coef, int npts,
                                                        float inv_extent, float* __restrict__ out, float* __restrict__ flow_out) {
   extern __shared__ double sm_pts[];            // [npts][4]: c_y, c_x (pixels), w_y, w_x
+  __shared__ TpsLogTab tab;
+  tps_log_tab_init(&tab);
   const int b = blockIdx.y, m = npts + 3;
   const int c = C > 0 ? C : c_rt;
   const float* d = dst + (size_t)b * npts * 2;
@@ -150,13 +194,15 @@ __global__ void __launch_bounds__(256) tps_warp_kernel(const float* __restrict__
     for (; i + 1 < npts; i += 2) {
       const double ay = (py - sm_pts[4 * i]) * inv, ax = (px - sm_pts[4 * i + 1]) * inv;
       const double by = (py - sm_pts[4 * i + 4]) * inv, bx = (px - sm_pts[4 * i + 5]) * inv;
-      const double pa = tps_phi(fma(ay, ay, ax * ax), eps), pb = tps_phi(fma(by, by, bx * bx), eps);
+      const double ra = fma(ay, ay, ax * ax), rb = fma(by, by, bx * bx);
+      const double pa = 0.5 * ra * tps_log(fmax(ra, eps), &tab), pb = 0.5 * rb * tps_log(fmax(rb, eps), &tab);
       f0 = fma(pa, sm_pts[4 * i + 2], f0); f1 = fma(pa, sm_pts[4 * i + 3], f1);
       g0 = fma(pb, sm_pts[4 * i + 6], g0); g1 = fma(pb, sm_pts[4 * i + 7], g1);
     }
     if (i < npts) {
       const double ay = (py - sm_pts[4 * i]) * inv, ax = (px - sm_pts[4 * i + 1]) * inv;
-      const double pa = tps_phi(fma(ay, ay, ax * ax), eps);
+      const double ra = fma(ay, ay, ax * ax);
+      const double pa = 0.5 * ra * tps_log(fmax(ra, eps), &tab);
       f0 = fma(pa, sm_pts[4 * i + 2], f0); f1 = fma(pa, sm_pts[4 * i + 3], f1);
     }
     const double qy = py * inv, qx = px * inv;
@@ -200,8 +246,20 @@ extern "C" int dnnca_tps_fit(void* stream, const float* source_points, const flo
   DNNCA_CHECK_ARG(workspace_bytes >= dnnca_tps_workspace_bytes(n, npoints), "tps_fit: workspace of %zu bytes needed (got %zu)",
                   dnnca_tps_workspace_bytes(n, npoints), workspace_bytes);
   DNNCA_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "tps_fit: workspace must be 8-byte aligned");
-  tps_solve_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(source_points, dest_points, npoints, 1.0f / extent,
-                                                       reinterpret_cast<double*>(workspace), coef, singular);
+  const size_t m = (size_t)npoints + 3, mat_bytes = m * (m + 2) * sizeof(double);
+  if (mat_bytes <= 220 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(tps_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "tps_fit: shared memory attribute");
+      attr_set = true;
+    }
+    tps_solve_kernel<true><<<n, TPS_SOLVE_THREADS, mat_bytes, (cudaStream_t)stream>>>(source_points, dest_points, npoints, 1.0f / extent,
+                                                                                  nullptr, coef, singular);
+  } else {
+    tps_solve_kernel<false><<<n, TPS_SOLVE_THREADS, 0, (cudaStream_t)stream>>>(source_points, dest_points, npoints, 1.0f / extent,
+                                                                           reinterpret_cast<double*>(workspace), coef, singular);
+  }
   DNNCA_LAUNCH_CHECK("tps_fit");
   return DNNCA_OK;
 }

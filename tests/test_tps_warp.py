@@ -84,7 +84,8 @@ def test_reference_precision_noise_is_reported():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('n,size,c,npts,max_diff,stddev', [(3, 64, 3, 50, 5, 3.0), (2, 256, 6, 100, 5, 2.0),
-                                                            (2, 200, 1, 150, 15, 20.0), (1, 96, 5, 7, 5, 2.0)])
+                                                            (2, 200, 1, 150, 15, 20.0), (1, 96, 5, 7, 5, 2.0),
+                                                            (2, 128, 2, 200, 5, 2.0)])      # 200 points: the system leaves shared memory
 def test_cuda_warp_matches_float64_oracle(n, size, c, npts, max_diff, stddev):
     from dnncancerannotator_b200 import data_tail as DT
     rng = np.random.default_rng(n * 1000 + size + npts)
