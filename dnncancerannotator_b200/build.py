@@ -37,6 +37,7 @@ UNITS = [
     ('tps_warp.cu', 'tps_warp', []),
     ('bn_fold.cu', 'bn_fold', []),
     ('p2p_adam.cu', 'p2p_adam', []),
+    ('nccl_wrap.cu', 'nccl_wrap', []),
 ]
 for dt in (0, 1):
     for kind in (0, 1, 2):
@@ -91,7 +92,7 @@ def build(force=False, verbose=False, jobs=None):
         results = list(ex.map(lambda u: _compile(u, hdr_time, verbose), UNITS))
     objs = [o for o, _ in results]
     if any(c for _, c in results) or not os.path.exists(LIB):
-        cmd = [nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcudart']
+        cmd = [nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcudart', '-ldl']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')

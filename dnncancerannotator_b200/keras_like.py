@@ -395,7 +395,7 @@ class Model:
         return self
 
     def _setup_p2p(self):
-        """Small models (whole gradient <= 4 MB) exchange gradients through NVLink peer memory inside the Adam kernel
+        """Small models (whole gradient <= 8 MB: unet.yaml, mulmo_unet.yaml) exchange gradients through NVLink peer memory inside the Adam kernel
         (csrc/p2p_adam.cu) instead of NCCL; larger ones keep the bucketed NCCL all-reduce overlapped with backward."""
         from . import parallel
         ps = self.params

@@ -106,6 +106,11 @@ _PROTOS = {
     'dnnca_p2p_close': [_vp],
     'dnnca_p2p_wait_done': [_vp, _vp, _i, _vp],
     'dnnca_p2p_adam_step': [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    'dnnca_nccl_unique_id': [C.c_char_p],
+    'dnnca_nccl_comm_init_rank': [C.POINTER(C.c_void_p), _i, C.c_char_p, _i],
+    'dnnca_nccl_comm_destroy': [_vp],
+    'dnnca_nccl_allreduce_bucket': [_vp, _vp, _vp, _i64, _i],
+    'dnnca_nccl_broadcast': [_vp, _vp, _vp, _i64, _i],
     'dnnca_host_alloc': [C.c_size_t, _i, C.POINTER(C.c_void_p)],
     'dnnca_host_free': [_vp],
     'dnnca_loss_total': [_vp, _vp, _i, _vp, _vp, _i64, _f, _vp],

@@ -43,7 +43,8 @@ typedef enum {
   DNNCA_OK = 0,
   DNNCA_ERR_BAD_ARG = -1,
   DNNCA_ERR_UNSUPPORTED = -2,
-  DNNCA_ERR_CUDA = -3
+  DNNCA_ERR_CUDA = -3,
+  DNNCA_ERR_NCCL = -4
 } dnnca_status_t;
 
 typedef enum { DNNCA_F32 = 0, DNNCA_BF16 = 1 } dnnca_dtype_t;
@@ -281,6 +282,25 @@ DNNCA_API int dnnca_head_bce_fwd_bwd(void* stream, const dnnca_tensor_t* f, cons
  * ------------------------------------------------------------------------- */
 DNNCA_API int dnnca_threshold_hist(void* stream, const float* probs, const float* labels, int64_t count,
                                    const float* thresholds, int nthr, uint64_t* hist);
+
+/* ---------------------------------------------------------------------------
+ * Gradient exchange through NCCL (SURVEY 8b(ii) `dnnca_nccl_*`)
+ *   replaces the cross-replica SUM all-reduce tf.distribute.MirroredStrategy performs on every gradient
+ *   (annotator/engine.py:260-263) for hosts that bind this library without torch.distributed: one process per GPU,
+ *   rank 0 calls dnnca_nccl_unique_id and hands the 128 bytes to the other ranks by any side channel, every rank calls
+ *   dnnca_nccl_comm_init_rank with its device current, then per step dnnca_nccl_allreduce_bucket on slices of the flat
+ *   gradient buffer in reverse layer order (in place, SUM; the loss is pre-scaled by 1/replicas through
+ *   dnnca_loss_config_t.grad_scale, so the sum IS the average), each on the stream it is given -- the caller
+ *   orders it after the kernel that wrote the bucket's last gradient and before dnnca_adam_step.  dnnca_nccl_broadcast
+ *   mirrors the variables at start-up (bytes from `root`).  libnccl.so.2 is opened on first use, not at load time;
+ *   failures return DNNCA_ERR_NCCL with the NCCL message in dnnca_last_error().
+ * ------------------------------------------------------------------------- */
+#define DNNCA_NCCL_UNIQUE_ID_BYTES 128
+DNNCA_API int dnnca_nccl_unique_id(unsigned char* id128);
+DNNCA_API int dnnca_nccl_comm_init_rank(void** comm, int nranks, const unsigned char* id128, int rank);
+DNNCA_API int dnnca_nccl_comm_destroy(void* comm);
+DNNCA_API int dnnca_nccl_allreduce_bucket(void* comm, void* stream, void* buf, int64_t count, int dtype);
+DNNCA_API int dnnca_nccl_broadcast(void* comm, void* stream, void* buf, int64_t bytes, int root);
 
 /* ---------------------------------------------------------------------------
  * Region-based detection counters ("later" row)

@@ -147,3 +147,66 @@ def test_two_rank_step_matches_oracle_subbatch_average(mode, graph, p2p):
         return
     # (with these 256-element test buckets the first layer's kernel + bias spill into the last two)
     assert len(log) >= 4 and sum(1 for f, _ in log if f > 0) >= len(log) - 2, log
+
+
+def _abi_worker(rank, world, idfile, out):
+    """C-ABI exchange (include/dnnca.h dnnca_nccl_*) without torch.distributed: the unique id travels through a file."""
+    import ctypes as C
+    import faulthandler
+    import sys
+    import time
+    faulthandler.dump_traceback_later(90, exit=True)
+    from dnncancerannotator_b200 import native as N
+    torch.cuda.set_device(rank)
+    lib = N.lib()
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        N.check(lib.dnnca_nccl_unique_id(buf), 'nccl_unique_id')
+        with open(idfile + '.tmp', 'wb') as f:
+            f.write(buf.raw)
+        os.replace(idfile + '.tmp', idfile)
+    else:
+        t0 = time.time()
+        while not os.path.exists(idfile):
+            assert time.time() - t0 < 60
+            time.sleep(0.05)
+    uid = open(idfile, 'rb').read()
+    assert len(uid) == 128
+    comm = C.c_void_p()
+    N.check(lib.dnnca_nccl_comm_init_rank(C.byref(comm), world, uid, rank), 'nccl_comm_init_rank')
+    rng = np.random.default_rng(100 + rank)
+    g = rng.normal(size=10007).astype(np.float32)
+    gd = torch.from_numpy(g).cuda()
+    w = torch.full((333,), float(rank + 1), device='cuda')
+    # mirrored variables from rank 0, then the flat gradient buffer in reverse-order buckets on the current stream
+    N.check(lib.dnnca_nccl_broadcast(comm, N.stream_ptr(), N.ptr(w), w.numel() * 4, 0), 'nccl_broadcast')
+    from dnncancerannotator_b200.parallel import bucket_ranges
+    for a, b in bucket_ranges(gd.numel(), 4096):
+        N.check(lib.dnnca_nccl_allreduce_bucket(comm, N.stream_ptr(), C.c_void_p(gd.data_ptr() + 4 * a), b - a, N.F32),
+                'nccl_allreduce_bucket')
+    hb = torch.from_numpy(g).cuda().bfloat16()
+    N.check(lib.dnnca_nccl_allreduce_bucket(comm, N.stream_ptr(), N.ptr(hb), hb.numel(), N.BF16), 'nccl_allreduce_bucket')
+    torch.cuda.synchronize()
+    rc = lib.dnnca_nccl_allreduce_bucket(comm, N.stream_ptr(), None, 4, N.F32)          # bad argument: loud, not a hang
+    out[rank] = dict(g=g, reduced=gd.cpu().numpy(), w=w.cpu().numpy(), bf16=hb.float().cpu().numpy(), bad_rc=int(rc))
+    N.check(lib.dnnca_nccl_comm_destroy(comm), 'nccl_comm_destroy')
+    faulthandler.cancel_dump_traceback_later()
+
+
+def test_c_abi_nccl_wrappers_two_ranks(tmp_path):
+    """include/dnnca.h `dnnca_nccl_*`: unique id -> communicator -> broadcast + bucketed SUM all-reduce"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_abi_worker, args=(world, str(tmp_path / 'nccl_id'), out), nprocs=world, join=True)
+    a, b = out[0], out[1]
+    want = a['g'] + b['g']
+    np.testing.assert_array_equal(a['reduced'], b['reduced'])
+    np.testing.assert_allclose(a['reduced'], want, rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(a['w'], np.ones(333, np.float32))
+    np.testing.assert_array_equal(b['w'], np.ones(333, np.float32))
+    np.testing.assert_array_equal(a['bf16'], b['bf16'])
+    np.testing.assert_allclose(a['bf16'], want, rtol=2e-2, atol=2e-2)
+    assert a['bad_rc'] == -1 and b['bad_rc'] == -1
