@@ -192,7 +192,9 @@ def test_multiresunet_forward(mode):
     REPORT[f'multires/{mode}/eval'] = dict(logits_rel_l2=rel_l2(logits, z['eval_logits']), logits_rel_max=rel_inf(logits, z['eval_logits']),
                                            launches_generic=fam[0], launches_small=fam[1], launches_tcgen05=fam[2])
     assert rel_l2(logits, z['eval_logits']) <= (2e-2 if mode == 'bf16' else 5e-4), rel_l2(logits, z['eval_logits'])
-    assert rel_inf(logits, z['eval_logits']) <= (6e-2 if mode == 'bf16' else 5e-4), rel_inf(logits, z['eval_logits'])
+    # measured on B200: rel-L2 8.2e-3, rel-max 1.2e-2 (61 bf16 layers deep, BatchNorm folded into the weights)
+    assert rel_l2(logits, z['eval_logits']) <= (1e-2 if mode == 'bf16' else 5e-4), rel_l2(logits, z['eval_logits'])
+    assert rel_inf(logits, z['eval_logits']) <= (2e-2 if mode == 'bf16' else 5e-4), rel_inf(logits, z['eval_logits'])
     if mode == 'bf16':                         # every conv / ConvT (odd widths padded to multiples of 8) on the tensor cores
         assert fam[0] == 0 and fam[1] == 0 and fam[2] >= 60, fam
     # new weights are honoured: the folded / packed copies are refreshed when the variables change
