@@ -47,9 +47,33 @@ __global__ void __launch_bounds__(256) input_tail_kernel(TailArgs a) {
   }
 }
 
+// binary label masks shipped as bits (numpy.packbits order: bit 7 of byte 0 is element 0): one thread expands one byte
+// into eight fp32 labels with two 16-byte stores
+__global__ void __launch_bounds__(256) unpack_label_bits_kernel(const uint8_t* __restrict__ bits, long long nbytes,
+                                                                float* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned b = bits[i];
+    float4 lo, hi;
+    lo.x = (float)((b >> 7) & 1u); lo.y = (float)((b >> 6) & 1u); lo.z = (float)((b >> 5) & 1u); lo.w = (float)((b >> 4) & 1u);
+    hi.x = (float)((b >> 3) & 1u); hi.y = (float)((b >> 2) & 1u); hi.z = (float)((b >> 1) & 1u); hi.w = (float)(b & 1u);
+    float4* o = reinterpret_cast<float4*>(y + i * 8);
+    o[0] = lo;
+    o[1] = hi;
+  }
+}
+
 }  // namespace dnnca
 
 using namespace dnnca;
+
+extern "C" int dnnca_unpack_label_bits(void* stream, const uint8_t* bits, int64_t count, float* y) {
+  DNNCA_CHECK_ARG(bits && y && count > 0 && count % 8 == 0, "unpack_label_bits: count must be a positive multiple of 8");
+  DNNCA_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "unpack_label_bits: output must be 16-byte aligned");
+  const long long nbytes = count / 8;
+  unpack_label_bits_kernel<<<grid_for(nbytes, 256, 8), 256, 0, (cudaStream_t)stream>>>(bits, nbytes, y);
+  DNNCA_LAUNCH_CHECK("unpack_label_bits");
+  return DNNCA_OK;
+}
 
 extern "C" int dnnca_input_tail(void* stream, const uint8_t* combined, int n, int hin, int win, int s,
                                 const int32_t* crop_yx, const uint8_t* flip, int hout, int wout,

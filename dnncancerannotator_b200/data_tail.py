@@ -76,6 +76,38 @@ def prepare_batch(combined, slice_types=DEFAULT_SLICE_TYPES, output_size=(256, 2
     return x_out, y_out
 
 
+# ---- binary labels as bits --------------------------------------------------------------------------------------------
+
+class PackedLabels:
+    """Binary label masks ``[B,H,W]`` as bits (``numpy.packbits`` along W): what ``pack_labels`` returns and
+    ``Model.train_step`` / ``prefetch`` accept in place of ``y``.  The label channel of the reference's
+    input contract is a PNG mask divided by 255 (data.py:193-206): 0 or 1, so one bit per pixel loses nothing and the
+    host->device copy of a batch shrinks from 4 to 3.125 bytes per pixel (uint8 images + labels)."""
+
+    def __init__(self, bits, shape):
+        self.bits, self.shape = bits, tuple(shape)
+
+    @property
+    def nbytes(self):
+        return int(self.bits.numel())
+
+
+def pack_labels(y, pinned=True):
+    """``y``: labels ``[B,H,W]``, float in {0, 1} or uint8 in {0, 255} (anything else raises: fractional labels, e.g. after
+    the warp augmentation on the host, cannot be packed).  W must be a multiple of 8."""
+    a = y.cpu().numpy() if torch.is_tensor(y) else np.asarray(y)
+    if a.ndim != 3 or a.shape[2] % 8:
+        raise ValueError('labels must be [B,H,W] with W a multiple of 8')
+    one = 255 if a.dtype == np.uint8 else 1
+    if not np.all((a == 0) | (a == one)):
+        raise ValueError('only binary label masks can be packed')
+    bits = torch.from_numpy(np.packbits(a != 0, axis=-1))
+    if pinned and torch.cuda.is_available():
+        from . import hostmem
+        bits = hostmem.pinned_like(bits, write_combined=False)
+    return PackedLabels(bits, a.shape)
+
+
 # ---- thin-plate-spline warp augmentation (data.py:628-645, 718-763) ---------------------------------------------------
 
 def draw_control_points(rng: np.random.Generator, n_images, width, n_points=100, max_diff=5, stddev=2.0):

@@ -72,6 +72,18 @@ class LoadStatus:
         return self
 
 
+def _is_packed(y):
+    from .data_tail import PackedLabels
+    return isinstance(y, PackedLabels)
+
+
+def _label_tensor(y):
+    """labels as a torch tensor: float32 / uint8 ``[B,H,W]``, or the bits of ``data_tail.PackedLabels``"""
+    if _is_packed(y):
+        return y.bits
+    return y if torch.is_tensor(y) else torch.from_numpy(np.ascontiguousarray(y))
+
+
 class Model:
     """Base of ``UNetAnnotator`` / ``MulmoUNetAnnotator`` / ``MultiResUnet``.
 
@@ -514,11 +526,11 @@ class Model:
         (the reference's contract, data.py:193-206) or the raw uint8 slices (the /255 then runs on the
         device: 4x fewer PCIe bytes).  The following ``train_step(x, y)`` with the same objects uses it."""
         xt = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))
-        yt = y if torch.is_tensor(y) else torch.from_numpy(np.ascontiguousarray(y))
+        yt = _label_tensor(y)
         plan = self._plan(*xt.shape[:3])
         plan.allocate(True)
         st = getattr(plan, '_stage', None)
-        if st is None or st['x'].dtype != xt.dtype or st['y'].dtype != yt.dtype:
+        if st is None or st['x'].dtype != xt.dtype or st['y'].dtype != yt.dtype or st['y'].shape != yt.shape:
             st = plan._stage = dict(x=torch.empty(xt.shape, dtype=xt.dtype, device=self.device),
                                     y=torch.empty(yt.shape, dtype=yt.dtype, device=self.device),
                                     stream=torch.cuda.Stream(), ready=torch.cuda.Event(), free=torch.cuda.Event(),
@@ -543,15 +555,19 @@ class Model:
         else:
             st = None
             xs = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))
-            ys = y if torch.is_tensor(y) else torch.from_numpy(np.ascontiguousarray(y))
+            ys = _label_tensor(y)
             xs, ys = xs.to(self.device, non_blocking=True), ys.to(self.device, non_blocking=True)
+        packed = _is_packed(y)
         # uint8 slices of a bf16 plan go straight into the cast input buffer (one pass: /255 and rounding, data.py:206);
         # the graph variant keyed '..._u8' then skips the fp32 -> bf16 convert
         cast = getattr(plan, 'input_cast', None)
         plan.prestaged = bool(xs.dtype == torch.uint8 and cast is not None and cast.buf.data is not None and
                               cast.buf.data.dtype == torch.bfloat16)
         for src, dst in ((xs, plan.x_in), (ys, plan.y_in)):
-            if src.dtype == torch.uint8:                                   # data.py:206: float32(uint8) / 255 on device
+            if dst is plan.y_in and packed:                                # binary masks shipped as bits (data_tail.pack_labels)
+                assert src.numel() * 8 == dst.numel(), 'packed labels do not match the batch shape'
+                N.call('dnnca_unpack_label_bits', N.stream_ptr(), N.ptr(src), dst.numel(), N.ptr(dst))
+            elif src.dtype == torch.uint8:                                 # data.py:206: float32(uint8) / 255 on device
                 if dst is plan.x_in and plan.prestaged:
                     N.call('dnnca_u8_to_unit', N.stream_ptr(), N.ptr(src), src.numel(), N.ptr(cast.buf.data), N.BF16)
                 else:

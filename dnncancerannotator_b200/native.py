@@ -94,6 +94,7 @@ _PROTOS = {
     'dnnca_add_relu_affine': [_vp, _TP, _vp, _TP, _vp, _vp, _TP],
     'dnnca_u8_to_unit': [_vp, _vp, _i64, _vp, _i],
     'dnnca_input_tail': [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, C.POINTER(C.c_int32), _i, _i, _vp, _i, _i, _vp],
+    'dnnca_unpack_label_bits': [_vp, _vp, _i64, _vp],
     'dnnca_tps_workspace_bytes': [_i, _i],
     'dnnca_tps_fit': [_vp, _vp, _vp, _i, _i, _f, _vp, C.c_size_t, _vp, _vp],
     'dnnca_tps_warp': [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp],

@@ -386,6 +386,10 @@ DNNCA_API int dnnca_input_tail(void* stream, const uint8_t* combined, int n, int
                                const int32_t* crop_yx, const uint8_t* flip, int hout, int wout,
                                const int32_t* feature_idx, int nf, int label_idx, void* x_out, int x_dtype,
                                int x_cstride, float* y_out);
+/* Binary label masks shipped as bits: y[i] = bit i of `bits` in numpy.packbits order (bit 7 of byte 0 first), as fp32
+ * 0 / 1 -- the label channel of data.py:193-206 (a PNG mask: label / 255 is 0 or 1) at 1/8 of the host->device bytes of
+ * the uint8 form.  count = number of labels, a multiple of 8; y 16-byte aligned. */
+DNNCA_API int dnnca_unpack_label_bits(void* stream, const uint8_t* bits, int64_t count, float* y);
 /* Thin-plate-spline warp augmentation ("later" row): random_warp (data.py:718-763) =
  * tfa.image.sparse_image_warp(image, source_control_point_locations, dest_control_point_locations) with its defaults
  * (interpolation_order 2, regularization_weight 0, num_boundary_points 0).  Control points are device fp32 [n,npoints,2]

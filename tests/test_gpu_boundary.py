@@ -211,3 +211,40 @@ def test_input_tail_crop_flip_split_bit_exact():
     np.testing.assert_array_equal(y.cpu().numpy(), wy)
     with pytest.raises(ValueError):
         data_tail.prepare_batch(comb, types, (48, 64), origin + 100, flip)
+
+
+def test_bit_packed_labels_train_like_float_labels():
+    """data_tail.pack_labels: binary masks shipped as bits (1/8 of the uint8 label bytes) land in the step's label buffer
+    bit for bit as the float32 labels do -- through train_step directly and through the prefetch staging -- so the first
+    loss (same weights, same forward) is identical; later steps agree to the run-to-run level of the weight-gradient
+    atomics.  Fractional labels and ragged widths are refused."""
+    from dnncancerannotator_b200 import data_tail
+    from dnncancerannotator_b200.models import tf_models
+    from dnncancerannotator_b200.synthetic import make_slices
+    x8, y8 = make_slices(4, 32, 32, 3, seed=7, as_uint8=True)
+    yf = (y8 / 255).astype(np.float32)
+    packed = data_tail.pack_labels(y8)
+    assert packed.nbytes * 8 == y8.size and packed.shape == y8.shape
+    assert np.array_equal(np.unpackbits(packed.bits.numpy(), axis=-1).astype(np.float32), yf)
+    runs = []
+    for labels, use_prefetch in ((yf, False), (packed, False), (packed, True), (data_tail.pack_labels(yf), True)):
+        m = tf_models.UNetAnnotator(n_filters_first=3, n_downsample=2, rate=2, kernel_size=3, conv_stride=1, padding='same',
+                                    dtype='bf16', seed=3)
+        m.build((None, 32, 32, 3))
+        m.compile()
+        losses = []
+        for _ in range(4):                                     # eager warm-ups, graph capture, replay
+            if use_prefetch:
+                m.prefetch(x8, labels)
+            losses.append(float(m.train_step(x8, labels)))
+            np.testing.assert_array_equal(m._plan(4, 32, 32).y_in.cpu().numpy(), yf)
+        runs.append((losses, m.get_weights()))
+    for losses, w in runs[1:]:
+        assert losses[0] == runs[0][0][0]
+        np.testing.assert_allclose(losses, runs[0][0], rtol=2e-3)
+        for k in w:
+            np.testing.assert_allclose(w[k], runs[0][1][k], atol=5e-3)         # 4 Adam steps of 1e-3 each at most
+    with pytest.raises(ValueError):
+        data_tail.pack_labels(yf * 0.5)
+    with pytest.raises(ValueError):
+        data_tail.pack_labels(yf[:, :, :12])
