@@ -38,6 +38,7 @@ UNITS = [
     ('bn_fold.cu', 'bn_fold', []),
     ('p2p_adam.cu', 'p2p_adam', []),
     ('nccl_wrap.cu', 'nccl_wrap', []),
+    ('multires_train.cu', 'multires_train', []),
 ]
 for dt in (0, 1):
     for kind in (0, 1, 2):

@@ -515,6 +515,7 @@ class Model:
             plan.head_loss(cfg)
             self._loss_total(plan)
             plan.backward()
+            plan.end_backward()
         self._run(plan, 'fwdbwd', seq)
         self.last_logits = plan.logits
         return plan.per_sample
@@ -626,9 +627,11 @@ class Model:
             self._loss_total(plan)
             if dp is None:
                 plan.backward(side_stream=self._side_stream())
+                plan.end_backward()
                 self._adam()
             elif p2p is not None:
                 plan.backward(side_stream=self._side_stream())
+                plan.end_backward()
                 ps.version += 1
                 p2p.adam_step(ps)                # all-reduce over NVLink peer memory fused into the Adam kernel
             else:
@@ -638,6 +641,7 @@ class Model:
                 plan.backward(after_op=lambda i: dp.launch_ready(ready[i], before=plan.join_side_streams),
                               side_stream=self._side_stream())
                 plan.join_side_streams()
+                plan.end_backward()
                 dp.finish()
                 self._adam()
         key = self._train_key(plan)

@@ -298,14 +298,18 @@ def MultiResBlock(U, inp, alpha=1.67):
 
 
 class MultiResUnet(Model):
-    """``MultiResUnet(height, width, n_channels)`` (multiresunet.py:167-223), inference path."""
+    """``MultiResUnet(height, width, n_channels)`` (multiresunet.py:167-223).
+
+    Two plans per input shape: inference (``model(x)``, ``predict``, ``evaluate``) runs the BatchNorm-folded, prepacked
+    tensor-core plan above; ``train_step`` / ``fit`` / ``forward_backward`` / ``model(x, training=True)`` run the training
+    plan of ``multires_train.py`` (batch statistics, full backward pass, the variables stay in the reference's shapes)."""
 
     def __init__(self, height=None, width=None, n_channels=5, dtype=None, seed=0):
         super().__init__(dtype=dtype, seed=seed)
         self.configs = dict(height=height, width=width, n_channels=n_channels)
         self.n_channels = n_channels
-        self.trainable_model = False
         self.input_shape = (None, height, width, n_channels)
+        self._train_plans = 0           # > 0 while a training entry point is choosing its plan
 
     def get_config(self):
         return dict(self.configs)
@@ -351,9 +355,35 @@ class MultiResUnet(Model):
         plan.head_forward = lambda: N.call('dnnca_head_fwd', N.stream_ptr(), feats.tref.ct(), N.ptr(wf), N.ptr(bf),
                                            N.ptr(plan.logits), N.ptr(plan.probs))
 
+    # ---- plan selection --------------------------------------------------------------------------------------
+    def _plan(self, batch, height, width, want_input_grad=False):
+        if want_input_grad:
+            raise NotImplementedError('MultiResUnet: the input-gradient chain (callbacks.py:290-299) is not built')
+        if not self._train_plans:
+            return super()._plan(batch, height, width)
+        key = (batch, height, width, 'train')
+        if key not in self._plans:
+            from .multires_train import emit_training_plan
+            super()._plan(batch, height, width)          # builds / materialises the variables (and the inference plan)
+            self._plans[key] = emit_training_plan(self, batch, height, width)
+        return self._plans[key]
+
+    def _training(self):
+        model = self
+
+        class _Ctx:
+            def __enter__(self):
+                model._train_plans += 1
+
+            def __exit__(self, *exc):
+                model._train_plans -= 1
+        return _Ctx()
+
     def _before_inference(self, plan):
         """Folded / packed weights are refreshed (one eager pass over the batch already staged in ``plan.x_in``) whenever
         the variables changed since the last call; the steady state replays a graph of prepacked tensor-core convs."""
+        if self._train_plans:
+            return
         if plan.weights_version != self.params.version:
             plan.prepacked = False
             plan.forward(False)                    # folds every kernel / affine and leaves the bf16 packings behind
@@ -362,5 +392,20 @@ class MultiResUnet(Model):
 
     def __call__(self, x, training=False):
         if training:
-            raise NotImplementedError('MultiResUnet is forward/inference-only in this build')
+            with self._training():
+                self.params.version += 1        # the call moves the BatchNorm averages: inference plans re-fold
+                return super().__call__(x, training=True)
         return super().__call__(x, training=False)
+
+    def train_step(self, x, y, lr=None):
+        with self._training():
+            return super().train_step(x, y, lr)
+
+    def forward_backward(self, x, y):
+        with self._training():
+            self.params.version += 1            # (moving statistics change)
+            return super().forward_backward(x, y)
+
+    def prefetch(self, x, y):
+        with self._training():
+            return super().prefetch(x, y)

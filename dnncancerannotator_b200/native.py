@@ -92,6 +92,11 @@ _PROTOS = {
     'dnnca_region_workspace_bytes': [_i, _i, _i, _i, _i],
     'dnnca_region_confusion': [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _f, _i, _vp, C.c_size_t, _i, _vp, _vp, _vp],
     'dnnca_add_relu_affine': [_vp, _TP, _vp, _TP, _vp, _vp, _TP],
+    'dnnca_bn_apply_act': [_vp, _TP, _vp, _TP, _i, _f],
+    'dnnca_act_bwd': [_vp, _TP, _TP, _TP, _i, _f],
+    'dnnca_accumulate': [_vp, _TP, _TP],
+    'dnnca_gather_f32': [_vp, _vp, _vp, _i64, _vp],
+    'dnnca_head_conv_bwd': [_vp, _TP, _vp, _vp, _TP, _i, _f, _vp],
     'dnnca_u8_to_unit': [_vp, _vp, _i64, _vp, _i],
     'dnnca_input_tail': [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, C.POINTER(C.c_int32), _i, _i, _vp, _i, _i, _vp],
     'dnnca_unpack_label_bits': [_vp, _vp, _i64, _vp],

@@ -854,3 +854,7 @@ class Plan:
         self.params.grads_full.zero_()
         if self.stats_len:
             self.stats.zero_()
+
+    def end_backward(self):
+        """Hook of the training launch sequences, run after the backward pass has been issued and its side streams joined
+        (plans that compute on padded copies of the variables hand the gradients back here)."""

@@ -371,6 +371,31 @@ DNNCA_API int dnnca_bn_inference_params_mapped(void* stream, int c_phys, const i
                                                const float* moving_var, float* scale_shift);
 
 /* ---------------------------------------------------------------------------
+ * MultiResUnet TRAINING (multiresunet.yaml is trained by the reference like every other config, engine.py:286):
+ * the elementwise steps of its backward pass that the U-Net kernels above do not cover.
+ *   bn_apply_act  : y = act(x*scale + shift) -- Conv2D -> BatchNormalization(scale=False) -> Activation('relu')
+ *                   (conv2d_bn, multiresunet.py:51-58); scale_shift as written by dnnca_bn_finalize.
+ *   act_bwd       : dx = dy * act'(y), y the stored activation OUTPUT -- the gradient through Activation('relu') after
+ *                   add([shortcut, out]) in ResPath (multiresunet.py:148-149, 160-161); dx may alias dy.
+ *   accumulate    : dst += src -- gradients of tensors with several consumers (MultiResBlock input -> 1x1 shortcut and
+ *                   3x3 chain, conv3x3 -> conv5x5 and concatenate, multiresunet.py:103-119).
+ *   gather_f32    : dst[i] = idx[i] >= 0 ? src[idx[i]] : 0 -- the variables live in the reference's shapes; the training
+ *                   plan computes on channel-padded (physical) copies: one gather scatters every variable into its padded
+ *                   layout before the forward pass, one gathers the gradients / moving statistics back.
+ *   head_conv_bwd : backward of the 1x1 conv to ONE channel of conv10 (multiresunet.py:219), whose fp32 output feeds a
+ *                   BatchNormalization: df = dz * w * act'(f) (f stored post-activation), dw[c] += sum dz * f[.,c];
+ *                   dz fp32 [n*h*w]; df or dw may be NULL.
+ * ------------------------------------------------------------------------- */
+DNNCA_API int dnnca_bn_apply_act(void* stream, const dnnca_tensor_t* x, const float* scale_shift, const dnnca_tensor_t* y,
+                                 int act, float alpha);
+DNNCA_API int dnnca_act_bwd(void* stream, const dnnca_tensor_t* y, const dnnca_tensor_t* dy, const dnnca_tensor_t* dx,
+                            int act, float alpha);
+DNNCA_API int dnnca_accumulate(void* stream, const dnnca_tensor_t* src, const dnnca_tensor_t* dst);
+DNNCA_API int dnnca_gather_f32(void* stream, const float* src, const int32_t* idx, int64_t count, float* dst);
+DNNCA_API int dnnca_head_conv_bwd(void* stream, const dnnca_tensor_t* f, const float* w, const float* dz,
+                                  const dnnca_tensor_t* df, int act, float alpha, float* dw);
+
+/* ---------------------------------------------------------------------------
  * Input tail: uint8 -> /255 -> activation dtype (data.py:193-206 `base`, 766-788)
  * ------------------------------------------------------------------------- */
 DNNCA_API int dnnca_u8_to_unit(void* stream, const uint8_t* src, int64_t count, void* dst, int dtype);

@@ -50,7 +50,7 @@ def _rw(k):
 
 
 @contextlib.contextmanager
-def emulate_bf16(round_weights_min_channels=16, mantissa_bits=7):
+def emulate_bf16(round_weights_min_channels=16, mantissa_bits=7, round_conv_outputs=False):
     global _MANTISSA
     saved_bits, _MANTISSA = _MANTISSA, mantissa_bits
     oc, ot, ob, oa = ops.conv2d, ops.conv2d_transpose, ops.batchnorm, ops.activation
@@ -59,7 +59,8 @@ def emulate_bf16(round_weights_min_channels=16, mantissa_bits=7):
     def conv2d(x, k, b=None, padding='same', stride=1):
         tc = k.shape[2] >= round_weights_min_channels and k.shape[3] >= round_weights_min_channels
         y = oc(x, _rw(k) if tc else k, b, padding, stride)
-        return y
+        # MultiResUnet's conv2d_bn is Conv2D -> BN -> activation: the conv output itself is a stored tensor there
+        return r(y) if round_conv_outputs else y
 
     def activation(x, act):
         return r(oa(x, act))

@@ -329,3 +329,44 @@ def test_ready_frontier_and_bucket_schedule():
         assert early >= len(issued) - 1, (cfgname, early, len(issued))      # only the last bucket waits for the end
         covered = sorted(i for _, (a, b) in dp.launch_log for i in (a, b))
         assert covered[0] == 0 and covered[-1] == flat.numel()
+
+
+def test_multiresunet_training_plan_structure_and_variable_maps():
+    """The channel-padded training plan of MultiResUnet (multires_train.py), inspected on the CPU: it declares exactly the
+    variables of the model, the index maps place every logical element at one physical position (holes read 0), the
+    gradient gather is the inverse, and the op list has the reference's 56 conv2d_bn + 28 full BatchNorms + 4 ConvT."""
+    import numpy as np
+    import torch
+    from collections import Counter
+    from dnncancerannotator_b200.models import tf_models
+    from dnncancerannotator_b200.models.tf_models import multires_train as T
+    m = tf_models.MultiResUnet(None, None, 5)
+    m.build((None, 32, 32, 5))
+    cpu = torch.device('cpu')
+    m.params.materialize(cpu)
+    plan = T.emit_training_plan(m, 2, 32, 32, device=cpu)
+    lg, ph, mp = plan.logical, plan.phys, plan.maps
+    assert set(plan.links) == set(lg.specs)
+    lg.params.copy_(torch.randn_like(lg.params))
+    lg.state.copy_(torch.rand_like(lg.state) + 0.5)
+
+    def gather(src, idx):               # what dnnca_gather_f32 computes
+        out = torch.zeros(idx.numel())
+        ok = idx >= 0
+        out[ok] = src[idx[ok].long()]
+        return out
+    ph.params.copy_(gather(lg.params, mp['p2l_t']))
+    ph.state.copy_(gather(lg.state, mp['p2l_s']))
+    for name, index in plan.links.items():
+        a, b = lg.view(name).numpy(), ph.view(name).numpy()
+        sel = b[np.ix_(*index)] if index is not None else b
+        assert np.array_equal(sel, a), name
+        assert np.count_nonzero(b) == np.count_nonzero(a), name          # holes are zeros
+        assert all(d % 16 == 0 or d in (1, 2, 3) for d in b.shape if d > 3), (name, b.shape)
+    for src, dst, idx in ((ph.params, lg.params, mp['l2p_t']), (ph.state, lg.state, mp['l2p_s'])):
+        back, valid = gather(src, idx), idx >= 0
+        assert torch.equal(back[valid], dst[valid])
+    assert int((mp['l2p_t'] >= 0).sum()) == lg.count(True) and int((mp['l2p_s'] >= 0).sum()) == lg.count(False)
+    kinds = Counter(type(o).__name__ for o in plan.ops)
+    assert kinds['ConvOp'] == 56 and kinds['BNActOp'] == 56 and kinds['BNOp'] == 28 and kinds['TConvOp'] == 4 and kinds['PoolOp'] == 4
+    assert plan.ready_frontier() == [lg.grads_full.numel()] * len(plan.ops)     # no gradient bucket leaves before the gather

@@ -214,8 +214,116 @@ def test_multiresunet_forward(mode):
     from oracle import ref_ops as ops
     wl = float(ops.weighted_crossentropy(torch.tensor(y), torch.tensor(want)).mean())
     assert abs(ev - wl) <= (3e-2 if mode == 'bf16' else 1e-4) * abs(wl), (ev, wl)
-    with pytest.raises(NotImplementedError):
-        m.train_step(z['x'], np.zeros((1, 32, 32), np.float32))
+
+
+def _multires_pair(mode, B, S):
+    from dnncancerannotator_b200.synthetic import make_slices
+    x, y = make_slices(B, S, S, 5, seed=11)
+    ref = rm.build_model('MultiResUnet', dict(height=None, width=None, n_channels=5), None, seed=0)
+    ref.randomize_bn(seed=1)
+    m = product_model('MultiResUnet', dict(height=None, width=None, n_channels=5), mode)
+    m.build((None, S, S, 5))
+    m.set_weights(ref.get_weights())
+    m.compile(loss=dict(class_name='WeightedCrossentropy', config=dict(weight_mul=3.0)))
+    return m, ref, x, y
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_multiresunet_training_step(mode):
+    """MultiResUnet TRAINS (multiresunet.yaml under engine.py:286): one step of the channel-padded training plan --
+    conv2d_bn with batch statistics, BN -> add -> relu -> BN tails, fan-out gradient accumulation, conv10 + BN head,
+    weighted BCE -- against the oracle's autograd, variable by variable.  fp32 mode: tight bounds.  bf16 mode: 61
+    BatchNorm layers deep at random initialisation ANY bf16-storage pipeline is far from the fp32 reference (the oracle's
+    own bf16-storage emulation: 7e-2 logits / 0.7 gradients), so the CUDA path is held to 1.25x that emulation."""
+    from dnncancerannotator_b200 import native as N
+    B, S = 2, 32
+    m, ref, x, y = _multires_pair(mode, B, S)
+    r = ref.train_step_grads(x, y, dict(weight_mul=3.0))
+    lib = N.lib()
+    for _ in range(4):                                   # eager warm-ups, graph capture, replay
+        per = m.forward_backward(x, y).cpu().numpy()
+    for f in range(3):
+        lib.dnnca_debug_family_count(f, 1)
+    m.use_cuda_graph, saved = False, m.use_cuda_graph
+    per = m.forward_backward(x, y).cpu().numpy()          # one eager pass: counts the kernel families of a step
+    m.use_cuda_graph = saved
+    fam = [int(lib.dnnca_debug_family_count(f, 0)) for f in range(3)]
+    logits, g, w = m.last_logits.cpu().numpy(), m.get_grads(), m.get_weights()
+    rl = r['logits'].numpy()
+    names = list(ref.trainable)
+    assert set(g) == set(names)
+    # the step ran 5 times on the same batch: moving <- moving*0.99^5 + batch*(1 - 0.99^5), batch statistic from the oracle's one step
+    w0, q = ref.get_weights(), 0.99 ** 5
+    moved = {k: w0[k] * q + (v.numpy() - 0.99 * w0[k]) / 0.01 * (1 - q) for k, v in r['new_moving'].items()}
+    allg = np.concatenate([g[k].ravel() for k in names])
+    allr = np.concatenate([r['grads'][k].numpy().ravel() for k in names])
+    assert np.isfinite(allg).all()
+    rep = dict(logits_rel_l2=rel_l2(logits, rl), logits_rel_max=rel_inf(logits, rl), grad_rel_l2=rel_l2(allg, allr),
+               loss_rel=abs(per.mean() - r['data_loss']) / abs(r['data_loss']), launches_generic=fam[0],
+               launches_small=fam[1], launches_tcgen05=fam[2])
+    REPORT[f'multires/{mode}/train'] = rep
+    if mode == 'fp32':
+        assert rep['logits_rel_l2'] <= 2e-4 and rep['logits_rel_max'] <= 2e-4, rep
+        assert rep['loss_rel'] <= 2e-5, rep
+        assert rep['grad_rel_l2'] <= 2e-3, rep              # measured 5.8e-4 (61 layers, batch statistics over 8..2048 samples)
+        scale = np.abs(allr).max()
+        for k in names:       # every variable: relative, or absolute against the gradient scale (bn83/beta is analytically 0:
+            e = np.abs(g[k] - r['grads'][k].numpy()).max()          # a shift ahead of conv10 + BatchNorm cancels)
+            assert rel_l2(g[k], r['grads'][k].numpy()) <= 5e-3 or e <= 1e-5 * scale, (k, rel_l2(g[k], r['grads'][k].numpy()), e)
+        for k, v in moved.items():
+            assert rel_l2(w[k], v) <= 1e-4 or np.abs(w[k] - v).max() <= 1e-6, k
+    else:
+        from oracle.ref_bf16 import emulate_bf16
+        with emulate_bf16(round_conv_outputs=True):
+            e = ref.train_step_grads(x, y, dict(weight_mul=3.0))
+        alle = np.concatenate([e['grads'][k].numpy().ravel() for k in names])
+        rep.update(emulated_bf16_logits_rel_l2=rel_l2(e['logits'].numpy(), rl), emulated_bf16_grad_rel_l2=rel_l2(alle, allr))
+        assert rep['logits_rel_l2'] <= 1.25 * rep['emulated_bf16_logits_rel_l2'] + 1e-3, rep
+        assert rep['grad_rel_l2'] <= 1.25 * rep['emulated_bf16_grad_rel_l2'] + 1e-3, rep
+        assert rep['loss_rel'] <= 3e-2, rep
+        for k, v in moved.items():
+            assert rel_l2(w[k], v) <= 5e-2 or np.abs(w[k] - v).max() <= 2e-3, k
+        assert fam[0] == 0 and fam[2] >= 170, fam        # all 178 conv / ConvT launches of the step on the tensor cores
+    # the inference plan sees the statistics the training step just moved (model(x) after training)
+    ref2 = rm.build_model('MultiResUnet', dict(height=None, width=None, n_channels=5), None, seed=0)
+    ref2.set_weights(m.get_weights())
+    want = ref2.forward(x, training=False)['logits'].numpy()
+    m(x)
+    assert rel_l2(m.last_logits.cpu().numpy(), want) <= (2e-2 if mode == 'bf16' else 5e-4)
+
+
+def test_multiresunet_training_trajectory_fp32():
+    """3 optimizer steps of MultiResUnet (gathers, forward, backward, gathers, fused Adam in ONE captured launch sequence)
+    vs the oracle's autograd + keras-form Adam; model(x, training=True) moves the BatchNorm averages like the oracle."""
+    m, ref, x, y = _multires_pair('fp32', 2, 32)
+    mom = {k: (torch.zeros_like(ref.weights[k]), torch.zeros_like(ref.weights[k])) for k in ref.trainable}
+    losses, rlosses = [], []
+    for step in range(3):
+        losses.append(float(m.train_step(x, y, lr=1e-3)))
+        r = ref.train_step_grads(x, y, dict(weight_mul=3.0))
+        rlosses.append(r['loss'])
+        for k in ref.trainable:
+            ref.weights[k], m_, v_ = ops.adam_step(ref.weights[k], r['grads'][k], mom[k][0], mom[k][1], step + 1, lr=1e-3)
+            mom[k] = (m_, v_)
+        for k, v in r['new_moving'].items():
+            ref.weights[k] = v
+    np.testing.assert_allclose(losses, rlosses, rtol=5e-3)
+    w = m.get_weights()
+    # Adam's first steps move every weight by ~lr whatever the gradient's size: a gradient whose sign is decided by
+    # rounding noise lands 2e-3 away after one step -- agreement is counted over all weights
+    bad = tot = 0
+    for k in ref.trainable:
+        d = np.abs(w[k] - ref.weights[k].numpy())
+        bad += int((d > 5e-4).sum())
+        tot += d.size
+    assert bad / tot < 2e-2, (bad, tot)
+    ref.set_weights(m.get_weights())                 # same variables on both sides for the training=True call
+    out = ref.forward(x, training=True)
+    p = m(x, training=True).cpu().numpy()
+    np.testing.assert_allclose(p, out['probs'].numpy(), atol=1e-3)
+    w2 = m.get_weights()
+    for k, v in out['new_moving'].items():
+        assert rel_l2(w2[k], v.numpy()) <= 1e-2 or np.abs(w2[k] - v.numpy()).max() <= 1e-3, k
 
 
 @pytest.mark.parametrize('case', ['unet_tiny', 'unet_bn_tiny', 'unet_leaky_l2_tiny'])
