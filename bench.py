@@ -114,7 +114,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': r['steps'], 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'configs/{args.config}.yaml UNetAnnotator training step, per-GPU batch {args.batch} of '
+        'config': {'workload': f'configs/{args.config}.yaml {cfg["model"]} training step, per-GPU batch {args.batch} of '
                                f'{args.size}x{args.size}x{args.channels} slices ({args.dtype} activations, fp32 accumulate/master weights)',
                    'global_batch': args.batch * args.gpus, 'parallelism': f'dp{args.gpus}',
                    'sample': f'each timed step = batch {args.cpu_batch} of the same slices on the host CPU (fp32)'},
@@ -291,7 +291,7 @@ def measure_training(cfgname, B, S, Cc, dtype, steps, warmup, world, rank, local
 
     W = max(warmup, 3)
     loss0 = float(m.train_step(xh, yh))            # untimed step 1: builds the plan, uploads the batch
-    plan = m._plan(B, S, S)
+    plan = m.training_plan(B, S, S)
     for _ in range(W - 1):                         # untimed steps 2..W: second eager warm-up, graph capture, replays
         m._train_on_static(plan)
     barrier()
@@ -577,7 +577,7 @@ def run_ours(args):
         'warmup': args.warmup, 'warmup_steps_run': r['warmup_done'], 'ms_per_step': r['ms_per_step'],
         'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-        'config': {'workload': f'configs/{args.config}.yaml UNetAnnotator training step, per-GPU batch {B} of '
+        'config': {'workload': f'configs/{args.config}.yaml {cfg["model"]} training step, per-GPU batch {B} of '
                                f'{S}x{S}x{Cc} slices ({args.dtype} activations, fp32 accumulate/master weights)',
                    'global_batch': B * world, 'parallelism': f'dp{world}',
                    'l2': 'working set per step (>1 GB of activations) exceeds the 126 MB L2; no flush needed',

@@ -304,6 +304,11 @@ class Model:
             self._plans[key] = plan
         return self._plans[key]
 
+    def training_plan(self, batch, height, width):
+        """The plan ``train_step`` / ``forward_backward`` run for this input shape (MultiResUnet keeps a separate,
+        channel-padded one beside its BatchNorm-folded inference plan)."""
+        return self._plan(batch, height, width)
+
     def _run(self, plan, key, fn):
         """Runs ``fn`` (a fixed launch sequence) eagerly twice (warm-up: lazy attribute setup,
         allocator) and from then on as a CUDA graph replay."""

@@ -368,6 +368,10 @@ class MultiResUnet(Model):
             self._plans[key] = emit_training_plan(self, batch, height, width)
         return self._plans[key]
 
+    def training_plan(self, batch, height, width):
+        with self._training():
+            return self._plan(batch, height, width)
+
     def _training(self):
         model = self
 

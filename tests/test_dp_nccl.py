@@ -210,3 +210,83 @@ def test_c_abi_nccl_wrappers_two_ranks(tmp_path):
     np.testing.assert_array_equal(a['bf16'], b['bf16'])
     np.testing.assert_allclose(a['bf16'], want, rtol=2e-2, atol=2e-2)
     assert a['bad_rc'] == -1 and b['bad_rc'] == -1
+
+
+def _worker_multires(rank, world, port, out):
+    """MultiResUnet under data parallelism: its training plan computes on channel-padded copies of the variables, so no
+    gradient bucket may leave before the gradients were gathered back (``MultiResTrainPlan.ready_frontier``)."""
+    import faulthandler
+    import torch.distributed as dist
+    logdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    os.makedirs(logdir, exist_ok=True)
+    log = open(os.path.join(logdir, f'dp_test_multires_rank{rank}.log'), 'w')
+    faulthandler.dump_traceback_later(120, file=log, exit=True)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from dnncancerannotator_b200.models import tf_models
+        from dnncancerannotator_b200.synthetic import make_slices
+        from oracle import ref_models as rm
+        H = 32
+        mo = dict(height=None, width=None, n_channels=5)
+        ref = rm.build_model('MultiResUnet', mo, None, seed=0)
+        ref.randomize_bn(seed=1)
+        m = tf_models.MultiResUnet(**mo, dtype='fp32', seed=rank)
+        m.build((None, H, H, 5))
+        m.compile(loss=dict(class_name='WeightedCrossentropy', config=LOSS))
+        if rank == 0:
+            m.set_weights(ref.get_weights())
+        m.enable_data_parallel(bucket_bytes=1 << 20)                         # variables mirrored from rank 0
+        batches = [make_slices(2, H, H, 5, seed=(1235, 35)[r]) for r in range(world)]
+        x, y = batches[rank]
+        per = [ref.train_step_grads(bx, by, LOSS) for bx, by in batches]
+        avg = {k: (sum(p['grads'][k] for p in per) / world).numpy() for k in ref.trainable}
+        # the same kernels WITHOUT data parallelism on this rank's sub-batch: their cross-rank mean is what the all-reduce
+        # must deliver to the last bit of fp32 summation (61 BatchNorm layers deep a max-pool / relu near-tie decided
+        # differently by two implementations moves the gradient by 1e-2, so the oracle bound below is loose)
+        solo = tf_models.MultiResUnet(**mo, dtype='fp32', seed=0)
+        solo.build((None, H, H, 5))
+        solo.compile(loss=dict(class_name='WeightedCrossentropy', config=LOSS))
+        solo.set_weights(ref.get_weights())
+        solo.forward_backward(x, y)
+        flat = solo.params.grads.clone()
+        dist.all_reduce(flat)
+        flat /= world
+        solo_avg = {k: flat[sp['offset']:sp['offset'] + sp['numel']].view(sp['shape']).cpu().numpy()
+                    for k, sp in solo.params.specs.items() if sp['trainable']}
+        l1 = float(m.train_step(x, y))
+        g1 = m.get_grads()
+        losses = [l1] + [float(m.train_step(x, y)) for _ in range(3)]        # eager, capture + replay, replay
+        out[rank] = dict(l1=l1, g1=g1, avg=avg, solo_avg=solo_avg, mean_loss=float(np.mean([p['loss'] for p in per])), losses=losses,
+                         w=m.get_weights(), nlog=len(m._dp.launch_log), frontier=[f for f, _ in m._dp.launch_log])
+        m.close()
+    finally:
+        dist.destroy_process_group()
+        faulthandler.cancel_dump_traceback_later()
+
+
+def test_two_rank_multiresunet_step_matches_oracle_subbatch_average():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_multires, args=(world, _free_port(), out), nprocs=world, join=True)
+    a, b = out[0], out[1]
+    names = list(a['avg'])
+    got = np.concatenate([a['g1'][k].ravel() for k in names])
+    want = np.concatenate([a['avg'][k].ravel() for k in names])
+    assert _rel(got, want) <= 2e-2, _rel(got, want)
+    solo = np.concatenate([a['solo_avg'][k].ravel() for k in names])
+    assert _rel(got, solo) <= 1e-5, _rel(got, solo)
+    for k in names:
+        np.testing.assert_array_equal(a['g1'][k], b['g1'][k])
+    assert abs(a['l1'] - a['mean_loss']) <= 1e-4 * abs(a['mean_loss'])
+    assert a['losses'] == b['losses']
+    trainable = set(names)
+    for k in a['w']:
+        if k in trainable:
+            np.testing.assert_array_equal(a['w'][k], b['w'][k])              # replicas stay mirrored (moving statistics are rank-local)
+    assert a['nlog'] >= 4 and all(f == 0 for f in a['frontier'])             # every bucket left after the gather (dp.finish)

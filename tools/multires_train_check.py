@@ -27,14 +27,25 @@ def main():
     ap.add_argument('--batch', type=int, default=2)
     ap.add_argument('--modes', default='fp32,bf16')
     ap.add_argument('--graph', type=int, default=1)
+    ap.add_argument('--seed', type=int, default=11)
+    ap.add_argument('--out', default='gpurun_out/multires_train_check.json')
     args = ap.parse_args()
     from dnncancerannotator_b200.models import tf_models
     from dnncancerannotator_b200.synthetic import make_slices
     B, S = args.batch, args.size
-    x, y = make_slices(B, S, S, 5, seed=11)
+    x, y = make_slices(B, S, S, 5, seed=args.seed)
     ref = rm.build_model('MultiResUnet', dict(height=None, width=None, n_channels=5), None, seed=0)
     ref.randomize_bn(seed=1)
+    from oracle import ref_ops
+    rec, orig = [], ref_ops.maxpool
+
+    def spy(t, rate=2, return_indices=False):
+        out, idx = orig(t, rate, return_indices=True)
+        rec.append((idx.numpy(), t.detach().numpy()))
+        return (out, idx) if return_indices else out
+    ref_ops.maxpool = spy
     want = ref.train_step_grads(x, y, dict(weight_mul=3.0))
+    ref_ops.maxpool = orig
     report = {}
     for mode in args.modes.split(','):
         m = tf_models.MultiResUnet(None, None, 5, dtype=mode)
@@ -58,10 +69,28 @@ def main():
                    grads_nonfinite=int((~np.isfinite(allg)).sum()), worst=worst,
                    moving_worst=sorted(mov.items(), key=lambda kv: -kv[1])[:4],
                    first_layers={k: rows[k] for k in list(rows)[:10]}, last_layers={k: rows[k] for k in list(rows)[-8:]})
+        # max-pool argmax of the training plan vs the oracle's (logical channels of the padded block outputs)
+        from dnncancerannotator_b200 import runtime as R
+        plan = m.training_plan(B, S, S)
+        pools = [op for op in plan.ops if isinstance(op, R.PoolOp)]
+        pm = []
+        for lvl, op in enumerate(pools):
+            W = 1.67 * 32 * 2 ** lvl
+            f = [int(W * 0.167), int(W * 0.333), int(W * 0.5)]
+            pp = [(c + 15) // 16 * 16 for c in f]
+            pos = np.concatenate([np.arange(f[0]), pp[0] + np.arange(f[1]), pp[0] + pp[1] + np.arange(f[2])])
+            ours = op.idx.cpu().numpy()[..., pos]
+            oidx, oin = rec[lvl]
+            diff = ours != oidx
+            xin = op.x.torch_view().float().cpu().numpy()[..., pos]
+            pm.append(dict(level=lvl, mismatches=int(diff.sum()), of=int(diff.size),
+                           input_rel_l2=rel_l2(xin, oin), input_max_abs=float(np.abs(xin - oin).max())))
+        rep['pool_argmax'] = pm
+        rep['all'] = rows
         report[mode] = rep
-        print(mode, json.dumps(rep, indent=1))
+        print(mode, json.dumps({k: v for k, v in rep.items() if k != 'all'}, indent=1))
     os.makedirs('gpurun_out', exist_ok=True)
-    with open('gpurun_out/multires_train_check.json', 'w') as f:
+    with open(args.out, 'w') as f:
         json.dump(report, f, indent=1)
 
 
