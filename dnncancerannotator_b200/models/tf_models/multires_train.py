@@ -128,10 +128,10 @@ class AccumOp(R.Op):
 class MultiResTrainPlan(R.Plan):
     """Physical (channel-padded) plan + the gathers between the logical variables and their padded copies."""
 
-    def __init__(self, logical: R.ParamStore, batch, height, width, channels, dtype, device):
+    def __init__(self, logical: R.ParamStore, batch, height, width, channels, dtype, device, want_input_grad=False):
         self.logical = logical
         self.phys = R.ParamStore()
-        super().__init__(self.phys, batch, height, width, channels, dtype, device)
+        super().__init__(self.phys, batch, height, width, channels, dtype, device, want_input_grad=want_input_grad)
         self.links = {}                    # variable name -> per-axis physical positions (np.ix_ arguments) or None
         self._scratch = {}
         self.maps = None
@@ -172,13 +172,21 @@ class MultiResTrainPlan(R.Plan):
         N.call('dnnca_gather_f32', N.stream_ptr(), N.ptr(src), N.ptr(idx), idx.numel(), N.ptr(dst))
 
     # ---- step protocol (keras_like.Model launch sequences) -------------------------------------------
+    def refresh_variables(self):
+        lg, ph, m = self.logical, self.phys, self.maps
+        self._gather(lg.params, m['p2l_t'], ph.params)
+        self._gather(lg.state, m['p2l_s'], ph.state)
+
     def zero_step_state(self):
         """Start of a training-mode launch sequence: gradients / statistics zeroed, physical variables refreshed."""
         super().zero_step_state()
-        lg, ph, m = self.logical, self.phys, self.maps
-        lg.grads_full.zero_()
-        self._gather(lg.params, m['p2l_t'], ph.params)
-        self._gather(lg.state, m['p2l_s'], ph.state)
+        self.logical.grads_full.zero_()
+        self.refresh_variables()
+
+    def forward(self, train=False):
+        if not train:          # the input-gradient chain (inference-mode forward) has no zero_step_state ahead of it
+            self.refresh_variables()
+        super().forward(train)
 
     def end_backward(self):
         lg, ph, m = self.logical, self.phys, self.maps
@@ -228,12 +236,35 @@ class MultiResTrainPlan(R.Plan):
         N.call('dnnca_bn_apply', s, v['hz'], N.ptr(self.hss), v['hl'])
         return v
 
+    def _head_folded(self):
+        """conv10 + its BatchNorm with the MOVING statistics as one weight vector + bias (``dnnca_fold_weights``)"""
+        ps = self.phys
+        cname, bname = self.head_names
+        cp = self.features.c
+        if getattr(self, 'hwf', None) is None:
+            self.hwf = torch.empty(cp, dtype=torch.float32, device=self.device)
+            self.hbf = torch.empty(1, dtype=torch.float32, device=self.device)
+        N.call('dnnca_fold_weights', N.stream_ptr(), ps.ptr(f'{cname}/kernel'), 1, cp, 1, 0, None, cp, None, 1, None,
+               ps.ptr(f'{bname}/beta'), ps.ptr(f'{bname}/moving_mean'), ps.ptr(f'{bname}/moving_var'), R.BN_EPSILON,
+               N.ptr(self.hwf), N.ptr(self.hbf))
+
     def head_forward(self):
-        """``model(x, training=True)``: batch statistics, moving averages updated, no gradients."""
+        """``model(x, training=True)``: batch statistics, moving averages updated, no gradients.  On the input-gradient
+        plan (callbacks.py:290-299: inference-mode forward): moving statistics, folded into the head weights."""
+        if self.want_input_grad:
+            self._head_folded()
+            N.call('dnnca_head_fwd', N.stream_ptr(), self.features.ct(), N.ptr(self.hwf), N.ptr(self.hbf), N.ptr(self.logits),
+                   N.ptr(self.probs))
+            return
         v = self._head_logits(self.train_bn)
         N.call('dnnca_head_fwd', N.stream_ptr(), v['hl'], N.ptr(self.hone), None, N.ptr(self.logits), N.ptr(self.probs))
         lg, ph, m = self.logical, self.phys, self.maps
         self._gather(ph.state, m['l2p_s'], lg.state)
+
+    def head_input_grad(self):
+        f = self.features
+        act = f.act or (N.ACT_NONE, 0.0)
+        N.call('dnnca_head_input_grad', N.stream_ptr(), f.ct(), N.ptr(self.hwf), N.ptr(self.hbf), f.gct(), act[0], act[1])
 
     def head_loss(self, loss_cfg: N.LossConfig, with_grads=True):
         ps, s = self.phys, N.stream_ptr()
@@ -406,17 +437,18 @@ class TrainBuilder:
         return x
 
 
-def emit_training_plan(model, batch, height, width, device=None):
+def emit_training_plan(model, batch, height, width, device=None, want_input_grad=False):
     """The training plan of ``model`` (a ``MultiResUnet`` whose logical variables are materialised).  ``device``: only the
     CPU-side structure test passes one (the plan is then inspected, never launched)."""
     nch = model.n_channels
-    plan = MultiResTrainPlan(model.params, batch, height, width, nch, model.compute_dtype, device or model.device)
+    plan = MultiResTrainPlan(model.params, batch, height, width, nch, model.compute_dtype, device or model.device,
+                             want_input_grad=want_input_grad)
     b = TrainBuilder(plan)
     x = plan.input
     buf = plan.new_buf(x.h, x.w, padc(nch), 'input_cast', zero=True)        # modalities in a 16-channel pixel, rest zero
     plan.add(R.ConvertOp(plan, x, R.TRef(buf, 0, nch)))
     xin = R.TRef(buf)
-    xin.needs_grad = False
+    xin.needs_grad = plan.want_input_grad          # callbacks.py:290-299 asks for d(output)/d(input); training never does
     feats = b.graph(TSym(xin, nch))
     cname, bname = b._next('conv'), b._next('bn')
     plan.add_var(f'{cname}/kernel', (1, 1, feats.cphys, 1), (np.arange(1), np.arange(1), feats.pos(), np.arange(1)))

@@ -358,7 +358,13 @@ class MultiResUnet(Model):
     # ---- plan selection --------------------------------------------------------------------------------------
     def _plan(self, batch, height, width, want_input_grad=False):
         if want_input_grad:
-            raise NotImplementedError('MultiResUnet: the input-gradient chain (callbacks.py:290-299) is not built')
+            # callbacks.py:290-299: the training plan's op list run with the moving statistics + its dgrad chain
+            key = (batch, height, width, 'dx')
+            if key not in self._plans:
+                from .multires_train import emit_training_plan
+                super()._plan(batch, height, width)
+                self._plans[key] = emit_training_plan(self, batch, height, width, want_input_grad=True)
+            return self._plans[key]
         if not self._train_plans:
             return super()._plan(batch, height, width)
         key = (batch, height, width, 'train')
@@ -404,6 +410,10 @@ class MultiResUnet(Model):
     def train_step(self, x, y, lr=None):
         with self._training():
             return super().train_step(x, y, lr)
+
+    def input_gradient(self, x):
+        with self._training():                  # (keeps _before_inference away from the padded plan)
+            return super().input_gradient(x)
 
     def forward_backward(self, x, y):
         with self._training():

@@ -216,9 +216,9 @@ def test_multiresunet_forward(mode):
     assert abs(ev - wl) <= (3e-2 if mode == 'bf16' else 1e-4) * abs(wl), (ev, wl)
 
 
-def _multires_pair(mode, B, S):
+def _multires_pair(mode, B, S, seed=11):
     from dnncancerannotator_b200.synthetic import make_slices
-    x, y = make_slices(B, S, S, 5, seed=11)
+    x, y = make_slices(B, S, S, 5, seed=seed)
     ref = rm.build_model('MultiResUnet', dict(height=None, width=None, n_channels=5), None, seed=0)
     ref.randomize_bn(seed=1)
     m = product_model('MultiResUnet', dict(height=None, width=None, n_channels=5), mode)
@@ -294,6 +294,28 @@ def test_multiresunet_training_step(mode):
     want = ref2.forward(x, training=False)['logits'].numpy()
     m(x)
     assert rel_l2(m.last_logits.cpu().numpy(), want) <= (2e-2 if mode == 'bf16' else 5e-4)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_multiresunet_input_gradient(mode):
+    """callbacks.py:290-299 on MultiResUnet: inference-mode forward (moving statistics) of the channel-padded plan + its
+    dgrad chain down to the 5 input modalities, against the oracle's autograd."""
+    # seed 1235: a batch on which the oracle agrees with itself in fp32 and fp64 to 5e-7 (on seed 11 a relu / max-pool
+    # near-tie moves the fp32 oracle 3.0e-3 away from its fp64 evaluation -- and the CUDA path lands on the fp64 side)
+    m, ref, x, y = _multires_pair(mode, 2, 32, seed=1235)
+    ref64 = rm.build_model('MultiResUnet', dict(height=None, width=None, n_channels=5), None, seed=0, dtype=torch.float64)
+    ref64.set_weights(ref.get_weights())
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    out = ref64.forward(xt, training=False)
+    out['probs'].sum().backward()
+    want = xt.grad.numpy()
+    for _ in range(4):                       # eager warm-ups, capture, replay
+        probs, dx = m.input_gradient(x)
+    e = rel_l2(dx.cpu().numpy(), want)
+    REPORT[f'multires/{mode}/input_gradient'] = dict(grad_rel_l2=e, probs_max_abs=float(np.abs(probs.cpu().numpy() - out['probs'].detach().numpy()).max()))
+    np.testing.assert_allclose(probs.cpu().numpy(), out['probs'].detach().numpy(), atol=3e-2 if mode == 'bf16' else 1e-5)
+    assert dx.shape == x.shape
+    assert e <= (0.3 if mode == 'bf16' else 1e-4), e
 
 
 def test_multiresunet_training_trajectory_fp32():
