@@ -36,6 +36,22 @@ CASES = {
 }
 
 
+def multires_train_summary(r, trainable, grads=None):
+    """The fixture's view of a MultiResUnet training step: ``r`` = oracle ``train_step_grads`` result, or (for the CUDA
+    path) a dict with logits / loss / per_sample / new_moving and ``grads`` = name -> array."""
+    g = grads if grads is not None else {k: v.numpy() for k, v in r['grads'].items()}
+    out = dict(loss=np.float32(r['loss']), logits=np.asarray(r['logits'], np.float32), per_sample=np.asarray(r['per_sample'], np.float32))
+    for k in trainable:
+        if k.endswith('/kernel'):
+            out['n:' + k] = np.float32(np.linalg.norm(g[k].astype(np.float64)))
+        else:
+            out['g:' + k] = g[k]
+    out['sample'] = np.concatenate([g[k].ravel() for k in trainable])[::997].copy()
+    for k, v in r['new_moving'].items():
+        out['m:' + k] = np.asarray(v, np.float32)
+    return out
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
@@ -71,6 +87,16 @@ def main():
     ev = m.forward(x, training=False)
     np.savez_compressed(os.path.join(HERE, 'multires_fwd_tiny.npz'), x=x, eval_logits=ev['logits'].detach().numpy())
     print('multires logits', float(ev['logits'].abs().mean()))
+    # MultiResUnet TRAINING step (batch statistics, weighted BCE, all gradients).  7.2 M gradient values do not belong in a
+    # fixture: kept are the logits, the loss, every BatchNorm gradient and moving statistic in full, the L2 norm of every
+    # kernel gradient and every 997th element of the concatenated gradient.  Batch seed 1235: the oracle agrees with its
+    # own fp64 evaluation to 1.4e-5 there (no relu / max-pool near-ties).
+    x, y = make_slices(2, 32, 32, 5, seed=1235)
+    r = m.train_step_grads(x, y, dict(weight_mul=3.0))
+    out = multires_train_summary(r, m.trainable)
+    out.update(x=x, y=y)
+    np.savez_compressed(os.path.join(HERE, 'multires_train_tiny.npz'), **out)
+    print('multires train loss', r['loss'])
 
 
 if __name__ == '__main__':
