@@ -84,6 +84,29 @@ def _label_tensor(y):
     return y if torch.is_tensor(y) else torch.from_numpy(np.ascontiguousarray(y))
 
 
+def load_model(path, dtype=None):
+    """Rebuilds what ``Model.save(path)`` wrote (the counterpart of ``tf.keras.models.load_model`` for the directory of
+    engine.py:226): class + constructor config from ``config.json``, compiled with the saved loss / optimizer settings,
+    variables and optimizer slots from ``weights.npz``.  ``dtype`` overrides the saved compute dtype."""
+    import json
+    from .models import tf_models
+    with open(os.path.join(path, 'config.json')) as f:
+        cfg = json.load(f)
+    cls = getattr(tf_models, cfg['class_name'], None)
+    if cls is None or not (isinstance(cls, type) and issubclass(cls, Model)):
+        raise ValueError(f"unknown model class {cfg['class_name']!r} in {path}/config.json")
+    model = cls(**cfg.get('config', {}), dtype=dtype or cfg.get('compute_dtype'))
+    shape = cfg.get('input_shape')
+    if not shape:
+        raise ValueError(f'{path}/config.json holds no input shape: the model was saved before it was built')
+    model.build(tuple(shape))
+    model.compile(optimizer=cfg.get('optimizer') or 'adam', loss=cfg.get('loss'))
+    if torch.cuda.is_available():
+        model.params.materialize(model.device)       # so that the Adam slots and the step counter are restored as well
+    model.load_weights(path).assert_existing_objects_matched()
+    return model
+
+
 class Model:
     """Base of ``UNetAnnotator`` / ``MulmoUNetAnnotator`` / ``MultiResUnet``.
 

@@ -370,3 +370,31 @@ def test_multiresunet_training_plan_structure_and_variable_maps():
     kinds = Counter(type(o).__name__ for o in plan.ops)
     assert kinds['ConvOp'] == 56 and kinds['BNActOp'] == 56 and kinds['BNOp'] == 28 and kinds['TConvOp'] == 4 and kinds['PoolOp'] == 4
     assert plan.ready_frontier() == [lg.grads_full.numel()] * len(plan.ops)     # no gradient bucket leaves before the gather
+
+
+def test_save_and_load_model_without_a_device(tmp_path):
+    """engine.py:226 ``model.save(path)`` + ``load_model``: class, constructor config, loss and optimizer settings and every
+    variable come back from the directory alone (host side; the device round trip incl. Adam slots is a -m gpu test)."""
+    import json
+    import numpy as np
+    from dnncancerannotator_b200.keras_like import load_model
+    from dnncancerannotator_b200.models import tf_models
+    cases = [('UNetAnnotator', dict(n_filters_first=3, n_downsample=2, rate=2, kernel_size=3, conv_stride=1, padding='same',
+                                   bn=True, activation=dict(class_name='LeakyReLU', config=dict(alpha=0.3)))),
+             ('MulmoUNetAnnotator', dict(n_filters_first=4, n_downsample=2, rate=2, kernel_size=3, conv_stride=1, padding='same')),
+             ('MultiResUnet', dict(height=None, width=None, n_channels=5))]
+    for i, (name, opts) in enumerate(cases):
+        m = getattr(tf_models, name)(**opts, dtype='fp32', seed=3)
+        m.build((None, 32, 32, 5 if name == 'MultiResUnet' else 3))
+        m.compile(optimizer=dict(learning_rate=5e-4), loss=dict(class_name='WeightedCrossentropy', config=dict(weight_mul=3.0)))
+        d = m.save(str(tmp_path / f'saved{i}'))
+        cfg = json.load(open(os.path.join(d, 'config.json')))
+        assert cfg['class_name'] == name and cfg['compute_dtype'] == 'fp32'
+        m2 = load_model(d)
+        assert type(m2) is type(m) and m2.get_config() == m.get_config()
+        assert m2.optimizer['learning_rate'] == 5e-4 and m2.loss.weight_mul == 3.0
+        w1, w2 = m.get_weights(), m2.get_weights()
+        assert list(w1) == list(w2) and all(np.array_equal(w1[k], w2[k]) for k in w1)
+    with pytest.raises(ValueError):
+        json.dump(dict(class_name='NoSuchModel', config={}), open(os.path.join(d, 'config.json'), 'w'))
+        load_model(d)

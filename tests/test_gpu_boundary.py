@@ -169,6 +169,15 @@ def test_save_and_load_roundtrip_on_device(tmp_path):
     assert a == b
     for k, v in m.get_weights().items():
         np.testing.assert_allclose(m2.get_weights()[k], v, rtol=1e-5, atol=5e-6)     # fp32 atomics reorder the gradient sums
+    # load_model: class, constructor config, loss, optimizer, variables, Adam slots from the directory alone
+    from dnncancerannotator_b200.keras_like import load_model
+    d2 = m.save(str(tmp_path / 'model2'))
+    m3 = load_model(d2)
+    assert type(m3) is type(m) and m3.get_config() == m.get_config() and m3.optimizer == m.optimizer
+    assert m3.loss.get_config() == m.loss.get_config()
+    np.testing.assert_array_equal(m3(z['x']).cpu().numpy(), m(z['x']).cpu().numpy())
+    c, e = float(m.train_step(z['x'], z['y'])), float(m3.train_step(z['x'], z['y']))
+    assert c == e
 
 
 def test_input_tail_crop_flip_split_bit_exact():
