@@ -228,18 +228,20 @@ class Model:
         return self.params.get_grads()
 
     # checkpoints: own format (TF checkpoints need TF), same ckpt-<step> naming as engine.py:52
-    def save_weights(self, path, save_format=None):
+    def save_weights(self, path, save_format=None, write=True):
         """Own ``.npz`` format by default; ``save_format='tf'`` writes a TensorFlow object-based checkpoint
         (``<path>.index`` + ``<path>.data-00000-of-00001``) laid out like the file the reference's
-        ``ModelCheckpoint(save_weights_only=True)`` writes (engine.py:105), see ``utils/tf_checkpoint.py``."""
+        ``ModelCheckpoint(save_weights_only=True)`` writes (engine.py:105), see ``utils/tf_checkpoint.py``.
+        Under data parallelism EVERY rank calls it (the BatchNorm moving statistics are averaged over the replicas, a
+        collective); ``write=False`` on the ranks that must not touch the file system."""
+        if self._dp is not None and self.params.device is not None and self._dp.world_size > 1:
+            self._dp.average(self.params.state)     # BN moving statistics are rank-local: saved as the replica mean
+        if not write:
+            return None
         os.makedirs(os.path.dirname(os.path.abspath(path)) or '.', exist_ok=True)
         if save_format == 'tf':
             from .utils import tf_checkpoint
-            if self._dp is not None and self.params.device is not None and self._dp.world_size > 1:
-                self._dp.average(self.params.state)
             return tf_checkpoint.export_from(self, path)
-        if self._dp is not None and self.params.device is not None and self._dp.world_size > 1:
-            self._dp.average(self.params.state)     # BN moving statistics are rank-local: saved as the replica mean
         w = self.get_weights()
         extra = {}
         if self.params.device is not None:
@@ -716,6 +718,7 @@ class Model:
             self.reset_metrics()
             losses = []
             n = steps_per_epoch or 1
+            self._last_epoch_steps = n           # batches of this epoch (engine.ModelCheckpoint counts them, keras save_freq)
             for _ in range(n):
                 xb, yb = nxt
                 losses.append(self.train_step(xb, yb, lr=lr))

@@ -474,7 +474,7 @@ def load_into(model, prefix, verify=True):
         it = nodes[opt]['children'].get('iter')
         if it is not None and 'VARIABLE_VALUE' in nodes[it]['attributes']:
             k = nodes[it]['attributes']['VARIABLE_VALUE'][1]
-            slots['iter'] = int(rd.get_tensor(k))
+            slots['iter'] = int(np.asarray(rd.get_tensor(k)).reshape(-1)[0])
             used.add(k)
     if slots and model.params.device is not None:
         import torch

@@ -119,3 +119,69 @@ def test_multiresunet_fit_alternates_training_and_inference_plans_fp32():
     for got, want in vals:                     # every epoch: the inference plan evaluated the CURRENT variables
         assert abs(got - want) <= 1e-4 * abs(want), (got, want)
     assert len({round(v[0], 6) for v in vals}) == 4            # and they did change from epoch to epoch
+
+
+def _engine_cfg(model='UNetAnnotator', **model_options):
+    return dict(model=model, model_options=model_options,
+                deploy_options=dict(optimizer='adam', LearningRateScheduler='lambda epoch, current_lr: 0.001 * 0.9 ** (epoch // 2)',
+                                    loss=dict(class_name='WeightedCrossentropy', config=dict(weight_mul=3.0)),
+                                    enable_multigpu=False))
+
+
+def test_engine_train_checkpoints_resume_and_eval(tmp_path):
+    """engine.py:80-137 / 139-210 through ``dnncancerannotator_b200.engine.TFKerasModel``: ``checkpoints/ckpt-<step>`` every
+    ``save_freq`` steps (TensorFlow-format files), validation at the same frequency, auto-resume from the latest
+    checkpoint (variables, Adam slots, iteration count, LR-schedule position) reproducing the uninterrupted run,
+    evaluation over the checkpoints with ``step_range`` / ``min_interval`` / ``results.csv``."""
+    from dnncancerannotator_b200 import engine as E
+    from dnncancerannotator_b200.synthetic import make_slices
+    cfg = _engine_cfg(n_filters_first=4, n_downsample=2, rate=2, kernel_size=3, conv_stride=1, bn=True, padding='same')
+    train = [make_slices(3, 32, 32, 3, seed=100 + i) for i in range(3)]
+    val = [make_slices(2, 32, 32, 3, seed=200)]
+    sp, sp_full = str(tmp_path / 'run'), str(tmp_path / 'run_full')
+    eng = E.TFKerasModel(cfg, dtype='fp32')
+    h1 = eng.train(train, val_data=val, save_path=sp, save_freq=3, max_steps=7)
+    assert h1.epoch == list(range(7)) and len(h1.history['val_loss']) == 2          # validated after steps 3 and 6
+    ck = eng.get_ckpts(os.path.join(sp, 'checkpoints'))
+    assert list(ck) == [3, 6] and all(os.path.exists(p + '.index') and os.path.exists(p + '.data-00000-of-00001') for p in ck.values())
+    full = E.TFKerasModel(cfg, dtype='fp32')
+    hf = full.train(train, val_data=val, save_path=sp_full, save_freq=3, max_steps=10)
+    np.testing.assert_allclose(hf.history['loss'][:7], h1.history['loss'], rtol=1e-4)
+    # a fresh process resumes: latest checkpoint, step counter -> initial_epoch
+    eng2 = E.TFKerasModel(cfg, dtype='fp32')
+    with pytest.warns(UserWarning, match='Resumed from 6'):
+        h2 = eng2.train(train, val_data=val, save_path=sp, save_freq=3, max_steps=10)
+    assert eng2.current_step == 6 and h2.epoch == [6, 7, 8, 9]
+    np.testing.assert_allclose(h2.history['loss'], hf.history['loss'][6:], rtol=2e-4)
+    np.testing.assert_allclose(h2.history['val_loss'], hf.history['val_loss'][2:], rtol=2e-4)
+    assert list(eng2.get_ckpts(os.path.join(sp, 'checkpoints'))) == [3, 6, 9]
+    # evaluation over the checkpoints
+    res = eng2.eval(val, sp, tag='val', export_csv=True)
+    assert list(res) == [3, 6, 9] and abs(res[9]['loss'] - h2.history['val_loss'][-1]) <= 1e-6 * abs(res[9]['loss'])
+    assert abs(res[6]['loss'] - h1.history['val_loss'][-1]) <= 1e-6 * abs(res[6]['loss'])
+    csv = open(os.path.join(sp, 'tfevents', 'val', 'results.csv')).read().splitlines()
+    assert csv[0].startswith('step') and [int(l.split(',')[0]) for l in csv[1:]] == [3, 6, 9]
+    with pytest.raises(ValueError):
+        eng2.eval(val, sp, tag='val')                                                 # "tag: val already exists."
+    assert list(eng2.eval(val, sp, tag='val', avoid_overwrite=True, step_range=(4, 9))) == [6, 9]
+    with pytest.warns(UserWarning, match='min_interval'):
+        assert list(eng2.eval(val, sp, tag='other', min_interval=4)) == [3, 9]
+    assert eng2.predict(val[0][0]).shape == (2, 32, 32, 1)
+
+
+def test_engine_multiresunet_checkpoints_and_resume(tmp_path):
+    from dnncancerannotator_b200 import engine as E
+    from dnncancerannotator_b200.synthetic import make_slices
+    cfg = _engine_cfg('MultiResUnet', height=None, width=None, n_channels=5)
+    train = [make_slices(2, 32, 32, 5, seed=1235)]
+    sp = str(tmp_path / 'run')
+    eng = E.TFKerasModel(cfg, dtype='fp32')
+    h1 = eng.train(train, val_data=train, save_path=sp, save_freq=1, max_steps=2)
+    ck = eng.get_ckpts(os.path.join(sp, 'checkpoints'))
+    assert list(ck) == [1, 2] and all(os.path.exists(p + '.npz') for p in ck.values())     # own format (DESIGN 3.6)
+    eng2 = E.TFKerasModel(cfg, dtype='fp32')
+    with pytest.warns(UserWarning, match='Resumed from 2'):
+        h2 = eng2.train(train, val_data=train, save_path=sp, save_freq=1, max_steps=3)
+    assert h2.epoch == [2] and np.isfinite(h2.history['loss'][0]) and h2.history['loss'][0] < h1.history['loss'][0]
+    w1, w2 = eng.model.get_weights(), eng2.model.get_weights()
+    assert any(not np.array_equal(w1[k], w2[k]) for k in w1)                # it trained on from the restored variables
