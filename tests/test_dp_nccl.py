@@ -290,3 +290,59 @@ def test_two_rank_multiresunet_step_matches_oracle_subbatch_average():
         if k in trainable:
             np.testing.assert_array_equal(a['w'][k], b['w'][k])              # replicas stay mirrored (moving statistics are rank-local)
     assert a['nlog'] >= 4 and all(f == 0 for f in a['frontier'])             # every bucket left after the gather (dp.finish)
+
+
+def _worker_engine(rank, world, port, save_path, out):
+    """engine.TFKerasModel under ``deploy_options.enable_multigpu`` (multigpu.yaml): one process per GPU instead of the
+    reference's MirroredStrategy; rank 0 writes the checkpoints, every rank resumes from them."""
+    import faulthandler
+    import warnings
+    import torch.distributed as dist
+    logdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    os.makedirs(logdir, exist_ok=True)
+    log = open(os.path.join(logdir, f'dp_test_engine_rank{rank}.log'), 'w')
+    faulthandler.dump_traceback_later(120, file=log, exit=True)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from dnncancerannotator_b200 import engine as E
+        from dnncancerannotator_b200.synthetic import make_slices
+        cfg = dict(model='UNetAnnotator', model_options=OPTS,
+                   deploy_options=dict(optimizer='adam', loss=dict(class_name='WeightedCrossentropy', config=LOSS),
+                                       LearningRateScheduler='lambda epoch, current_lr: 0.001', enable_multigpu=True))
+        train = [make_slices(3, 32, 32, 3, seed=500 + 10 * i + rank) for i in range(2)]      # every rank its own shard
+        val = [make_slices(2, 32, 32, 3, seed=900)]
+        eng = E.TFKerasModel(cfg, dtype='fp32')
+        h1 = eng.train(train, val_data=val, save_path=save_path, save_freq=2, max_steps=4)
+        dist.barrier()
+        ck = list(eng.get_ckpts(os.path.join(save_path, 'checkpoints')))
+        eng2 = E.TFKerasModel(cfg, dtype='fp32')
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            h2 = eng2.train(train, val_data=val, save_path=save_path, save_freq=2, max_steps=6)
+        out[rank] = dict(ck=ck, loss1=h1.history['loss'], val1=h1.history['val_loss'], epoch2=h2.epoch, loss2=h2.history['loss'],
+                         step=eng2.current_step, w=eng2.model.get_weights(), world=eng.model._dp.world_size)
+        eng.model.close()
+        eng2.model.close()
+    finally:
+        dist.destroy_process_group()
+        faulthandler.cancel_dump_traceback_later()
+
+
+def test_two_rank_engine_train_checkpoint_resume(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_engine, args=(2, _free_port(), str(tmp_path / 'run'), out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    assert a['world'] == 2 and a['ck'] == [2, 4] and b['ck'] == [2, 4]
+    assert a['loss1'] == b['loss1']                        # the reported loss is the global mean on every rank
+    assert a['step'] == 4 and b['step'] == 4 and a['epoch2'] == [4, 5] and a['loss2'] == b['loss2']
+    files = sorted(os.listdir(tmp_path / 'run' / 'checkpoints'))
+    assert files == sorted(f'ckpt-{s}.{e}' for s in (2, 4, 6) for e in ('index', 'data-00000-of-00001'))       # rank 0 alone wrote
+    trainable = [k for k in a['w'] if not k.endswith(('moving_mean', 'moving_var'))]
+    for k in trainable:
+        np.testing.assert_array_equal(a['w'][k], b['w'][k])
