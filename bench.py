@@ -196,8 +196,13 @@ def profile_step(m, plan, cfg, world):
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    # every iteration is queued behind a device-side delay long enough for the host to enqueue the whole step first: the
+    # events then bracket kernel execution alone (a Python launch costs ~50 us -- about one of these kernels -- and with an
+    # empty queue the gap between an event record and the launch behind it would be counted into the kernel)
+    delay_cycles = int(min(max(launches_per_step * 60e-6, 3e-3), 60e-3) * 2.0e9)
     with N.Profiler() as prof:
         for _ in range(3):
+            torch.cuda._sleep(delay_cycles)
             m._train_on_static(plan)
     agg = prof.summary()
     for k, v in saved_env.items():
@@ -260,7 +265,8 @@ def profile_step(m, plan, cfg, world):
                                       'tflops': round(conv_fl / conv_ms / 1e9, 1) if conv_ms else None,
                                       'frac_of_bf16_sustained_peak': round(conv_fl / conv_ms / 1e9 / tens_sus, 4) if conv_ms else None,
                                       'frac_of_bf16_burst_peak': round(conv_fl / conv_ms / 1e9 / tens_burst, 4) if conv_ms else None},
-                     'note': 'CUDA events around each C-ABI call in an eager single-stream pass after the timed region '
+                     'note': 'CUDA events around each C-ABI call in an eager single-stream pass after the timed region, each '
+                             'iteration queued behind a device-side delay so that host launch gaps are not counted '
                              '(the step graph itself overlaps weight gradients / encoder branches on side streams); '
                              'algorithmic bytes = every operand read once + result written once at its storage dtype'})
     return dict(launches_per_step=launches_per_step, roofline=roofline, breakdown=breakdown, categories=categories,
