@@ -345,6 +345,50 @@ __global__ void __launch_bounds__(256) add_relu_affine_vec8_kernel(View a, const
   }
 }
 
+// Same operation with the affine tables in REGISTERS: the 256 threads of a block are (pixel lane, channel group) with the
+// group fastest, so a thread keeps its group for the whole grid-stride loop and loads its 6 x 8 parameters once.  The
+// shared-memory variant above reads 48 table words per 16-byte element; at the MultiRes widths (15 / 28 / 54 / 108 groups,
+// no power of two) those reads also conflict: add_relu_affine[120@128] ran at 2.4 TB/s, [224@64] at 1.8 TB/s against
+// 6.1 TB/s for [32@256] (profiles/r02h_multires_sweep.json).  ng <= 256.
+// HA / HB: affine_a / affine_b present (an absent table costs no registers: 4 resident blocks per SM).
+template <bool HA, bool HB>
+__global__ void __launch_bounds__(256, 4) add_relu_affine_vec8_reg_kernel(View a, const float* __restrict__ fa, View b,
+                                                                         const float* __restrict__ fb,
+                                                                         const float* __restrict__ fo, View y, long long P,
+                                                                         int ng, int ppb) {
+  const int g = threadIdx.x % ng, pl = threadIdx.x / ng;
+  if (pl >= ppb) return;                      // 256 - ppb * ng idle threads (no barrier follows)
+  const int C = a.c;
+  float sa[8], ta[8], sb[8], tb[8], so[8], to[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = 8 * g + j;
+    sa[j] = HA ? fa[c] : 1.f; ta[j] = HA ? fa[C + c] : 0.f;
+    sb[j] = HB ? fb[c] : 1.f; tb[j] = HB ? fb[C + c] : 0.f;
+    so[j] = fo ? fo[c] : 1.f; to[j] = fo ? fo[C + c] : 0.f;
+  }
+  for (long long p = (long long)blockIdx.x * ppb + pl; p < P; p += (long long)gridDim.x * ppb) {
+    const uint4 ra = __ldg(vptr(a, p, g)), rb = __ldg(vptr(b, p, g));
+    const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float va = __uint_as_float((j & 1) ? (wa[j >> 1] & 0xffff0000u) : (wa[j >> 1] << 16));
+      const float vb = __uint_as_float((j & 1) ? (wb[j >> 1] & 0xffff0000u) : (wb[j >> 1] << 16));
+      float v = (HA ? fmaf(va, sa[j], ta[j]) : va) + (HB ? fmaf(vb, sb[j], tb[j]) : vb);
+      v = fmaxf(v, 0.f);
+      o[j] = fmaf(v, so[j], to[j]);
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 q = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&q);
+    }
+    *vptr_w(y, p, g) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // MODE 0: channel stats (x)            -> acc[0..C) += sum x, acc[C..2C) += sum x^2
 // MODE 1: BN backward reduce (x, dy)   -> acc[0..C) += sum dy, acc[C..2C) += sum dy*xhat
 template <int MODE>
@@ -790,6 +834,21 @@ extern "C" int dnnca_add_relu_affine(void* stream, const dnnca_tensor_t* a, cons
   DNNCA_CHECK_ARG(view_ok(a) && view_ok(b) && view_ok(y) && same_shape(a, b) && same_shape(a, y), "add_relu_affine: bad arguments");
   DNNCA_CHECK_ARG(a->dtype == b->dtype && a->dtype == y->dtype, "add_relu_affine: dtype mismatch");
   long long P = (long long)a->n * a->h * a->w;
+  // <= 4 groups (<= 32 channels): the shared-memory tables are read as warp-wide broadcasts there (6.1 TB/s measured)
+  if (vec8_ok(a) && vec8_ok(b) && vec8_ok(y) && a->c / 8 > 4 && a->c / 8 <= 256) {
+    const int ng = a->c / 8, ppb = 256 / ng;
+    const int grid = grid_for(P, ppb * 4, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH_ARA(HA, HB) add_relu_affine_vec8_reg_kernel<HA, HB><<<grid, 256, 0, s>>>(mk(a), affine_a, mk(b), affine_b, affine_out, \
+                                                                                     mk(y), P, ng, ppb)
+    if (affine_a && affine_b) LAUNCH_ARA(true, true);
+    else if (affine_a) LAUNCH_ARA(true, false);
+    else if (affine_b) LAUNCH_ARA(false, true);
+    else LAUNCH_ARA(false, false);
+#undef LAUNCH_ARA
+    DNNCA_LAUNCH_CHECK("add_relu_affine");
+    return DNNCA_OK;
+  }
   if (vec8_ok(a) && vec8_ok(b) && vec8_ok(y) && a->c * 6 * 4 <= 48 * 1024) {
     add_relu_affine_vec8_kernel<<<grid_for(P * (a->c / 8), 256 * 4, 8), 256, (size_t)a->c * 6 * 4, (cudaStream_t)stream>>>(
         mk(a), affine_a, mk(b), affine_b, affine_out, mk(y), P);

@@ -80,6 +80,40 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(View f, const float* __re
   }
 }
 
+// bf16 features, F = 8 * NG with NG a power of two <= 32: NG lanes per pixel, one 16-byte load each, the dot product is
+// finished with shuffles.  The scalar kernel above reads a pixel's F features from ONE thread (2-byte loads, 128-byte
+// stride between the lanes of a warp): head_fwd[64@256] ran at 0.58 TB/s and cost 8 % of the MultiResUnet forward
+// (profiles/r02h_multires_sweep.json).
+template <int NG>
+__global__ void __launch_bounds__(256) head_fwd_vec_kernel(View f, const float* __restrict__ w, const float* __restrict__ b,
+                                                          float* __restrict__ logits, float* __restrict__ probs, long long P) {
+  const int g = threadIdx.x % NG;
+  float wr[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wr[j] = w[8 * g + j];
+  const float bias = b ? b[0] : 0.f;
+  const long long total = P * NG, padded = (total + 31) / 32 * 32;      // warp-uniform trip count (shuffles inside)
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < padded; e += (long long)gridDim.x * blockDim.x) {
+    const bool live = e < total;                       // the NG lanes of a pixel are live or dead together
+    const long long p = live ? e / NG : P - 1;
+    const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(f.data) + p * f.cstride + f.coff + 8 * g);
+    const uint32_t wd[4] = {r.x, r.y, r.z, r.w};
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      z = fmaf(__uint_as_float(wd[j] << 16), wr[2 * j], z);
+      z = fmaf(__uint_as_float(wd[j] & 0xffff0000u), wr[2 * j + 1], z);
+    }
+#pragma unroll
+    for (int o = 1; o < NG; o <<= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if (live && g == 0) {
+      z += bias;
+      if (logits) logits[p] = z;
+      if (probs) probs[p] = 1.f / (1.f + expf(-z));
+    }
+  }
+}
+
 // FMAX = compile-time bound on the feature count (register-resident dw partials)
 template <typename T, int FMAX>
 __global__ void __launch_bounds__(256) head_bce_kernel(View f, const float* __restrict__ w,
@@ -492,6 +526,22 @@ extern "C" int dnnca_head_fwd(void* stream, const dnnca_tensor_t* f, const float
                               float* probs) {
   DNNCA_CHECK_ARG(view_ok(f) && w && (logits || probs), "head_fwd: bad arguments");
   long long P = (long long)f->n * f->h * f->w;
+  const int ngv = f->c / 8;
+  if (f->dtype == DNNCA_BF16 && f->c % 8 == 0 && ngv <= 32 && (ngv & (ngv - 1)) == 0 && f->coff % 8 == 0 && f->cstride % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(f->data) & 15) == 0) {
+    const int gv = grid_for(P * ngv, 256 * 4, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (ngv) {
+      case 1: head_fwd_vec_kernel<1><<<gv, 256, 0, s>>>(mk(f), w, b, logits, probs, P); break;
+      case 2: head_fwd_vec_kernel<2><<<gv, 256, 0, s>>>(mk(f), w, b, logits, probs, P); break;
+      case 4: head_fwd_vec_kernel<4><<<gv, 256, 0, s>>>(mk(f), w, b, logits, probs, P); break;
+      case 8: head_fwd_vec_kernel<8><<<gv, 256, 0, s>>>(mk(f), w, b, logits, probs, P); break;
+      case 16: head_fwd_vec_kernel<16><<<gv, 256, 0, s>>>(mk(f), w, b, logits, probs, P); break;
+      default: head_fwd_vec_kernel<32><<<gv, 256, 0, s>>>(mk(f), w, b, logits, probs, P); break;
+    }
+    DNNCA_LAUNCH_CHECK("head_fwd");
+    return DNNCA_OK;
+  }
   int grid = grid_for(P, 256, 8);
   DNNCA_DISPATCH_DTYPE(f->dtype, head_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(mk(f), w, b, logits, probs, P);)
   DNNCA_LAUNCH_CHECK("head_fwd");

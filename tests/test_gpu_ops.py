@@ -494,6 +494,51 @@ def test_add_relu_affine(N):
     np.testing.assert_allclose(yb.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize('c,pads', [(32, (0, 0)), (120, (8, 16)), (216, (0, 8)), (864, (0, 0)), (2056, (0, 0))])
+def test_add_relu_affine_bf16_vector_paths(N, c, pads):
+    """bf16 views with 8-channel alignment: the register-table kernel (c / 8 <= 256 groups, incl. the MultiRes widths that
+    are no power of two) and the shared-memory one beyond; ragged pixel counts; every affine present / absent."""
+    rng = np.random.default_rng(c)
+    shape = (2, 5, 7, c)
+    a, b = q(rng.normal(size=shape).astype(np.float32), torch.bfloat16), q(rng.normal(size=shape).astype(np.float32), torch.bfloat16)
+    fa, fb, fo = (rng.normal(size=2 * c).astype(np.float32) for _ in range(3))
+    ab, ao, _ = embed(a, torch.bfloat16, *pads)
+    bb, bo, _ = embed(b, torch.bfloat16)
+    for use in ((True, True, True), (False, True, False), (False, False, True)):
+        yb = torch.zeros(*shape, dtype=torch.bfloat16, device='cuda')
+        av, bv, yv = view(N, ab, ao, c), view(N, bb, bo, c), view(N, yb, 0, c)
+        N.call('dnnca_add_relu_affine', None, C.byref(av), N.ptr(dev(fa)) if use[0] else None, C.byref(bv),
+               N.ptr(dev(fb)) if use[1] else None, N.ptr(dev(fo)) if use[2] else None, C.byref(yv))
+        sync()
+        va = a * fa[:c] + fa[c:] if use[0] else a
+        vb = b * fb[:c] + fb[c:] if use[1] else b
+        ref = np.maximum(va + vb, 0)
+        ref = ref * fo[:c] + fo[c:] if use[2] else ref
+        close(yb.float().cpu().numpy(), ref, 'bf16')
+        assert float(ab[..., :ao].float().abs().min()) == 7.0 if ao else True          # neighbours of the view untouched
+
+
+@pytest.mark.parametrize('F', [8, 16, 64, 256, 24])
+def test_head_fwd_bf16_vector_path(N, F):
+    """dnnca_head_fwd on bf16 features: F = 8 * 2^k takes the 16-byte / shuffle kernel (F = 24 stays on the scalar one);
+    35 pixels = a ragged last warp."""
+    rng = np.random.default_rng(F)
+    f = q(rng.normal(size=(1, 5, 7, F)).astype(np.float32), torch.bfloat16)
+    wt, b = rng.normal(size=F).astype(np.float32), rng.normal(size=1).astype(np.float32)
+    fbuf, fo_, _ = embed(f, torch.bfloat16, 8, 8)
+    fv = view(N, fbuf, fo_, F)
+    lg, pr = torch.zeros(1, 5, 7, device='cuda'), torch.zeros(1, 5, 7, device='cuda')
+    N.call('dnnca_head_fwd', None, C.byref(fv), N.ptr(dev(wt)), N.ptr(dev(b)), N.ptr(lg), N.ptr(pr))
+    sync()
+    z = f.astype(np.float64) @ wt.astype(np.float64) + b[0]
+    np.testing.assert_allclose(lg.cpu().numpy(), z, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(pr.cpu().numpy(), 1 / (1 + np.exp(-z)), rtol=1e-5, atol=1e-6)
+    only = torch.zeros(1, 5, 7, device='cuda')
+    N.call('dnnca_head_fwd', None, C.byref(fv), N.ptr(dev(wt)), None, N.ptr(only), None)      # no bias, logits only
+    sync()
+    np.testing.assert_allclose(only.cpu().numpy(), z - b[0], rtol=1e-5, atol=1e-5)
+
+
 def test_bad_arguments_fail_loudly(N):
     x = torch.zeros(1, 4, 4, 3, device='cuda')
     xv = N.tensor_view(x)
