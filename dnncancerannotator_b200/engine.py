@@ -154,6 +154,15 @@ class TFKerasModel:
         if world > 1 and self.model._dp is None:
             self.model.enable_data_parallel()
 
+    @staticmethod
+    def _peek_input_shape(dataset):
+        """``dataset.element_spec[0].shape`` of the reference (engine.py:93): read from the first batch of a re-iterable
+        dataset; a one-shot iterator would lose that batch, so it needs ``input_shape=``."""
+        if iter(dataset) is dataset:
+            raise ValueError('a one-shot iterator cannot be inspected without consuming a batch: pass input_shape=(None, H, W, C)')
+        first = next(iter(dataset))[0]
+        return (None, *first.shape[1:])
+
     # engine.py:55-78
     def get_ckpts(self, base_path):
         """{step: path prefix} of ``ckpt-<step>`` files (TensorFlow ``.index`` checkpoints as the reference lists them, and
@@ -185,10 +194,7 @@ class TFKerasModel:
             raise NotImplementedError('the Visualizer callback (callbacks.py:55-446) is outside the hot path')
         self._enter_strategy_section()
         if not self.model.built:
-            if input_shape is None:
-                first = next(iter(dataset))[0]
-                input_shape = (None, *first.shape[1:])
-            self.model.build(tuple(input_shape))
+            self.model.build(tuple(input_shape or self._peek_input_shape(dataset)))
         if self.model.params.device is None:
             self.model.params.materialize(self.model.device)      # Adam slots / step counter can be restored
         if auto_resume and save_path is not None:
@@ -217,10 +223,7 @@ class TFKerasModel:
             raise NotImplementedError('the Visualizer callback (callbacks.py:55-446) is outside the hot path')
         self._enter_strategy_section()
         if not self.model.built:
-            if input_shape is None:
-                first = next(iter(dataset))[0]
-                input_shape = (None, *first.shape[1:])
-            self.model.build(tuple(input_shape))
+            self.model.build(tuple(input_shape or self._peek_input_shape(dataset)))
         if self.model.params.device is None:
             self.model.params.materialize(self.model.device)
         ckpt_path = os.path.join(save_path, 'checkpoints')

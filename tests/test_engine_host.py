@@ -127,3 +127,12 @@ def test_get_ckpts_lists_tf_and_npz_checkpoints(tmp_path):
     assert E.solve_learning_rate_scheduler(None) is None
     with pytest.raises(ValueError):
         E.solve_learning_rate_scheduler('3')
+
+
+def test_input_shape_is_peeked_only_from_reiterable_datasets():
+    x = np.zeros((2, 32, 32, 3), np.float32)
+    assert E.TFKerasModel._peek_input_shape([(x, x[..., 0])]) == (None, 32, 32, 3)
+    gen = ((x, x[..., 0]) for _ in range(3))
+    with pytest.raises(ValueError, match='input_shape'):
+        E.TFKerasModel._peek_input_shape(gen)
+    assert len(list(gen)) == 3                      # nothing was consumed
