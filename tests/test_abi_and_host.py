@@ -398,3 +398,25 @@ def test_save_and_load_model_without_a_device(tmp_path):
     with pytest.raises(ValueError):
         json.dump(dict(class_name='NoSuchModel', config={}), open(os.path.join(d, 'config.json'), 'w'))
         load_model(d)
+
+
+def test_integration_doc_names_every_exported_symbol():
+    """INTEGRATION.md lists the reference call site of every entry point include/dnnca.h declares (names may be grouped as
+    ``dnnca_x_{a,b}`` or ``dnnca_x_*``)."""
+    import itertools
+    from dnncancerannotator_b200 import native
+    integ = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    named, wild = set(), []
+    for tok in re.findall(r'`(dnnca_[A-Za-z0-9_{},*]+)`', integ):
+        parts = re.split(r'(\{[^}]*\})', tok)
+        options = [p[1:-1].split(',') if p.startswith('{') else [p] for p in parts]
+        for combo in itertools.product(*options):
+            name = ''.join(combo)
+            if name.endswith('*'):
+                wild.append(name[:-1])
+            else:
+                named.add(name)
+    missing = [s for s in native.exported_symbols() if s not in named and not any(s.startswith(w) for w in wild)]
+    assert not missing, missing
+    unknown = sorted(n for n in named if n not in native.exported_symbols() and not n.endswith('_t'))       # (types)
+    assert not unknown, unknown                       # the document names nothing the library does not export
