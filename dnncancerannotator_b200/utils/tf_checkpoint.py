@@ -397,6 +397,11 @@ def reference_paths(model):
     ``downsamples`` / ``upsamples`` lists (components.py:203,276), ``convchain`` Sequential of conv[, bn] pairs, ``pool``
     Sequential [MaxPool, BN], ``conv_transpose`` layer or Sequential [ConvT, BN] (components.py:46-61,118-134).
     A ``keras.Sequential`` names its children ``layer_with_weights-<i>`` (layers that own variables) and ``layer-<i>``."""
+    if type(model).__name__ not in ('UNetAnnotator', 'MulmoUNetAnnotator'):
+        # MultiResUnet is a Keras FUNCTIONAL model: its checkpoint keys are `layer_with_weights-<i>` in the order Keras'
+        # graph traversal assigns, which is not restated here (nothing to pin it against) -- use the .npz format for it
+        raise NotImplementedError(f'TensorFlow-format checkpoints are mapped for UNetAnnotator / MulmoUNetAnnotator only, not '
+                                  f'{type(model).__name__}: save / load its weights in the .npz format')
     bn = bool(model.configs.get('bn'))
     out = {}
     for name in model.params.specs:

@@ -115,3 +115,18 @@ def test_export_and_load_through_the_reference_object_graph(tmp_path, cls, bn):
     for name, cands in T.reference_paths(other).items():
         (loaded if any(rd2.resolve(p, nodes2) for p in cands) else missing).append(name)
     assert missing and all('d2' in n or 'u2' in n for n in missing), missing
+
+
+def test_multiresunet_tf_format_is_refused_clearly(tmp_path):
+    """Keras' functional-model key order is not restated: the TF format says so instead of mis-mapping same-shaped layers."""
+    from dnncancerannotator_b200.models import tf_models
+    m = tf_models.MultiResUnet(None, None, 5)
+    m.build((None, 32, 32, 5))
+    with pytest.raises(NotImplementedError, match='npz'):
+        m.save_weights(str(tmp_path / 'ckpt-1'), save_format='tf')
+    m.save_weights(str(tmp_path / 'ckpt-1'))                     # own format works without a device
+    m2 = tf_models.MultiResUnet(None, None, 5, seed=5)
+    m2.build((None, 32, 32, 5))
+    m2.load_weights(str(tmp_path / 'ckpt-1')).assert_existing_objects_matched()
+    w1, w2 = m.get_weights(), m2.get_weights()
+    assert all(np.array_equal(w1[k], w2[k]) for k in w1)
