@@ -420,3 +420,29 @@ def test_integration_doc_names_every_exported_symbol():
     assert not missing, missing
     unknown = sorted(n for n in named if n not in native.exported_symbols() and not n.endswith('_t'))       # (types)
     assert not unknown, unknown                       # the document names nothing the library does not export
+
+
+def test_pack_labels_host_side():
+    """data_tail.pack_labels: bit order = numpy.packbits (what dnnca_unpack_label_bits expands), uint8 {0,255} and float
+    {0,1} masks give the same bits, anything fractional / ragged is refused."""
+    from hypothesis import given, settings, strategies as st
+    from dnncancerannotator_b200 import data_tail
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(1, 3), st.integers(1, 9), st.integers(1, 5), st.integers(0, 2 ** 31 - 1))
+    def roundtrip(b, h, w8, seed):
+        rng = np.random.default_rng(seed)
+        y = (rng.random((b, h, 8 * w8)) > 0.7)
+        for arr in (y.astype(np.float32), (y * 255).astype(np.uint8), torch.from_numpy(y.astype(np.float32))):
+            p = data_tail.pack_labels(arr, pinned=False)
+            assert p.shape == y.shape and p.nbytes * 8 == y.size and p.bits.dtype == torch.uint8
+            assert np.array_equal(np.unpackbits(p.bits.numpy(), axis=-1).astype(bool), y)
+    roundtrip()
+    y = np.zeros((1, 4, 16), np.float32)
+    y[0, 0, 0] = 0.5
+    with pytest.raises(ValueError):
+        data_tail.pack_labels(y, pinned=False)
+    with pytest.raises(ValueError):
+        data_tail.pack_labels(np.zeros((1, 4, 12), np.float32), pinned=False)
+    with pytest.raises(ValueError):
+        data_tail.pack_labels(np.zeros((4, 16), np.float32), pinned=False)
