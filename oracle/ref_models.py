@@ -74,7 +74,7 @@ class _Base:
         self.device = torch.device('cpu')
 
     def to(self, device):
-        """Evaluate the SAME restatement with torch on another device (tools/parity_real_shapes.py runs the fp32
+        """Evaluate the SAME restatement with torch on another device (tests/tools/parity_real_shapes.py runs the fp32
         oracle at the configs' full sizes on the GPU box's device with TF32 disabled; checked against the CPU
         evaluation at a small size there).  Test infrastructure only."""
         self.device = torch.device(device)

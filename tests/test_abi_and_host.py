@@ -67,12 +67,21 @@ def test_no_cuda_device_fails_loudly():
 
 
 def test_product_never_imports_the_oracle():
+    """Only tests/ (incl. tests/tools), __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/: neither the package
+    nor the scripts under tools/ import it."""
     bad = []
-    for d, _, files in os.walk(os.path.join(ROOT, 'dnncancerannotator_b200')):
-        for f in files:
-            if f.endswith('.py') and re.search(r'^\s*(from|import)\s+oracle\b', open(os.path.join(d, f)).read(), re.M):
-                bad.append(f)
+    for top in ('dnncancerannotator_b200', 'tools'):
+        for d, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith('.py') and re.search(r'^\s*(from|import)\s+oracle\b', open(os.path.join(d, f)).read(), re.M):
+                    bad.append(os.path.join(top, f))
     assert not bad, bad
+    # bench.py: the oracle appears only inside the CPU comparator / reference arm
+    src = open(os.path.join(ROOT, 'bench.py')).read()
+    for m in re.finditer(r'^\s*(from|import)\s+oracle\b.*$', src, re.M):
+        head = src[:m.start()]
+        fn = re.findall(r'^def (\w+)\(', head, re.M)[-1]
+        assert fn in ('cpu_reference_rate', 'run_reference'), fn
 
 
 # ---- config surface -------------------------------------------------------------------

@@ -237,7 +237,7 @@ def test_multiresunet_training_step(mode):
     own bf16-storage emulation: 7e-2 logits / 0.7 gradients), so the CUDA path is held to 1.25x that emulation.
     The batch (seed 11) is one without max-pool near-ties: a 2x2 window whose two largest values differ by a few fp32 ulps
     can be decided differently by two implementations, which re-routes one gradient element and moves the gradient of
-    this 61-BatchNorm-deep net by ~1e-2 (tools/multires_train_check.py --seed 1234 shows it: 1 of 3 408 argmax
+    this 61-BatchNorm-deep net by ~1e-2 (tests/tools/multires_train_check.py --seed 1234 shows it: 1 of 3 408 argmax
     entries differs at the deepest pool; the oracle in fp32 vs fp64 differs the same way on other batches)."""
     from dnncancerannotator_b200 import native as N
     B, S = 2, 32
@@ -445,7 +445,7 @@ def test_wide_configs_run_on_tensor_cores_bf16(cfgname, C, size, B):
     ConvT wide enough must be served by the tcgen05 implicit-GEMM kernels.
 
     These nets are ill-conditioned at random initialisation: rounding ONLY the weights to bf16 moves the
-    parameter gradient by ~35 % (tools/bf16_sensitivity.py), so no bf16 tensor-core path can meet
+    parameter gradient by ~35 % (tests/tools/bf16_sensitivity.py), so no bf16 tensor-core path can meet
     the 2e-2 gradient bound here.  The CUDA path is therefore required to deviate from the fp32 oracle by
     no more than 1.5x what the bf16-storage emulation of the oracle itself deviates (oracle/ref_bf16.py);
     the exactness of the lowering for the same configs is pinned by the fp32-mode test below."""

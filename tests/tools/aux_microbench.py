@@ -2,7 +2,7 @@
 """CUDA-event timings of the evaluation / augmentation kernels outside the training step (region-based metrics,
 thin-plate-spline warp) at the configs' sizes, with the oracle timed beside them on a bounded sample.
 
-  python tools/aux_microbench.py > gpurun_out/aux_microbench.txt
+  python tests/tools/aux_microbench.py > gpurun_out/aux_microbench.txt
 """
 import os
 import sys
@@ -11,7 +11,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from dnncancerannotator_b200 import data_tail as DT                  # noqa: E402
 from dnncancerannotator_b200 import native as N                      # noqa: E402

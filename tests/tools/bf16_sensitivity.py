@@ -1,6 +1,6 @@
 """Which bf16 roundings move the gradient of configs/unet_big.yaml at random init? (CPU, oracle only)
-   python tools/bf16_sensitivity.py"""
-import sys; sys.path.insert(0,'/root/repo')
+   python tests/tools/bf16_sensitivity.py"""
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, yaml
 from oracle import ref_models as rm, ref_ops as ops
 from dnncancerannotator_b200.synthetic import make_slices

@@ -11,7 +11,7 @@ the north-star tolerances (logits 1e-2, gradients 2e-2).  m = 10 is what the ref
 
 Also after 20 fp32 Adam steps ("conditioned weights").
 
-  python tools/conditioning_study.py [--size 128 --batch 8 --steps 20] > profiles/r02_conditioning.json
+  python tests/tools/conditioning_study.py [--size 128 --batch 8 --steps 20] > profiles/r02_conditioning.json
 """
 import argparse
 import json
@@ -23,7 +23,7 @@ import numpy as np
 import torch
 import yaml
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import ref_models as rm, ref_ops as ops                  # noqa: E402
 from oracle.ref_bf16 import emulate_bf16, round_mantissa             # noqa: E402

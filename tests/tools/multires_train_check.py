@@ -1,7 +1,7 @@
 """MultiResUnet training parity on the GPU box: one training step (forward with batch statistics, weighted BCE,
 full backward) of the CUDA path against the torch-CPU oracle (oracle/ref_models.py, autograd), per variable.
 
-    python tools/multires_train_check.py [--size 32] [--batch 2] [--modes fp32,bf16] [--steps 0]
+    python tests/tools/multires_train_check.py [--size 32] [--batch 2] [--modes fp32,bf16] [--steps 0]
 
 Writes gpurun_out/multires_train_check.json.  Test infrastructure (imports the oracle)."""
 import argparse
@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import ref_models as rm          # noqa: E402
 
 

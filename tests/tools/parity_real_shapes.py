@@ -7,7 +7,7 @@ The fp32 oracle is evaluated with torch ON THE GPU BOX'S DEVICE with TF32 disabl
 CPU evaluation of it is compared at a small size first and reported as `oracle_device_vs_cpu`), because 20 Adam steps of
 unet_big at 256^2 x 8 cost minutes on the host cores.  Test infrastructure only: nothing here is on the product path.
 
-  python tools/parity_real_shapes.py --out gpurun_out/parity_real_shapes.json [--size 256 --batch 8 --steps 20]
+  python tests/tools/parity_real_shapes.py --out gpurun_out/parity_real_shapes.json [--size 256 --batch 8 --steps 20]
 """
 import argparse
 import json
@@ -18,7 +18,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import ref_models as rm, ref_ops as ops                  # noqa: E402
 from oracle.ref_bf16 import emulate_bf16                             # noqa: E402
